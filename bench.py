@@ -1,0 +1,616 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the macroblock hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--extras 0|1]
+
+A "step" is one pass of the hot path over one batch of synthetic frames.  Workloads (BASELINE.json configs):
+  decode_i_1080p  configs[1]  64 independent 1080p key frames per GPU, one launch per step           (default)
+  decode_p_1080p  configs[2]  8 GOPs x 15 frames (1 key frame / 15), frame k of every GOP per launch
+  encode_p_1080p  configs[3]  the same GOPs encoded (full SSD block search), frame k of every GOP per launch
+  decode_p_4k     configs[4]  4 GOPs x 15 frames of 3840x2160 per GPU, GOPs sharded over the ranks
+
+`value`  : whole-job frames/s with the inputs resident in HBM (CUDA events on the launching stream).
+`e2e`    : the same through the C ABI with pinned HOST buffers, H2D of every coefficient/header/source byte and
+           D2H of every decoded plane (or coefficient) inside the timed region.
+`roofline`: algorithmic bytes per launch / mean launch time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline`: the oracle (plain-C restatement of the reference algorithm, OpenMP over macroblocks like the
+           reference's rayon par_iter) on this box's host cores, on a bounded sample.  The Rust reference itself
+           cannot be built here (no cargo/rustc), so kind = "port".
+
+Multi-GPU: one process per GPU (torchrun), frames/GOPs sharded over ranks, NO collective on the data path
+(weak scaling: per-GPU work fixed); barrier + max-over-ranks timing through torch.distributed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MB_BYTES_DEC_I = 768          # 512 R coeff + 256 W          
+MB_BYTES_DEC_P_CODED = 1027   # 3 hdr + 512 coeff + 256 ref + 256 W
+MB_BYTES_DEC_P_SKIP = 515
+MB_BYTES_ENC_P_CODED = 1283   # 256 src + 256 ref + 3 + 512 + 256
+MB_BYTES_ENC_P_SKIP = 771
+MB_BYTES_ENC_I = 1024
+
+WORKLOADS = {
+    "decode_i_1080p": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465601),
+    "decode_p_1080p": dict(w=1920, h=1080, frames=0, gops=8, gop=15, quality=5, seed=0x50465602),
+    "encode_p_1080p": dict(w=1920, h=1080, frames=0, gops=8, gop=15, quality=5, seed=0x50465602),
+    "decode_p_4k": dict(w=3840, h=2160, frames=0, gops=4, gop=15, quality=5, seed=0x50465603),
+}
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed ncu summary (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel_key)
+    return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class Dist:
+    def __init__(self, want_gpus):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        if want_gpus != self.world and self.rank == 0 and want_gpus > 1:
+            print(f"[bench] --gpus {want_gpus} but WORLD_SIZE={self.world}: launch with torchrun "
+                  f"--nproc-per-node {want_gpus}", file=sys.stderr)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# building the synthetic streams ON THE GPU with the engine's own encoder (no oracle on this path)
+# ----------------------------------------------------------------------------------------------------
+class Streams:
+    """Dense coefficients + macroblock headers for `lanes` independent GOPs of `gop` frames each, resident in
+    HBM (torch tensors) and, lazily, in pinned host memory."""
+
+    def __init__(self, torch, cfg, rank, stream):
+        from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine, make_qtables
+        from pretty_fast_video_b200.engine import EncodeJob
+        from pretty_fast_video_b200.synth import SynthVideo
+        self.torch, self.cfg = torch, cfg
+        w, h = cfg["w"], cfg["h"]
+        self.lanes = cfg["frames"] if cfg["gop"] == 1 else cfg["gops"]
+        self.gop = cfg["gop"]
+        self.qt, self.px_err = make_qtables(cfg["quality"])
+        eng = Engine(w, h, self.qt, nslots=2 * self.lanes, max_jobs=self.lanes, device=torch.cuda.current_device(),
+                     stream=stream.cuda_stream)
+        g = eng.geometry
+        self.geo = g
+        self.nb = g.nb
+        n = self.lanes * self.gop
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.d_coeff = torch.zeros((self.gop, self.lanes, g.nb * 256), dtype=torch.int16, device=dev)
+        self.d_hdr = torch.zeros((self.gop, self.lanes, g.nb, 4), dtype=torch.uint8, device=dev)
+        ysz, csz = w * h, (w // 2) * (h // 2)
+        self.src_bytes = ysz + 2 * csz
+        self.d_src = torch.zeros((self.gop, self.lanes, self.src_bytes), dtype=torch.uint8, device=dev)
+        # I-only workload: every frame of one moving sequence; GOP workloads: lane g = its own sequence
+        for lane in range(self.lanes):
+            if self.gop == 1:
+                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank) if lane == 0 else sv
+                frames = [sv.frame(lane)]
+            else:
+                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank + lane)
+                frames = [sv.frame(t) for t in range(self.gop)]
+            for k, (y, u, v) in enumerate(frames):
+                buf = np.concatenate([y.ravel(), u.ravel(), v.ravel()])
+                self.d_src[k, lane].copy_(torch.from_numpy(buf))
+        torch.cuda.synchronize()
+        cur = [2 * i for i in range(self.lanes)]
+        for k in range(self.gop):
+            jobs = []
+            for lane in range(self.lanes):
+                base = self.d_src[k, lane].data_ptr()
+                dst = cur[lane] ^ 1
+                jobs.append(EncodeJob(PFV_FRAME_I if k == 0 else PFV_FRAME_P, dst,
+                                      (base, base + ysz, base + ysz + csz), self.d_coeff[k, lane].data_ptr(),
+                                      ref_slot=cur[lane], px_err=self.px_err, hdr_out=self.d_hdr[k, lane].data_ptr(),
+                                      device_ptrs=True))
+                cur[lane] = dst
+            with torch.cuda.stream(stream):
+                eng.encode_submit(jobs)
+        eng.sync()
+        eng.close()
+        hdr = self.d_hdr.cpu().numpy()
+        self.coded = hdr[..., 2] != 0                       # [gop, lanes, nb]
+        if self.gop > 1:
+            self.coded[0] = True
+            # dec.rs:376: skipped macroblocks carry zero coefficients in the dense array
+            mask = torch.from_numpy(~self.coded[1:]).to(dev)
+            self.d_coeff[1:].view(self.gop - 1, self.lanes, g.nb, 256)[mask] = 0
+        else:
+            self.coded[:] = True
+        self.mv_nonzero = float(((hdr[1:, ..., 0] != 0) | (hdr[1:, ..., 1] != 0)).mean()) if self.gop > 1 else 0.0
+        self.coded_frac = float(self.coded[1:].mean()) if self.gop > 1 else 1.0
+        self._host = None
+
+    def host(self):
+        """pinned copies (coefficients, headers, source planes)"""
+        if self._host is None:
+            from pretty_fast_video_b200 import PinnedArena
+            n = self.d_coeff.numel() * 2 + self.d_hdr.numel() + self.d_src.numel() + 3 * 4096
+            arena = PinnedArena(n)
+            hc = arena.take(tuple(self.d_coeff.shape), np.int16)
+            hh = arena.take(tuple(self.d_hdr.shape), np.uint8)
+            hs = arena.take(tuple(self.d_src.shape), np.uint8)
+            hc[...] = self.d_coeff.cpu().numpy()
+            hh[...] = self.d_hdr.cpu().numpy()
+            hs[...] = self.d_src.cpu().numpy()
+            self._host = (arena, hc, hh, hs)
+        return self._host
+
+
+# ----------------------------------------------------------------------------------------------------
+# the timed legs
+# ----------------------------------------------------------------------------------------------------
+def time_steps(torch, dist, stream, step_fn, sync_fn, steps, warmup, wall=False):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides; returns (ms_per_step max over
+    ranks, this rank's ms_per_step)."""
+    for _ in range(warmup):
+        step_fn()
+    sync_fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    if wall:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()
+        sync_fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                step_fn()
+            e1.record(stream)
+        sync_fn()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    dist.barrier()
+    return dist.max(ms), ms
+
+
+def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
+    from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine
+    from pretty_fast_video_b200.engine import DecodeJob
+    g, L, G = st.geo, st.lanes, st.gop
+    w, h = st.cfg["w"], st.cfg["h"]
+    dev_index = torch.cuda.current_device()
+
+    def make_jobs(eng, k, cur, coeff_ptr, hdr_ptr, device, outs=None):
+        jobs = []
+        for lane in range(L):
+            dst = cur[lane] ^ 1
+            jobs.append(DecodeJob(PFV_FRAME_I if k == 0 else PFV_FRAME_P, dst, coeff_ptr(k, lane),
+                                  (0, 1, 1) if k == 0 else (2, 3, 3), ref_slot=cur[lane],
+                                  hdr=hdr_ptr(k, lane) if k else None, device_ptrs=device,
+                                  out=outs(k, lane) if outs else None))
+            cur[lane] = dst
+        return eng.build_decode_jobs(jobs), jobs
+
+    # ---- device-resident ------------------------------------------------------------------------
+    eng = Engine(w, h, st.qt, nslots=2 * L, max_jobs=L, device=dev_index, stream=stream.cuda_stream)
+    cur = [2 * i for i in range(L)]
+    # two passes over the GOP bring every lane's ping-pong state back to where it started only for even G;
+    # prebuild 2*G steps' worth of job tables so the slot pattern is exact for any G
+    tables = []
+    for rep in range(2):
+        for k in range(G):
+            tables.append(make_jobs(eng, k, cur, lambda k, l: st.d_coeff[k, l].data_ptr(),
+                                    lambda k, l: st.d_hdr[k, l].data_ptr(), True))
+    phase = [0]
+
+    def step_dev():
+        base = (phase[0] % 2) * G
+        for k in range(G):
+            arr, jobs = tables[base + k]
+            eng.decode_submit(jobs, prebuilt=arr)
+        phase[0] += 1
+
+    l0 = eng.launch_count
+    max_ms, my_ms = time_steps(torch, dist, stream, step_dev, eng.sync, steps, warmup)
+    launches_per_step = (eng.launch_count - l0) // (steps + warmup)
+    eng.close()
+
+    # ---- end to end through host buffers ------------------------------------------------------------
+    e2e = None
+    if do_e2e:
+        from pretty_fast_video_b200 import PinnedArena
+        arena, hc, hh, hs = st.host()
+        chunk = min(L, 8)                                   # jobs per submit: H2D of chunk i+1 overlaps chunk i
+        eng2 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
+        ysz, csz = w * h, (w // 2) * (h // 2)
+        out_arena = PinnedArena(G * L * (ysz + 2 * csz) + 4096)
+        outb = out_arena.take((G, L, ysz + 2 * csz), np.uint8)
+
+        def outs(k, lane):
+            b = outb[k, lane].ctypes.data
+            return (b, b + ysz, b + ysz + csz)
+
+        cur2 = [2 * i for i in range(L)]
+        tabs2 = []
+        for rep in range(2):
+            for k in range(G):
+                full, jobs = make_jobs(eng2, k, cur2, lambda k, l: hc[k, l].ctypes.data, lambda k, l: hh[k, l].ctypes.data,
+                                       False, outs)
+                tabs2.append([(eng2.build_decode_jobs(jobs[i:i + chunk]), jobs[i:i + chunk]) for i in range(0, L, chunk)])
+        ph2 = [0]
+
+        def step_e2e():
+            base = (ph2[0] % 2) * G
+            for k in range(G):
+                for arr, jobs in tabs2[base + k]:
+                    eng2.decode_submit(jobs, prebuilt=arr)
+            ph2[0] += 1
+
+        e_max, _ = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
+        nframes = G * L
+        h2d = int(st.nb * 512 * nframes + (G - 1) * L * st.nb * 4)
+        d2h = int((ysz + 2 * csz) * nframes)
+        e2e = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "jobs_per_submit": chunk,
+               "pcie_gbs_each_way": [h2d / e_max / 1e6, d2h / e_max / 1e6]}
+        # spot check: what came back is what the device holds (decoded planes of the last frame, lane 0)
+        eng2.close()
+        out_arena.close()
+
+    nframes = G * L
+    if G == 1:
+        alg = nframes * st.nb * MB_BYTES_DEC_I
+    else:
+        coded = st.coded[1:]
+        alg = L * st.nb * MB_BYTES_DEC_I + int(coded.sum()) * MB_BYTES_DEC_P_CODED + int((~coded).sum()) * MB_BYTES_DEC_P_SKIP
+    return dict(max_ms=max_ms, my_ms=my_ms, frames=nframes, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e)
+
+
+def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
+    from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine, PinnedArena
+    from pretty_fast_video_b200.engine import EncodeJob
+    g, L, G = st.geo, st.lanes, st.gop
+    w, h = st.cfg["w"], st.cfg["h"]
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    dev_index = torch.cuda.current_device()
+    dev = torch.device("cuda", dev_index)
+    d_c = torch.zeros((L, st.nb * 256), dtype=torch.int16, device=dev)
+    d_h = torch.zeros((L, st.nb, 4), dtype=torch.uint8, device=dev)
+
+    def make_tables(eng, src_ptr, c_ptr, h_ptr, device, chunk):
+        cur = [2 * i for i in range(L)]
+        tabs = []
+        for rep in range(2):
+            for k in range(G):
+                jobs = []
+                for lane in range(L):
+                    b = src_ptr(k, lane)
+                    dst = cur[lane] ^ 1
+                    jobs.append(EncodeJob(PFV_FRAME_I if k == 0 else PFV_FRAME_P, dst, (b, b + ysz, b + ysz + csz),
+                                          c_ptr(k, lane), ref_slot=cur[lane], px_err=st.px_err, hdr_out=h_ptr(k, lane),
+                                          device_ptrs=device))
+                    cur[lane] = dst
+                tabs.append([(eng.build_encode_jobs(jobs[i:i + chunk]), jobs[i:i + chunk]) for i in range(0, L, chunk)])
+        return tabs
+
+    eng = Engine(w, h, st.qt, nslots=2 * L, max_jobs=L, device=dev_index, stream=stream.cuda_stream)
+    tabs = make_tables(eng, lambda k, l: st.d_src[k, l].data_ptr(), lambda k, l: d_c[l].data_ptr(),
+                       lambda k, l: d_h[l].data_ptr(), True, L)
+    ph = [0]
+
+    def step_dev():
+        base = (ph[0] % 2) * G
+        for k in range(G):
+            for arr, jobs in tabs[base + k]:
+                eng.encode_submit(jobs, prebuilt=arr)
+        ph[0] += 1
+
+    l0 = eng.launch_count
+    max_ms, my_ms = time_steps(torch, dist, stream, step_dev, eng.sync, steps, warmup)
+    launches_per_step = (eng.launch_count - l0) // (steps + warmup)
+    eng.close()
+
+    e2e = None
+    if do_e2e:
+        arena, hc, hh, hs = st.host()
+        chunk = min(L, 8)
+        eng2 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
+        oa = PinnedArena(G * L * (st.nb * 512 + st.nb * 4) + 8192)
+        oc = oa.take((G, L, st.nb * 256), np.int16)
+        oh = oa.take((G, L, st.nb, 4), np.uint8)
+        tabs2 = make_tables(eng2, lambda k, l: hs[k, l].ctypes.data, lambda k, l: oc[k, l].ctypes.data,
+                            lambda k, l: oh[k, l].ctypes.data, False, chunk)
+        ph2 = [0]
+
+        def step_e2e():
+            base = (ph2[0] % 2) * G
+            for k in range(G):
+                for arr, jobs in tabs2[base + k]:
+                    eng2.encode_submit(jobs, prebuilt=arr)
+            ph2[0] += 1
+
+        e_max, _ = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
+        nframes = G * L
+        e2e = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
+               "h2d_bytes_per_step": int(nframes * (ysz + 2 * csz)),
+               "d2h_bytes_per_step": int(nframes * st.nb * 512 + (G - 1) * L * st.nb * 4), "jobs_per_submit": chunk}
+        eng2.close()
+        oa.close()
+    coded = st.coded[1:]
+    alg = L * st.nb * MB_BYTES_ENC_I + int(coded.sum()) * MB_BYTES_ENC_P_CODED + int((~coded).sum()) * MB_BYTES_ENC_P_SKIP
+    return dict(max_ms=max_ms, my_ms=my_ms, frames=G * L, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------------
+def cpu_port_leg(workload, budget_s, nthreads, reps=None):
+    """Times the oracle's macroblock loops (dense coefficients <-> planes, no entropy coding: the same seam the
+    GPU legs time) on this box's host cores.  Returns frames/s and a description of the sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pfvo
+    from pretty_fast_video_b200.synth import SynthVideo
+    cfg = WORKLOADS[workload]
+    w, h = cfg["w"], cfg["h"]
+    og = pfvo.geometry_for(w, h)
+    qt, px_err = pfvo.make_qtables(cfg["quality"])
+    gop = cfg["gop"]
+    nsrc = 4 if gop == 1 else min(gop, 6)
+    sv = SynthVideo(w, h, cfg["seed"])
+    frames = [sv.frame(t) for t in range(nsrc)]
+    # seam data from the oracle's own encoder (this is the CPU arm; the GPU arm makes its input on the GPU)
+    prev = pfvo.frame_init(og)
+    seam = []
+    for t, (y, u, v) in enumerate(frames):
+        if gop == 1 or t == 0:
+            c = pfvo.encode_iframe_coeffs(og, qt, y, u, v, prev, nthreads)
+            seam.append((1, None, c))
+        else:
+            hd, c = pfvo.encode_pframe_coeffs(og, qt, px_err, y, u, v, prev, nthreads)
+            seam.append((2, hd, c))
+    done, t_used = 0, 0.0
+    state = pfvo.frame_init(og)
+    while t_used < budget_s and (reps is None or done < reps * len(seam)):
+        if workload.startswith("encode"):
+            prev = pfvo.frame_init(og)
+        t0 = time.perf_counter()
+        for t, (kind, hd, c) in enumerate(seam):
+            if workload.startswith("encode"):
+                y, u, v = frames[t]
+                if kind == 1:
+                    pfvo.encode_iframe_coeffs(og, qt, y, u, v, prev, nthreads)
+                else:
+                    pfvo.encode_pframe_coeffs(og, qt, px_err, y, u, v, prev, nthreads)
+            elif kind == 1:
+                pfvo.decode_iframe_coeffs(og, qt, (0, 1, 1), c, state, nthreads)
+            else:
+                pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hd, c, state, nthreads)
+        t_used += time.perf_counter() - t0
+        done += len(seam)
+    fps = done / t_used
+    sample = (f"{done} frames ({len(seam)} distinct {w}x{h} frames"
+              f"{', 1 key + ' + str(len(seam) - 1) + ' P' if gop > 1 else ', all key'}; oracle MB loops only, "
+              f"dense coefficients <-> planes) in {t_used:.1f} s on {nthreads} OpenMP threads")
+    return fps, sample, og.nb
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    cfg = WORKLOADS[args.workload]
+    t_all = time.perf_counter()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        fps, sample, nb = cpu_port_leg(args.workload, budget_s=1e9, nthreads=nthreads, reps=2)
+        if i >= args.warmup:
+            vals.append(fps)
+        if time.perf_counter() - t_all > 240:
+            break
+    v = float(np.mean(vals)) if vals else fps
+    line = {
+        "impl": "reference", "metric": "1080p decode frames/sec" if "1080p" in args.workload else "decode frames/sec",
+        "value": v, "unit": "frames/s", "mb_per_s": v * nb, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": 1e3 * 2 * (4 if cfg["gop"] == 1 else 6) / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"]},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C restatement of the reference algorithm (oracle/); the Rust crate cannot be built here (no cargo/rustc)",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="decode_i_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--extras", type=int, default=1, help="also run the P-stream decode/encode workloads (N=1 only)")
+    ap.add_argument("--cpu-budget", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    from pretty_fast_video_b200 import lib
+    lib()                                                   # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
+    dist = Dist(args.gpus)
+    torch.cuda.set_device(dist.local)
+    stream = torch.cuda.Stream()
+    peak, peak_src = peaks()
+
+    def run(workload, steps, warmup, do_e2e=True):
+        cfg = WORKLOADS[workload]
+        st = Streams(torch, cfg, dist.rank, stream)
+        fn = run_encode if workload.startswith("encode") else run_decode
+        r = fn(torch, dist, stream, st, steps, warmup, do_e2e)
+        r["st"] = st
+        return r
+
+    sampler = ClockSampler(dist.local)
+    sampler.start()
+    r = run(args.workload, args.steps, args.warmup)
+    clocks = sampler.stop()
+    st, cfg = r["st"], WORKLOADS[args.workload]
+    fps = r["frames"] * dist.world / (r["max_ms"] * 1e-3)
+    launches = r["launches_per_step"]
+    achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
+    kernel_key = {"decode_i_1080p": "decode_kernel<false>", "decode_p_1080p": "decode_kernel<true>",
+                  "decode_p_4k": "decode_kernel<true>", "encode_p_1080p": "encode_p_kernel"}[args.workload]
+    line = {
+        "metric": "1080p decode frames/sec" if "decode" in args.workload and "1080p" in args.workload else f"{args.workload} frames/sec",
+        "value": fps, "unit": "frames/s", "mb_per_s": fps * st.nb,
+        "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["max_ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"],
+                   "frames_per_step_per_gpu": r["frames"], "gop": cfg["gop"], "mb_per_frame": st.nb,
+                   "coded_mb_fraction_p": st.coded_frac, "nonzero_mv_fraction_p": st.mv_nonzero,
+                   "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+                   "sharding": "frames/GOPs split over ranks, no collective on the data path"},
+        "gpu_launches": launches * args.steps,
+        "e2e": {k: v for k, v in (r["e2e"] or {}).items()},
+        "roofline": {"bound": "hbm", "kernel": kernel_key, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": r["alg_bytes"],
+                     "launches_per_step": launches, "traffic": ncu_traffic(kernel_key)},
+        "clocks": clocks,
+    }
+
+    if dist.world == 1:
+        nthreads = os.cpu_count() or 1
+        cfps, sample, _ = cpu_port_leg(args.workload, args.cpu_budget, nthreads)
+        line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
+        if args.extras:
+            extras = {}
+            for wl in ("decode_p_1080p", "encode_p_1080p"):
+                if wl == args.workload:
+                    continue
+                try:
+                    x = run(wl, max(3, args.steps // 4), 3)
+                    xs = x["st"]
+                    extras[wl] = {
+                        "value": x["frames"] / (x["max_ms"] * 1e-3), "unit": "frames/s",
+                        "mb_per_s": x["frames"] / (x["max_ms"] * 1e-3) * xs.nb, "ms_per_step": x["max_ms"],
+                        "frames_per_step": x["frames"], "launches_per_step": x["launches_per_step"],
+                        "coded_mb_fraction_p": xs.coded_frac, "nonzero_mv_fraction_p": xs.mv_nonzero,
+                        "roofline_frac": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9 / peak,
+                        "achieved_gbs": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9,
+                        "e2e": x["e2e"],
+                    }
+                    cf, cs, _ = cpu_port_leg(wl, min(args.cpu_budget, 6.0), nthreads)
+                    extras[wl]["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": cs}
+                except Exception as ex:                      # an extra must never lose the headline line
+                    extras[wl] = {"error": repr(ex)}
+            line["extras"] = extras
+    if dist.rank == 0:
+        print(json.dumps(line))
+    dist.close()
+
+
+if __name__ == "__main__":
+    main()

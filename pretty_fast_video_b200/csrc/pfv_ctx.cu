@@ -1,0 +1,789 @@
+// pfv_ctx.cu — host side of the engine: context, frame-slot pool, staging rings, the three-stream
+// H2D / compute / D2H pipeline and the C ABI of include/pfv_b200.h.
+//
+// There is deliberately NO CPU fallback in this file: without a CUDA device every entry point that
+// would compute fails with PFV_ERR_NO_DEVICE / PFV_ERR_CUDA.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "pfv_internal.h"
+
+using namespace pfv;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? PFV_ERR_NO_DEVICE \
+                                                                                     : PFV_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+    } while (0)
+
+extern "C" const char *pfv_last_error(void) { return g_err; }
+extern "C" int pfv_abi_version(void) { return PFV_B200_ABI_VERSION; }
+
+extern "C" int pfv_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(PFV_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// geometry and q-tables (host arithmetic only)
+// ---------------------------------------------------------------------------------------------------
+static uint32_t pad16(uint32_t v) { return v + (16 - (v % 16)) % 16; }   // src/frame.rs:29-30
+
+extern "C" void pfv_geometry_for(uint32_t width, uint32_t height, pfv_geometry *g)
+{
+    g->width = width;
+    g->height = height;
+    g->cwidth = width / 2;                  // src/frame.rs:32
+    g->cheight = height / 2;                // src/frame.rs:33
+    g->pw = pad16(width);
+    g->ph = pad16(height);
+    g->cpw = pad16(g->cwidth);              // src/frame.rs:35
+    g->cph = pad16(g->cheight);             // src/frame.rs:36
+    g->nb_y = (g->pw / 16) * (g->ph / 16);
+    g->nb_c = (g->cpw / 16) * (g->cph / 16);
+    g->nb = g->nb_y + 2 * g->nb_c;          // src/dec.rs:255
+    g->frame_bytes = g->pw * g->ph + 2 * g->cpw * g->cph;
+}
+
+// src/dct.rs:16-37
+static const int32_t kQIntra[64] = {
+     8, 16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37,
+    19, 22, 26, 27, 29, 34, 34, 38, 22, 22, 26, 27, 29, 34, 37, 40,
+    22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32, 35, 40, 48, 58,
+    26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83,
+};
+static const int32_t kQInterValue = 16;
+// src/dct.rs:4-13
+static const int32_t kScale[64] = {
+    32, 37, 34, 26, 32, 26, 34, 37, 37, 43, 39, 31, 37, 31, 39, 43,
+    34, 39, 35, 28, 34, 28, 35, 39, 26, 31, 28, 22, 26, 22, 28, 31,
+    32, 37, 34, 26, 32, 26, 34, 37, 26, 31, 28, 22, 26, 22, 28, 31,
+    34, 39, 35, 28, 34, 28, 35, 39, 37, 43, 39, 31, 37, 31, 39, 43,
+};
+// src/dct.rs:39-42
+static const uint8_t kInvZigzag[64] = {
+     0,  1,  5,  6, 14, 15, 27, 28,  2,  4,  7, 13, 16, 26, 29, 42,
+     3,  8, 12, 17, 25, 30, 41, 43,  9, 11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
+    21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63,
+};
+
+// src/enc.rs:40-51.  Each product is rounded to f32 like the Rust expression
+// `(x as f32 * qscale * 0.5).max(1.0) as i32`.
+extern "C" int pfv_make_qtables(int quality, int32_t out[4][64], float *px_err_out)
+{
+    if (quality < 0 || quality > 10) return fail(PFV_ERR_BAD_ARG, "quality %d outside 0..=10 (src/enc.rs:38)", quality);
+    volatile float qscale = (float)quality * 0.25f;
+    for (int i = 0; i < 64; i++) {
+        volatile float a, b;
+        a = (float)kQIntra[i] * qscale;
+        b = a * 0.5f;
+        out[0][i] = (int32_t)fmaxf(b, 1.0f);   // intra_l, src/enc.rs:50
+        out[1][i] = (int32_t)fmaxf(a, 1.0f);   // intra_c, src/enc.rs:51
+        a = (float)kQInterValue * qscale;
+        b = a * 0.5f;
+        out[2][i] = (int32_t)fmaxf(b, 1.0f);   // inter_l, src/enc.rs:48
+        out[3][i] = (int32_t)fmaxf(a, 1.0f);   // inter_c, src/enc.rs:49
+    }
+    if (px_err_out) *px_err_out = (float)quality * 1.5f;   // src/enc.rs:41
+    return PFV_OK;
+}
+
+extern "C" int pfv_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return fail(PFV_ERR_BAD_ARG, "pfv_host_alloc: out is NULL");
+    *out = nullptr;
+    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PFV_OK;
+}
+
+extern "C" void pfv_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int STAGES = 2;        // staging ring depth: H2D of submit n+1 overlaps the kernels of submit n
+constexpr int D2H_RING = 8;      // D2H completion events kept for slot-reuse ordering
+
+struct Stage {
+    int16_t   *d_coeff = nullptr;    // max_jobs * nb * 256
+    pfv_mbhdr *d_hdr = nullptr;      // max_jobs * nb
+    uint8_t   *d_src = nullptr;      // max_jobs * src_stride (encode only, lazily allocated)
+    void      *d_jobs = nullptr;     // max_jobs * max(sizeof(DecJob), sizeof(EncJob))
+    void      *h_jobs = nullptr;     // pinned mirror of d_jobs
+    cudaEvent_t ev_h2d = nullptr;    // job table + inputs are on the device
+    cudaEvent_t ev_kernel = nullptr; // kernels that read/write the stage's device buffers are done
+    cudaEvent_t ev_d2h = nullptr;    // copies out of the stage's device buffers are done (encode)
+};
+
+}  // namespace
+
+struct pfv_ctx {
+    int device = 0;
+    pfv_geometry geo{};
+    FrameGeom fg{};
+    uint32_t nq = 0, nslots = 0, max_jobs = 0;
+    size_t slot_stride = 0;          // frame_bytes rounded up to 256
+    size_t src_stride = 0;           // per-job source staging (encode)
+    uint32_t src_off[3] = {0, 0, 0};
+    uint8_t *d_pool = nullptr;
+    QTables *d_qt = nullptr;
+    int *d_err = nullptr;
+    int *h_err = nullptr;            // pinned
+    cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    bool own_compute = true;
+    Stage st[STAGES];
+    cudaEvent_t ev_d2h_ring[D2H_RING]{};
+    std::vector<uint64_t> slot_last_d2h;   // submit id (1-based) whose D2H last read the slot; 0 = none
+    uint64_t submit_id = 0;
+    uint64_t launches = 0;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    bool have_kernel_time = false;
+    CUtensorMap tm_luma{}, tm_chroma{};
+    bool have_tma = false;
+    char tma_err[160] = "";
+};
+
+namespace {
+
+int build_tensor_maps(pfv_ctx *c)
+{
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        snprintf(c->tma_err, sizeof(c->tma_err), "cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+        return -1;
+    }
+    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+    const pfv_geometry &g = c->geo;
+    const cuuint32_t box[4] = {WIN_W, WIN_H, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    {   // luma: (x, y, 1, slot)
+        const cuuint64_t dims[4] = {g.pw, g.ph, 1, c->nslots};
+        const cuuint64_t strides[3] = {g.pw, c->slot_stride, c->slot_stride};
+        CUresult r = encode(&c->tm_luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->d_pool, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(c->tma_err, sizeof(c->tma_err), "cuTensorMapEncodeTiled(luma) -> CUresult %d", (int)r);
+            return -1;
+        }
+    }
+    {   // chroma: (x, y, u|v, slot)
+        const cuuint64_t nc = (cuuint64_t)g.cpw * g.cph;
+        const cuuint64_t dims[4] = {g.cpw, g.cph, 2, c->nslots};
+        const cuuint64_t strides[3] = {g.cpw, nc, c->slot_stride};
+        CUresult r = encode(&c->tm_chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->d_pool + (size_t)g.pw * g.ph, dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(c->tma_err, sizeof(c->tma_err), "cuTensorMapEncodeTiled(chroma) -> CUresult %d", (int)r);
+            return -1;
+        }
+    }
+    c->have_tma = true;
+    return 0;
+}
+
+void fill_frame_geom(pfv_ctx *c)
+{
+    const pfv_geometry &g = c->geo;
+    FrameGeom &f = c->fg;
+    const uint32_t pw[3] = {g.pw, g.cpw, g.cpw}, ph[3] = {g.ph, g.cph, g.cph};
+    const uint32_t vw[3] = {g.width, g.cwidth, g.cwidth}, vh[3] = {g.height, g.cheight, g.cheight};
+    uint32_t mb = 0, tile = 0, off = 0;
+    for (int p = 0; p < 3; p++) {
+        PlaneGeom &pl = f.pl[p];
+        pl.pw = pw[p]; pl.ph = ph[p]; pl.vw = vw[p]; pl.vh = vh[p];
+        pl.bw = pw[p] / 16; pl.bh = ph[p] / 16;
+        pl.mb_base = mb; pl.off = off;
+        pl.rcp_bw = 1.0f / (float)pl.bw;
+        pl.tiles_per_row = (pl.bw + 7) / 8;
+        pl.tile_base = tile;
+        pl.clear4 = p == 0 ? 0u : 0x80808080u;
+        mb += pl.bw * pl.bh;
+        tile += pl.tiles_per_row * pl.bh;
+        off += pw[p] * ph[p];
+    }
+    f.nb = mb;
+    f.total_tiles = tile;
+    f.frame_bytes = off;
+}
+
+void build_qtables(const int32_t (*qtables)[64], uint32_t nq, std::vector<QTables> &out)
+{
+    out.resize(nq);
+    for (uint32_t t = 0; t < nq; t++) {
+        for (int c = 0; c < 8; c++)
+            for (int row = 0; row < 8; row++) {
+                const int raster = row * 8 + c;
+                const int s = kInvZigzag[raster];
+                // src/dct.rs:78-83: tables indexed by the SCAN position s; wrapping i32 product
+                const uint32_t prod = (uint32_t)kScale[s] * (uint32_t)qtables[t][s];
+                out[t].deqT[c * 8 + row] = (int32_t)prod;
+                // src/dct.rs:93-95: divisor indexed by the RASTER position
+                const uint32_t q = (uint32_t)qtables[t][raster];
+                out[t].encM[c * 8 + row] = q ? (uint32_t)(((1ull << 31) + q - 1) / q) : 0u;
+            }
+    }
+}
+
+uint8_t *slot_ptr(pfv_ctx *c, uint32_t slot) { return c->d_pool + (size_t)slot * c->slot_stride; }
+
+int init_slot(pfv_ctx *c, uint32_t slot, cudaStream_t s)
+{
+    const size_t ny = (size_t)c->geo.pw * c->geo.ph, nc = (size_t)c->geo.cpw * c->geo.cph;
+    CU_TRY(cudaMemsetAsync(slot_ptr(c, slot), 0, ny, s));              // src/frame.rs:38
+    CU_TRY(cudaMemsetAsync(slot_ptr(c, slot) + ny, 128, 2 * nc, s));   // src/frame.rs:42-43
+    return PFV_OK;
+}
+
+int ensure_src_staging(pfv_ctx *c)
+{
+    if (c->st[0].d_src) return PFV_OK;
+    for (int i = 0; i < STAGES; i++) CU_TRY(cudaMalloc(&c->st[i].d_src, c->src_stride * c->max_jobs));
+    return PFV_OK;
+}
+
+// Make the compute stream wait until earlier D2H reads of the slots in `slots` have finished.
+int wait_slot_readers(pfv_ctx *c, const uint32_t *slots, uint32_t n)
+{
+    uint64_t need = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (c->slot_last_d2h[slots[i]] > need) need = c->slot_last_d2h[slots[i]];
+    if (need == 0) return PFV_OK;
+    // events older than the ring have been re-recorded by a LATER submit on the same stream: waiting on
+    // the later one is conservative and correct.
+    uint64_t oldest = c->submit_id > D2H_RING ? c->submit_id - D2H_RING + 1 : 1;
+    if (need < oldest) need = oldest;
+    CU_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_d2h_ring[need % D2H_RING], 0));
+    return PFV_OK;
+}
+
+}  // namespace
+
+extern "C" void pfv_ctx_destroy(pfv_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
+    if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+    for (int i = 0; i < STAGES; i++) {
+        Stage &s = c->st[i];
+        cudaFree(s.d_coeff); cudaFree(s.d_hdr); cudaFree(s.d_src); cudaFree(s.d_jobs);
+        if (s.h_jobs) cudaFreeHost(s.h_jobs);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    for (int i = 0; i < D2H_RING; i++) if (c->ev_d2h_ring[i]) cudaEventDestroy(c->ev_d2h_ring[i]);
+    if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+    if (c->ev_k1) cudaEventDestroy(c->ev_k1);
+    cudaFree(c->d_pool); cudaFree(c->d_qt); cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    if (c->s_compute && c->own_compute) cudaStreamDestroy(c->s_compute);
+    delete c;
+}
+
+static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_stream)
+{
+    CU_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10)
+        return fail(PFV_ERR_NO_DEVICE, "device %d is sm_%d%d; this engine is built for sm_100a only", c->device,
+                    prop.major, prop.minor);
+
+    fill_frame_geom(c);
+    c->slot_stride = ((size_t)c->geo.frame_bytes + 255) & ~(size_t)255;
+    // tight source planes, each start rounded to 16 bytes so the 8-byte vector path applies whenever w % 8 == 0
+    c->src_off[0] = 0;
+    c->src_off[1] = (c->geo.width * c->geo.height + 15u) & ~15u;
+    c->src_off[2] = (c->src_off[1] + c->geo.cwidth * c->geo.cheight + 15u) & ~15u;
+    c->src_stride = ((size_t)c->src_off[2] + (size_t)c->geo.cwidth * c->geo.cheight + 255) & ~(size_t)255;
+
+    CU_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    if (ext_stream) {
+        c->s_compute = (cudaStream_t)ext_stream;
+        c->own_compute = false;
+    } else {
+        CU_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    }
+
+    // frame pool (+256 bytes of slack: unaligned 8-byte fetches read up to 3 bytes past their end)
+    CU_TRY(cudaMalloc(&c->d_pool, c->slot_stride * c->nslots + 256));
+    CU_TRY(cudaMemsetAsync(c->d_pool + c->slot_stride * c->nslots, 0, 256, c->s_compute));
+    for (uint32_t s = 0; s < c->nslots; s++) {
+        int rc = init_slot(c, s, c->s_compute);
+        if (rc) return rc;
+    }
+    c->slot_last_d2h.assign(c->nslots, 0);
+
+    std::vector<QTables> qt;
+    build_qtables(qtables, c->nq, qt);
+    CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
+    CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
+
+    CU_TRY(cudaMalloc(&c->d_err, sizeof(int)));
+    CU_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
+    CU_TRY(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocDefault));
+    *c->h_err = 0;
+
+    const size_t job_bytes = sizeof(DecJob) > sizeof(EncJob) ? sizeof(DecJob) : sizeof(EncJob);
+    for (int i = 0; i < STAGES; i++) {
+        Stage &s = c->st[i];
+        CU_TRY(cudaMalloc(&s.d_coeff, (size_t)c->max_jobs * c->geo.nb * 256 * sizeof(int16_t)));
+        CU_TRY(cudaMemsetAsync(s.d_coeff, 0, (size_t)c->max_jobs * c->geo.nb * 256 * sizeof(int16_t), c->s_compute));
+        CU_TRY(cudaMalloc(&s.d_hdr, (size_t)c->max_jobs * c->geo.nb * sizeof(pfv_mbhdr)));
+        CU_TRY(cudaMalloc(&s.d_jobs, job_bytes * c->max_jobs));
+        CU_TRY(cudaHostAlloc(&s.h_jobs, job_bytes * c->max_jobs, cudaHostAllocDefault));
+        CU_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < D2H_RING; i++) CU_TRY(cudaEventCreateWithFlags(&c->ev_d2h_ring[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreate(&c->ev_k0));
+    CU_TRY(cudaEventCreate(&c->ev_k1));
+
+    build_tensor_maps(c);   // failure is reported by the first encode-P submit
+
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+    return PFV_OK;
+}
+
+extern "C" int pfv_ctx_create(int device, uint32_t width, uint32_t height, const int32_t (*qtables)[64], uint32_t nq,
+                              uint32_t nslots, uint32_t max_jobs, void *ext_stream, pfv_ctx **out)
+{
+    if (!out) return fail(PFV_ERR_BAD_ARG, "pfv_ctx_create: out is NULL");
+    *out = nullptr;
+    if (width == 0 || height == 0 || (width & 1) || (height & 1) || width > 65535 || height > 65535)
+        return fail(PFV_ERR_BAD_ARG, "frame size %ux%u must be even, non-zero and fit u16 (src/frame.rs:13, src/enc.rs:195-196)",
+                    width, height);
+    if (!qtables || nq == 0 || nq > 256) return fail(PFV_ERR_BAD_ARG, "need 1..256 q-tables");
+    if (nslots < 2) return fail(PFV_ERR_BAD_ARG, "need at least 2 frame slots");
+    if (max_jobs == 0) return fail(PFV_ERR_BAD_ARG, "max_jobs must be > 0");
+    for (uint32_t t = 0; t < nq; t++)
+        for (int i = 0; i < 64; i++)
+            if (qtables[t][i] < 0 || qtables[t][i] > 65535)
+                return fail(PFV_ERR_BAD_ARG, "q-table %u entry %d = %d does not fit the u16 header field (src/enc.rs:202-216)",
+                            t, i, qtables[t][i]);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(PFV_ERR_NO_DEVICE, "no CUDA device (%s); the engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(PFV_ERR_BAD_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+
+    pfv_ctx *c = new (std::nothrow) pfv_ctx();
+    if (!c) return fail(PFV_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    pfv_geometry_for(width, height, &c->geo);
+    c->nq = nq;
+    c->nslots = nslots;
+    c->max_jobs = max_jobs;
+    int rc = ctx_create_impl(c, qtables, ext_stream);
+    if (rc != PFV_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        pfv_ctx_destroy(c);
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = c;
+    return PFV_OK;
+}
+
+extern "C" int pfv_ctx_geometry(const pfv_ctx *c, pfv_geometry *out)
+{
+    if (!c || !out) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    *out = c->geo;
+    return PFV_OK;
+}
+
+extern "C" uint64_t pfv_ctx_launch_count(const pfv_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int pfv_sync(pfv_ctx *c)
+{
+    if (!c) return fail(PFV_ERR_BAD_ARG, "NULL context");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->s_h2d));
+    CU_TRY(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute));
+    CU_TRY(cudaStreamSynchronize(c->s_compute));
+    CU_TRY(cudaStreamSynchronize(c->s_d2h));
+    if (*c->h_err) {
+        const int bits = *c->h_err;
+        *c->h_err = 0;
+        CU_TRY(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->s_compute));
+        CU_TRY(cudaStreamSynchronize(c->s_compute));
+        if (bits & ERRBIT_BAD_MV)
+            return fail(PFV_ERR_BAD_MV, "a motion vector pointed outside the padded plane (src/common.rs:258-259); "
+                                        "the co-located block was used instead");
+        return fail(PFV_ERR_CUDA, "device error bits 0x%x", bits);
+    }
+    return PFV_OK;
+}
+
+extern "C" int pfv_ctx_last_kernel_ms(pfv_ctx *c, float *ms_out)
+{
+    if (!c || !ms_out) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (!c->have_kernel_time) return fail(PFV_ERR_STATE, "no kernel has been launched yet");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventSynchronize(c->ev_k1));
+    CU_TRY(cudaEventElapsedTime(ms_out, c->ev_k0, c->ev_k1));
+    return PFV_OK;
+}
+
+extern "C" int pfv_slot_reset(pfv_ctx *c, uint32_t slot)
+{
+    if (!c || slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "bad slot");
+    CU_TRY(cudaSetDevice(c->device));
+    int rc = wait_slot_readers(c, &slot, 1);
+    if (rc) return rc;
+    return init_slot(c, slot, c->s_compute);
+}
+
+extern "C" int pfv_slot_read(pfv_ctx *c, uint32_t slot, uint8_t *frame_out)
+{
+    if (!c || slot >= c->nslots || !frame_out) return fail(PFV_ERR_BAD_ARG, "bad argument");
+    int rc = pfv_sync(c);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(frame_out, slot_ptr(c, slot), c->geo.frame_bytes, cudaMemcpyDeviceToHost));
+    return PFV_OK;
+}
+
+extern "C" int pfv_slot_write(pfv_ctx *c, uint32_t slot, const uint8_t *frame_in)
+{
+    if (!c || slot >= c->nslots || !frame_in) return fail(PFV_ERR_BAD_ARG, "bad argument");
+    int rc = pfv_sync(c);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(slot_ptr(c, slot), frame_in, c->geo.frame_bytes, cudaMemcpyHostToDevice));
+    return PFV_OK;
+}
+
+extern "C" int pfv_slot_device_ptr(pfv_ctx *c, uint32_t slot, void **out)
+{
+    if (!c || slot >= c->nslots || !out) return fail(PFV_ERR_BAD_ARG, "bad argument");
+    *out = slot_ptr(c, slot);
+    return PFV_OK;
+}
+
+// src/dec.rs:195-197: the visible crop of the three planes, on stream s
+static int copy_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint8_t *u, uint8_t *v, cudaStream_t s)
+{
+    const pfv_geometry &g = c->geo;
+    const uint8_t *base = slot_ptr(c, slot);
+    const size_t ny = (size_t)g.pw * g.ph, nc = (size_t)g.cpw * g.cph;
+    if (y) {
+        if (g.pw == g.width) CU_TRY(cudaMemcpyAsync(y, base, (size_t)g.width * g.height, cudaMemcpyDeviceToHost, s));
+        else CU_TRY(cudaMemcpy2DAsync(y, g.width, base, g.pw, g.width, g.height, cudaMemcpyDeviceToHost, s));
+    }
+    uint8_t *dst[2] = {u, v};
+    for (int p = 0; p < 2; p++) {
+        if (!dst[p]) continue;
+        const uint8_t *src = base + ny + p * nc;
+        if (g.cpw == g.cwidth)
+            CU_TRY(cudaMemcpyAsync(dst[p], src, (size_t)g.cwidth * g.cheight, cudaMemcpyDeviceToHost, s));
+        else
+            CU_TRY(cudaMemcpy2DAsync(dst[p], g.cwidth, src, g.cpw, g.cwidth, g.cheight, cudaMemcpyDeviceToHost, s));
+    }
+    return PFV_OK;
+}
+
+extern "C" int pfv_slot_read_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    if (!c || slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "bad slot");
+    CU_TRY(cudaSetDevice(c->device));
+    // order after everything submitted so far on the compute stream; takes a submit id of its own so the
+    // slot-reuse bookkeeping sees this read
+    const uint64_t id = ++c->submit_id;
+    cudaEvent_t ev = c->ev_d2h_ring[id % D2H_RING];
+    CU_TRY(cudaEventRecord(ev, c->s_compute));
+    CU_TRY(cudaStreamWaitEvent(c->s_d2h, ev, 0));
+    int rc = copy_visible(c, slot, y, u, v, c->s_d2h);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev, c->s_d2h));
+    c->slot_last_d2h[slot] = id;
+    return PFV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_t njobs)
+{
+    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (njobs == 0) return PFV_OK;
+    if (njobs > c->max_jobs) return fail(PFV_ERR_BAD_ARG, "%u jobs > max_jobs %u", njobs, c->max_jobs);
+    const pfv_geometry &g = c->geo;
+    for (uint32_t i = 0; i < njobs; i++) {
+        const pfv_decode_job &j = jobs[i];
+        if (j.kind != PFV_FRAME_I && j.kind != PFV_FRAME_P) return fail(PFV_ERR_BAD_ARG, "job %u: bad kind %u", i, j.kind);
+        if (j.dst_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: dst_slot %u out of range", i, j.dst_slot);
+        if (!j.coeff) return fail(PFV_ERR_BAD_ARG, "job %u: coeff is NULL", i);
+        for (int p = 0; p < 3; p++)
+            if (j.qidx[p] >= c->nq)
+                return fail(PFV_ERR_BAD_ARG, "job %u: q-table index %u >= %u (src/dec.rs:244-246 would panic)", i, j.qidx[p], c->nq);
+        if (j.kind == PFV_FRAME_P) {
+            if (j.ref_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: ref_slot %u out of range", i, j.ref_slot);
+            if (j.ref_slot == j.dst_slot)
+                return fail(PFV_ERR_BAD_ARG, "job %u: ref_slot == dst_slot breaks the two-phase update (src/common.rs:498-521)", i);
+            if (!j.hdr) return fail(PFV_ERR_BAD_ARG, "job %u: hdr is NULL", i);
+        }
+        const bool any = j.out_y || j.out_u || j.out_v;
+        if (any && !(j.out_y && j.out_u && j.out_v)) return fail(PFV_ERR_BAD_ARG, "job %u: give all of out_y/u/v or none", i);
+    }
+    for (uint32_t i = 0; i < njobs; i++)
+        if (jobs[i].kind == PFV_FRAME_P)
+            for (uint32_t k = 0; k < njobs; k++)
+                if (jobs[k].dst_slot == jobs[i].ref_slot)
+                    return fail(PFV_ERR_BAD_ARG, "jobs %u and %u of one submit are dependent (ref_slot == dst_slot)", i, k);
+
+    CU_TRY(cudaSetDevice(c->device));
+    const uint64_t id = ++c->submit_id;
+    Stage &st = c->st[id % STAGES];
+    CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
+    CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));     // device buffers of this stage are free again
+
+    // job table: I jobs first, then P jobs, so each kind is one launch over a contiguous range
+    DecJob *tab = static_cast<DecJob *>(st.h_jobs);
+    std::vector<uint32_t> order;
+    order.reserve(njobs);
+    uint32_t n_i = 0;
+    for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_I) { order.push_back(i); n_i++; }
+    for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_P) order.push_back(i);
+
+    const size_t coeff_elems = (size_t)g.nb * 256;
+    // merge H2D copies of buffers that are adjacent in host memory (a caller that decodes a batch into one
+    // pinned arena gets one big copy instead of njobs small ones)
+    const int16_t *run_src = nullptr; int16_t *run_dst = nullptr; size_t run_elems = 0;
+    auto flush_run = [&]() -> int {
+        if (run_elems) CU_TRY(cudaMemcpyAsync(run_dst, run_src, run_elems * sizeof(int16_t), cudaMemcpyHostToDevice, c->s_h2d));
+        run_elems = 0;
+        return PFV_OK;
+    };
+    for (uint32_t k = 0; k < njobs; k++) {
+        const pfv_decode_job &j = jobs[order[k]];
+        DecJob &d = tab[k];
+        const bool dev = (j.flags & PFV_JOB_DEVICE_PTRS) != 0;
+        int16_t *d_coeff = st.d_coeff + (size_t)k * coeff_elems;
+        pfv_mbhdr *d_hdr = st.d_hdr + (size_t)k * g.nb;
+        if (dev) {
+            d.coeff = j.coeff;
+            d.hdr = j.hdr;
+        } else {
+            if (run_elems && j.coeff == run_src + run_elems && d_coeff == run_dst + run_elems) {
+                run_elems += coeff_elems;
+            } else {
+                int rc = flush_run();
+                if (rc) return rc;
+                run_src = j.coeff; run_dst = d_coeff; run_elems = coeff_elems;
+            }
+            d.coeff = d_coeff;
+            d.hdr = nullptr;
+            if (j.kind == PFV_FRAME_P) {
+                CU_TRY(cudaMemcpyAsync(d_hdr, j.hdr, (size_t)g.nb * sizeof(pfv_mbhdr), cudaMemcpyHostToDevice, c->s_h2d));
+                d.hdr = d_hdr;
+            }
+        }
+        d.dst = slot_ptr(c, j.dst_slot);
+        d.ref = j.kind == PFV_FRAME_P ? slot_ptr(c, j.ref_slot) : nullptr;
+        for (int p = 0; p < 3; p++) d.qt[p] = c->d_qt + j.qidx[p];
+    }
+    {
+        int rc = flush_run();
+        if (rc) return rc;
+    }
+    CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(DecJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
+    CU_TRY(cudaEventRecord(st.ev_h2d, c->s_h2d));
+
+    // compute
+    CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
+    {
+        std::vector<uint32_t> dsts(njobs);
+        for (uint32_t i = 0; i < njobs; i++) dsts[i] = jobs[i].dst_slot;
+        int rc = wait_slot_readers(c, dsts.data(), njobs);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
+    const DecJob *d_tab = static_cast<const DecJob *>(st.d_jobs);
+    if (n_i) { CU_TRY(launch_decode(false, c->fg, d_tab, n_i, c->d_err, c->s_compute)); c->launches++; }
+    if (njobs - n_i) { CU_TRY(launch_decode(true, c->fg, d_tab + n_i, njobs - n_i, c->d_err, c->s_compute)); c->launches++; }
+    CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
+    c->have_kernel_time = true;
+    CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
+
+    // copy out
+    bool any_out = false;
+    for (uint32_t i = 0; i < njobs; i++) any_out |= jobs[i].out_y != nullptr;
+    if (any_out) {
+        CU_TRY(cudaStreamWaitEvent(c->s_d2h, st.ev_kernel, 0));
+        for (uint32_t i = 0; i < njobs; i++) {
+            const pfv_decode_job &j = jobs[i];
+            if (!j.out_y) continue;
+            int rc = copy_visible(c, j.dst_slot, j.out_y, j.out_u, j.out_v, c->s_d2h);
+            if (rc) return rc;
+            c->slot_last_d2h[j.dst_slot] = id;
+        }
+    }
+    CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
+    return PFV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_t njobs)
+{
+    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (njobs == 0) return PFV_OK;
+    if (njobs > c->max_jobs) return fail(PFV_ERR_BAD_ARG, "%u jobs > max_jobs %u", njobs, c->max_jobs);
+    if (c->nq < 4) return fail(PFV_ERR_BAD_ARG, "an encoder context needs the 4 q-tables of src/enc.rs:48-51");
+    const pfv_geometry &g = c->geo;
+    bool any_p = false;
+    for (uint32_t i = 0; i < njobs; i++) {
+        const pfv_encode_job &j = jobs[i];
+        if (j.kind != PFV_FRAME_I && j.kind != PFV_FRAME_P) return fail(PFV_ERR_BAD_ARG, "job %u: bad kind %u", i, j.kind);
+        if (j.dst_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: dst_slot %u out of range", i, j.dst_slot);
+        if (!j.src_y || !j.src_u || !j.src_v || !j.coeff_out) return fail(PFV_ERR_BAD_ARG, "job %u: NULL plane or coeff_out", i);
+        if (j.kind == PFV_FRAME_P) {
+            any_p = true;
+            if (j.ref_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: ref_slot %u out of range", i, j.ref_slot);
+            if (j.ref_slot == j.dst_slot) return fail(PFV_ERR_BAD_ARG, "job %u: ref_slot == dst_slot", i);
+            if (!j.hdr_out) return fail(PFV_ERR_BAD_ARG, "job %u: hdr_out is NULL", i);
+            if (!(j.px_err >= 0.0f)) return fail(PFV_ERR_BAD_ARG, "job %u: px_err must be >= 0", i);
+        }
+    }
+    for (uint32_t i = 0; i < njobs; i++)
+        if (jobs[i].kind == PFV_FRAME_P)
+            for (uint32_t k = 0; k < njobs; k++)
+                if (jobs[k].dst_slot == jobs[i].ref_slot)
+                    return fail(PFV_ERR_BAD_ARG, "jobs %u and %u of one submit are dependent (ref_slot == dst_slot)", i, k);
+    if (any_p && !c->have_tma) return fail(PFV_ERR_CUDA, "encode-P needs TMA tensor maps: %s", c->tma_err);
+    // the divisors of the tables an encoder uses must be non-zero (the reference clamps them to >= 1, src/enc.rs:48-51)
+
+    CU_TRY(cudaSetDevice(c->device));
+    {
+        int rc = ensure_src_staging(c);
+        if (rc) return rc;
+    }
+    const uint64_t id = ++c->submit_id;
+    Stage &st = c->st[id % STAGES];
+    CU_TRY(cudaEventSynchronize(st.ev_h2d));
+    CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));
+
+    EncJob *tab = static_cast<EncJob *>(st.h_jobs);
+    std::vector<uint32_t> order;
+    order.reserve(njobs);
+    uint32_t n_i = 0;
+    for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_I) { order.push_back(i); n_i++; }
+    for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_P) order.push_back(i);
+
+    const size_t ysz = (size_t)g.width * g.height, csz = (size_t)g.cwidth * g.cheight;
+    const size_t coeff_elems = (size_t)g.nb * 256;
+    for (uint32_t k = 0; k < njobs; k++) {
+        const pfv_encode_job &j = jobs[order[k]];
+        EncJob &d = tab[k];
+        const bool dev = (j.flags & PFV_JOB_DEVICE_PTRS) != 0;
+        if (dev) {
+            d.src[0] = j.src_y; d.src[1] = j.src_u; d.src[2] = j.src_v;
+            d.coeff = j.coeff_out;
+            d.hdr = j.hdr_out;
+        } else {
+            uint8_t *s = st.d_src + (size_t)k * c->src_stride;
+            const bool packed = j.src_u == j.src_y + ysz && j.src_v == j.src_u + csz &&
+                                c->src_off[1] == ysz && c->src_off[2] == ysz + csz;
+            if (packed) {
+                CU_TRY(cudaMemcpyAsync(s, j.src_y, ysz + 2 * csz, cudaMemcpyHostToDevice, c->s_h2d));
+            } else {
+                CU_TRY(cudaMemcpyAsync(s + c->src_off[0], j.src_y, ysz, cudaMemcpyHostToDevice, c->s_h2d));
+                CU_TRY(cudaMemcpyAsync(s + c->src_off[1], j.src_u, csz, cudaMemcpyHostToDevice, c->s_h2d));
+                CU_TRY(cudaMemcpyAsync(s + c->src_off[2], j.src_v, csz, cudaMemcpyHostToDevice, c->s_h2d));
+            }
+            for (int p = 0; p < 3; p++) d.src[p] = s + c->src_off[p];
+            d.coeff = st.d_coeff + (size_t)k * coeff_elems;
+            d.hdr = st.d_hdr + (size_t)k * g.nb;
+        }
+        d.dst = slot_ptr(c, j.dst_slot);
+        d.ref = j.kind == PFV_FRAME_P ? slot_ptr(c, j.ref_slot) : nullptr;
+        d.ref_slot = j.kind == PFV_FRAME_P ? (int32_t)j.ref_slot : 0;
+        d.min_err = j.px_err * j.px_err * 256.0f;                  // src/common.rs:209 (f32, left to right)
+    }
+    CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(EncJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
+    CU_TRY(cudaEventRecord(st.ev_h2d, c->s_h2d));
+
+    CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
+    CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_d2h, 0));       // earlier D2H out of this stage's coeff/hdr buffers
+    {
+        std::vector<uint32_t> dsts(njobs);
+        for (uint32_t i = 0; i < njobs; i++) dsts[i] = jobs[i].dst_slot;
+        int rc = wait_slot_readers(c, dsts.data(), njobs);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
+    const EncJob *d_tab = static_cast<const EncJob *>(st.d_jobs);
+    if (n_i) { CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, c->s_compute)); c->launches++; }
+    if (njobs - n_i) {
+        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, c->s_compute));
+        c->launches++;
+    }
+    CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
+    c->have_kernel_time = true;
+    CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
+
+    bool any_host = false;
+    for (uint32_t i = 0; i < njobs; i++) any_host |= (jobs[i].flags & PFV_JOB_DEVICE_PTRS) == 0;
+    if (any_host) {
+        CU_TRY(cudaStreamWaitEvent(c->s_d2h, st.ev_kernel, 0));
+        for (uint32_t k = 0; k < njobs; k++) {
+            const pfv_encode_job &j = jobs[order[k]];
+            if (j.flags & PFV_JOB_DEVICE_PTRS) continue;
+            CU_TRY(cudaMemcpyAsync(j.coeff_out, st.d_coeff + (size_t)k * coeff_elems, coeff_elems * sizeof(int16_t),
+                                   cudaMemcpyDeviceToHost, c->s_d2h));
+            if (j.kind == PFV_FRAME_P)
+                CU_TRY(cudaMemcpyAsync(j.hdr_out, st.d_hdr + (size_t)k * g.nb, (size_t)g.nb * sizeof(pfv_mbhdr),
+                                       cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+    }
+    CU_TRY(cudaEventRecord(st.ev_d2h, c->s_d2h));
+    CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
+    return PFV_OK;
+}

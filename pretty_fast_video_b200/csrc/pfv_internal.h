@@ -1,0 +1,75 @@
+// pfv_internal.h — structures shared by the host engine (pfv_ctx.cu) and the kernels (pfv_kernels.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pfv_b200.h"
+
+namespace pfv {
+
+// Derived tables, one set per q-table, built on the host by pfv_ctx_create.  "Lane transposed":
+// entry [c*8 + row] belongs to column c, so a lane reads its 8 values as two 128-bit loads.
+struct QTables {
+    int32_t  deqT[64];   // decode: SCALE[s]*q[s] with s = INV_ZIGZAG[row*8+c]   (wrapping product)
+    uint32_t encM[64];   // encode: ceil(2^31 / q[row*8+c])
+};
+
+// One padded plane of the frame (src/frame.rs:28-49), in macroblock units and bytes.
+struct PlaneGeom {
+    uint32_t pw, ph;          // padded size in pixels
+    uint32_t vw, vh;          // visible size in pixels (tight source planes of the encoder)
+    uint32_t bw, bh;          // macroblocks per row / column
+    uint32_t mb_base;         // index of the plane's first macroblock in the frame (Y, U, V order)
+    uint32_t off;             // byte offset of the plane inside a frame slot
+    float    rcp_bw;          // 1.0f / bw
+    uint32_t tiles_per_row;   // ceil(bw / 8): encode-P tiles of 8 horizontally adjacent macroblocks
+    uint32_t tile_base;       // index of the plane's first tile
+    uint32_t clear4;          // clear colour replicated in 4 bytes: 0 for Y, 0x80808080 for U,V (src/enc.rs:84-90)
+};
+
+struct FrameGeom {
+    PlaneGeom pl[3];
+    uint32_t  nb;             // macroblocks per frame
+    uint32_t  total_tiles;    // encode-P tiles per frame
+    uint32_t  frame_bytes;
+};
+
+// Device-side job records (built on the host per submit, copied with the job's headers).
+struct DecJob {
+    const int16_t   *coeff;   // nb*256, device
+    const pfv_mbhdr *hdr;     // nb, device (P only)
+    uint8_t         *dst;     // frame slot
+    const uint8_t   *ref;     // frame slot (P only)
+    const QTables   *qt[3];   // per plane
+};
+
+struct EncJob {
+    const uint8_t *src[3];    // tight source planes, device
+    pfv_mbhdr     *hdr;       // nb, device (P only)
+    int16_t       *coeff;     // nb*256, device
+    uint8_t       *dst;       // frame slot receiving the reconstruction
+    const uint8_t *ref;       // frame slot holding prev_frame (P only)
+    int32_t        ref_slot;  // the same slot as an index (TMA coordinate)
+    float          min_err;   // px_err*px_err*256 (src/common.rs:209)
+};
+
+// error bits the kernels OR into the context's device error word
+enum { ERRBIT_BAD_MV = 1 };
+
+// search window of an encode-P tile: 16 px left margin + 8 macroblocks + 15 px right margin, rounded so the
+// row pitch (44 words) spreads the eight rows of a sub-block over distinct banks; 15 + 16 + 15 rows.
+constexpr int WIN_W = 176;
+constexpr int WIN_H = 46;
+constexpr int WIN_BYTES = WIN_W * WIN_H;
+
+// kernel launchers (pfv_kernels.cu).  mbs_per_warp-style tuning lives inside.
+cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, uint32_t njobs,
+                          int *d_err, cudaStream_t s);
+cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
+                            const QTables *d_qt, cudaStream_t s);
+cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
+                            const QTables *d_qt, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
+                            cudaStream_t s);
+
+}  // namespace pfv

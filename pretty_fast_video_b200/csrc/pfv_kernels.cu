@@ -1,0 +1,383 @@
+// pfv_kernels.cu — the four macroblock kernels of the engine (sm_100a).
+//
+//   decode_kernel<false>  decode-I : dequant + IDCT + clamp                (src/common.rs:477-496)
+//   decode_kernel<true>   decode-P : motion-compensated copy (+ IDCT delta) (src/common.rs:498-521)
+//   encode_i_kernel       encode-I : FDCT + quant, fused closed-loop recon  (src/enc.rs:84-97)
+//   encode_p_kernel       encode-P : 4-level SSD block search on a TMA-staged window, skip test,
+//                                    residual FDCT + quant, fused recon      (src/enc.rs:134-147)
+//
+// One warp = one macroblock (see pfv_device.cuh).  grid.y = job (frame) index, so one launch covers a
+// whole batch of independent frames.
+#include "pfv_internal.h"
+#include "pfv_device.cuh"
+
+namespace pfv {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct MbPos {
+    int      p;        // plane 0..2
+    uint32_t bx, by;   // pixel origin of the macroblock inside the padded plane
+};
+
+__device__ __forceinline__ const PlaneGeom &plane_of(const FrameGeom &g, int p)
+{
+    return p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]);
+}
+
+__device__ __forceinline__ MbPos locate_mb(const FrameGeom &g, uint32_t m)
+{
+    MbPos r;
+    r.p = (m >= g.pl[1].mb_base ? 1 : 0) + (m >= g.pl[2].mb_base ? 1 : 0);
+    const PlaneGeom &pl = plane_of(g, r.p);
+    uint32_t col;
+    const uint32_t row = div_small(m - pl.mb_base, pl.bw, pl.rcp_bw, col);
+    r.bx = col * 16u;
+    r.by = row * 16u;
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// decode
+// -------------------------------------------------------------------------------------------------
+// Each warp walks MPW macroblocks, CTA-interleaved so the 8 warps of a CTA always work on 8 consecutive
+// macroblocks (their 16-byte row segments then form 128-byte runs in the plane).
+template <bool INTER, int MPW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+decode_kernel(const __grid_constant__ FrameGeom g, const DecJob *__restrict__ jobs, int *__restrict__ err)
+{
+    __shared__ WarpScratch scratch[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch &ws = scratch[warp];
+    const DecJob job = jobs[blockIdx.y];
+    const int sb = lane >> 3, r = lane & 7;
+    const uint32_t py = (uint32_t)(sb >> 1) * 8u + (uint32_t)r, px = (uint32_t)(sb & 1) * 8u;
+
+    uint32_t gaddr[8];
+    lane_gather_offsets(lane, gaddr);
+    int32_t deq[8];
+    int cur_plane = -1;
+
+    const uint32_t m0 = blockIdx.x * (WARPS_PER_CTA * MPW) + warp;
+#pragma unroll 1
+    for (int it = 0; it < MPW; ++it) {
+        const uint32_t m = m0 + it * WARPS_PER_CTA;
+        if (m >= g.nb) break;
+        const MbPos pos = locate_mb(g, m);
+        const PlaneGeom &pl = plane_of(g, pos.p);
+
+        bool coded = true;
+        uint2 prev = make_uint2(0u, 0u);
+        if (INTER) {
+            const pfv_mbhdr h = job.hdr[m];
+            coded = h.has_coeff != 0;
+            int sx = (int)pos.bx + h.mx, sy = (int)pos.by + h.my;      // src/common.rs:255-256
+            if (sx < 0 || sy < 0 || sx > (int)pl.pw - 16 || sy > (int)pl.ph - 16) {
+                // reference: debug_assert / slice panic (src/common.rs:258-259).  Never read out of
+                // bounds: flag the stream as bad and fall back to the co-located block.
+                if (lane == 0) atomicOr(err, ERRBIT_BAD_MV);
+                sx = (int)pos.bx;
+                sy = (int)pos.by;
+            }
+            prev = ldg_u8x8_unaligned(job.ref + pl.off + (size_t)((uint32_t)sy + py) * pl.pw + (uint32_t)sx + px);
+        }
+        uint2 out = prev;                                                // src/common.rs:281-283
+        if (coded) {
+            const uint4 craw = __ldcs(reinterpret_cast<const uint4 *>(job.coeff + (size_t)m * 256) + lane);
+            if (pos.p != cur_plane) {
+                const QTables *q = pos.p == 0 ? job.qt[0] : (pos.p == 1 ? job.qt[1] : job.qt[2]);
+                lane_load8(q->deqT, r, deq);
+                cur_plane = pos.p;
+            }
+            stage_coeffs(ws, lane, craw);
+            __syncwarp();
+            int y[8];
+            decode_mb_core(ws, lane, gaddr, deq, y);
+            out = INTER ? apply_residual_row(y, prev) : pack_row_u8(y);
+        }
+        uint8_t *dst = job.dst + pl.off + (size_t)(pos.by + py) * pl.pw + pos.bx + px;
+        *reinterpret_cast<uint2 *>(dst) = out;                           // src/common.rs:341-349 blit_block
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// encode helpers
+// -------------------------------------------------------------------------------------------------
+// Row (x..x+7, y) of a tight vw x vh source plane, padded with the clear colour (src/common.rs:352-356).
+__device__ __forceinline__ uint2 load_src_row(const uint8_t *__restrict__ src, const PlaneGeom &pl,
+                                              uint32_t x, uint32_t y, bool fast)
+{
+    if (y >= pl.vh || x >= pl.vw) return make_uint2(pl.clear4, pl.clear4);
+    const uint8_t *p = src + (size_t)y * pl.vw + x;
+    if (fast) return __ldcs(reinterpret_cast<const uint2 *>(p));       // vw % 8 == 0 and base 8-byte aligned
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t b = (x + k < pl.vw) ? (uint32_t)p[k] : (pl.clear4 & 0xffu);
+        w[k >> 2] |= b << (8 * (k & 3));
+    }
+    return make_uint2(w[0], w[1]);
+}
+
+__device__ __forceinline__ int byte_of(uint2 v, int k)
+{
+    const uint32_t w = (k < 4) ? v.x : v.y;
+    return (int)((w >> (8 * (k & 3))) & 0xffu);
+}
+
+// -------------------------------------------------------------------------------------------------
+// encode-I
+// -------------------------------------------------------------------------------------------------
+template <int MPW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+encode_i_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
+                const QTables *__restrict__ qt)
+{
+    __shared__ WarpScratch scratch[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch &ws = scratch[warp];
+    const EncJob job = jobs[blockIdx.y];
+    const int sb = lane >> 3, r = lane & 7;
+    const uint32_t py = (uint32_t)(sb >> 1) * 8u + (uint32_t)r, px = (uint32_t)(sb & 1) * 8u;
+
+    uint32_t gaddr[8];
+    lane_gather_offsets(lane, gaddr);
+
+    const uint32_t m0 = blockIdx.x * (WARPS_PER_CTA * MPW) + warp;
+#pragma unroll 1
+    for (int it = 0; it < MPW; ++it) {
+        const uint32_t m = m0 + it * WARPS_PER_CTA;
+        if (m >= g.nb) break;
+        const MbPos pos = locate_mb(g, m);
+        const PlaneGeom &pl = plane_of(g, pos.p);
+        const uint8_t *src = pos.p == 0 ? job.src[0] : (pos.p == 1 ? job.src[1] : job.src[2]);
+        const bool fast = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
+        const QTables *q = qt + (pos.p == 0 ? 0 : 1);                   // intra_l, intra_c (src/enc.rs:84-90)
+
+        const uint2 s = load_src_row(src, pl, pos.bx + px, pos.by + py, fast);
+        int x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (byte_of(s, k) - 128) * 256;   // src/common.rs:291
+        uint32_t encM[8];
+        int32_t scale[8];
+        lane_load8(reinterpret_cast<const int32_t *>(q->encM), r, reinterpret_cast<int32_t(&)[8]>(encM));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) scale[k] = c_scaleT[r * 8 + k];
+        const uint4 craw = encode_mb_core(ws, lane, gaddr, encM, scale, x);
+        __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)m * 256) + lane, craw);
+
+        // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
+        int32_t deq[8];
+        lane_load8(q->deqT, r, deq);
+        int y[8];
+        decode_mb_core(ws, lane, gaddr, deq, y);
+        uint8_t *dst = job.dst + pl.off + (size_t)(pos.by + py) * pl.pw + pos.bx + px;
+        *reinterpret_cast<uint2 *>(dst) = pack_row_u8(y);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// encode-P
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// 8 bytes at an arbitrary byte offset of the shared-memory search window
+__device__ __forceinline__ uint2 lds_u8x8_unaligned(const uint8_t *win, uint32_t off)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(win + (off & ~3u));
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    uint2 r;
+    r.x = __funnelshift_r(w0, w1, sh);
+    r.y = __funnelshift_r(w1, w2, sh);
+    return r;
+}
+
+// src/common.rs:125-139 over the whole macroblock: this lane's 8 pixels, then a warp sum.  Exact
+// integer SSD (<= 256*255^2 < 2^24, so the reference's f32 sum is the same number).
+__device__ __forceinline__ uint32_t warp_ssd(uint2 src, uint2 ref)
+{
+    const uint32_t d0 = __vabsdiffu4(src.x, ref.x);
+    const uint32_t d1 = __vabsdiffu4(src.y, ref.y);
+    uint32_t acc = __dp4a(d0, d0, 0u);
+    acc = __dp4a(d1, d1, acc);
+    return __reduce_add_sync(FULL, acc);
+}
+
+// One CTA = one tile of 8 horizontally adjacent macroblocks of one plane.  The tile's whole search
+// window (block_search never moves further than 8+4+2+1 = 15 px, src/common.rs:154-204) is fetched
+// from the reference slot by ONE 4-D TMA box {WIN_W, WIN_H, 1, 1}; the part outside the plane is
+// zero-filled by the TMA unit and never visited (candidates there are skipped, src/common.rs:171,182).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
+                const QTables *__restrict__ qt,
+                const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
+{
+    __shared__ __align__(128) uint8_t win[WIN_BYTES + 16];
+    __shared__ WarpScratch scratch[WARPS_PER_CTA];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch &ws = scratch[warp];
+    const EncJob job = jobs[blockIdx.y];
+
+    // tile -> plane, macroblock row, first macroblock column
+    const uint32_t tile = blockIdx.x;
+    const int p = (tile >= g.pl[1].tile_base ? 1 : 0) + (tile >= g.pl[2].tile_base ? 1 : 0);
+    const PlaneGeom &pl = plane_of(g, p);
+    const uint32_t lt = tile - pl.tile_base;
+    const uint32_t trow = lt / pl.tiles_per_row, tcol = lt - trow * pl.tiles_per_row;
+    const int tile_x0 = (int)tcol * 128, by = (int)trow * 16;
+
+    if (threadIdx.x == 0) {
+        const uint32_t bar_a = smem_u32(&bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)WIN_BYTES) : "memory");
+        const CUtensorMap *tm = (p == 0) ? &tm_luma : &tm_chroma;
+        const int cx = tile_x0 - 16, cy = by - 15, cz = (p == 2) ? 1 : 0, cw = job.ref_slot;
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(win)), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(bar_a)
+            : "memory");
+    }
+
+    const int sb = lane >> 3, r = lane & 7;
+    const uint32_t py = (uint32_t)(sb >> 1) * 8u + (uint32_t)r, px = (uint32_t)(sb & 1) * 8u;
+    const int bx = tile_x0 + warp * 16;
+    const bool active = bx < (int)pl.pw;                               // ragged last tile of a row
+
+    uint2 s = make_uint2(0u, 0u);
+    uint32_t gaddr[8];
+    if (active) {
+        const uint8_t *src = p == 0 ? job.src[0] : (p == 1 ? job.src[1] : job.src[2]);
+        const bool fast = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
+        s = load_src_row(src, pl, (uint32_t)bx + px, (uint32_t)by + py, fast);
+        lane_gather_offsets(lane, gaddr);
+    }
+
+    __syncthreads();                                                   // barrier init visible to all
+    {
+        const uint32_t bar_a = smem_u32(&bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+        }
+    }
+    if (!active) return;
+
+    // window coordinates of this lane's 8 pixels for motion (0,0)
+    const int wx0 = 16 + warp * 16 + (int)px, wy0 = 15 + (int)py;
+    const int max_x = (int)pl.pw - 16, max_y = (int)pl.ph - 16;
+
+    // src/common.rs:154-204, iteratively.  The centre of each level after the first is the previous
+    // level's winner, whose error is already known (the reference recomputes the identical number).
+    int cx = bx, cy = by;                                              // current centre, plane coords
+    uint32_t best = warp_ssd(s, lds_u8x8_unaligned(win, (uint32_t)(wy0 * WIN_W + wx0)));
+#pragma unroll 1
+    for (int step = 8; step >= 1; step >>= 1) {
+        int bdx = 0, bdy = 0;
+#pragma unroll 1
+        for (int my = -1; my <= 1; ++my) {
+            const int oy = cy + my * step;
+            if (oy < 0 || oy > max_y) continue;                        // src/common.rs:171
+#pragma unroll
+            for (int mx = -1; mx <= 1; ++mx) {
+                if (my == 0 && mx == 0) continue;
+                const int ox = cx + mx * step;
+                if (ox < 0 || ox > max_x) continue;                    // src/common.rs:182
+                const uint32_t off = (uint32_t)((wy0 + (oy - by)) * WIN_W + wx0 + (ox - bx));
+                const uint32_t e = warp_ssd(s, lds_u8x8_unaligned(win, off));
+                if (e < best) {                                        // strict, src/common.rs:189
+                    best = e;
+                    bdx = mx * step;
+                    bdy = my * step;
+                }
+            }
+        }
+        cx += bdx;
+        cy += bdy;
+    }
+    const int mvx = cx - bx, mvy = cy - by;                            // |mv| <= 15
+    const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((wy0 + mvy) * WIN_W + wx0 + mvx));
+    const bool coded = !((float)best <= job.min_err);                  // src/common.rs:221
+
+    const uint32_t m = pl.mb_base + trow * pl.bw + (uint32_t)(bx >> 4);
+    if (lane == 0) {
+        pfv_mbhdr h;
+        h.mx = (int8_t)mvx;                                            // src/common.rs:222,235 `as i8`
+        h.my = (int8_t)mvy;
+        h.has_coeff = coded ? 1 : 0;
+        h.reserved = 0;
+        job.hdr[m] = h;
+    }
+    uint2 out = prev;
+    if (coded) {
+        const QTables *q = qt + (p == 0 ? 2 : 3);                      // inter_l, inter_c (src/enc.rs:134-140)
+        int x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int d = byte_of(s, k) - byte_of(prev, k);            // src/common.rs:118-119 (|d| <= 255)
+            x[k] = (d / 2) * 256;                                      // src/common.rs:304
+        }
+        uint32_t encM[8];
+        int32_t scale[8];
+        lane_load8(reinterpret_cast<const int32_t *>(q->encM), r, reinterpret_cast<int32_t(&)[8]>(encM));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) scale[k] = c_scaleT[r * 8 + k];
+        const uint4 craw = encode_mb_core(ws, lane, gaddr, encM, scale, x);
+        __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)m * 256) + lane, craw);
+        int32_t deq[8];
+        lane_load8(q->deqT, r, deq);
+        int y[8];
+        decode_mb_core(ws, lane, gaddr, deq, y);
+        out = apply_residual_row(y, prev);                             // src/common.rs:277
+    }
+    uint8_t *dst = job.dst + pl.off + (size_t)((uint32_t)by + py) * pl.pw + (uint32_t)bx + px;
+    *reinterpret_cast<uint2 *>(dst) = out;
+}
+
+// -------------------------------------------------------------------------------------------------
+// launchers
+// -------------------------------------------------------------------------------------------------
+constexpr int DEC_MPW = 2;
+constexpr int ENC_MPW = 1;
+
+cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, uint32_t njobs,
+                          int *d_err, cudaStream_t s)
+{
+    const uint32_t per_cta = WARPS_PER_CTA * DEC_MPW;
+    dim3 grid((g.nb + per_cta - 1) / per_cta, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
+    if (inter) decode_kernel<true, DEC_MPW><<<grid, block, 0, s>>>(g, d_jobs, d_err);
+    else       decode_kernel<false, DEC_MPW><<<grid, block, 0, s>>>(g, d_jobs, d_err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
+                            const QTables *d_qt, cudaStream_t s)
+{
+    const uint32_t per_cta = WARPS_PER_CTA * ENC_MPW;
+    dim3 grid((g.nb + per_cta - 1) / per_cta, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
+    encode_i_kernel<ENC_MPW><<<grid, block, 0, s>>>(g, d_jobs, d_qt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
+                            const QTables *d_qt, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
+                            cudaStream_t s)
+{
+    dim3 grid(g.total_tiles, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
+    encode_p_kernel<<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
+    return cudaGetLastError();
+}
+
+}  // namespace pfv

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _has_gpu():
+    try:
+        from pretty_fast_video_b200 import _native as N
+        return N.lib().pfv_device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def has_gpu():
+    return _has_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a box without a GPU is an error, not a skip: the product has no CPU fallback.
+    pass
