@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -170,6 +171,9 @@ struct pfv_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     bool have_kernel_time = false;
+    std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
+    uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
+    bool decode_i_warp_variant = false;    // PFV_DECODE_I_VARIANT=warp selects the warp-per-macroblock kernel
     CUtensorMap tm_luma{}, tm_chroma{};
     bool have_tma = false;
     char tma_err[160] = "";
@@ -361,6 +365,19 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
 
     std::vector<QTables> qt;
     build_qtables(qtables, c->nq, qt);
+    c->h_deq_scan.resize((size_t)c->nq * 64);
+    for (uint32_t t = 0; t < c->nq; t++)
+        for (int i = 0; i < 64; i++)
+            c->h_deq_scan[t * 64 + i] = (int32_t)((uint32_t)kScale[i] * (uint32_t)qtables[t][i]);
+    {
+        uint32_t cta = 0;
+        for (int p = 0; p < 3; p++) {
+            c->cta_base[p] = cta;
+            cta += (c->fg.pl[p].bw * c->fg.pl[p].bh + SB_MBS_PER_CTA - 1) / SB_MBS_PER_CTA;
+        }
+        c->cta_total = cta;
+    }
+    if (const char *v = getenv("PFV_DECODE_I_VARIANT")) c->decode_i_warp_variant = strcmp(v, "warp") == 0;
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -589,6 +606,9 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
     order.reserve(njobs);
     uint32_t n_i = 0;
     for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_I) { order.push_back(i); n_i++; }
+    // key frames that share a q-index triple form one launch of the sub-block kernel (tables are kernel parameters)
+    auto qkey = [&](uint32_t i) { return (uint32_t)jobs[i].qidx[0] << 16 | (uint32_t)jobs[i].qidx[1] << 8 | jobs[i].qidx[2]; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return qkey(a) < qkey(b); });
     for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_P) order.push_back(i);
 
     const size_t coeff_elems = (size_t)g.nb * 256;
@@ -645,7 +665,25 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
     }
     CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
     const DecJob *d_tab = static_cast<const DecJob *>(st.d_jobs);
-    if (n_i) { CU_TRY(launch_decode(false, c->fg, d_tab, n_i, c->d_err, c->s_compute)); c->launches++; }
+    if (n_i && c->decode_i_warp_variant) {
+        CU_TRY(launch_decode(false, c->fg, d_tab, n_i, c->d_err, c->s_compute));
+        c->launches++;
+    } else {
+        for (uint32_t a = 0; a < n_i;) {
+            uint32_t b = a + 1;
+            while (b < n_i && qkey(order[b]) == qkey(order[a])) b++;
+            SbParams P;
+            P.g = c->fg;
+            for (int p = 0; p < 3; p++) {
+                memcpy(P.deq[p], &c->h_deq_scan[(size_t)jobs[order[a]].qidx[p] * 64], 64 * sizeof(int32_t));
+                P.cta_base[p] = c->cta_base[p];
+            }
+            P.cta_total = c->cta_total;
+            CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
+            c->launches++;
+            a = b;
+        }
+    }
     if (njobs - n_i) { CU_TRY(launch_decode(true, c->fg, d_tab + n_i, njobs - n_i, c->d_err, c->s_compute)); c->launches++; }
     CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
     c->have_kernel_time = true;

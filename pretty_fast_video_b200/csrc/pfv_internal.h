@@ -54,6 +54,16 @@ struct EncJob {
     float          min_err;   // px_err*px_err*256 (src/common.rs:209)
 };
 
+// Parameters of the register-resident sub-block kernels (pfv_kernels_sb.cu): the three per-plane tables of
+// ONE q-index triple travel as kernel parameters so the multiplies take them as constant-bank operands.
+constexpr uint32_t SB_MBS_PER_CTA = 32;
+struct SbParams {
+    FrameGeom g;
+    int32_t   deq[3][64];     // per plane, by SCAN position s: SCALE[s]*q[s] (wrapping)
+    uint32_t  cta_base[3];    // first CTA of each plane (a CTA = 32 consecutive macroblocks of one plane)
+    uint32_t  cta_total;
+};
+
 // error bits the kernels OR into the context's device error word
 enum { ERRBIT_BAD_MV = 1 };
 
@@ -66,6 +76,7 @@ constexpr int WIN_BYTES = WIN_W * WIN_H;
 // kernel launchers (pfv_kernels.cu).  mbs_per_warp-style tuning lives inside.
 cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, uint32_t njobs,
                           int *d_err, cudaStream_t s);
+cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, cudaStream_t s);
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
