@@ -1,0 +1,157 @@
+//! `src/cuda.rs` — the FFI shim a pfv-rs maintainer adds behind `--features cuda`.
+//!
+//! UNCOMPILED: the build image for this engine has no `cargo`/`rustc`; this file is the source a maintainer
+//! would drop into the crate (INTEGRATION.md walks through the call sites).  It binds exactly the entry points
+//! declared in `include/pfv_b200.h` and keeps the `pfv_rs::dec::Decoder` / `pfv_rs::enc::Encoder` API unchanged.
+#![allow(non_camel_case_types)]
+
+use std::ffi::CStr;
+use std::io;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct pfv_mbhdr {
+    pub mx: i8,
+    pub my: i8,
+    pub has_coeff: u8,
+    pub reserved: u8,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct pfv_geometry {
+    pub width: u32, pub height: u32,
+    pub cwidth: u32, pub cheight: u32,
+    pub pw: u32, pub ph: u32,
+    pub cpw: u32, pub cph: u32,
+    pub nb_y: u32, pub nb_c: u32, pub nb: u32,
+    pub frame_bytes: u32,
+}
+
+#[repr(C)]
+pub struct pfv_decode_job {
+    pub kind: u32,
+    pub flags: u32,
+    pub dst_slot: u32,
+    pub ref_slot: u32,
+    pub qidx: [u8; 3],
+    pub reserved: u8,
+    pub hdr: *const pfv_mbhdr,
+    pub coeff: *const i16,
+    pub out_y: *mut u8,
+    pub out_u: *mut u8,
+    pub out_v: *mut u8,
+}
+
+#[repr(C)]
+pub struct pfv_encode_job {
+    pub kind: u32,
+    pub flags: u32,
+    pub dst_slot: u32,
+    pub ref_slot: u32,
+    pub px_err: f32,
+    pub reserved: u32,
+    pub src_y: *const u8,
+    pub src_u: *const u8,
+    pub src_v: *const u8,
+    pub hdr_out: *mut pfv_mbhdr,
+    pub coeff_out: *mut i16,
+}
+
+pub enum pfv_ctx {}
+
+pub const PFV_FRAME_I: u32 = 1;
+pub const PFV_FRAME_P: u32 = 2;
+
+#[link(name = "pfv_b200")]
+extern "C" {
+    pub fn pfv_abi_version() -> c_int;
+    pub fn pfv_last_error() -> *const c_char;
+    pub fn pfv_ctx_create(device: c_int, width: u32, height: u32, qtables: *const [i32; 64], nq: u32,
+                          nslots: u32, max_jobs: u32, ext_stream: *mut c_void, out: *mut *mut pfv_ctx) -> c_int;
+    pub fn pfv_ctx_destroy(ctx: *mut pfv_ctx);
+    pub fn pfv_ctx_geometry(ctx: *const pfv_ctx, out: *mut pfv_geometry) -> c_int;
+    pub fn pfv_sync(ctx: *mut pfv_ctx) -> c_int;
+    pub fn pfv_slot_reset(ctx: *mut pfv_ctx, slot: u32) -> c_int;
+    pub fn pfv_slot_read_visible(ctx: *mut pfv_ctx, slot: u32, y: *mut u8, u: *mut u8, v: *mut u8) -> c_int;
+    pub fn pfv_decode_submit(ctx: *mut pfv_ctx, jobs: *const pfv_decode_job, njobs: u32) -> c_int;
+    pub fn pfv_encode_submit(ctx: *mut pfv_ctx, jobs: *const pfv_encode_job, njobs: u32) -> c_int;
+    pub fn pfv_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn pfv_host_free(p: *mut c_void);
+}
+
+fn check(rc: c_int) -> io::Result<()> {
+    if rc == 0 {
+        return Ok(());
+    }
+    let msg = unsafe { CStr::from_ptr(pfv_last_error()) }.to_string_lossy().into_owned();
+    Err(io::Error::new(io::ErrorKind::Other, format!("pfv_b200 error {}: {}", rc, msg)))
+}
+
+/// Device-side replacement of `Decoder.framebuffer` / `Encoder.prev_frame`: two frame slots that ping-pong,
+/// which is how the two-phase update of `VideoPlane::decode_plane_delta_into` (common.rs:498-521) is kept.
+pub struct CudaPlanes {
+    ctx: *mut pfv_ctx,
+    cur: u32,
+}
+
+impl CudaPlanes {
+    pub fn new(width: usize, height: usize, qtables: &[[i32; 64]]) -> io::Result<CudaPlanes> {
+        let mut ctx: *mut pfv_ctx = std::ptr::null_mut();
+        check(unsafe {
+            pfv_ctx_create(0, width as u32, height as u32, qtables.as_ptr(), qtables.len() as u32, 2, 1,
+                           std::ptr::null_mut(), &mut ctx)
+        })?;
+        Ok(CudaPlanes { ctx, cur: 0 })
+    }
+
+    /// replaces the three `deserialize_plane` calls of dec.rs:303-310
+    pub fn decode_iframe(&mut self, coeff: &[i16], qidx: [u8; 3]) -> io::Result<()> {
+        let job = pfv_decode_job {
+            kind: PFV_FRAME_I, flags: 0, dst_slot: self.cur ^ 1, ref_slot: 0, qidx, reserved: 0,
+            hdr: std::ptr::null(), coeff: coeff.as_ptr(),
+            out_y: std::ptr::null_mut(), out_u: std::ptr::null_mut(), out_v: std::ptr::null_mut(),
+        };
+        check(unsafe { pfv_decode_submit(self.ctx, &job, 1) })?;
+        self.cur ^= 1;
+        check(unsafe { pfv_sync(self.ctx) })   // `coeff` is a borrowed Vec: it must outlive the copy
+    }
+
+    /// replaces the three `deserialize_plane_delta` calls of dec.rs:425-432
+    pub fn decode_pframe(&mut self, hdr: &[pfv_mbhdr], coeff: &[i16], qidx: [u8; 3]) -> io::Result<()> {
+        let job = pfv_decode_job {
+            kind: PFV_FRAME_P, flags: 0, dst_slot: self.cur ^ 1, ref_slot: self.cur, qidx, reserved: 0,
+            hdr: hdr.as_ptr(), coeff: coeff.as_ptr(),
+            out_y: std::ptr::null_mut(), out_u: std::ptr::null_mut(), out_v: std::ptr::null_mut(),
+        };
+        check(unsafe { pfv_decode_submit(self.ctx, &job, 1) })?;
+        self.cur ^= 1;
+        check(unsafe { pfv_sync(self.ctx) })
+    }
+
+    /// replaces the retframe blits of dec.rs:195-197 (tight visible planes)
+    pub fn read_visible(&mut self, y: &mut [u8], u: &mut [u8], v: &mut [u8]) -> io::Result<()> {
+        check(unsafe { pfv_slot_read_visible(self.ctx, self.cur, y.as_mut_ptr(), u.as_mut_ptr(), v.as_mut_ptr()) })?;
+        check(unsafe { pfv_sync(self.ctx) })
+    }
+
+    /// replaces enc.rs:84-97 (kind = I) / enc.rs:134-147 (kind = P): encode + closed-loop recon into prev_frame
+    pub fn encode(&mut self, kind: u32, y: &[u8], u: &[u8], v: &[u8], px_err: f32,
+                  hdr_out: &mut [pfv_mbhdr], coeff_out: &mut [i16]) -> io::Result<()> {
+        let job = pfv_encode_job {
+            kind, flags: 0, dst_slot: self.cur ^ 1, ref_slot: self.cur, px_err, reserved: 0,
+            src_y: y.as_ptr(), src_u: u.as_ptr(), src_v: v.as_ptr(),
+            hdr_out: hdr_out.as_mut_ptr(), coeff_out: coeff_out.as_mut_ptr(),
+        };
+        check(unsafe { pfv_encode_submit(self.ctx, &job, 1) })?;
+        self.cur ^= 1;
+        check(unsafe { pfv_sync(self.ctx) })
+    }
+}
+
+impl Drop for CudaPlanes {
+    fn drop(&mut self) {
+        unsafe { pfv_ctx_destroy(self.ctx) }
+    }
+}
