@@ -173,7 +173,7 @@ struct pfv_ctx {
     bool have_kernel_time = false;
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
-    bool decode_i_warp_variant = false;    // PFV_DECODE_I_VARIANT=warp selects the warp-per-macroblock kernel
+    int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "sbq" (default), 1 "sb" (dense), 2 "warp"
     CUtensorMap tm_luma{}, tm_chroma{};
     bool have_tma = false;
     char tma_err[160] = "";
@@ -377,7 +377,8 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
         }
         c->cta_total = cta;
     }
-    if (const char *v = getenv("PFV_DECODE_I_VARIANT")) c->decode_i_warp_variant = strcmp(v, "warp") == 0;
+    if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
+        c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : 0);
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -665,7 +666,7 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
     }
     CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
     const DecJob *d_tab = static_cast<const DecJob *>(st.d_jobs);
-    if (n_i && c->decode_i_warp_variant) {
+    if (n_i && c->decode_i_variant == 2) {
         CU_TRY(launch_decode(false, c->fg, d_tab, n_i, c->d_err, c->s_compute));
         c->launches++;
     } else {
@@ -679,7 +680,8 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
                 P.cta_base[p] = c->cta_base[p];
             }
             P.cta_total = c->cta_total;
-            CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
+            if (c->decode_i_variant == 1) CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
+            else CU_TRY(launch_decode_i_sbq(P, d_tab + a, b - a, c->s_compute));
             c->launches++;
             a = b;
         }

@@ -22,6 +22,23 @@ def rand_coeffs(rng, nb, mode):
         c[rng.random(nb * 256) < 0.7] = 0
     elif mode == "mid":
         c = rng.integers(-1024, 1025, nb * 256)
+    elif mode in ("dc_only", "mixed"):
+        # stream-like sparsity: most sub-blocks carry only a DC term (or nothing), incl. DC extremes that
+        # saturate or wrap; "mixed" sprinkles sub-blocks with a few AC terms among them so the kernel's
+        # DC-only path, its queue of general sub-blocks and the carry between tiles are all exercised
+        sbk = np.zeros((nb * 4, 64), np.int64)
+        sbk[:, 0] = rng.integers(-300, 301, nb * 4)
+        sbk[rng.random(nb * 4) < 0.1, 0] = 0
+        ext = rng.random(nb * 4) < 0.05
+        sbk[ext, 0] = rng.choice([-32768, 32767, -2048, 2047], int(ext.sum()))
+        if mode == "mixed":
+            for frac, npos in ((0.15, 3), (0.05, 40)):
+                pick = np.flatnonzero(rng.random(nb * 4) < frac)
+                for i in pick:
+                    pos = rng.integers(1, 64, npos)
+                    sbk[i, pos] = rng.integers(-200, 201, npos)
+            sbk[np.flatnonzero(rng.random(nb * 4) < 0.02), 63] = 1     # lone last coefficient, zero DC
+        c = sbk.reshape(-1)
     else:  # full i16 range: exercises the wrapping i32 arithmetic
         c = rng.integers(-32768, 32768, nb * 256)
     return c.astype(np.int16)
@@ -46,7 +63,7 @@ def rand_headers(rng, g, p_coded=0.5):
 
 
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("mode", ["small", "mid", "full"])
+@pytest.mark.parametrize("mode", ["small", "mid", "full", "dc_only", "mixed"])
 def test_decode_iframe_matches_oracle(size, mode):
     w, h = size
     rng = np.random.default_rng(w * 7919 + h * 31 + len(mode))
@@ -64,7 +81,7 @@ def test_decode_iframe_matches_oracle(size, mode):
 
 
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("mode", ["small", "full"])
+@pytest.mark.parametrize("mode", ["small", "full", "dc_only", "mixed"])
 def test_decode_pframe_matches_oracle(size, mode):
     w, h = size
     rng = np.random.default_rng(w * 7919 + h * 31 + len(mode) + 5)
