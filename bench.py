@@ -47,6 +47,8 @@ WORKLOADS = {
     "decode_p_1080p": dict(w=1920, h=1080, frames=0, gops=8, gop=15, quality=5, seed=0x50465602),
     "encode_p_1080p": dict(w=1920, h=1080, frames=0, gops=8, gop=15, quality=5, seed=0x50465602),
     "decode_p_4k": dict(w=3840, h=2160, frames=0, gops=4, gop=15, quality=5, seed=0x50465603),
+    # stress stream of SURVEY 8d: uniform-random pixels, every sub-block dense (worst case for the decode kernels)
+    "decode_i_1080p_dense": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465604, kind="random"),
 }
 
 
@@ -183,10 +185,10 @@ class Streams:
         # I-only workload: every frame of one moving sequence; GOP workloads: lane g = its own sequence
         for lane in range(self.lanes):
             if self.gop == 1:
-                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank) if lane == 0 else sv
+                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank, kind=cfg.get("kind", "moving")) if lane == 0 else sv
                 frames = [sv.frame(lane)]
             else:
-                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank + lane)
+                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank + lane, kind=cfg.get("kind", "moving"))
                 frames = [sv.frame(t) for t in range(self.gop)]
             for k, (y, u, v) in enumerate(frames):
                 buf = np.concatenate([y.ravel(), u.ravel(), v.ravel()])
@@ -218,6 +220,8 @@ class Streams:
             self.coded[:] = True
         self.mv_nonzero = float(((hdr[1:, ..., 0] != 0) | (hdr[1:, ..., 1] != 0)).mean()) if self.gop > 1 else 0.0
         self.coded_frac = float(self.coded[1:].mean()) if self.gop > 1 else 1.0
+        # share of sub-blocks with any AC coefficient (the ones that take the full transform in the decode kernels)
+        self.general_frac = float((self.d_coeff.view(-1, 64)[:, 1:] != 0).any(dim=1).float().mean().item())
         self._host = None
 
     def host(self):
@@ -452,7 +456,7 @@ def cpu_port_leg(workload, budget_s, nthreads, reps=None):
     qt, px_err = pfvo.make_qtables(cfg["quality"])
     gop = cfg["gop"]
     nsrc = 4 if gop == 1 else min(gop, 6)
-    sv = SynthVideo(w, h, cfg["seed"])
+    sv = SynthVideo(w, h, cfg["seed"], kind=cfg.get("kind", "moving"))
     frames = [sv.frame(t) for t in range(nsrc)]
     # seam data from the oracle's own encoder (this is the CPU arm; the GPU arm makes its input on the GPU)
     prev = pfvo.frame_init(og)
@@ -561,8 +565,9 @@ def main():
     fps = r["frames"] * dist.world / (r["max_ms"] * 1e-3)
     launches = r["launches_per_step"]
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
-    kernel_key = {"decode_i_1080p": "decode_kernel<false>", "decode_p_1080p": "decode_kernel<true>",
-                  "decode_p_4k": "decode_kernel<true>", "encode_p_1080p": "encode_p_kernel"}[args.workload]
+    kernel_key = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_stream_kernel",
+                  "decode_p_1080p": "decode_sbw_kernel<true>", "decode_p_4k": "decode_sbw_kernel<true>",
+                  "encode_p_1080p": "encode_p_kernel"}[args.workload]
     line = {
         "metric": "1080p decode frames/sec" if "decode" in args.workload and "1080p" in args.workload else f"{args.workload} frames/sec",
         "value": fps, "unit": "frames/s", "mb_per_s": fps * st.nb,
@@ -571,6 +576,7 @@ def main():
         "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"],
                    "frames_per_step_per_gpu": r["frames"], "gop": cfg["gop"], "mb_per_frame": st.nb,
                    "coded_mb_fraction_p": st.coded_frac, "nonzero_mv_fraction_p": st.mv_nonzero,
+                   "ac_subblock_fraction": st.general_frac,
                    "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
                    "sharding": "frames/GOPs split over ranks, no collective on the data path"},
         "gpu_launches": launches * args.steps,
@@ -587,7 +593,7 @@ def main():
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
         if args.extras:
             extras = {}
-            for wl in ("decode_p_1080p", "encode_p_1080p"):
+            for wl in ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p"):
                 if wl == args.workload:
                     continue
                 try:
@@ -598,6 +604,7 @@ def main():
                         "mb_per_s": x["frames"] / (x["max_ms"] * 1e-3) * xs.nb, "ms_per_step": x["max_ms"],
                         "frames_per_step": x["frames"], "launches_per_step": x["launches_per_step"],
                         "coded_mb_fraction_p": xs.coded_frac, "nonzero_mv_fraction_p": xs.mv_nonzero,
+                        "ac_subblock_fraction": xs.general_frac,
                         "roofline_frac": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9 / peak,
                         "achieved_gbs": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9,
                         "e2e": x["e2e"],

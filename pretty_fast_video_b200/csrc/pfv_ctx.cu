@@ -173,7 +173,8 @@ struct pfv_ctx {
     bool have_kernel_time = false;
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
-    int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "sbq" (default), 1 "sb" (dense), 2 "warp"
+    int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "tma" (default), 3 "sbw", 1 "sb" (dense), 2 "warp"
+    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "sbw" (default), 2 "warp"
     CUtensorMap tm_luma{}, tm_chroma{};
     bool have_tma = false;
     char tma_err[160] = "";
@@ -378,7 +379,8 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
         c->cta_total = cta;
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
-        c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : 0);
+        c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : (strcmp(v, "sbw") == 0 ? 3 : 0));
+    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : 0;
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -577,6 +579,8 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         if (j.kind != PFV_FRAME_I && j.kind != PFV_FRAME_P) return fail(PFV_ERR_BAD_ARG, "job %u: bad kind %u", i, j.kind);
         if (j.dst_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: dst_slot %u out of range", i, j.dst_slot);
         if (!j.coeff) return fail(PFV_ERR_BAD_ARG, "job %u: coeff is NULL", i);
+        if ((j.flags & PFV_JOB_DEVICE_PTRS) && (reinterpret_cast<uintptr_t>(j.coeff) & 15u))
+            return fail(PFV_ERR_BAD_ARG, "job %u: device coefficient pointer must be 16-byte aligned", i);
         for (int p = 0; p < 3; p++)
             if (j.qidx[p] >= c->nq)
                 return fail(PFV_ERR_BAD_ARG, "job %u: q-table index %u >= %u (src/dec.rs:244-246 would panic)", i, j.qidx[p], c->nq);
@@ -601,16 +605,18 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));     // device buffers of this stage are free again
 
-    // job table: I jobs first, then P jobs, so each kind is one launch over a contiguous range
+    // job table: I jobs first, then P jobs, each kind sorted by q-index triple: jobs that share a triple form
+    // one launch (the sub-block kernels take the dequantiser tables as kernel parameters)
     DecJob *tab = static_cast<DecJob *>(st.h_jobs);
     std::vector<uint32_t> order;
     order.reserve(njobs);
     uint32_t n_i = 0;
-    for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_I) { order.push_back(i); n_i++; }
-    // key frames that share a q-index triple form one launch of the sub-block kernel (tables are kernel parameters)
     auto qkey = [&](uint32_t i) { return (uint32_t)jobs[i].qidx[0] << 16 | (uint32_t)jobs[i].qidx[1] << 8 | jobs[i].qidx[2]; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return qkey(a) < qkey(b); });
+    auto by_qkey = [&](uint32_t a, uint32_t b) { return qkey(a) < qkey(b); };
+    for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_I) { order.push_back(i); n_i++; }
+    std::stable_sort(order.begin(), order.end(), by_qkey);
     for (uint32_t i = 0; i < njobs; i++) if (jobs[i].kind == PFV_FRAME_P) order.push_back(i);
+    std::stable_sort(order.begin() + n_i, order.end(), by_qkey);
 
     const size_t coeff_elems = (size_t)g.nb * 256;
     // merge H2D copies of buffers that are adjacent in host memory (a caller that decodes a batch into one
@@ -666,6 +672,17 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
     }
     CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
     const DecJob *d_tab = static_cast<const DecJob *>(st.d_jobs);
+    auto sb_params = [&](uint32_t job_index) {
+        SbParams P;
+        P.g = c->fg;
+        for (int p = 0; p < 3; p++) {
+            memcpy(P.deq[p], &c->h_deq_scan[(size_t)jobs[job_index].qidx[p] * 64], 64 * sizeof(int32_t));
+            P.cta_base[p] = c->cta_base[p];
+        }
+        P.cta_total = c->cta_total;
+        P.tiles_per_warp = 1;
+        return P;
+    };
     if (n_i && c->decode_i_variant == 2) {
         CU_TRY(launch_decode(false, c->fg, d_tab, n_i, c->d_err, c->s_compute));
         c->launches++;
@@ -673,20 +690,26 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         for (uint32_t a = 0; a < n_i;) {
             uint32_t b = a + 1;
             while (b < n_i && qkey(order[b]) == qkey(order[a])) b++;
-            SbParams P;
-            P.g = c->fg;
-            for (int p = 0; p < 3; p++) {
-                memcpy(P.deq[p], &c->h_deq_scan[(size_t)jobs[order[a]].qidx[p] * 64], 64 * sizeof(int32_t));
-                P.cta_base[p] = c->cta_base[p];
-            }
-            P.cta_total = c->cta_total;
+            const SbParams P = sb_params(order[a]);
             if (c->decode_i_variant == 1) CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
-            else CU_TRY(launch_decode_i_sbq(P, d_tab + a, b - a, c->s_compute));
+            else if (c->decode_i_variant == 3) CU_TRY(launch_decode_sbw(false, P, d_tab + a, b - a, c->d_err, c->s_compute));
+            else CU_TRY(launch_decode_i_stream(P, d_tab + a, b - a, c->s_compute));
             c->launches++;
             a = b;
         }
     }
-    if (njobs - n_i) { CU_TRY(launch_decode(true, c->fg, d_tab + n_i, njobs - n_i, c->d_err, c->s_compute)); c->launches++; }
+    if (njobs - n_i && c->decode_p_variant == 2) {
+        CU_TRY(launch_decode(true, c->fg, d_tab + n_i, njobs - n_i, c->d_err, c->s_compute));
+        c->launches++;
+    } else {
+        for (uint32_t a = n_i; a < njobs;) {
+            uint32_t b = a + 1;
+            while (b < njobs && qkey(order[b]) == qkey(order[a])) b++;
+            CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            c->launches++;
+            a = b;
+        }
+    }
     CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
     c->have_kernel_time = true;
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));

@@ -62,6 +62,7 @@ struct SbParams {
     int32_t   deq[3][64];     // per plane, by SCAN position s: SCALE[s]*q[s] (wrapping)
     uint32_t  cta_base[3];    // first CTA of each plane (a CTA = 32 consecutive macroblocks of one plane)
     uint32_t  cta_total;
+    uint32_t  tiles_per_warp; // streaming kernels: consecutive 8-macroblock tiles one warp walks
 };
 
 // error bits the kernels OR into the context's device error word
@@ -77,7 +78,8 @@ constexpr int WIN_BYTES = WIN_W * WIN_H;
 cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, uint32_t njobs,
                           int *d_err, cudaStream_t s);
 cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
-cudaError_t launch_decode_i_sbq(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
+cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
+cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, cudaStream_t s);
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,

@@ -90,25 +90,27 @@ decode_i_sb_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict_
 
 
 // -------------------------------------------------------------------------------------------------
-// decode-I, "classify, compact, transform" (the default)
+// decode, "classify, compact, transform" (the default for I and P frames)
 // -------------------------------------------------------------------------------------------------
 // The exact integer IDCT costs ~1300 instructions per sub-block, which at 48 960 sub-blocks per 1080p frame is
 // more issue time than the frame's HBM time.  Real streams are sparse: most sub-blocks carry only a DC
 // coefficient, and for those both passes collapse exactly (src/dct.rs:241-293 with v[1..7] = 0 returns v[0] in
-// every output; all-zero columns stay zero): every pixel is clamp(((c0 * deq0 + 32768) >> 8)).  So each CTA
-//   A. loads one 128-sub-block tile (thread = sub-block, 8 x 16 B), finishes the DC-only sub-blocks on the
-//      spot and appends the others to a shared-memory ring (warp ballot + one atomic per warp);
-//   B. runs the full register-resident transform on the ring 32 entries at a time, so those warps are full.
-// A remainder (< 32 entries) is carried into the CTA's next tile; the last tile flushes.  Results do not
-// depend on the path taken — tests/test_gpu_parity.py drives dense, sparse and mixed inputs through it.
-constexpr int SBQ_THREADS = 128;
-constexpr int SBQ_CAP = 160;                // ring slots: up to 31 carried + 128 new
-constexpr int SBQ_TILES_PER_CTA = 4;
+// every output; all-zero columns stay zero): every pixel is clamp((c0 * deq0 + 32768) >> 8).
+//
+// Each WARP streams over `tiles_per_warp` consecutive tiles of 8 macroblocks (lane = macroblock*4 + sub-block):
+//   A. load the tile (8 x 16 B per lane; P frames: header, motion-compensated predictor), finish the sub-blocks
+//      that need no transform on the spot (DC-only, skipped) and append the others to the warp's private
+//      shared-memory ring (ballot + prefix, no atomics, no CTA barrier);
+//   B. whenever the ring holds 32 entries, run the full register-resident transform on them: a full warp.
+// What is left at the end (< 32 entries per warp) is pooled across the CTA's four warps and flushed.
+// Results do not depend on the path taken; tests/test_gpu_parity.py drives dense, sparse and mixed inputs.
+constexpr int SBW_WARPS = 4;
+constexpr int SBW_RING = 64;                // slots per warp: up to 31 carried + 32 new
 
-struct __align__(16) SbQueue {
-    uint4    coef[SBQ_CAP * 8];             // slot s keeps 16-byte chunk k at [s*8 + (k ^ (s & 7))]: conflict-free both ways
-    uint32_t id[SBQ_CAP];                   // (macroblock inside the plane << 2) | sub-block
-    uint32_t tail;                          // entries appended so far (monotonic)
+struct __align__(16) WarpRing {
+    uint4    coef[SBW_RING * 8];            // slot s keeps 16-byte chunk k at [s*8 + (k ^ (s & 7))]: conflict-free both ways
+    uint32_t id[SBW_RING];                  // (macroblock inside the plane << 2) | sub-block
+    uint32_t hw[SBW_RING];                  // P frames: the macroblock's header word {mx, my, has_coeff, 0}
 };
 
 __device__ __forceinline__ void unpack_dequant(const uint4 (&raw)[8], const int32_t *deq, int (&m)[64])
@@ -123,100 +125,357 @@ __device__ __forceinline__ void unpack_dequant(const uint4 (&raw)[8], const int3
     }
 }
 
-__device__ __forceinline__ uint8_t *sb_dst(const DecJob &job, const PlaneGeom &pl, uint32_t lm, int sb)
+// out = clamp(prev + delta) on four packed pixels; pos4/neg4 = max(delta,0) / min(max(-delta,0),255) in every byte
+// (src/common.rs:100-102; delta is in [-256, 254], and prev - 255 already clamps to 0 for every prev)
+__device__ __forceinline__ uint32_t add_delta_sat4(uint32_t prev, uint32_t pos4, uint32_t neg4)
 {
-    uint32_t col;
-    const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
-    return job.dst + pl.off + (size_t)(row * 16u + (uint32_t)(sb >> 1) * 8u) * pl.pw + col * 16u + (uint32_t)(sb & 1) * 8u;
+    return __vsubus4(__vaddus4(prev, pos4), neg4);            // one of pos4/neg4 is zero
 }
 
-__global__ void __launch_bounds__(SBQ_THREADS, 4)
-decode_i_sbq_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs)
+struct SbWhere {
+    uint8_t       *dst;                     // top-left of the 8x8 in the destination slot
+    const uint8_t *ref;                     // P: top-left of the motion-compensated 8x8 in the reference slot
+    bool           bad_mv;
+};
+
+template <bool INTER>
+__device__ __forceinline__ SbWhere sb_where(const DecJob &job, const PlaneGeom &pl, uint32_t lm, int sb, uint32_t hw)
 {
-    __shared__ SbQueue q;
+    SbWhere w;
+    uint32_t col;
+    const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+    const uint32_t bx = col * 16u, by = row * 16u;
+    const uint32_t oy = (uint32_t)(sb >> 1) * 8u, ox = (uint32_t)(sb & 1) * 8u;
+    w.dst = job.dst + pl.off + (size_t)(by + oy) * pl.pw + bx + ox;
+    w.ref = nullptr;
+    w.bad_mv = false;
+    if (INTER) {
+        int sx = (int)bx + (int)(int8_t)(hw & 0xffu), sy = (int)by + (int)(int8_t)((hw >> 8) & 0xffu);   // src/common.rs:255-256
+        if (sx < 0 || sy < 0 || sx > (int)pl.pw - 16 || sy > (int)pl.ph - 16) {
+            // reference: debug_assert / slice panic (src/common.rs:258-259).  Never read out of bounds: the
+            // stream is flagged bad and the co-located block is used.
+            w.bad_mv = true;
+            sx = (int)bx;
+            sy = (int)by;
+        }
+        w.ref = job.ref + pl.off + (size_t)((uint32_t)sy + oy) * pl.pw + (uint32_t)sx + ox;
+    }
+    return w;
+}
+
+// Phase B for one ring entry per lane: full transform (+ residual on the re-fetched predictor for P frames).
+template <bool INTER>
+__device__ __forceinline__ void transform_entry(const WarpRing &ring, uint32_t slot, const DecJob &job,
+                                                const PlaneGeom &pl, const int32_t *deq)
+{
+    uint4 r2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r2[k] = ring.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
+    const uint32_t id = ring.id[slot];
+    const SbWhere w = sb_where<INTER>(job, pl, id >> 2, (int)(id & 3u), INTER ? ring.hw[slot] : 0u);
+    int m[64];
+    unpack_dequant(r2, deq, m);
+    idct8x8_regs(m);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint2 o;
+        if (INTER) {
+            int y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = m[r * 8 + i];
+            o = apply_residual_row(y, ldg_u8x8_unaligned(w.ref + (size_t)r * pl.pw));   // src/common.rs:277
+        } else {
+            o.x = pack4_sat_u8(m[r * 8 + 0], m[r * 8 + 1], m[r * 8 + 2], m[r * 8 + 3]);
+            o.y = pack4_sat_u8(m[r * 8 + 4], m[r * 8 + 5], m[r * 8 + 6], m[r * 8 + 7]);
+        }
+        __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)r * pl.pw), o);
+    }
+}
+
+template <bool INTER>
+__global__ void __launch_bounds__(SBW_WARPS * 32, 4)
+decode_sbw_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs, int *__restrict__ err)
+{
+    __shared__ WarpRing rings[SBW_WARPS];
+    __shared__ uint32_t left_head[SBW_WARPS], left_cnt[SBW_WARPS];
+
     const uint32_t cta = blockIdx.x;
     const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
     const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
     const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
-    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 31u) / 32u;
-    const uint32_t tile0 = (cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * SBQ_TILES_PER_CTA;
+    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * SBW_WARPS + warp) * P.tiles_per_warp;
+    const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
     const DecJob job = jobs[blockIdx.y];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const int sb = (int)(tid & 3u);
+    const int sb = (int)(lane & 3u);
+    WarpRing &ring = rings[warp];
+    const uint32_t *hdr32 = INTER ? reinterpret_cast<const uint32_t *>(job.hdr) + pl.mb_base : nullptr;
 
-    if (tid == 0) q.tail = 0;
-    __syncthreads();
-    uint32_t head = 0;                                        // entries consumed so far (same in every thread)
+    uint32_t head = 0, tail = 0;                              // warp-uniform ring positions
+    uint32_t hnext = 0;
+    if (INTER && tile_begin < tile_end && tile_begin * 8u + (lane >> 2) < nmb) hnext = __ldg(hdr32 + tile_begin * 8u + (lane >> 2));
 
 #pragma unroll 1
-    for (uint32_t t = 0; t < SBQ_TILES_PER_CTA; ++t) {
-        const uint32_t tile = tile0 + t;
-        if (tile >= ntiles) break;
-        const bool last = (t + 1 == SBQ_TILES_PER_CTA) || (tile + 1 >= ntiles);
-        const uint32_t lm = tile * 32u + (tid >> 2);
+    for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+        const uint32_t lm = tile * 8u + (lane >> 2);
         const bool valid = lm < nmb;
+        const uint32_t hw = hnext;                            // {mx, my, has_coeff, 0} (src/dec.rs:9-13)
+        if (INTER && tile + 1 < tile_end && lm + 8u < nmb) hnext = __ldg(hdr32 + lm + 8u);
 
-        // ---- A: load, classify ----
+        // ---- A: load, classify, finish what needs no transform ----
+        bool general = false;
         uint4 raw[8];
         if (valid) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64));
+            const SbWhere w = sb_where<INTER>(job, pl, lm, sb, hw);
+            if (INTER && w.bad_mv) atomicOr(err, ERRBIT_BAD_MV);
+            uint2 prev[8];
+            if (INTER) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) raw[k] = __ldcs(src + k);
-        } else {
+                for (int r = 0; r < 8; ++r) prev[r] = ldg_u8x8_unaligned(w.ref + (size_t)r * pl.pw);   // get_block, src/common.rs:327-339
+            }
+            const bool coded = !INTER || ((hw >> 16) & 0xffu) != 0u;
+            uint32_t pos4 = 0u, neg4 = 0u, dc4 = 0u;
+            if (coded) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) raw[k] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        uint32_t ac = raw[0].x & 0xffff0000u;
-        ac |= raw[0].y | raw[0].z | raw[0].w;
+                for (int k = 0; k < 8; ++k) raw[k] = __ldcs(src + k);
+                uint32_t ac = raw[0].x & 0xffff0000u;
+                ac |= raw[0].y | raw[0].z | raw[0].w;
 #pragma unroll
-        for (int k = 1; k < 8; ++k) ac |= raw[k].x | raw[k].y | raw[k].z | raw[k].w;
-        const bool general = ac != 0u;
-        const uint32_t vote = __ballot_sync(0xffffffffu, general);
-        uint32_t base = 0;
-        if (lane == 0 && vote) base = atomicAdd(&q.tail, (uint32_t)__popc(vote));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (general) {
-            const uint32_t slot = (base + (uint32_t)__popc(vote & ((1u << lane) - 1u))) % SBQ_CAP;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) q.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = raw[k];
-            q.id[slot] = (lm << 2) | (uint32_t)sb;
-        } else if (valid) {
-            const int c0 = (int)(int16_t)(raw[0].x & 0xffffu);
-            const int v = (c0 * deq[0] + (128 << 8)) >> 8;   // both passes collapse to the DC term
-            const uint32_t b4 = pack4_sat_u8(v, v, v, v);
-            uint8_t *dst = sb_dst(job, pl, lm, sb);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), make_uint2(b4, b4));
-        }
-        __syncthreads();
-
-        // ---- B: full transform on whole warps of queued sub-blocks ----
-        const uint32_t avail = q.tail - head;
-        const uint32_t nproc = last ? avail : (avail & ~31u);
-#pragma unroll 1
-        for (uint32_t c = warp * 32u; c < nproc; c += SBQ_THREADS) {
-            const uint32_t e = c + lane;
-            if (e < nproc) {
-                const uint32_t slot = (head + e) % SBQ_CAP;
-                uint4 r2[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) r2[k] = q.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
-                const uint32_t id = q.id[slot];
-                int m[64];
-                unpack_dequant(r2, deq, m);
-                idct8x8_regs(m);
-                uint8_t *dst = sb_dst(job, pl, id >> 2, (int)(id & 3u));
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    uint2 o;
-                    o.x = pack4_sat_u8(m[r * 8 + 0], m[r * 8 + 1], m[r * 8 + 2], m[r * 8 + 3]);
-                    o.y = pack4_sat_u8(m[r * 8 + 4], m[r * 8 + 5], m[r * 8 + 6], m[r * 8 + 7]);
-                    __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), o);
+                for (int k = 1; k < 8; ++k) ac |= raw[k].x | raw[k].y | raw[k].z | raw[k].w;
+                general = ac != 0u;
+                const int c0 = (int)(int16_t)(raw[0].x & 0xffffu);
+                const int v = (c0 * deq[0] + (128 << 8)) >> 8;                           // both passes collapse to the DC term
+                if (INTER) {
+                    const int delta = (min(max(v, 0), 255) - 128) * 2;                   // src/common.rs:101
+                    pos4 = (uint32_t)max(delta, 0) * 0x01010101u;
+                    neg4 = (uint32_t)min(max(-delta, 0), 255) * 0x01010101u;
+                } else {
+                    dc4 = pack4_sat_u8(v, v, v, v);
                 }
             }
+            if (!general) {
+                if (INTER && (pos4 | neg4) != 0u) {                                      // DC-only residual
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        prev[r].x = add_delta_sat4(prev[r].x, pos4, neg4);
+                        prev[r].y = add_delta_sat4(prev[r].y, pos4, neg4);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)                                              // skipped: the copy, src/common.rs:281-283
+                    __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)r * pl.pw), INTER ? prev[r] : make_uint2(dc4, dc4));
+            }
         }
-        head += nproc;
-        __syncthreads();                                      // ring slots are free again before the next tile appends
+        const uint32_t vote = __ballot_sync(0xffffffffu, general);
+        if (general) {
+            const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ring.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = raw[k];
+            ring.id[slot] = (lm << 2) | (uint32_t)sb;
+            if (INTER) ring.hw[slot] = hw;
+        }
+        tail += (uint32_t)__popc(vote);
+        __syncwarp();
+
+        // ---- B: a full warp of queued sub-blocks ----
+        if (tail - head >= 32u) {
+            transform_entry<INTER>(ring, (head + lane) & (SBW_RING - 1), job, pl, deq);
+            head += 32u;
+            __syncwarp();
+        }
+    }
+
+    // ---- flush: pool what the four warps have left ----
+    if (lane == 0) { left_head[warp] = head; left_cnt[warp] = tail - head; }
+    __syncthreads();
+    uint32_t pre[SBW_WARPS + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int w = 0; w < SBW_WARPS; ++w) pre[w + 1] = pre[w] + left_cnt[w];
+#pragma unroll 1
+    for (uint32_t c = warp * 32u; c < pre[SBW_WARPS]; c += SBW_WARPS * 32u) {
+        const uint32_t e = c + lane;
+        if (e < pre[SBW_WARPS]) {
+            int w = 0;
+#pragma unroll
+            for (int k = 1; k < SBW_WARPS; ++k) w += e >= pre[k] ? 1 : 0;
+            transform_entry<INTER>(rings[w], (left_head[w] + (e - pre[w])) & (SBW_RING - 1), job, pl, deq);
+        }
+    }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// decode-I with TMA-staged tiles (the default for key frames)
+// -------------------------------------------------------------------------------------------------
+// Same classify/compact/transform structure, but the 4 KB coefficient tile of a warp (8 macroblocks x 512 B,
+// contiguous in the dense layout) is fetched by ONE bulk async copy (cp.async.bulk, the TMA unit) into a
+// per-warp double buffer, completion signalled on a per-stage mbarrier.  While a warp classifies or transforms
+// tile i, tiles i+1 and i+2 are in flight without holding registers or LSU slots, which is what the load phase
+// of decode_sbw_kernel<false> lacked (ncu: 25 % issue utilisation, long-scoreboard stalls, 45 % DRAM).
+// Lanes read their 128 B from the stage with the chunk order rotated by (lane & 7) so the 128-byte-strided
+// reads are bank-conflict free; the rotation is undone by address arithmetic when an entry is queued.
+constexpr int STG_STAGES = 2;
+constexpr int STG_TILE_BYTES = 8 * 512;
+
+struct __align__(128) StreamSmem {
+    uint4    stage[SBW_WARPS][STG_STAGES][STG_TILE_BYTES / 16];
+    uint4    coef[SBW_WARPS][SBW_RING * 8];
+    uint32_t id[SBW_WARPS][SBW_RING];
+    uint64_t bar[SBW_WARPS][STG_STAGES];
+    uint32_t left_head[SBW_WARPS], left_cnt[SBW_WARPS];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    const uint32_t b = smem_addr(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t b = smem_addr(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    }
+}
+
+__device__ __forceinline__ void transform_entry_i(const uint4 *coef, const uint32_t *idv, uint32_t slot, const DecJob &job,
+                                                  const PlaneGeom &pl, const int32_t *deq)
+{
+    uint4 r2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r2[k] = coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
+    const uint32_t id = idv[slot];
+    const SbWhere w = sb_where<false>(job, pl, id >> 2, (int)(id & 3u), 0u);
+    int m[64];
+    unpack_dequant(r2, deq, m);
+    idct8x8_regs(m);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint2 o;
+        o.x = pack4_sat_u8(m[r * 8 + 0], m[r * 8 + 1], m[r * 8 + 2], m[r * 8 + 3]);
+        o.y = pack4_sat_u8(m[r * 8 + 4], m[r * 8 + 5], m[r * 8 + 6], m[r * 8 + 7]);
+        __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)r * pl.pw), o);
+    }
+}
+
+__global__ void __launch_bounds__(SBW_WARPS * 32, 3)
+decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+
+    const uint32_t cta = blockIdx.x;
+    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
+    const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+    const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
+    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * SBW_WARPS + warp) * P.tiles_per_warp;
+    const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
+    const uint32_t ntl = tile_end > tile_begin ? tile_end - tile_begin : 0u;
+    const DecJob job = jobs[blockIdx.y];
+    const int sb = (int)(lane & 3u);
+    const uint32_t rot = lane & 7u;
+    uint4 *ring = sm.coef[warp];
+    uint32_t *ring_id = sm.id[warp];
+    const char *plane_coeff = reinterpret_cast<const char *>(job.coeff + (size_t)pl.mb_base * 256);
+
+    auto issue = [&](uint32_t i) {                            // lane 0 only: tile (tile_begin + i) into stage i % STAGES
+        const uint32_t tile = tile_begin + i;
+        const uint32_t mbs = min(8u, nmb - tile * 8u);
+        bulk_load(sm.stage[warp][i % STG_STAGES], plane_coeff + (size_t)tile * STG_TILE_BYTES, mbs * 512u,
+                  &sm.bar[warp][i % STG_STAGES]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s2 = 0; s2 < STG_STAGES; ++s2)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bar[warp][s2])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (uint32_t i = 0; i < STG_STAGES; ++i)
+            if (i < ntl) issue(i);
+    }
+    __syncwarp();
+
+    uint32_t head = 0, tail = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < ntl; ++i) {
+        const uint32_t tile = tile_begin + i;
+        const uint32_t lm = tile * 8u + (lane >> 2);
+        const bool valid = lm < nmb;
+        const uint4 *stg = sm.stage[warp][i % STG_STAGES];
+
+        // ---- A: take this lane's 128 B out of the stage (chunk k ^ rot lands in raw[k]) ----
+        bar_wait(&sm.bar[warp][i % STG_STAGES], (i / STG_STAGES) & 1u);
+        uint4 raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) raw[k] = stg[lane * 8u + ((uint32_t)k ^ rot)];
+        __syncwarp();                                         // every lane has read: the stage may be refilled
+        if (lane == 0 && i + STG_STAGES < ntl) issue(i + STG_STAGES);
+
+        uint32_t ac = 0u, w0 = 0u;                            // w0: the word that holds the DC coefficient (chunk 0)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool is0 = rot == (uint32_t)k;
+            w0 = is0 ? raw[k].x : w0;
+            ac |= (is0 ? (raw[k].x & 0xffff0000u) : raw[k].x) | raw[k].y | raw[k].z | raw[k].w;
+        }
+        const bool general = valid && ac != 0u;
+        const uint32_t vote = __ballot_sync(0xffffffffu, general);
+        if (general) {
+            const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+            const uint32_t y = rot ^ (slot & 7u);             // raw[k] is chunk k ^ rot; the ring keeps chunk j at j ^ (slot & 7)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ring[slot * 8u + ((uint32_t)k ^ y)] = raw[k];
+            ring_id[slot] = (lm << 2) | (uint32_t)sb;
+        } else if (valid) {
+            const int c0 = (int)(int16_t)(w0 & 0xffffu);
+            const int v = (c0 * deq[0] + (128 << 8)) >> 8;   // both passes collapse to the DC term
+            const uint32_t dc4 = pack4_sat_u8(v, v, v, v);
+            const SbWhere w = sb_where<false>(job, pl, lm, sb, 0u);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)r * pl.pw), make_uint2(dc4, dc4));
+        }
+        tail += (uint32_t)__popc(vote);
+        __syncwarp();
+
+        // ---- B: a full warp of queued sub-blocks ----
+        if (tail - head >= 32u) {
+            transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job, pl, deq);
+            head += 32u;
+            __syncwarp();
+        }
+    }
+
+    // ---- flush: pool what the four warps have left ----
+    if (lane == 0) { sm.left_head[warp] = head; sm.left_cnt[warp] = tail - head; }
+    __syncthreads();
+    uint32_t pre[SBW_WARPS + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int w = 0; w < SBW_WARPS; ++w) pre[w + 1] = pre[w] + sm.left_cnt[w];
+#pragma unroll 1
+    for (uint32_t c = warp * 32u; c < pre[SBW_WARPS]; c += SBW_WARPS * 32u) {
+        const uint32_t e = c + lane;
+        if (e < pre[SBW_WARPS]) {
+            int w = 0;
+#pragma unroll
+            for (int k = 1; k < SBW_WARPS; ++k) w += e >= pre[k] ? 1 : 0;
+            transform_entry_i(sm.coef[w], sm.id[w], (sm.left_head[w] + (e - pre[w])) & (SBW_RING - 1), job, pl, deq);
+        }
     }
 }
 
@@ -227,18 +486,48 @@ cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t
     return cudaGetLastError();
 }
 
-// `P` arrives with g and deq filled; the CTA map (CTAs never straddle a plane) is completed here.
-cudaError_t launch_decode_i_sbq(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
+// `P` arrives with g and deq filled; the work split is completed here.  tiles_per_warp trades the per-warp
+// remainder (one partly filled transform pass per warp at the end) against having enough warps to fill the
+// chip: aim at ~2 waves of the 148 SMs x 16 resident warps, at most 16 tiles per warp.
+static void sbw_split(SbParams &P, uint32_t njobs, uint32_t waves_x_warps, uint32_t max_tpw)
 {
+    uint32_t tiles = 0;
+    for (int p = 0; p < 3; p++) tiles += (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
+    const uint64_t total = (uint64_t)tiles * njobs;
+    uint32_t tpw = (uint32_t)(total / waves_x_warps);
+    tpw = tpw < 1 ? 1 : (tpw > max_tpw ? max_tpw : tpw);
+    P.tiles_per_warp = tpw;
     uint32_t cta = 0;
     for (int p = 0; p < 3; p++) {
         P.cta_base[p] = cta;
-        const uint32_t ntiles = (P.g.pl[p].bw * P.g.pl[p].bh + 31u) / 32u;
-        cta += (ntiles + SBQ_TILES_PER_CTA - 1) / SBQ_TILES_PER_CTA;
+        const uint32_t ntiles = (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
+        cta += (ntiles + SBW_WARPS * tpw - 1) / (SBW_WARPS * tpw);
     }
     P.cta_total = cta;
-    dim3 grid(P.cta_total, njobs, 1), block(SBQ_THREADS, 1, 1);
-    decode_i_sbq_kernel<<<grid, block, 0, s>>>(P, d_jobs);
+}
+
+cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s)
+{
+    sbw_split(P, njobs, 2u * 148u * 16u, 16u);
+    dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);
+    if (inter) decode_sbw_kernel<true><<<grid, block, 0, s>>>(P, d_jobs, d_err);
+    else       decode_sbw_kernel<false><<<grid, block, 0, s>>>(P, d_jobs, d_err);
+    return cudaGetLastError();
+}
+
+// Job coefficient pointers must be 16-byte aligned (bulk copies); pfv_decode_submit checks.
+cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(StreamSmem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    sbw_split(P, njobs, 6u * 148u * 12u, 16u);               // ~6 waves of 148 SMs x 12 resident warps
+    dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);
+    decode_i_stream_kernel<<<grid, block, sizeof(StreamSmem), s>>>(P, d_jobs);
     return cudaGetLastError();
 }
 

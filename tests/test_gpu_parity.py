@@ -102,6 +102,31 @@ def test_decode_pframe_matches_oracle(size, mode):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("variant", ["tma", "sbw", "sb", "warp"])
+def test_decode_kernel_variants_agree(variant, monkeypatch):
+    """The dense sub-block kernel and the warp-per-macroblock kernels stay selectable (PFV_DECODE_*_VARIANT)."""
+    monkeypatch.setenv("PFV_DECODE_I_VARIANT", variant)
+    monkeypatch.setenv("PFV_DECODE_P_VARIANT", variant)
+    w, h = 208, 112
+    rng = np.random.default_rng(99)
+    qt, _ = make_qtables(4)
+    og = pfvo.geometry_for(w, h)
+    ci = rand_coeffs(rng, og.nb, "mixed")
+    cp = rand_coeffs(rng, og.nb, "mixed")
+    hdr = rand_headers(rng, og)
+    cp.reshape(-1, 256)[hdr[:, 2] == 0] = 0
+    want0 = pfvo.frame_init(og)
+    pfvo.decode_iframe_coeffs(og, qt, (0, 1, 1), ci, want0)
+    want1 = want0.copy()
+    pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdr, cp, want1)
+    with Engine(w, h, qt, nslots=2, max_jobs=1) as e:
+        e.decode_submit([DecodeJob(PFV_FRAME_I, 0, ci, (0, 1, 1))])
+        e.decode_submit([DecodeJob(PFV_FRAME_P, 1, cp, (2, 3, 3), ref_slot=0, hdr=hdr)])
+        e.sync()
+        assert np.array_equal(e.slot_read(0), want0)
+        assert np.array_equal(e.slot_read(1), want1)
+
+
 def test_decode_pframe_all_skipped_is_a_copy():
     w, h = 320, 240
     qt, _ = make_qtables(5)
