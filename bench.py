@@ -5,7 +5,7 @@
 
 A "step" is one pass of the hot path over one batch of synthetic frames.  Workloads (BASELINE.json configs):
   decode_i_1080p  configs[1]  64 independent 1080p key frames per GPU, one launch per step           (default)
-  decode_p_1080p  configs[2]  8 GOPs x 15 frames (1 key frame / 15), frame k of every GOP per launch
+  decode_p_1080p  configs[2]  32 GOPs x 15 frames (1 key frame / 15), frame k of every GOP per launch
   encode_p_1080p  configs[3]  the same GOPs encoded (full SSD block search), frame k of every GOP per launch
   decode_p_4k     configs[4]  4 GOPs x 15 frames of 3840x2160 per GPU, GOPs sharded over the ranks
 
@@ -44,8 +44,8 @@ MB_BYTES_ENC_I = 1024
 
 WORKLOADS = {
     "decode_i_1080p": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465601),
-    "decode_p_1080p": dict(w=1920, h=1080, frames=0, gops=8, gop=15, quality=5, seed=0x50465602),
-    "encode_p_1080p": dict(w=1920, h=1080, frames=0, gops=8, gop=15, quality=5, seed=0x50465602),
+    "decode_p_1080p": dict(w=1920, h=1080, frames=0, gops=32, gop=15, quality=5, seed=0x50465602),
+    "encode_p_1080p": dict(w=1920, h=1080, frames=0, gops=32, gop=15, quality=5, seed=0x50465602),
     "decode_p_4k": dict(w=3840, h=2160, frames=0, gops=4, gop=15, quality=5, seed=0x50465603),
     # stress stream of SURVEY 8d: uniform-random pixels, every sub-block dense (worst case for the decode kernels)
     "decode_i_1080p_dense": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465604, kind="random"),
@@ -532,6 +532,7 @@ def main():
     ap.add_argument("--workload", default="decode_i_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--extras", type=int, default=1, help="also run the P-stream decode/encode workloads (N=1 only)")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
+    ap.add_argument("--e2e", type=int, default=1, help="0 skips the host-buffer leg (kernel tuning runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -559,14 +560,14 @@ def main():
 
     sampler = ClockSampler(dist.local)
     sampler.start()
-    r = run(args.workload, args.steps, args.warmup)
+    r = run(args.workload, args.steps, args.warmup, bool(args.e2e))
     clocks = sampler.stop()
     st, cfg = r["st"], WORKLOADS[args.workload]
     fps = r["frames"] * dist.world / (r["max_ms"] * 1e-3)
     launches = r["launches_per_step"]
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
     kernel_key = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_stream_kernel",
-                  "decode_p_1080p": "decode_sbw_kernel<true>", "decode_p_4k": "decode_sbw_kernel<true>",
+                  "decode_p_1080p": "decode_p_stream_kernel", "decode_p_4k": "decode_p_stream_kernel",
                   "encode_p_1080p": "encode_p_kernel"}[args.workload]
     line = {
         "metric": "1080p decode frames/sec" if "decode" in args.workload and "1080p" in args.workload else f"{args.workload} frames/sec",

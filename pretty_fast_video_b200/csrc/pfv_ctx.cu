@@ -174,7 +174,7 @@ struct pfv_ctx {
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
     int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "tma" (default), 3 "sbw", 1 "sb" (dense), 2 "warp"
-    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "sbw" (default), 2 "warp"
+    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "stream" (default), 3 "sbw", 2 "warp"
     CUtensorMap tm_luma{}, tm_chroma{};
     bool have_tma = false;
     char tma_err[160] = "";
@@ -380,7 +380,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
         c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : (strcmp(v, "sbw") == 0 ? 3 : 0));
-    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : 0;
+    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : 0);
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -705,7 +705,8 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         for (uint32_t a = n_i; a < njobs;) {
             uint32_t b = a + 1;
             while (b < njobs && qkey(order[b]) == qkey(order[a])) b++;
-            CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            if (c->decode_p_variant == 3) CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            else CU_TRY(launch_decode_p_stream(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
             c->launches++;
             a = b;
         }

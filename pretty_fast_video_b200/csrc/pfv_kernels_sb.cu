@@ -8,6 +8,8 @@
 // and amortises the addressing over 8 macroblocks (ncu: 255 -> ~150 warp instructions per macroblock).
 //
 // Arithmetic is the reference's (see pfv_device.cuh for the file:line map).
+#include <stdlib.h>
+
 #include "pfv_internal.h"
 #include "pfv_device.cuh"
 
@@ -479,6 +481,240 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// decode-P with cp.async-staged predictors (the default for P frames; src/common.rs:498-521 -> :254-285)
+// -------------------------------------------------------------------------------------------------
+// ncu on decode_sbw_kernel<true> showed the motion-compensated fetch done as 24 scalar, arbitrarily aligned
+// LDG.32 per lane is bound by L1 wavefronts, not by bytes.  Here a warp stages the predictor of each of its 8
+// macroblocks with ONE warp-wide 16-byte cp.async (lane = row*2 + half: the two aligned 16-byte chunks that
+// cover the row's 16 unaligned bytes; get_block, src/common.rs:327-339) into a double-buffered shared tile,
+// one tile ahead of use, and lanes then take their unaligned 8 bytes per row from shared memory.
+//   A. skipped macroblocks (src/common.rs:281-283) store the copy; coded sub-blocks are appended to the warp's
+//      ring: predictor (64 B), id, and their 128 B of coefficients fetched by cp.async straight into the slot;
+//   B. whenever 32 coded sub-blocks are queued: DC-only ones apply one clamped delta, the others run the full
+//      transform + residual (src/common.rs:98-104).
+constexpr int PST_MB_STRIDE = 16 * 32 + 16;                   // bytes: 16 rows x 32 B, +16 so macroblocks start 4 banks apart
+struct __align__(16) PWarpSmem {
+    uint4    ref[2][8 * PST_MB_STRIDE / 16];                  // double-buffered predictor tile
+    uint4    coef[SBW_RING * 8];                              // slot s keeps chunk k at [s*8 + (k ^ (s & 7))]
+    uint4    prev[SBW_RING * 4];                              // rows 2k,2k+1 at [s*4 + (k ^ ((s >> 1) & 3))]
+    uint32_t id[SBW_RING];
+};
+struct __align__(16) PStreamSmem {
+    PWarpSmem w[SBW_WARPS];
+    uint32_t  left_head[SBW_WARPS], left_cnt[SBW_WARPS];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 8 bytes at byte offset `off` of a shared-memory row (off + 8 <= 32)
+__device__ __forceinline__ uint2 lds_u8x8(const unsigned char *row, uint32_t off)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + (off & ~3u));
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];             // off <= 23, so all three words lie inside the 32-byte row
+    uint2 r;
+    r.x = __funnelshift_r(w0, w1, sh);
+    r.y = __funnelshift_r(w1, w2, sh);
+    return r;
+}
+
+__device__ __forceinline__ void transform_entry_p(PWarpSmem &ws, uint32_t slot, const DecJob &job, const PlaneGeom &pl,
+                                                  const int32_t *deq)
+{
+    uint4 r2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r2[k] = ws.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
+    const uint32_t id = ws.id[slot];
+    const SbWhere w = sb_where<false>(job, pl, id >> 2, (int)(id & 3u), 0u);
+    uint32_t ac = r2[0].x & 0xffff0000u;
+    ac |= r2[0].y | r2[0].z | r2[0].w;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) ac |= r2[k].x | r2[k].y | r2[k].z | r2[k].w;
+    if (ac == 0u) {                                           // DC only: one delta for the whole sub-block
+        const int c0 = (int)(int16_t)(r2[0].x & 0xffffu);
+        const int v = (c0 * deq[0] + (128 << 8)) >> 8;
+        const int delta = (min(max(v, 0), 255) - 128) * 2;    // src/common.rs:101
+        const uint32_t pos4 = (uint32_t)max(delta, 0) * 0x01010101u;
+        const uint32_t neg4 = (uint32_t)min(max(-delta, 0), 255) * 0x01010101u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 pv = ws.prev[slot * 4u + ((uint32_t)k ^ ((slot >> 1) & 3u))];
+            __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)(2 * k) * pl.pw),
+                   make_uint2(add_delta_sat4(pv.x, pos4, neg4), add_delta_sat4(pv.y, pos4, neg4)));
+            __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)(2 * k + 1) * pl.pw),
+                   make_uint2(add_delta_sat4(pv.z, pos4, neg4), add_delta_sat4(pv.w, pos4, neg4)));
+        }
+        return;
+    }
+    int m[64];
+    unpack_dequant(r2, deq, m);
+    idct8x8_regs(m);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint4 pv = ws.prev[slot * 4u + ((uint32_t)k ^ ((slot >> 1) & 3u))];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = 2 * k + h;
+            int y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = m[r * 8 + i];
+            const uint2 o = apply_residual_row(y, h == 0 ? make_uint2(pv.x, pv.y) : make_uint2(pv.z, pv.w));   // src/common.rs:277
+            __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)r * pl.pw), o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SBW_WARPS * 32, 2)
+decode_p_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs, int *__restrict__ err)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PStreamSmem &sm = *reinterpret_cast<PStreamSmem *>(smem_raw);
+
+    const uint32_t cta = blockIdx.x;
+    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
+    const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+    const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
+    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * SBW_WARPS + warp) * P.tiles_per_warp;
+    const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
+    const DecJob job = jobs[blockIdx.y];
+    const int sb = (int)(lane & 3u);
+    PWarpSmem &ws = sm.w[warp];
+    const uint32_t *hdr32 = reinterpret_cast<const uint32_t *>(job.hdr) + pl.mb_base;
+    const uint8_t *ref_plane = job.ref + pl.off;
+
+    // Per-lane view of "its" macroblock of a tile: header word -> 16-byte aligned source of the predictor rows
+    // and the byte offset of the block inside the 32-byte staged rows.
+    struct Mc { const uint8_t *src; uint32_t off; };
+    auto locate = [&](uint32_t lm, uint32_t hw) {
+        uint32_t col;
+        const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+        const int bx = (int)col * 16, by = (int)row * 16;
+        int sx = bx + (int)(int8_t)(hw & 0xffu), sy = by + (int)(int8_t)((hw >> 8) & 0xffu);   // src/common.rs:255-256
+        if (sx < 0 || sy < 0 || sx > (int)pl.pw - 16 || sy > (int)pl.ph - 16) {
+            atomicOr(err, ERRBIT_BAD_MV);                     // src/common.rs:258-259: never read out of bounds
+            sx = bx;
+            sy = by;
+        }
+        Mc m;
+        m.off = (uint32_t)sx & 15u;
+        m.src = ref_plane + (size_t)sy * pl.pw + ((uint32_t)sx & ~15u);
+        return m;
+    };
+    // all lanes: stage the predictors of tile `tile` (headers in hw, one per lane's macroblock) into buffer b
+    auto stage_tile = [&](uint32_t tile, uint32_t hw, int b) -> uint32_t {
+        const uint32_t lm = tile * 8u + (lane >> 2);
+        Mc mc = {ref_plane, 0u};
+        if (lm < nmb) mc = locate(lm, hw);
+        const unsigned long long sp = reinterpret_cast<unsigned long long>(mc.src);
+        const uint32_t row = lane >> 1, half = lane & 1u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned long long pj = __shfl_sync(0xffffffffu, sp, 4 * j);
+            if (tile * 8u + (uint32_t)j < nmb)
+                cp_async16(reinterpret_cast<unsigned char *>(ws.ref[b]) + j * PST_MB_STRIDE + row * 32u + half * 16u,
+                           reinterpret_cast<const uint8_t *>(pj) + (size_t)row * pl.pw + half * 16u);
+        }
+        cp_async_commit();
+        return mc.off;
+    };
+
+    uint32_t head = 0, tail = 0;
+    uint32_t hw_cur = 0, hw_next = 0, off_cur = 0, off_next = 0;
+    if (tile_begin < tile_end) {
+        if (tile_begin * 8u + (lane >> 2) < nmb) hw_cur = __ldg(hdr32 + tile_begin * 8u + (lane >> 2));
+        if (tile_begin + 1 < tile_end && (tile_begin + 1) * 8u + (lane >> 2) < nmb)
+            hw_next = __ldg(hdr32 + (tile_begin + 1) * 8u + (lane >> 2));
+        off_cur = stage_tile(tile_begin, hw_cur, 0);
+        cp_async_commit();                                    // empty group: keeps the R(t), C(t-1), R(t+1) commit pattern uniform
+    }
+
+#pragma unroll 1
+    for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+        const int b = (int)((tile - tile_begin) & 1u);
+        const uint32_t lm = tile * 8u + (lane >> 2);
+        const bool valid = lm < nmb;
+        uint32_t hw_next2 = 0;
+        if (tile + 1 < tile_end) {
+            off_next = stage_tile(tile + 1, hw_next, b ^ 1);                       // one tile ahead
+            if (tile + 2 < tile_end && lm + 16u < nmb) hw_next2 = __ldg(hdr32 + lm + 16u);
+            cp_async_wait<2>();       // commit order is R(t), C(t-1), R(t+1): R(t) must have landed, the two newer may be in flight
+        } else {
+            cp_async_wait<1>();       // R(t), C(t-1)
+        }
+        __syncwarp();
+
+        // ---- A ----
+        const bool coded = valid && ((hw_cur >> 16) & 0xffu) != 0u;
+        uint2 prev[8];
+        if (valid) {
+            const unsigned char *rows = reinterpret_cast<const unsigned char *>(ws.ref[b]) + (lane >> 2) * PST_MB_STRIDE +
+                                        (uint32_t)(sb >> 1) * 8u * 32u;
+            const uint32_t off = off_cur + (uint32_t)(sb & 1) * 8u;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) prev[r] = lds_u8x8(rows + r * 32, off);
+        }
+        const uint32_t vote = __ballot_sync(0xffffffffu, coded);
+        if (coded) {
+            const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cp_async16(&ws.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))], src + k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                ws.prev[slot * 4u + ((uint32_t)k ^ ((slot >> 1) & 3u))] =
+                    make_uint4(prev[2 * k].x, prev[2 * k].y, prev[2 * k + 1].x, prev[2 * k + 1].y);
+            ws.id[slot] = (lm << 2) | (uint32_t)sb;
+        } else if (valid) {                                                          // skipped: src/common.rs:281-283
+            uint32_t col;
+            const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+            uint8_t *dst = job.dst + pl.off + (size_t)(row * 16u + (uint32_t)(sb >> 1) * 8u) * pl.pw + col * 16u + (uint32_t)(sb & 1) * 8u;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), prev[r]);
+        }
+        cp_async_commit();
+        tail += (uint32_t)__popc(vote);
+        hw_cur = hw_next; hw_next = hw_next2; off_cur = off_next;
+
+        // ---- B ----
+        if (tail - head >= 32u) {
+            cp_async_wait<0>();
+            __syncwarp();
+            transform_entry_p(ws, (head + lane) & (SBW_RING - 1), job, pl, deq);
+            head += 32u;
+        }
+        __syncwarp();
+    }
+
+    // ---- flush ----
+    cp_async_wait<0>();
+    if (lane == 0) { sm.left_head[warp] = head; sm.left_cnt[warp] = tail - head; }
+    __syncthreads();
+    uint32_t pre[SBW_WARPS + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int w = 0; w < SBW_WARPS; ++w) pre[w + 1] = pre[w] + sm.left_cnt[w];
+#pragma unroll 1
+    for (uint32_t c = warp * 32u; c < pre[SBW_WARPS]; c += SBW_WARPS * 32u) {
+        const uint32_t e = c + lane;
+        if (e < pre[SBW_WARPS]) {
+            int w = 0;
+#pragma unroll
+            for (int k = 1; k < SBW_WARPS; ++k) w += e >= pre[k] ? 1 : 0;
+            transform_entry_p(sm.w[w], (sm.left_head[w] + (e - pre[w])) & (SBW_RING - 1), job, pl, deq);
+        }
+    }
+}
+
 cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
     dim3 grid(P.cta_total, njobs, 1), block(SB_WARPS * 32, 1, 1);
@@ -496,6 +732,8 @@ static void sbw_split(SbParams &P, uint32_t njobs, uint32_t waves_x_warps, uint3
     const uint64_t total = (uint64_t)tiles * njobs;
     uint32_t tpw = (uint32_t)(total / waves_x_warps);
     tpw = tpw < 1 ? 1 : (tpw > max_tpw ? max_tpw : tpw);
+    static const int tpw_env = getenv("PFV_TILES_PER_WARP") ? atoi(getenv("PFV_TILES_PER_WARP")) : 0;   // tuning aid
+    if (tpw_env > 0) tpw = (uint32_t)tpw_env;
     P.tiles_per_warp = tpw;
     uint32_t cta = 0;
     for (int p = 0; p < 3; p++) {
@@ -528,6 +766,21 @@ cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t nj
     sbw_split(P, njobs, 6u * 148u * 12u, 16u);               // ~6 waves of 148 SMs x 12 resident warps
     dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);
     decode_i_stream_kernel<<<grid, block, sizeof(StreamSmem), s>>>(P, d_jobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(decode_p_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(PStreamSmem));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    sbw_split(P, njobs, 6u * 148u * 8u, 16u);                 // ~6 waves of 148 SMs x 8 resident warps
+    dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);
+    decode_p_stream_kernel<<<grid, block, sizeof(PStreamSmem), s>>>(P, d_jobs, d_err);
     return cudaGetLastError();
 }
 
