@@ -567,7 +567,7 @@ def main():
     launches = r["launches_per_step"]
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
     kernel_key = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_stream_kernel",
-                  "decode_p_1080p": "decode_p_stream_kernel", "decode_p_4k": "decode_p_stream_kernel",
+                  "decode_p_1080p": "mc_copy_kernel+residual_sb_kernel", "decode_p_4k": "mc_copy_kernel+residual_sb_kernel",
                   "encode_p_1080p": "encode_p_kernel"}[args.workload]
     line = {
         "metric": "1080p decode frames/sec" if "decode" in args.workload and "1080p" in args.workload else f"{args.workload} frames/sec",

@@ -174,7 +174,9 @@ struct pfv_ctx {
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
     int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "tma" (default), 3 "sbw", 1 "sb" (dense), 2 "warp"
-    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "stream" (default), 3 "sbw", 2 "warp"
+    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "two" (default), 1 "stream", 3 "sbw", 2 "warp"
+    uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
+    uint32_t *d_pcount = nullptr;          // max_jobs * 4
     CUtensorMap tm_luma{}, tm_chroma{};
     bool have_tma = false;
     char tma_err[160] = "";
@@ -321,7 +323,7 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     for (int i = 0; i < D2H_RING; i++) if (c->ev_d2h_ring[i]) cudaEventDestroy(c->ev_d2h_ring[i]);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
     if (c->ev_k1) cudaEventDestroy(c->ev_k1);
-    cudaFree(c->d_pool); cudaFree(c->d_qt); cudaFree(c->d_err);
+    cudaFree(c->d_pool); cudaFree(c->d_qt); cudaFree(c->d_err); cudaFree(c->d_plist); cudaFree(c->d_pcount);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -380,10 +382,12 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
         c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : (strcmp(v, "sbw") == 0 ? 3 : 0));
-    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : 0);
+    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : (strcmp(v, "stream") == 0 ? 1 : 0));
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
+    CU_TRY(cudaMalloc(&c->d_plist, (size_t)c->max_jobs * c->geo.nb * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->d_pcount, (size_t)c->max_jobs * 4 * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_err, sizeof(int)));
     CU_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
     CU_TRY(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocDefault));
@@ -705,8 +709,17 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         for (uint32_t a = n_i; a < njobs;) {
             uint32_t b = a + 1;
             while (b < njobs && qkey(order[b]) == qkey(order[a])) b++;
-            if (c->decode_p_variant == 3) CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
-            else CU_TRY(launch_decode_p_stream(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            if (c->decode_p_variant == 3) {
+                CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            } else if (c->decode_p_variant == 1) {
+                CU_TRY(launch_decode_p_stream(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            } else {
+                const uint32_t k0 = a - n_i;
+                CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)(b - a) * 4 * sizeof(uint32_t), c->s_compute));
+                CU_TRY(launch_decode_p_two_pass(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
+                                                c->d_pcount + (size_t)k0 * 4, c->d_err, c->s_compute));
+                c->launches++;
+            }
             c->launches++;
             a = b;
         }

@@ -65,6 +65,12 @@ struct SbParams {
     uint32_t  tiles_per_warp; // streaming kernels: consecutive 8-macroblock tiles one warp walks
 };
 
+// mc_copy_kernel: tiles of 8 consecutive macroblocks, never straddling a plane
+struct McTiles {
+    uint32_t base[3];         // first tile of each plane
+    uint32_t total;
+};
+
 // error bits the kernels OR into the context's device error word
 enum { ERRBIT_BAD_MV = 1 };
 
@@ -79,6 +85,8 @@ cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, 
                           int *d_err, cudaStream_t s);
 cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
+cudaError_t launch_decode_p_two_pass(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
+                                     uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,

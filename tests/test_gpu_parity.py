@@ -102,11 +102,11 @@ def test_decode_pframe_matches_oracle(size, mode):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", ["tma", "sbw", "sb", "warp"])
+@pytest.mark.parametrize("variant", ["tma", "stream", "sbw", "sb", "warp"])
 def test_decode_kernel_variants_agree(variant, monkeypatch):
     """The earlier kernels stay selectable (PFV_DECODE_*_VARIANT) and agree with the default ones."""
     monkeypatch.setenv("PFV_DECODE_I_VARIANT", variant)
-    monkeypatch.setenv("PFV_DECODE_P_VARIANT", "stream" if variant == "tma" else variant)
+    monkeypatch.setenv("PFV_DECODE_P_VARIANT", "two" if variant == "tma" else variant)
     w, h = 208, 112
     rng = np.random.default_rng(99)
     qt, _ = make_qtables(4)
