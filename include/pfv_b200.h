@@ -165,11 +165,130 @@ int  pfv_slot_device_ptr(pfv_ctx *ctx, uint32_t slot, void **out);
 int  pfv_decode_submit(pfv_ctx *ctx, const pfv_decode_job *jobs, uint32_t njobs);
 int  pfv_encode_submit(pfv_ctx *ctx, const pfv_encode_job *jobs, uint32_t njobs);
 
+/*
+ * Sparse coefficient transport.  What the entropy decoder's symbol loop produces
+ * (src/dec.rs:261-296, :378-417) before it is scattered into the dense Vec<i16>: for every macroblock the
+ * list of its non-zero coefficients.  tok[i] = (position << 16) | uint16(value), position = index 0..255 inside
+ * the macroblock (sub-block * 64 + scan position); the tokens of macroblock m are tok[mb_off[m] .. mb_off[m+1]).
+ * The engine copies only the tokens over PCIe and expands them on the device (expand_tokens_kernel) into the same
+ * dense layout pfv_decode_submit takes, so results are identical by construction.  A P macroblock with
+ * has_coeff = 0 must own no tokens.  Positions may repeat; the last token of a position wins (src/dec.rs:288).
+ */
+typedef struct pfv_decode_job_sparse {
+    uint32_t kind;             /* PFV_FRAME_I or PFV_FRAME_P                                         */
+    uint32_t flags;            /* must be 0 (host pointers only)                                     */
+    uint32_t dst_slot, ref_slot;
+    uint8_t  qidx[3];
+    uint8_t  reserved;
+    const pfv_mbhdr *hdr;      /* P: nb headers                                                      */
+    const uint32_t  *mb_off;   /* nb + 1 offsets into tok, mb_off[0] = 0, mb_off[nb] = ntok          */
+    const uint32_t  *tok;      /* ntok tokens                                                        */
+    uint32_t ntok;
+    uint32_t reserved2;
+    uint8_t *out_y, *out_u, *out_v;
+} pfv_decode_job_sparse;
+int  pfv_decode_submit_sparse(pfv_ctx *ctx, const pfv_decode_job_sparse *jobs, uint32_t njobs);
+
+/* Every *_submit (and pfv_slot_read_visible) call takes the next submit id (1, 2, ...).  pfv_ctx_wait_submit blocks
+ * until the device-to-host copies of that submit have landed (it must be one of the 8 most recent ids); unlike
+ * pfv_sync it does not wait for later submits, which is what a read-ahead decoder needs. */
+uint64_t pfv_ctx_last_submit_id(const pfv_ctx *ctx);
+int      pfv_ctx_wait_submit(pfv_ctx *ctx, uint64_t submit_id);
+
 /* number of kernel launches this context has issued (bench.py's gpu_launches) */
 uint64_t pfv_ctx_launch_count(const pfv_ctx *ctx);
 /* device time in ms of the compute-stream work between the first and last kernel of the most recent
  * *_submit call (CUDA events recorded on the compute stream around the launches); valid after pfv_sync. */
 int  pfv_ctx_last_kernel_ms(pfv_ctx *ctx, float *ms_out);
+
+
+/* ---- host side of the codec: container + entropy layer + the reference's Encoder / Decoder ---------------- */
+/*
+ * Everything below runs on the host (north_star keeps src/huffman.rs and src/rle.rs there) and is built on the
+ * hot-path entry points above.  pfv_decoder / pfv_encoder mirror pfv_rs::dec::Decoder (src/dec.rs:15-224) and
+ * pfv_rs::enc::Encoder (src/enc.rs:12-188): same constructor arguments, same packet semantics, same error
+ * classes (PFV_ERR_BAD_STREAM = DecodeError::FormatError, PFV_ERR_BAD_VERSION = VersionError, PFV_ERR_IO =
+ * io::Error / IOError).  The reader R / writer W of the Rust generics are an in-memory byte range / a growable
+ * byte buffer here.
+ */
+typedef struct pfv_stream_info {            /* file header, src/dec.rs:38-118 / src/enc.rs:190-219 */
+    uint32_t version;                        /* 211 */
+    uint32_t width, height, framerate;
+    uint32_t num_qtables;
+    uint64_t first_packet;                   /* byte offset of the first packet = Decoder.reset_pos */
+} pfv_stream_info;
+
+typedef struct pfv_packet {                 /* one packet of the container, src/dec.rs:179-220 */
+    uint8_t  type;                           /* 0 EOF, 1 I-frame (len 0 = drop frame), 2 P-frame, other = skipped */
+    uint8_t  reserved[3];
+    uint32_t len;                            /* payload bytes */
+    uint64_t payload;                        /* byte offset of the payload in the stream */
+} pfv_packet;
+
+/* Header parse (Decoder::new).  qtables_out may be NULL; otherwise it receives min(num_qtables, qcap) tables. */
+int pfv_stream_parse_header(const uint8_t *data, size_t len, pfv_stream_info *info,
+                            int32_t (*qtables_out)[64], uint32_t qcap);
+/* Packet scan from `offset` (no entropy decoding: u8 type + u32 len per packet).  Stops after the EOF packet, at
+ * the end of the data, or when `cap` packets are written; *n_out = packets written, *truncated_out = 1 if the data
+ * ends inside a packet (the reference would fail with an io::Error when it reaches it).  This is what a host uses
+ * to find GOP boundaries for frame-parallel sharding. */
+int pfv_stream_index(const uint8_t *data, size_t len, uint64_t offset, pfv_packet *out, uint32_t cap,
+                     uint32_t *n_out, int *truncated_out);
+
+/* Entropy decode of one frame payload into the sparse seam (Decoder::decode_iframe src/dec.rs:226-296 /
+ * decode_pframe :328-417, without the macroblock loops).  kind = PFV_FRAME_I / PFV_FRAME_P.  hdr_out: nb headers
+ * (P only, may be NULL for I).  mb_off_out: nb+1.  tok_out: capacity tok_cap tokens (nb*256 always suffices). */
+int pfv_packet_decode(const pfv_geometry *g, uint32_t kind, const uint8_t *payload, size_t len, uint8_t qidx_out[3],
+                      pfv_mbhdr *hdr_out, uint32_t *mb_off_out, uint32_t *tok_out, uint32_t tok_cap, uint32_t *ntok_out);
+/* Entropy encode of one frame from the dense seam (Encoder::write_iframe_packet src/enc.rs:237-330 /
+ * write_pframe_packet :332-481): writes the 5-byte packet header + payload to out (capacity cap), *len_out = bytes. */
+int pfv_packet_encode(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff,
+                      uint8_t *out, size_t cap, size_t *len_out);
+size_t pfv_packet_encode_bound(const pfv_geometry *g);   /* a capacity that always suffices */
+
+/* -- Decoder (src/dec.rs) -------------------------------------------------------------------------------------- */
+typedef struct pfv_decoder pfv_decoder;
+/* Decoder::new(reader, num_threads) (src/dec.rs:38-134).  `data` stays owned by the caller and must outlive the
+ * decoder.  num_threads sizes the host entropy-decode pool (the reference's rayon pool is replaced by the GPU).
+ * read_ahead = how many frames may be in flight (entropy decoded / on the GPU) ahead of the one being returned;
+ * 0 picks a default.  The decoded pictures are identical for any value. */
+int  pfv_decoder_open(const uint8_t *data, size_t len, int device, uint32_t num_threads, uint32_t read_ahead,
+                      pfv_decoder **out);
+void pfv_decoder_close(pfv_decoder *d);
+uint32_t pfv_decoder_width(const pfv_decoder *d);        /* src/dec.rs:136 */
+uint32_t pfv_decoder_height(const pfv_decoder *d);       /* src/dec.rs:140 */
+uint32_t pfv_decoder_framerate(const pfv_decoder *d);    /* src/dec.rs:144 */
+int  pfv_decoder_reset(pfv_decoder *d);                  /* src/dec.rs:148-152: rewinds; the framebuffer is NOT cleared */
+/* Decoder::advance_frame (src/dec.rs:169-224): consumes packets up to and including the next frame or drop frame.
+ * Returns 1 = Ok(true), 0 = Ok(false) (EOF packet reached), <0 = error.  *got_frame = 1 when a picture was
+ * produced (the reference's onvideo callback fired); then *y,*u,*v point at the tight visible planes (retframe,
+ * src/dec.rs:195-197) in pinned host memory owned by the decoder, valid until the next call on this decoder. */
+int  pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const uint8_t **y, const uint8_t **u, const uint8_t **v);
+/* Decoder::advance_delta (src/dec.rs:154-167): onvideo is called once per produced frame. */
+typedef void (*pfv_onvideo_fn)(void *user, const uint8_t *y, const uint8_t *u, const uint8_t *v);
+int  pfv_decoder_advance_delta(pfv_decoder *d, double delta, pfv_onvideo_fn onvideo, void *user);
+/* the engine context under the decoder (e.g. to read the padded framebuffer slot in tests) and the slot that
+ * currently holds Decoder.framebuffer */
+pfv_ctx *pfv_decoder_ctx(pfv_decoder *d);
+uint32_t pfv_decoder_framebuffer_slot(const pfv_decoder *d);
+
+/* -- Encoder (src/enc.rs) -------------------------------------------------------------------------------------- */
+typedef struct pfv_encoder pfv_encoder;
+/* Encoder::new(writer, width, height, framerate, quality, num_threads) (src/enc.rs:37-73); the header is written
+ * at once.  num_threads sizes the host entropy-coding pool. */
+int  pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framerate, int quality, uint32_t num_threads,
+                      int device, pfv_encoder **out);
+void pfv_encoder_close(pfv_encoder *e);                  /* Drop: finishes the stream if finish() was not called */
+/* src/enc.rs:75-123 / :125-173.  y,u,v: tight planes w*h, w/2*h/2, w/2*h/2 (VideoFrame); read before return. */
+int  pfv_encoder_encode_iframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v);
+int  pfv_encoder_encode_pframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v);
+int  pfv_encoder_encode_dropframe(pfv_encoder *e);       /* src/enc.rs:175-180 */
+int  pfv_encoder_finish(pfv_encoder *e);                 /* src/enc.rs:182-188 */
+/* the writer: everything written so far (all frames submitted are flushed first).  Pointer valid until the next
+ * call on this encoder. */
+int  pfv_encoder_bytes(pfv_encoder *e, const uint8_t **data, size_t *len);
+pfv_ctx *pfv_encoder_ctx(pfv_encoder *e);
+uint32_t pfv_encoder_prev_frame_slot(const pfv_encoder *e);
 
 #ifdef __cplusplus
 }

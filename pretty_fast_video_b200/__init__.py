@@ -7,6 +7,8 @@ from ._native import (  # noqa: F401
     PFV_FRAME_I, PFV_FRAME_P, PFV_JOB_DEVICE_PTRS, Geometry, MbHdr, PfvError, lib,
 )
 from .engine import Engine, PinnedArena, geometry_for, make_qtables  # noqa: F401
+from . import codec  # noqa: F401
+from .codec import Decoder, Encoder, DecodeError  # noqa: F401
 
-__all__ = ["Engine", "PinnedArena", "geometry_for", "make_qtables", "Geometry", "MbHdr", "PfvError",
+__all__ = ["Decoder", "Encoder", "DecodeError", "codec", "Engine", "PinnedArena", "geometry_for", "make_qtables", "Geometry", "MbHdr", "PfvError",
            "PFV_FRAME_I", "PFV_FRAME_P", "PFV_JOB_DEVICE_PTRS", "lib"]

@@ -61,6 +61,27 @@ class EncodeJob(C.Structure):
     ]
 
 
+class DecodeJobSparse(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("flags", C.c_uint32), ("dst_slot", C.c_uint32), ("ref_slot", C.c_uint32),
+        ("qidx", C.c_uint8 * 3), ("reserved", C.c_uint8),
+        ("hdr", C.c_void_p), ("mb_off", C.c_void_p), ("tok", C.c_void_p),
+        ("ntok", C.c_uint32), ("reserved2", C.c_uint32),
+        ("out_y", C.c_void_p), ("out_u", C.c_void_p), ("out_v", C.c_void_p),
+    ]
+
+
+class StreamInfo(C.Structure):
+    _fields_ = [("version", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("framerate", C.c_uint32),
+                ("num_qtables", C.c_uint32), ("first_packet", C.c_uint64)]
+
+
+class Packet(C.Structure):
+    _fields_ = [("type", C.c_uint8), ("reserved", C.c_uint8 * 3), ("len", C.c_uint32), ("payload", C.c_uint64)]
+
+
+ONVIDEO = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+
 # every symbol include/pfv_b200.h declares: name -> (restype, argtypes)
 _QT = C.POINTER(C.c_int32 * 64)
 SYMBOLS = {
@@ -83,8 +104,40 @@ SYMBOLS = {
     "pfv_slot_device_ptr": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "pfv_decode_submit": (C.c_int, [C.c_void_p, C.POINTER(DecodeJob), C.c_uint32]),
     "pfv_encode_submit": (C.c_int, [C.c_void_p, C.POINTER(EncodeJob), C.c_uint32]),
+    "pfv_decode_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(DecodeJobSparse), C.c_uint32]),
+    "pfv_ctx_last_submit_id": (C.c_uint64, [C.c_void_p]),
+    "pfv_ctx_wait_submit": (C.c_int, [C.c_void_p, C.c_uint64]),
     "pfv_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "pfv_ctx_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    # host codec layer
+    "pfv_stream_parse_header": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(StreamInfo), C.c_void_p, C.c_uint32]),
+    "pfv_stream_index": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(Packet), C.c_uint32,
+                                   C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
+    "pfv_packet_decode": (C.c_int, [C.POINTER(Geometry), C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "pfv_packet_encode": (C.c_int, [C.POINTER(Geometry), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_size_t)]),
+    "pfv_packet_encode_bound": (C.c_size_t, [C.POINTER(Geometry)]),
+    "pfv_decoder_open": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "pfv_decoder_close": (None, [C.c_void_p]),
+    "pfv_decoder_width": (C.c_uint32, [C.c_void_p]),
+    "pfv_decoder_height": (C.c_uint32, [C.c_void_p]),
+    "pfv_decoder_framerate": (C.c_uint32, [C.c_void_p]),
+    "pfv_decoder_reset": (C.c_int, [C.c_void_p]),
+    "pfv_decoder_advance_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p)]),
+    "pfv_decoder_advance_delta": (C.c_int, [C.c_void_p, C.c_double, ONVIDEO, C.c_void_p]),
+    "pfv_decoder_ctx": (C.c_void_p, [C.c_void_p]),
+    "pfv_decoder_framebuffer_slot": (C.c_uint32, [C.c_void_p]),
+    "pfv_encoder_open": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
+    "pfv_encoder_close": (None, [C.c_void_p]),
+    "pfv_encoder_encode_iframe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pfv_encoder_encode_pframe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pfv_encoder_encode_dropframe": (C.c_int, [C.c_void_p]),
+    "pfv_encoder_finish": (C.c_int, [C.c_void_p]),
+    "pfv_encoder_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "pfv_encoder_ctx": (C.c_void_p, [C.c_void_p]),
+    "pfv_encoder_prev_frame_slot": (C.c_uint32, [C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,1035 @@
+// pfv_codec.cpp — host side of the codec: container, entropy layer and the reference's Decoder / Encoder objects,
+// built on the hot-path C ABI (pfv_decode_submit_sparse / pfv_encode_submit).  No device code here.
+//
+// What it mirrors (paths relative to the reference root):
+//   container      src/enc.rs:190-235 (header, EOF, drop packet), src/dec.rs:38-134 (header parse), :169-224 (packets)
+//   I/P payloads   src/enc.rs:237-481 (write), src/dec.rs:226-296, :328-417 (read)
+//   RLE            src/rle.rs:9-66          Huffman  src/huffman.rs:71-119, :156-217
+//   bit order      bitstream-io 1.6 LittleEndian: value bits LSB first, write_signed(n) = n-bit two's complement
+//   objects        pfv_rs::dec::Decoder src/dec.rs:15-224, pfv_rs::enc::Encoder src/enc.rs:12-188
+//
+// Design (not the reference's): the reference decodes one symbol at a time through a seekable BitReader
+// (position_in_bits + read + seek_bits per symbol, src/huffman.rs:156-197) on the caller's thread and then runs the
+// macroblock loops on a rayon pool.  Here the macroblock loops are GPU kernels, so the host's job is to keep them
+// fed: packets are length-prefixed and their entropy state is per frame, so a pool of host threads entropy-decodes
+// frames AHEAD of the one being returned (64-bit window, 11-bit code LUT, one refill per token), straight into the
+// sparse token form that crosses PCIe; frames are submitted to the engine in stream order (P frames chain on the
+// previous picture) and handed back in order from a ring of pinned pictures.  The encoder is the mirror image:
+// kernels emit dense coefficients + headers into pinned rings, a pool entropy-codes finished frames while the GPU
+// works on the next ones, packets are appended in order.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "pfv_internal.h"
+
+using pfv::set_error;
+
+namespace {
+
+const uint8_t kMagic[8] = {'P', 'F', 'V', 'I', 'D', 'E', 'O', 0};   // src/common.rs:1
+const uint32_t kVersion = 211;                                      // src/common.rs:2
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline void wr16(std::vector<uint8_t> &v, uint32_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); }
+inline void wr32(uint8_t *p, uint32_t x) { p[0] = (uint8_t)x; p[1] = (uint8_t)(x >> 8); p[2] = (uint8_t)(x >> 16); p[3] = (uint8_t)(x >> 24); }
+
+// ---------------------------------------------------------------------------------------------------
+// Huffman code of one frame (src/huffman.rs:71-119): 16 symbols, weights from the packet
+// ---------------------------------------------------------------------------------------------------
+constexpr int LUT_BITS = 11;
+
+struct Huffman {
+    uint32_t val[16];          // code bits, first bit of the code in bit 0 (Code::append, src/huffman.rs:30-32)
+    uint8_t  len[16];          // 0 = symbol unused (or the only symbol: zero-length code)
+    int      nsym = 0;         // symbols with weight > 0
+    int      only = -1;        // the single symbol when nsym == 1
+    // tree for codes longer than LUT_BITS: node i has child[i][bit]; leaves carry sym >= 0
+    int16_t  child[31][2];
+    int8_t   sym[31];
+    int      root = -1;
+    uint8_t  lut[1 << LUT_BITS];   // (len << 4) | symbol, 0 = longer than LUT_BITS
+
+    void build(const uint8_t table[16])
+    {
+        memset(val, 0, sizeof(val));
+        memset(len, 0, sizeof(len));
+        memset(lut, 0, sizeof(lut));
+        nsym = 0; only = -1; root = -1;
+        struct N { uint32_t freq; int id; };
+        N list[16];
+        int n = 0, nodes = 0;
+        uint32_t freq[31];
+        for (int ch = 0; ch < 16; ch++)
+            if (table[ch] > 0) {
+                sym[nodes] = (int8_t)ch; child[nodes][0] = child[nodes][1] = -1; freq[nodes] = table[ch];
+                list[n++] = {table[ch], nodes++};
+            }
+        nsym = n;
+        if (n == 0) return;
+        std::stable_sort(list, list + n, [](const N &a, const N &b) { return a.freq > b.freq; });   // descending, stable
+        while (n > 1) {
+            const N a = list[--n], b = list[--n];                    // a = last (smallest), b = the one before it
+            sym[nodes] = -1; child[nodes][0] = (int16_t)a.id; child[nodes][1] = (int16_t)b.id;   // left = a, right = b
+            freq[nodes] = a.freq + b.freq;
+            int pos = n;
+            for (int i = 0; i < n; i++) if (freq[nodes] > list[i].freq) { pos = i; break; }      // get_insert_index
+            for (int i = n; i > pos; i--) list[i] = list[i - 1];
+            list[pos] = {freq[nodes], nodes};
+            n++; nodes++;
+        }
+        root = list[0].id;
+        if (nsym == 1) { only = sym[root]; return; }                // zero-length code (legal, src/huffman.rs:125-131)
+        // assign_codes (src/huffman.rs:204-217), iteratively
+        struct S { int node; uint32_t v; uint8_t l; };
+        S stack[32];
+        int sp = 0;
+        stack[sp++] = {root, 0u, 0};
+        while (sp) {
+            const S s = stack[--sp];
+            if (sym[s.node] >= 0) {
+                val[sym[s.node]] = s.v; len[sym[s.node]] = s.l;
+                if (s.l <= LUT_BITS)
+                    for (uint32_t v = s.v; v < (1u << LUT_BITS); v += 1u << s.l) lut[v] = (uint8_t)((s.l << 4) | sym[s.node]);
+                continue;
+            }
+            stack[sp++] = {child[s.node][1], s.v | (1u << s.l), (uint8_t)(s.l + 1)};
+            stack[sp++] = {child[s.node][0], s.v, (uint8_t)(s.l + 1)};
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// LSB-first bit reader over one payload
+// ---------------------------------------------------------------------------------------------------
+struct BitReader {
+    const uint8_t *p;
+    size_t   nbytes;
+    uint64_t total;            // bits
+    uint64_t pos = 0;          // bits consumed
+
+    BitReader(const uint8_t *data, size_t n) : p(data), nbytes(n), total((uint64_t)n * 8) {}
+    // at least 57 valid bits starting at the current position (zeros past the end)
+    inline uint64_t peek() const
+    {
+        const size_t b = (size_t)(pos >> 3);
+        uint64_t w = 0;
+        if (b + 8 <= nbytes) memcpy(&w, p + b, 8);
+        else for (size_t i = 0; b + i < nbytes && i < 8; i++) w |= (uint64_t)p[b + i] << (8 * i);
+        return w >> (pos & 7);
+    }
+    inline bool overrun() const { return pos > total; }
+    inline uint32_t take(int n) { const uint32_t v = (uint32_t)(peek() & ((1ull << n) - 1)); pos += (uint64_t)n; return v; }
+};
+
+inline int32_t sign_extend(uint32_t raw, int bits) { return (int32_t)(raw << (32 - bits)) >> (32 - bits); }
+
+// one Huffman symbol out of window w; returns its length (bits consumed) or -1
+inline int huff_symbol(const Huffman &h, uint64_t w, int &symbol)
+{
+    const uint8_t e = h.lut[w & ((1u << LUT_BITS) - 1)];
+    if (e) { symbol = e & 15; return e >> 4; }
+    int node = h.root, l = 0;                                        // read_slow, src/huffman.rs:125-154
+    while (h.sym[node] < 0) {
+        node = h.child[node][(w >> l) & 1];
+        if (++l > 16) return -1;
+    }
+    symbol = h.sym[node];
+    return l;
+}
+
+struct PlaneDims { uint32_t pw, ph, bw, bh; };
+
+void plane_dims(const pfv_geometry &g, PlaneDims out[3])
+{
+    out[0] = {g.pw, g.ph, g.pw / 16, g.ph / 16};
+    out[1] = out[2] = {g.cpw, g.cph, g.cpw / 16, g.cph / 16};
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// container
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pfv_stream_parse_header(const uint8_t *data, size_t len, pfv_stream_info *info, int32_t (*qtables_out)[64], uint32_t qcap)
+{
+    if (!data || !info) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    memset(info, 0, sizeof(*info));
+    if (len < 8) return set_error(PFV_ERR_IO, "stream ends inside the magic (src/dec.rs:41-46)");
+    if (memcmp(data, kMagic, 8) != 0) return set_error(PFV_ERR_BAD_STREAM, "bad magic: not a PFV stream (src/dec.rs:48-52)");
+    if (len < 12) return set_error(PFV_ERR_IO, "stream ends inside the version field");
+    info->version = rd32(data + 8);
+    if (info->version != kVersion)
+        return set_error(PFV_ERR_BAD_VERSION, "codec version %u, this decoder reads %u (src/dec.rs:55-60)", info->version, kVersion);
+    if (len < 20) return set_error(PFV_ERR_IO, "stream ends inside the header");
+    info->width = rd16(data + 12);
+    info->height = rd16(data + 14);
+    info->framerate = rd16(data + 16);
+    info->num_qtables = rd16(data + 18);
+    const size_t need = 20 + (size_t)info->num_qtables * 128;
+    if (len < need) return set_error(PFV_ERR_IO, "stream ends inside the q-tables (src/dec.rs:96-111)");
+    if (qtables_out)
+        for (uint32_t t = 0; t < info->num_qtables && t < qcap; t++)
+            for (int i = 0; i < 64; i++) qtables_out[t][i] = rd16(data + 20 + (size_t)t * 128 + i * 2);
+    info->first_packet = need;
+    return PFV_OK;
+}
+
+extern "C" int pfv_stream_index(const uint8_t *data, size_t len, uint64_t offset, pfv_packet *out, uint32_t cap, uint32_t *n_out,
+                                int *truncated_out)
+{
+    if (!data || !n_out || (!out && cap)) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    uint32_t n = 0;
+    int trunc = 0;
+    uint64_t off = offset;
+    while (n < cap) {
+        if (off == len) { trunc = 1; break; }                       // no EOF packet: read_u8 would fail (src/dec.rs:179)
+        if (off + 5 > len) { trunc = 1; break; }
+        pfv_packet pk;
+        memset(&pk, 0, sizeof(pk));
+        pk.type = data[off];
+        pk.len = rd32(data + off + 1);
+        pk.payload = off + 5;
+        const bool has_payload = pk.type != 0;
+        if (has_payload && pk.payload + pk.len > len) { trunc = 1; break; }
+        out[n++] = pk;
+        if (pk.type == 0) break;                                    // EOF marker (src/dec.rs:183-187)
+        off = pk.payload + pk.len;
+    }
+    *n_out = n;
+    if (truncated_out) *truncated_out = trunc;
+    return PFV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// entropy decode of one payload -> sparse seam
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pfv_packet_decode(const pfv_geometry *g, uint32_t kind, const uint8_t *payload, size_t len, uint8_t qidx_out[3],
+                                 pfv_mbhdr *hdr_out, uint32_t *mb_off_out, uint32_t *tok_out, uint32_t tok_cap, uint32_t *ntok_out)
+{
+    if (!g || !payload || !qidx_out || !mb_off_out || !ntok_out || (!tok_out && tok_cap))
+        return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    if (kind != PFV_FRAME_I && kind != PFV_FRAME_P) return set_error(PFV_ERR_BAD_ARG, "bad kind %u", kind);
+    if (kind == PFV_FRAME_P && !hdr_out) return set_error(PFV_ERR_BAD_ARG, "P frames need hdr_out");
+    if (len < 19) return set_error(PFV_ERR_IO, "payload of %zu bytes ends inside the symbol table / q-table indices", len);
+    Huffman h;
+    h.build(payload);                                               // src/dec.rs:234-241
+    qidx_out[0] = payload[16]; qidx_out[1] = payload[17]; qidx_out[2] = payload[18];   // src/dec.rs:244-246
+    BitReader br(payload, len);
+    br.pos = 19 * 8;
+    const uint32_t nb = g->nb;
+    uint32_t ntok = 0;
+
+    // one (run, size[, value]) token; returns false on a malformed stream
+    auto token = [&](uint32_t &run, int &size, int32_t &value) -> bool {
+        if (h.nsym == 0) return false;                              // empty tree: reference hits unreachable!()
+        if (h.only >= 0) {                                          // zero-length codes
+            if (h.only == 0) return false;                           // (0, 0) forever: the reference would never return
+            run = (uint32_t)h.only; size = h.only;
+        }
+        else {
+            uint64_t w = br.peek();
+            int s1, s2;
+            const int l1 = huff_symbol(h, w, s1);
+            if (l1 < 0) return false;
+            w >>= l1;
+            const int l2 = huff_symbol(h, w, s2);
+            if (l2 < 0) return false;
+            br.pos += (uint64_t)(l1 + l2);
+            run = (uint32_t)s1; size = s2;
+        }
+        value = 0;
+        if (size > 0) value = sign_extend(br.take(size), size);      // read_signed::<i16>(size), src/dec.rs:286
+        return !br.overrun();
+    };
+
+    if (kind == PFV_FRAME_I) {
+        // src/dec.rs:258-296: one continuous run over nb*256 coefficients
+        const uint64_t total = (uint64_t)nb * 256;
+        uint64_t out_idx = 0;
+        uint32_t cur_mb = 0;
+        mb_off_out[0] = 0;
+        while (out_idx < total) {
+            uint32_t run; int size; int32_t value;
+            if (!token(run, size, value))
+                return set_error(br.overrun() ? PFV_ERR_IO : PFV_ERR_BAD_STREAM, "I-frame payload: %s at coefficient %llu",
+                                 br.overrun() ? "bit stream ends" : "undecodable symbol", (unsigned long long)out_idx);
+            out_idx += run;
+            if (size > 0) {
+                if (out_idx >= total) return set_error(PFV_ERR_BAD_STREAM, "I-frame payload: coefficient index past the frame (src/dec.rs:288 would panic)");
+                const uint32_t mb = (uint32_t)(out_idx >> 8);
+                while (cur_mb < mb) mb_off_out[++cur_mb] = ntok;
+                if (ntok >= tok_cap) return set_error(PFV_ERR_NOMEM, "token buffer of %u entries is too small", tok_cap);
+                tok_out[ntok++] = ((uint32_t)(out_idx & 255) << 16) | (uint32_t)(uint16_t)value;
+                out_idx++;
+            }
+        }
+        while (cur_mb < nb) mb_off_out[++cur_mb] = ntok;
+    } else {
+        // src/dec.rs:359-372 headers, then :376-417 the coded macroblocks
+        PlaneDims pd[3];
+        plane_dims(*g, pd);
+        uint32_t m = 0;
+        for (int p = 0; p < 3; p++)
+            for (uint32_t by = 0; by < pd[p].bh; by++)
+                for (uint32_t bx = 0; bx < pd[p].bw; bx++, m++) {
+                    const uint64_t w = br.peek();
+                    pfv_mbhdr hd;
+                    hd.mx = 0; hd.my = 0; hd.reserved = 0;
+                    hd.has_coeff = (uint8_t)((w >> 1) & 1);
+                    if (w & 1) {
+                        hd.mx = (int8_t)sign_extend((uint32_t)(w >> 2) & 127u, 7);
+                        hd.my = (int8_t)sign_extend((uint32_t)(w >> 9) & 127u, 7);
+                        br.pos += 16;
+                    } else {
+                        br.pos += 2;
+                    }
+                    if (br.overrun()) return set_error(PFV_ERR_IO, "P-frame payload ends inside the macroblock headers");
+                    const int sx = (int)bx * 16 + hd.mx, sy = (int)by * 16 + hd.my;
+                    if (sx < 0 || sy < 0 || sx > (int)pd[p].pw - 16 || sy > (int)pd[p].ph - 16)
+                        return set_error(PFV_ERR_BAD_MV, "macroblock %u: motion vector (%d,%d) leaves the padded plane (src/common.rs:258-259)",
+                                         m, hd.mx, hd.my);
+                    hdr_out[m] = hd;
+                }
+        mb_off_out[0] = 0;
+        for (m = 0; m < nb; m++) {
+            if (hdr_out[m].has_coeff) {
+                uint32_t out_idx = 0;
+                while (out_idx < 256) {
+                    uint32_t run; int size; int32_t value;
+                    if (!token(run, size, value))
+                        return set_error(br.overrun() ? PFV_ERR_IO : PFV_ERR_BAD_STREAM, "P-frame payload: %s in macroblock %u",
+                                         br.overrun() ? "bit stream ends" : "undecodable symbol", m);
+                    out_idx += run;
+                    if (size > 0) {
+                        if (out_idx >= 256) return set_error(PFV_ERR_BAD_STREAM, "P-frame payload: coefficient index past the macroblock (src/dec.rs:410 would panic)");
+                        if (ntok >= tok_cap) return set_error(PFV_ERR_NOMEM, "token buffer of %u entries is too small", tok_cap);
+                        tok_out[ntok++] = (out_idx << 16) | (uint32_t)(uint16_t)value;
+                        out_idx++;
+                    }
+                }
+            }
+            mb_off_out[m + 1] = ntok;
+        }
+    }
+    *ntok_out = ntok;
+    return PFV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// entropy encode of one frame from the dense seam
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// RLE tokens of one macroblock (src/rle.rs:9-39): packed (run) | (size << 4) | (uint16 value << 16)
+inline uint32_t rle_macroblock(const int16_t *c, uint32_t *out, uint32_t hist[16])
+{
+    uint32_t n = 0, run = 0;
+    for (int i = 0; i < 256; i += 4) {
+        uint64_t four;
+        memcpy(&four, c + i, 8);
+        if (four == 0) { run += 4; continue; }
+        for (int k = 0; k < 4; k++) {
+            const int16_t v = c[i + k];
+            if (v == 0) { run++; continue; }
+            while (run > 15) { out[n++] = 15u; hist[15]++; hist[0]++; run -= 15; }
+            const uint32_t a = (uint16_t)(v < 0 ? -v : v);           // i16::abs wraps for -32768 -> 32768 as u16
+            const uint32_t size = (32u - (uint32_t)__builtin_clz(a)) + 1u;   // bit length of |v| plus the sign bit, src/rle.rs:23-24
+            out[n++] = run | (size << 4) | ((uint32_t)(uint16_t)v << 16);
+            hist[run]++; hist[size & 15u]++;
+            run = 0;
+        }
+    }
+    while (run > 15) { out[n++] = 15u; hist[15]++; hist[0]++; run -= 15; }
+    if (run > 0) { out[n++] = run; hist[run]++; hist[0]++; }
+    return n;
+}
+
+struct BitWriter {
+    uint8_t *p;
+    uint64_t acc = 0;
+    int      n = 0;
+    explicit BitWriter(uint8_t *dst) : p(dst) {}
+    inline void put(uint32_t v, int bits)                           // bits <= 32, v < 2^bits
+    {
+        acc |= (uint64_t)v << n;
+        n += bits;
+        if (n >= 32) { const uint32_t w = (uint32_t)acc; memcpy(p, &w, 4); p += 4; acc >>= 32; n -= 32; }
+    }
+    inline uint8_t *finish()                                        // byte_align: zero padding
+    {
+        while (n > 0) { *p++ = (uint8_t)acc; acc >>= 8; n -= 8; }
+        n = 0;
+        return p;
+    }
+};
+
+// Encodes into `out` (resized); returns PFV_OK or an error.  scratch is reused across calls by the caller.
+int encode_packet(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff, std::vector<uint32_t> &scratch,
+                  std::vector<uint8_t> &out)
+{
+    const uint32_t nb = g.nb;
+    uint32_t hist[16] = {0};
+    scratch.resize((size_t)nb * 256);
+    uint32_t *tok = scratch.data();
+    size_t ntok = 0;
+    for (uint32_t m = 0; m < nb; m++) {
+        if (kind == PFV_FRAME_P && !hdr[m].has_coeff) continue;      // subblocks: None (src/enc.rs:357-358)
+        ntok += rle_macroblock(coeff + (size_t)m * 256, tok + ntok, hist);
+    }
+    // rle_create_huffman (src/rle.rs:49-66): weights normalised to u8, i32 arithmetic
+    int32_t mx = 0;
+    for (int i = 0; i < 16; i++) mx = std::max(mx, (int32_t)hist[i]);
+    uint8_t table[16];
+    for (int i = 0; i < 16; i++) {
+        if (hist[i] > 0) {
+            const int32_t prod = (int32_t)((uint32_t)hist[i] * 255u);   // wrapping like release-mode Rust
+            int32_t v = prod / mx;
+            if (v < 1) v = 1;
+            table[i] = (uint8_t)v;
+        } else table[i] = 0;
+    }
+    Huffman h;
+    h.build(table);
+    // exact payload size
+    uint64_t bits = 19 * 8;
+    if (kind == PFV_FRAME_P)
+        for (uint32_t m = 0; m < nb; m++) bits += (hdr[m].mx != 0 || hdr[m].my != 0) ? 16 : 2;
+    for (size_t i = 0; i < ntok; i++) {
+        const uint32_t t = tok[i], run = t & 15u, size = (t >> 4) & 31u;
+        if (size > 15) return set_error(PFV_ERR_BAD_ARG, "coefficient %d needs %u bits: not representable (src/rle.rs:24, :43)", (int)(int16_t)(t >> 16), size);
+        bits += h.len[run] + h.len[size] + size;
+    }
+    const size_t payload = (size_t)((bits + 7) / 8);
+    out.resize(5 + payload + 8);                                     // +8: the writer stores 4 bytes at a time
+    out[0] = (uint8_t)(kind == PFV_FRAME_I ? 1 : 2);                 // src/enc.rs:324, :475
+    wr32(&out[1], (uint32_t)payload);
+    uint8_t *p = &out[5];
+    memcpy(p, table, 16);                                            // src/enc.rs:290-292
+    if (kind == PFV_FRAME_I) { p[16] = 0; p[17] = 1; p[18] = 1; }    // src/enc.rs:296-298
+    else { p[16] = 2; p[17] = 3; p[18] = 3; }                        // src/enc.rs:409-411
+    BitWriter bw(p + 19);
+    if (kind == PFV_FRAME_P)
+        for (uint32_t m = 0; m < nb; m++) {                         // src/enc.rs:414-452
+            const bool has_mvec = hdr[m].mx != 0 || hdr[m].my != 0;
+            bw.put((has_mvec ? 1u : 0u) | (hdr[m].has_coeff ? 2u : 0u), 2);
+            if (has_mvec) bw.put(((uint32_t)hdr[m].mx & 127u) | (((uint32_t)hdr[m].my & 127u) << 7), 14);
+        }
+    for (size_t i = 0; i < ntok; i++) {                              // src/enc.rs:301-315, :455-466
+        const uint32_t t = tok[i], run = t & 15u, size = (t >> 4) & 15u;
+        bw.put(h.val[run] | (h.val[size] << h.len[run]), h.len[run] + h.len[size]);
+        if (size) bw.put((t >> 16) & ((1u << size) - 1u), (int)size);
+    }
+    uint8_t *end = bw.finish();
+    if ((size_t)(end - &out[5]) != payload) return set_error(PFV_ERR_STATE, "internal: packet size mismatch");
+    out.resize(5 + payload);
+    return PFV_OK;
+}
+
+}  // namespace
+
+extern "C" size_t pfv_packet_encode_bound(const pfv_geometry *g)
+{
+    if (!g) return 0;
+    return 5 + 19 + (size_t)g->nb * 2 + (size_t)g->nb * 256 * 6 + 16;
+}
+
+extern "C" int pfv_packet_encode(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff, uint8_t *out,
+                                 size_t cap, size_t *len_out)
+{
+    if (!g || !coeff || !out || !len_out) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    if (kind != PFV_FRAME_I && kind != PFV_FRAME_P) return set_error(PFV_ERR_BAD_ARG, "bad kind %u", kind);
+    if (kind == PFV_FRAME_P && !hdr) return set_error(PFV_ERR_BAD_ARG, "P frames need headers");
+    std::vector<uint32_t> scratch;
+    std::vector<uint8_t> pkt;
+    int rc = encode_packet(*g, kind, hdr, coeff, scratch, pkt);
+    if (rc) return rc;
+    if (pkt.size() > cap) return set_error(PFV_ERR_NOMEM, "packet of %zu bytes does not fit %zu", pkt.size(), cap);
+    memcpy(out, pkt.data(), pkt.size());
+    *len_out = pkt.size();
+    return PFV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a small fixed pool of host threads
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+class Pool {
+public:
+    explicit Pool(unsigned n)
+    {
+        if (n == 0) n = 1;
+        for (unsigned i = 0; i < n; i++) th_.emplace_back([this] { run(); });
+    }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void post(std::function<void()> f)
+    {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(std::move(f)); }
+        cv_.notify_one();
+    }
+private:
+    void run()
+    {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> th_;
+    bool stop_ = false;
+};
+
+struct Pinned {
+    void  *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n)
+    {
+        if (n <= bytes) return PFV_OK;
+        if (p) pfv_host_free(p);
+        p = nullptr; bytes = 0;
+        int rc = pfv_host_alloc(&p, n);
+        if (rc) return rc;
+        bytes = n;
+        return PFV_OK;
+    }
+    ~Pinned() { if (p) pfv_host_free(p); }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// Decoder
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+enum { W_FREE = 0, W_QUEUED, W_READY, W_SUBMITTED };
+
+struct DecWork {
+    Pinned   tok, meta, out;       // tokens | mb_off + headers | decoded visible planes
+    uint32_t ntok = 0, kind = 0;
+    uint8_t  qidx[3] = {0, 0, 0};
+    int      state = W_FREE;       // guarded by pfv_decoder::m
+    int      status = PFV_OK;
+    char     err[256] = "";
+    uint64_t submit_id = 0;
+    uint32_t slot = 0;
+    uint32_t packet = 0;           // index into packets
+    uint64_t epoch = 0;
+};
+
+}  // namespace
+
+struct pfv_decoder {
+    const uint8_t *data = nullptr;
+    size_t len = 0;
+    pfv_stream_info info{};
+    pfv_geometry geo{};
+    std::vector<pfv_packet> packets;
+    bool truncated = false;
+    pfv_ctx *ctx = nullptr;
+    std::unique_ptr<Pool> pool;
+    uint32_t depth = 0, nslots = 0;
+    std::vector<std::unique_ptr<DecWork>> work;
+    std::mutex m;
+    std::condition_variable cv;
+    // stream position
+    uint32_t cursor = 0;           // next packet advance_frame looks at
+    uint32_t sched = 0;            // next packet to consider for read-ahead
+    std::deque<DecWork *> inflight;   // frames scheduled (entropy queued or later), in stream order
+    DecWork *delivered = nullptr;  // the picture handed out by the previous call
+    uint32_t fb_slot = 0;          // slot that holds Decoder.framebuffer (last submitted frame)
+    uint32_t delivered_slot = 0;   // slot of the last picture handed out
+    bool eof = false;
+    double delta_accum = 0.0;
+    uint64_t epoch = 0;            // bumped by reset(): results of older entropy jobs are dropped
+    size_t ysz = 0, csz = 0;
+};
+
+static void decoder_entropy_job(pfv_decoder *d, DecWork *w)
+{
+    const pfv_packet &pk = d->packets[w->packet];
+    const uint32_t nb = d->geo.nb;
+    uint32_t *mb_off = static_cast<uint32_t *>(w->meta.p);
+    pfv_mbhdr *hdr = reinterpret_cast<pfv_mbhdr *>(mb_off + nb + 1);
+    uint32_t ntok = 0;
+    int rc = pfv_packet_decode(&d->geo, w->kind, d->data + pk.payload, pk.len, w->qidx, hdr, mb_off,
+                               static_cast<uint32_t *>(w->tok.p), (uint32_t)(w->tok.bytes / 4), &ntok);
+    if (rc) snprintf(w->err, sizeof(w->err), "%s", pfv_last_error());
+    {
+        std::lock_guard<std::mutex> l(d->m);
+        w->status = rc;
+        w->ntok = ntok;
+        w->state = W_READY;
+    }
+    d->cv.notify_all();
+}
+
+// schedule entropy decoding of frames ahead of the cursor (caller thread only)
+static int decoder_schedule(pfv_decoder *d)
+{
+    while (d->inflight.size() < d->depth && d->sched < d->packets.size()) {
+        const pfv_packet &pk = d->packets[d->sched];
+        if (pk.type == 0) break;
+        const bool frame = (pk.type == 1 && pk.len > 0) || pk.type == 2;
+        if (!frame) { d->sched++; continue; }
+        DecWork *w = nullptr;
+        for (auto &x : d->work) if (x->state == W_FREE && x.get() != d->delivered) { w = x.get(); break; }
+        if (!w) break;
+        // token capacity: an emitted token costs at least 3 bits when the tree has two or more symbols, and a
+        // one-symbol tree emits none
+        const uint64_t cap = std::min<uint64_t>((uint64_t)d->geo.nb * 256, (uint64_t)pk.len * 8 / 3 + 1);
+        int rc = w->tok.reserve((size_t)cap * 4);
+        if (rc) return rc;
+        rc = w->meta.reserve(((size_t)d->geo.nb + 1) * 4 + (size_t)d->geo.nb * sizeof(pfv_mbhdr));
+        if (rc) return rc;
+        rc = w->out.reserve(d->ysz + 2 * d->csz);
+        if (rc) return rc;
+        w->kind = pk.type == 1 ? PFV_FRAME_I : PFV_FRAME_P;
+        w->packet = d->sched;
+        w->status = PFV_OK;
+        w->err[0] = 0;
+        w->epoch = d->epoch;
+        { std::lock_guard<std::mutex> l(d->m); w->state = W_QUEUED; }
+        d->inflight.push_back(w);
+        d->pool->post([d, w] { decoder_entropy_job(d, w); });
+        d->sched++;
+    }
+    return PFV_OK;
+}
+
+// submit, in stream order, every scheduled frame whose entropy decode is done; `must` = wait for this one
+static int decoder_submit_ready(pfv_decoder *d, DecWork *must)
+{
+    for (DecWork *w : d->inflight) {
+        if (w->state == W_SUBMITTED) continue;
+        {
+            std::unique_lock<std::mutex> l(d->m);
+            if (w->state != W_READY) {
+                if (!must) return PFV_OK;
+                d->cv.wait(l, [w] { return w->state == W_READY; });
+            }
+        }
+        if (w->status != PFV_OK) {
+            if (w == must) return set_error(w->status, "%s", w->err);
+            return PFV_OK;                                          // reported when the cursor reaches it
+        }
+        const uint32_t nb = d->geo.nb;
+        pfv_decode_job_sparse j;
+        memset(&j, 0, sizeof(j));
+        j.kind = w->kind;
+        j.ref_slot = d->fb_slot;
+        j.dst_slot = (d->fb_slot + 1) % d->nslots;                   // at most `depth` < nslots - 1 frames run ahead of the
+                                                                     // returned picture, so its slot is never overwritten
+        memcpy(j.qidx, w->qidx, 3);
+        j.mb_off = static_cast<const uint32_t *>(w->meta.p);
+        j.hdr = reinterpret_cast<const pfv_mbhdr *>(j.mb_off + nb + 1);
+        j.tok = static_cast<const uint32_t *>(w->tok.p);
+        j.ntok = w->ntok;
+        j.out_y = static_cast<uint8_t *>(w->out.p);
+        j.out_u = j.out_y + d->ysz;
+        j.out_v = j.out_u + d->csz;
+        for (int p = 0; p < 3; p++)
+            if (j.qidx[p] >= d->info.num_qtables)
+                return set_error(PFV_ERR_BAD_STREAM, "q-table index %u >= %u (src/dec.rs:244-246 would panic)", j.qidx[p], d->info.num_qtables);
+        int rc = pfv_decode_submit_sparse(d->ctx, &j, 1);
+        if (rc) return rc;
+        w->submit_id = pfv_ctx_last_submit_id(d->ctx);
+        w->slot = j.dst_slot;
+        d->fb_slot = j.dst_slot;
+        { std::lock_guard<std::mutex> l(d->m); w->state = W_SUBMITTED; }
+        if (w == must) must = nullptr;
+    }
+    return PFV_OK;
+}
+
+extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uint32_t num_threads, uint32_t read_ahead, pfv_decoder **out)
+{
+    if (!out) return set_error(PFV_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (!data) return set_error(PFV_ERR_BAD_ARG, "data is NULL");
+    std::unique_ptr<pfv_decoder> d(new (std::nothrow) pfv_decoder());
+    if (!d) return set_error(PFV_ERR_NOMEM, "out of host memory");
+    int rc = pfv_stream_parse_header(data, len, &d->info, nullptr, 0);
+    if (rc) return rc;
+    if (d->info.width == 0 || d->info.height == 0 || (d->info.width & 1) || (d->info.height & 1))
+        return set_error(PFV_ERR_BAD_STREAM, "frame size %ux%u must be even and non-zero (src/frame.rs:13)", d->info.width, d->info.height);
+    if (d->info.num_qtables == 0) return set_error(PFV_ERR_BAD_STREAM, "stream carries no q-tables");
+    std::vector<int32_t> qt((size_t)d->info.num_qtables * 64);
+    rc = pfv_stream_parse_header(data, len, &d->info, reinterpret_cast<int32_t(*)[64]>(qt.data()), d->info.num_qtables);
+    if (rc) return rc;
+    d->data = data;
+    d->len = len;
+    pfv_geometry_for(d->info.width, d->info.height, &d->geo);
+    d->ysz = (size_t)d->geo.width * d->geo.height;
+    d->csz = (size_t)d->geo.cwidth * d->geo.cheight;
+    // packet index: O(1) per packet, no entropy decoding (src/dec.rs:179-180)
+    {
+        uint32_t cap = 1024, n = 0;
+        int trunc = 0;
+        for (;;) {
+            d->packets.resize(cap);
+            rc = pfv_stream_index(data, len, d->info.first_packet, d->packets.data(), cap, &n, &trunc);
+            if (rc) return rc;
+            if (n < cap) break;
+            cap *= 4;
+        }
+        d->packets.resize(n);
+        d->truncated = trunc != 0;
+    }
+    d->depth = read_ahead ? read_ahead : 6;
+    if (d->depth > 6) d->depth = 6;                                  // pfv_ctx_wait_submit reaches 8 submits back
+    d->nslots = d->depth + 3;
+    rc = pfv_ctx_create(device, d->info.width, d->info.height, reinterpret_cast<const int32_t(*)[64]>(qt.data()),
+                        d->info.num_qtables, d->nslots, 1, nullptr, &d->ctx);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < d->depth + 1; i++) d->work.emplace_back(new DecWork());
+    d->pool.reset(new Pool(num_threads ? num_threads : 1));
+    *out = d.release();
+    return PFV_OK;
+}
+
+static void decoder_drain(pfv_decoder *d)
+{
+    // wait for entropy jobs still running (they hold pointers into the work items)
+    for (DecWork *w : d->inflight) {
+        std::unique_lock<std::mutex> l(d->m);
+        d->cv.wait(l, [w] { return w->state != W_QUEUED; });
+    }
+    if (d->ctx) pfv_sync(d->ctx);
+    for (DecWork *w : d->inflight) { std::lock_guard<std::mutex> l(d->m); w->state = W_FREE; }
+    d->inflight.clear();
+}
+
+extern "C" void pfv_decoder_close(pfv_decoder *d)
+{
+    if (!d) return;
+    decoder_drain(d);
+    d->pool.reset();
+    if (d->ctx) pfv_ctx_destroy(d->ctx);
+    delete d;
+}
+
+extern "C" uint32_t pfv_decoder_width(const pfv_decoder *d) { return d ? d->info.width : 0; }
+extern "C" uint32_t pfv_decoder_height(const pfv_decoder *d) { return d ? d->info.height : 0; }
+extern "C" uint32_t pfv_decoder_framerate(const pfv_decoder *d) { return d ? d->info.framerate : 0; }
+extern "C" pfv_ctx *pfv_decoder_ctx(pfv_decoder *d) { return d ? d->ctx : nullptr; }
+extern "C" uint32_t pfv_decoder_framebuffer_slot(const pfv_decoder *d) { return d ? d->delivered_slot : 0; }
+
+extern "C" int pfv_decoder_reset(pfv_decoder *d)
+{
+    if (!d) return set_error(PFV_ERR_BAD_ARG, "NULL decoder");
+    // frames decoded ahead of the cursor are dropped; Decoder.framebuffer stays what the last returned picture
+    // left there (src/dec.rs:148-152 does not clear it)
+    decoder_drain(d);
+    d->epoch++;
+    d->fb_slot = d->delivered_slot;
+    d->cursor = d->sched = 0;
+    d->eof = false;
+    return PFV_OK;
+}
+
+extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const uint8_t **y, const uint8_t **u, const uint8_t **v)
+{
+    if (!d) return set_error(PFV_ERR_BAD_ARG, "NULL decoder");
+    if (got_frame) *got_frame = 0;
+    if (d->eof) return 0;                                            // src/dec.rs:171-173
+    if (d->delivered) {                                              // the previous picture's buffer may be reused now
+        std::lock_guard<std::mutex> l(d->m);
+        d->delivered->state = W_FREE;
+        d->delivered = nullptr;
+    }
+    for (;;) {
+        if (d->cursor >= d->packets.size())
+            return set_error(PFV_ERR_IO, "stream ends without an EOF packet%s (src/dec.rs:179-180 read fails)",
+                             d->truncated ? " (last packet is cut short)" : "");
+        const pfv_packet &pk = d->packets[d->cursor];
+        if (pk.type == 0) { d->eof = true; return 0; }               // src/dec.rs:183-187
+        if (pk.type == 1 && pk.len == 0) { d->cursor++; if (d->sched < d->cursor) d->sched = d->cursor; return 1; }   // drop frame, src/dec.rs:190-201
+        if (pk.type != 1 && pk.type != 2) { d->cursor++; if (d->sched < d->cursor) d->sched = d->cursor; continue; }  // src/dec.rs:216-219
+        break;
+    }
+    int rc = decoder_schedule(d);
+    if (rc) return rc;
+    if (d->inflight.empty() || d->inflight.front()->packet != d->cursor)
+        return set_error(PFV_ERR_STATE, "internal: read-ahead queue out of step with the cursor");
+    DecWork *w = d->inflight.front();
+    rc = decoder_submit_ready(d, w);
+    if (rc) {
+        // the failing frame is consumed, like a reference decode that returned Err after reading the packet
+        decoder_drain(d);
+        d->cursor++;
+        d->sched = d->cursor;
+        return rc;
+    }
+    rc = pfv_ctx_wait_submit(d->ctx, w->submit_id);
+    if (rc) return rc;
+    d->inflight.pop_front();
+    d->delivered = w;
+    d->delivered_slot = w->slot;
+    d->cursor++;
+    // keep the pipeline full for the next call
+    rc = decoder_schedule(d);
+    if (rc) return rc;
+    rc = decoder_submit_ready(d, nullptr);
+    if (rc) return rc;
+    if (got_frame) *got_frame = 1;
+    const uint8_t *base = static_cast<const uint8_t *>(w->out.p);
+    if (y) *y = base;
+    if (u) *u = base + d->ysz;
+    if (v) *v = base + d->ysz + d->csz;
+    return 1;
+}
+
+extern "C" int pfv_decoder_advance_delta(pfv_decoder *d, double delta, pfv_onvideo_fn onvideo, void *user)
+{
+    if (!d) return set_error(PFV_ERR_BAD_ARG, "NULL decoder");
+    d->delta_accum += delta;                                         // src/dec.rs:156
+    const double per_frame = 1.0 / (double)d->info.framerate;
+    while (d->delta_accum >= per_frame) {
+        int got = 0;
+        const uint8_t *y, *u, *v;
+        const int rc = pfv_decoder_advance_frame(d, &got, &y, &u, &v);
+        if (rc < 0) return rc;
+        if (got && onvideo) onvideo(user, y, u, v);
+        if (rc == 0) return 0;                                       // src/dec.rs:160-162
+        d->delta_accum -= per_frame;
+    }
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Encoder
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct EncWork {
+    Pinned   src, coeff, hdr;
+    uint32_t kind = 0;
+    uint64_t submit_id = 0;
+    bool     busy = false;         // guarded by pfv_encoder::m
+};
+
+struct OutPacket {
+    std::vector<uint8_t> bytes;
+    bool ready = false;
+    int  status = PFV_OK;
+    char err[256] = "";
+};
+
+}  // namespace
+
+struct pfv_encoder {
+    uint32_t width = 0, height = 0, framerate = 0;
+    float px_err = 0.f;
+    pfv_geometry geo{};
+    pfv_ctx *ctx = nullptr;
+    std::unique_ptr<Pool> pool;
+    std::vector<std::unique_ptr<EncWork>> work;
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::shared_ptr<OutPacket>> pending;   // packets in stream order, not yet appended to `stream`
+    std::vector<uint8_t> stream;                      // the writer W
+    uint32_t prev_slot = 0;
+    bool finished = false;
+    size_t ysz = 0, csz = 0;
+};
+
+// append finished packets, in order; wait_all = block until everything submitted so far is in `stream`
+static int encoder_flush(pfv_encoder *e, bool wait_all)
+{
+    std::unique_lock<std::mutex> l(e->m);
+    while (!e->pending.empty()) {
+        std::shared_ptr<OutPacket> p = e->pending.front();
+        if (!p->ready) {
+            if (!wait_all) break;
+            e->cv.wait(l, [&p] { return p->ready; });
+        }
+        e->pending.pop_front();
+        if (p->status != PFV_OK) return set_error(p->status, "%s", p->err);
+        e->stream.insert(e->stream.end(), p->bytes.begin(), p->bytes.end());
+    }
+    return PFV_OK;
+}
+
+extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framerate, int quality, uint32_t num_threads, int device,
+                                pfv_encoder **out)
+{
+    if (!out) return set_error(PFV_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    int32_t qt[4][64];
+    float px_err = 0.f;
+    int rc = pfv_make_qtables(quality, qt, &px_err);                 // assert!(quality >= 0 && quality <= 10), src/enc.rs:38
+    if (rc) return rc;
+    if (framerate > 65535) return set_error(PFV_ERR_BAD_ARG, "framerate %u does not fit the u16 header field (src/enc.rs:197)", framerate);
+    std::unique_ptr<pfv_encoder> e(new (std::nothrow) pfv_encoder());
+    if (!e) return set_error(PFV_ERR_NOMEM, "out of host memory");
+    e->width = width; e->height = height; e->framerate = framerate; e->px_err = px_err;
+    rc = pfv_ctx_create(device, width, height, qt, 4, 2, 1, nullptr, &e->ctx);
+    if (rc) return rc;
+    pfv_ctx_geometry(e->ctx, &e->geo);
+    e->ysz = (size_t)e->geo.width * e->geo.height;
+    e->csz = (size_t)e->geo.cwidth * e->geo.cheight;
+    const uint32_t depth = 4;
+    for (uint32_t i = 0; i < depth; i++) {
+        std::unique_ptr<EncWork> w(new EncWork());
+        if ((rc = w->src.reserve(e->ysz + 2 * e->csz)) || (rc = w->coeff.reserve((size_t)e->geo.nb * 512)) ||
+            (rc = w->hdr.reserve((size_t)e->geo.nb * sizeof(pfv_mbhdr)))) {
+            pfv_ctx_destroy(e->ctx);
+            return rc;
+        }
+        e->work.push_back(std::move(w));
+    }
+    e->pool.reset(new Pool(num_threads ? std::min<uint32_t>(num_threads, depth) : 1));
+    // write_header, src/enc.rs:190-219
+    std::vector<uint8_t> &s = e->stream;
+    s.insert(s.end(), kMagic, kMagic + 8);
+    s.resize(12);
+    wr32(&s[8], kVersion);
+    wr16(s, width); wr16(s, height); wr16(s, framerate);
+    wr16(s, 4);
+    for (int t = 0; t < 4; t++)                                      // intra_l, intra_c, inter_l, inter_c
+        for (int i = 0; i < 64; i++) wr16(s, (uint32_t)qt[t][i]);
+    *out = e.release();
+    return PFV_OK;
+}
+
+static int encoder_frame(pfv_encoder *e, uint32_t kind, const uint8_t *y, const uint8_t *u, const uint8_t *v)
+{
+    if (!e) return set_error(PFV_ERR_BAD_ARG, "NULL encoder");
+    if (e->finished) return set_error(PFV_ERR_STATE, "encoder is finished (assert!(!self.finished), src/enc.rs:80,130)");
+    if (!y || !u || !v) return set_error(PFV_ERR_BAD_ARG, "NULL plane");
+    int rc = encoder_flush(e, false);
+    if (rc) return rc;
+    EncWork *w = nullptr;
+    {
+        std::unique_lock<std::mutex> l(e->m);
+        e->cv.wait(l, [e] { for (auto &x : e->work) if (!x->busy) return true; return false; });
+        for (auto &x : e->work) if (!x->busy) { w = x.get(); break; }
+        w->busy = true;
+    }
+    uint8_t *src = static_cast<uint8_t *>(w->src.p);
+    memcpy(src, y, e->ysz);
+    memcpy(src + e->ysz, u, e->csz);
+    memcpy(src + e->ysz + e->csz, v, e->csz);
+    pfv_encode_job j;
+    memset(&j, 0, sizeof(j));
+    j.kind = kind;
+    j.ref_slot = e->prev_slot;
+    j.dst_slot = e->prev_slot ^ 1u;
+    j.px_err = e->px_err;
+    j.src_y = src; j.src_u = src + e->ysz; j.src_v = src + e->ysz + e->csz;
+    j.hdr_out = static_cast<pfv_mbhdr *>(w->hdr.p);
+    j.coeff_out = static_cast<int16_t *>(w->coeff.p);
+    rc = pfv_encode_submit(e->ctx, &j, 1);
+    if (rc) { std::lock_guard<std::mutex> l(e->m); w->busy = false; return rc; }
+    e->prev_slot = j.dst_slot;                                       // src/enc.rs:95-97, :145-147
+    w->kind = kind;
+    w->submit_id = pfv_ctx_last_submit_id(e->ctx);
+    std::shared_ptr<OutPacket> pkt(new OutPacket());
+    { std::lock_guard<std::mutex> l(e->m); e->pending.push_back(pkt); }
+    e->pool->post([e, w, pkt] {
+        int rc2 = pfv_ctx_wait_submit(e->ctx, w->submit_id);
+        if (rc2 == PFV_OK) {
+            static thread_local std::vector<uint32_t> scratch;
+            rc2 = encode_packet(e->geo, w->kind, static_cast<const pfv_mbhdr *>(w->hdr.p), static_cast<const int16_t *>(w->coeff.p),
+                                scratch, pkt->bytes);
+        }
+        if (rc2) snprintf(pkt->err, sizeof(pkt->err), "%s", pfv_last_error());
+        {
+            std::lock_guard<std::mutex> l(e->m);
+            pkt->status = rc2;
+            pkt->ready = true;
+            w->busy = false;
+        }
+        e->cv.notify_all();
+    });
+    return PFV_OK;
+}
+
+extern "C" int pfv_encoder_encode_iframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v)
+{
+    return encoder_frame(e, PFV_FRAME_I, y, u, v);
+}
+
+extern "C" int pfv_encoder_encode_pframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v)
+{
+    return encoder_frame(e, PFV_FRAME_P, y, u, v);
+}
+
+static int encoder_literal_packet(pfv_encoder *e, uint8_t type)
+{
+    std::shared_ptr<OutPacket> pkt(new OutPacket());
+    pkt->bytes.assign(5, 0);
+    pkt->bytes[0] = type;                                            // u32 length 0 follows
+    pkt->ready = true;
+    std::lock_guard<std::mutex> l(e->m);
+    e->pending.push_back(pkt);
+    return PFV_OK;
+}
+
+extern "C" int pfv_encoder_encode_dropframe(pfv_encoder *e)
+{
+    if (!e) return set_error(PFV_ERR_BAD_ARG, "NULL encoder");
+    if (e->finished) return set_error(PFV_ERR_STATE, "encoder is finished (src/enc.rs:176)");
+    return encoder_literal_packet(e, 1);                             // write_drop_packet, src/enc.rs:229-235
+}
+
+extern "C" int pfv_encoder_finish(pfv_encoder *e)
+{
+    if (!e) return set_error(PFV_ERR_BAD_ARG, "NULL encoder");
+    if (e->finished) return set_error(PFV_ERR_STATE, "finish() called twice (assert!(!self.finished), src/enc.rs:183)");
+    e->finished = true;
+    encoder_literal_packet(e, 0);                                    // write_eof, src/enc.rs:221-227
+    return encoder_flush(e, true);
+}
+
+extern "C" int pfv_encoder_bytes(pfv_encoder *e, const uint8_t **data, size_t *len)
+{
+    if (!e || !data || !len) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    int rc = encoder_flush(e, true);
+    if (rc) return rc;
+    *data = e->stream.data();
+    *len = e->stream.size();
+    return PFV_OK;
+}
+
+extern "C" pfv_ctx *pfv_encoder_ctx(pfv_encoder *e) { return e ? e->ctx : nullptr; }
+extern "C" uint32_t pfv_encoder_prev_frame_slot(const pfv_encoder *e) { return e ? e->prev_slot : 0; }
+
+extern "C" void pfv_encoder_close(pfv_encoder *e)
+{
+    if (!e) return;
+    if (!e->finished) pfv_encoder_finish(e);                         // Drop, src/enc.rs:28-34
+    else encoder_flush(e, true);
+    e->pool.reset();
+    if (e->ctx) { pfv_sync(e->ctx); pfv_ctx_destroy(e->ctx); }
+    delete e;
+}

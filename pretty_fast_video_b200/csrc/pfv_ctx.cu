@@ -31,6 +31,16 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
+// the same error slot for the host codec layer (pfv_codec.cpp)
+int pfv::set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 #define CU_TRY(expr)                                                                                   \
     do {                                                                                               \
         cudaError_t e_ = (expr);                                                                       \
@@ -143,6 +153,10 @@ struct Stage {
     uint8_t   *d_src = nullptr;      // max_jobs * src_stride (encode only, lazily allocated)
     void      *d_jobs = nullptr;     // max_jobs * max(sizeof(DecJob), sizeof(EncJob))
     void      *h_jobs = nullptr;     // pinned mirror of d_jobs
+    uint32_t  *d_tok = nullptr;      // sparse transport: max_jobs * nb * 256 tokens (lazily allocated)
+    uint32_t  *d_mboff = nullptr;    // max_jobs * (nb + 1)
+    SparseJob *d_sjobs = nullptr;    // max_jobs
+    SparseJob *h_sjobs = nullptr;    // pinned mirror
     cudaEvent_t ev_h2d = nullptr;    // job table + inputs are on the device
     cudaEvent_t ev_kernel = nullptr; // kernels that read/write the stage's device buffers are done
     cudaEvent_t ev_d2h = nullptr;    // copies out of the stage's device buffers are done (encode)
@@ -281,6 +295,19 @@ int init_slot(pfv_ctx *c, uint32_t slot, cudaStream_t s)
     return PFV_OK;
 }
 
+int ensure_sparse_staging(pfv_ctx *c)
+{
+    if (c->st[0].d_tok) return PFV_OK;
+    for (int i = 0; i < STAGES; i++) {
+        Stage &s = c->st[i];
+        CU_TRY(cudaMalloc(&s.d_tok, (size_t)c->max_jobs * c->geo.nb * 256 * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&s.d_mboff, (size_t)c->max_jobs * (c->geo.nb + 1) * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&s.d_sjobs, sizeof(SparseJob) * c->max_jobs));
+        CU_TRY(cudaHostAlloc(&s.h_sjobs, sizeof(SparseJob) * c->max_jobs, cudaHostAllocDefault));
+    }
+    return PFV_OK;
+}
+
 int ensure_src_staging(pfv_ctx *c)
 {
     if (c->st[0].d_src) return PFV_OK;
@@ -315,7 +342,9 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     for (int i = 0; i < STAGES; i++) {
         Stage &s = c->st[i];
         cudaFree(s.d_coeff); cudaFree(s.d_hdr); cudaFree(s.d_src); cudaFree(s.d_jobs);
+        cudaFree(s.d_tok); cudaFree(s.d_mboff); cudaFree(s.d_sjobs);
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
+        if (s.h_sjobs) cudaFreeHost(s.h_sjobs);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
@@ -572,19 +601,44 @@ extern "C" int pfv_slot_read_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint
 // ---------------------------------------------------------------------------------------------------
 // decode
 // ---------------------------------------------------------------------------------------------------
-extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_t njobs)
+namespace {
+// one decode job in internal form: dense (coeff) or sparse (mb_off/tok) coefficients
+struct DecIn {
+    uint32_t kind, flags, dst_slot, ref_slot;
+    uint8_t  qidx[3];
+    bool     sparse;
+    const pfv_mbhdr *hdr;
+    const int16_t   *coeff;
+    const uint32_t  *mb_off, *tok;
+    uint32_t ntok;
+    uint8_t *out_y, *out_u, *out_v;
+};
+}  // namespace
+
+static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
 {
-    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
-    if (njobs == 0) return PFV_OK;
     if (njobs > c->max_jobs) return fail(PFV_ERR_BAD_ARG, "%u jobs > max_jobs %u", njobs, c->max_jobs);
     const pfv_geometry &g = c->geo;
+    bool any_sparse = false;
     for (uint32_t i = 0; i < njobs; i++) {
-        const pfv_decode_job &j = jobs[i];
+        const DecIn &j = jobs[i];
         if (j.kind != PFV_FRAME_I && j.kind != PFV_FRAME_P) return fail(PFV_ERR_BAD_ARG, "job %u: bad kind %u", i, j.kind);
         if (j.dst_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: dst_slot %u out of range", i, j.dst_slot);
-        if (!j.coeff) return fail(PFV_ERR_BAD_ARG, "job %u: coeff is NULL", i);
-        if ((j.flags & PFV_JOB_DEVICE_PTRS) && (reinterpret_cast<uintptr_t>(j.coeff) & 15u))
-            return fail(PFV_ERR_BAD_ARG, "job %u: device coefficient pointer must be 16-byte aligned", i);
+        if (j.sparse) {
+            any_sparse = true;
+            if (j.flags) return fail(PFV_ERR_BAD_ARG, "job %u: sparse jobs take host pointers only (flags must be 0)", i);
+            if (!j.mb_off || (j.ntok && !j.tok)) return fail(PFV_ERR_BAD_ARG, "job %u: mb_off/tok is NULL", i);
+            if ((uint64_t)j.ntok > (uint64_t)g.nb * 256) return fail(PFV_ERR_BAD_ARG, "job %u: %u tokens > nb*256", i, j.ntok);
+            if (j.mb_off[0] != 0 || j.mb_off[g.nb] != j.ntok)
+                return fail(PFV_ERR_BAD_ARG, "job %u: mb_off[0] must be 0 and mb_off[nb] must equal ntok", i);
+            for (uint32_t m = 0; m < g.nb; m++)
+                if (j.mb_off[m + 1] < j.mb_off[m] || j.mb_off[m + 1] - j.mb_off[m] > 256)
+                    return fail(PFV_ERR_BAD_ARG, "job %u: mb_off is not a prefix of per-macroblock counts <= 256 (macroblock %u)", i, m);
+        } else {
+            if (!j.coeff) return fail(PFV_ERR_BAD_ARG, "job %u: coeff is NULL", i);
+            if ((j.flags & PFV_JOB_DEVICE_PTRS) && (reinterpret_cast<uintptr_t>(j.coeff) & 15u))
+                return fail(PFV_ERR_BAD_ARG, "job %u: device coefficient pointer must be 16-byte aligned", i);
+        }
         for (int p = 0; p < 3; p++)
             if (j.qidx[p] >= c->nq)
                 return fail(PFV_ERR_BAD_ARG, "job %u: q-table index %u >= %u (src/dec.rs:244-246 would panic)", i, j.qidx[p], c->nq);
@@ -604,6 +658,10 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
                     return fail(PFV_ERR_BAD_ARG, "jobs %u and %u of one submit are dependent (ref_slot == dst_slot)", i, k);
 
     CU_TRY(cudaSetDevice(c->device));
+    if (any_sparse) {
+        int rc = ensure_sparse_staging(c);
+        if (rc) return rc;
+    }
     const uint64_t id = ++c->submit_id;
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
@@ -631,8 +689,9 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         run_elems = 0;
         return PFV_OK;
     };
+    uint32_t nsparse = 0;
     for (uint32_t k = 0; k < njobs; k++) {
-        const pfv_decode_job &j = jobs[order[k]];
+        const DecIn &j = jobs[order[k]];
         DecJob &d = tab[k];
         const bool dev = (j.flags & PFV_JOB_DEVICE_PTRS) != 0;
         int16_t *d_coeff = st.d_coeff + (size_t)k * coeff_elems;
@@ -641,7 +700,17 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
             d.coeff = j.coeff;
             d.hdr = j.hdr;
         } else {
-            if (run_elems && j.coeff == run_src + run_elems && d_coeff == run_dst + run_elems) {
+            if (j.sparse) {
+                uint32_t *d_tok = st.d_tok + (size_t)k * coeff_elems;
+                uint32_t *d_mboff = st.d_mboff + (size_t)k * (g.nb + 1);
+                if (j.ntok) CU_TRY(cudaMemcpyAsync(d_tok, j.tok, (size_t)j.ntok * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
+                CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, (size_t)(g.nb + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
+                SparseJob &sj = st.h_sjobs[nsparse++];
+                sj.mb_off = d_mboff;
+                sj.tok = d_tok;
+                sj.hdr = j.kind == PFV_FRAME_P ? d_hdr : nullptr;
+                sj.coeff = d_coeff;
+            } else if (run_elems && j.coeff == run_src + run_elems && d_coeff == run_dst + run_elems) {
                 run_elems += coeff_elems;
             } else {
                 int rc = flush_run();
@@ -663,6 +732,7 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         int rc = flush_run();
         if (rc) return rc;
     }
+    if (nsparse) CU_TRY(cudaMemcpyAsync(st.d_sjobs, st.h_sjobs, sizeof(SparseJob) * nsparse, cudaMemcpyHostToDevice, c->s_h2d));
     CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(DecJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
     CU_TRY(cudaEventRecord(st.ev_h2d, c->s_h2d));
 
@@ -675,6 +745,10 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         if (rc) return rc;
     }
     CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
+    if (nsparse) {
+        CU_TRY(launch_expand_tokens(g.nb, st.d_sjobs, nsparse, c->s_compute));
+        c->launches++;
+    }
     const DecJob *d_tab = static_cast<const DecJob *>(st.d_jobs);
     auto sb_params = [&](uint32_t job_index) {
         SbParams P;
@@ -734,7 +808,7 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
     if (any_out) {
         CU_TRY(cudaStreamWaitEvent(c->s_d2h, st.ev_kernel, 0));
         for (uint32_t i = 0; i < njobs; i++) {
-            const pfv_decode_job &j = jobs[i];
+            const DecIn &j = jobs[i];
             if (!j.out_y) continue;
             int rc = copy_visible(c, j.dst_slot, j.out_y, j.out_u, j.out_v, c->s_d2h);
             if (rc) return rc;
@@ -742,6 +816,57 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         }
     }
     CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
+    return PFV_OK;
+}
+
+extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_t njobs)
+{
+    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (njobs == 0) return PFV_OK;
+    std::vector<DecIn> in(njobs);
+    for (uint32_t i = 0; i < njobs; i++) {
+        const pfv_decode_job &j = jobs[i];
+        DecIn &d = in[i];
+        d.kind = j.kind; d.flags = j.flags; d.dst_slot = j.dst_slot; d.ref_slot = j.ref_slot;
+        memcpy(d.qidx, j.qidx, 3);
+        d.sparse = false;
+        d.hdr = j.hdr; d.coeff = j.coeff;
+        d.mb_off = nullptr; d.tok = nullptr; d.ntok = 0;
+        d.out_y = j.out_y; d.out_u = j.out_u; d.out_v = j.out_v;
+    }
+    return decode_submit_impl(c, in.data(), njobs);
+}
+
+extern "C" int pfv_decode_submit_sparse(pfv_ctx *c, const pfv_decode_job_sparse *jobs, uint32_t njobs)
+{
+    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (njobs == 0) return PFV_OK;
+    std::vector<DecIn> in(njobs);
+    for (uint32_t i = 0; i < njobs; i++) {
+        const pfv_decode_job_sparse &j = jobs[i];
+        DecIn &d = in[i];
+        d.kind = j.kind; d.flags = j.flags; d.dst_slot = j.dst_slot; d.ref_slot = j.ref_slot;
+        memcpy(d.qidx, j.qidx, 3);
+        d.sparse = true;
+        d.hdr = j.hdr; d.coeff = nullptr;
+        d.mb_off = j.mb_off; d.tok = j.tok; d.ntok = j.ntok;
+        d.out_y = j.out_y; d.out_u = j.out_u; d.out_v = j.out_v;
+    }
+    return decode_submit_impl(c, in.data(), njobs);
+}
+
+extern "C" uint64_t pfv_ctx_last_submit_id(const pfv_ctx *c) { return c ? __atomic_load_n(&c->submit_id, __ATOMIC_RELAXED) : 0; }
+
+extern "C" int pfv_ctx_wait_submit(pfv_ctx *c, uint64_t id)
+{
+    if (!c) return fail(PFV_ERR_BAD_ARG, "NULL context");
+    // may be called from a helper thread while the owning thread keeps submitting: only the id counter is read
+    const uint64_t last = __atomic_load_n(&c->submit_id, __ATOMIC_RELAXED);
+    if (id == 0 || id > last) return fail(PFV_ERR_BAD_ARG, "submit id %llu has not been issued", (unsigned long long)id);
+    if (id + D2H_RING <= last)
+        return fail(PFV_ERR_BAD_ARG, "submit id %llu is older than the %d most recent submits", (unsigned long long)id, D2H_RING);
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaEventSynchronize(c->ev_d2h_ring[id % D2H_RING]));
     return PFV_OK;
 }
 

@@ -44,6 +44,14 @@ struct DecJob {
     const QTables   *qt[3];   // per plane
 };
 
+// sparse coefficient transport (pfv_decode_submit_sparse): one frame's token lists and where to expand them
+struct SparseJob {
+    const uint32_t  *mb_off;  // nb + 1, device
+    const uint32_t  *tok;     // device
+    const pfv_mbhdr *hdr;     // P: nb headers (macroblocks without coefficients are not expanded); I: nullptr
+    int16_t         *coeff;   // nb*256 dense destination, device
+};
+
 struct EncJob {
     const uint8_t *src[3];    // tight source planes, device
     pfv_mbhdr     *hdr;       // nb, device (P only)
@@ -80,6 +88,9 @@ constexpr int WIN_W = 176;
 constexpr int WIN_H = 46;
 constexpr int WIN_BYTES = WIN_W * WIN_H;
 
+// records the calling thread's error text (pfv_last_error) and returns `code`
+int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+
 // kernel launchers (pfv_kernels.cu).  mbs_per_warp-style tuning lives inside.
 cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, uint32_t njobs,
                           int *d_err, cudaStream_t s);
@@ -89,6 +100,7 @@ cudaError_t launch_decode_p_two_pass(const SbParams &P, const DecJob *d_jobs, ui
                                      uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
+cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, cudaStream_t s);
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,

@@ -90,6 +90,18 @@ class DecodeJob:
 
 
 @dataclass
+class SparseDecodeJob:
+    kind: int
+    dst_slot: int
+    mb_off: np.ndarray             # uint32[nb+1]
+    tok: np.ndarray                # uint32[ntok]: (position << 16) | uint16(value)
+    qidx: Sequence[int] = (0, 1, 1)
+    ref_slot: int = 0
+    hdr: Buf = None
+    out: Optional[Sequence[Buf]] = None
+
+
+@dataclass
 class EncodeJob:
     kind: int
     dst_slot: int
@@ -156,6 +168,24 @@ class Engine:
             a.src_y, a.src_u, a.src_v = (_addr(b) for b in j.src)
             a.hdr_out, a.coeff_out = _addr(j.hdr_out), _addr(j.coeff_out)
         return arr
+
+    def build_sparse_decode_jobs(self, jobs: Sequence[SparseDecodeJob]):
+        arr = (N.DecodeJobSparse * len(jobs))()
+        for a, j in zip(arr, jobs):
+            a.kind, a.dst_slot, a.ref_slot, a.flags = j.kind, j.dst_slot, j.ref_slot, 0
+            for p in range(3):
+                a.qidx[p] = int(j.qidx[p])
+            a.hdr, a.mb_off, a.tok = _addr(j.hdr), _addr(j.mb_off), _addr(j.tok)
+            a.ntok = int(j.tok.size) if isinstance(j.tok, np.ndarray) else 0
+            if j.out is not None:
+                a.out_y, a.out_u, a.out_v = (_addr(b) for b in j.out)
+        return arr
+
+    def decode_submit_sparse(self, jobs, prebuilt=None):
+        """Sparse coefficient transport (pfv_decode_submit_sparse): tokens cross PCIe, the dense layout is rebuilt on the GPU."""
+        arr = prebuilt if prebuilt is not None else self.build_sparse_decode_jobs(jobs)
+        self._keep.append((jobs, arr))
+        N.check(N.lib().pfv_decode_submit_sparse(self._ctx, arr, len(arr)))
 
     def decode_submit(self, jobs, prebuilt=None):
         """Asynchronous; buffers must stay alive until sync() (a reference is kept for you)."""

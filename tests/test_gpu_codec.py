@@ -1,0 +1,247 @@
+"""GPU: the Decoder / Encoder objects (csrc/pfv_codec.cpp) and the sparse coefficient transport, against the oracle's
+restatement of pfv_rs::dec::Decoder / pfv_rs::enc::Encoder on the same streams.  Bit-exact everywhere."""
+import numpy as np
+import pytest
+
+import pfvo
+from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine, PfvError, codec, geometry_for, make_qtables
+from pretty_fast_video_b200 import _native as N
+from pretty_fast_video_b200.engine import DecodeJob, SparseDecodeJob
+from pretty_fast_video_b200.synth import SynthVideo
+from test_codec_cpu import oracle_stream
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_decode_all(data):
+    """[(frame planes or None for a drop frame)], final framebuffer"""
+    dec = pfvo.Decoder(data)
+    out = []
+    while True:
+        more, fr = dec.advance_frame()
+        if not more:
+            break
+        out.append(None if fr is None else tuple(p.copy() for p in fr))
+    return out, dec.framebuffer().copy()
+
+
+def gpu_decode_all(data, **kw):
+    out = []
+    with codec.Decoder(data, **kw) as dec:
+        while True:
+            got = []
+            more = dec.advance_frame(lambda fr: got.append(tuple(p.copy() for p in fr)))
+            if not more:
+                assert not got
+                break
+            out.append(got[0] if got else None)
+        fb = dec.framebuffer()
+        assert dec.advance_frame(lambda fr: None) is False           # eof stays eof (src/dec.rs:171-173)
+    return out, fb
+
+
+def same_frames(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert (x is None) == (y is None)
+        if x is not None:
+            for p, q in zip(x, y):
+                assert np.array_equal(p, q)
+
+
+@pytest.mark.parametrize("mode", ["small", "mixed", "mid", "full"])
+@pytest.mark.parametrize("size", [(64, 48), (176, 144), (1920, 1080)])
+def test_sparse_submit_equals_dense_submit(size, mode):
+    from test_gpu_parity import rand_coeffs, rand_headers
+    w, h = size
+    rng = np.random.default_rng(hash((size, mode)) & 0xFFFF)
+    qt, _ = make_qtables(5)
+    g = geometry_for(w, h)
+    ci = rand_coeffs(rng, g.nb, mode)
+    cp = rand_coeffs(rng, g.nb, mode)
+    hdr = rand_headers(rng, g)
+    cp.reshape(g.nb, 256)[hdr[:, 2] == 0] = 0
+    with Engine(w, h, qt, nslots=4, max_jobs=2) as e:
+        e.decode_submit([DecodeJob(PFV_FRAME_I, 0, ci, (0, 1, 1))])
+        e.decode_submit([DecodeJob(PFV_FRAME_P, 1, cp, (2, 3, 3), ref_slot=0, hdr=hdr)])
+        mo_i, tk_i = codec.dense_to_tokens(ci, g.nb)
+        mo_p, tk_p = codec.dense_to_tokens(cp, g.nb)
+        e.decode_submit_sparse([SparseDecodeJob(PFV_FRAME_I, 2, mo_i, tk_i, (0, 1, 1))])
+        e.decode_submit_sparse([SparseDecodeJob(PFV_FRAME_P, 3, mo_p, tk_p, (2, 3, 3), ref_slot=2, hdr=hdr)])
+        e.sync()
+        assert np.array_equal(e.slot_read(0), e.slot_read(2))
+        assert np.array_equal(e.slot_read(1), e.slot_read(3))
+        # and against the oracle
+        of = pfvo.frame_init(pfvo.geometry_for(w, h))
+        pfvo.decode_iframe_coeffs(pfvo.geometry_for(w, h), qt, (0, 1, 1), ci, of)
+        assert np.array_equal(e.slot_read(2), of)
+        pfvo.decode_pframe_coeffs(pfvo.geometry_for(w, h), qt, (2, 3, 3), hdr, cp, of)
+        assert np.array_equal(e.slot_read(3), of)
+
+
+def test_sparse_submit_argument_errors():
+    qt, _ = make_qtables(5)
+    g = geometry_for(64, 48)
+    with Engine(64, 48, qt, nslots=2, max_jobs=1) as e:
+        mo = np.zeros(g.nb + 1, np.uint32)
+        tk = np.zeros(4, np.uint32)
+        mo[1:] = 4
+        with pytest.raises(PfvError):                                # ntok does not match mb_off[nb]
+            e.decode_submit_sparse([SparseDecodeJob(PFV_FRAME_I, 0, mo, tk[:3], (0, 1, 1))])
+        mo2 = mo.copy(); mo2[1] = 7                                  # not monotonic
+        with pytest.raises(PfvError):
+            e.decode_submit_sparse([SparseDecodeJob(PFV_FRAME_I, 0, mo2, tk, (0, 1, 1))])
+        e.decode_submit_sparse([SparseDecodeJob(PFV_FRAME_I, 0, mo, tk, (0, 1, 1))])
+        e.sync()
+
+
+@pytest.mark.parametrize("size,quality,kind,n,key", [((96, 64), 3, "moving", 12, 4), ((130, 70), 5, "moving", 9, 3),
+                                                     ((64, 48), 10, "random", 6, 3), ((176, 144), 0, "moving", 6, 6),
+                                                     ((64, 64), 5, "static", 5, 5)])
+def test_decoder_matches_oracle_decoder(size, quality, kind, n, key):
+    w, h = size
+    data, _ = oracle_stream(w, h, n, quality, key, 4321, kind=kind, drop_at=(5,) if n > 6 else ())
+    want, want_fb = oracle_decode_all(data)
+    got, fb = gpu_decode_all(data, num_threads=3)
+    same_frames(got, want)
+    assert np.array_equal(fb, want_fb)
+
+
+def test_decoder_accessors_reset_and_delta():
+    data, _ = oracle_stream(96, 64, 8, 3, 4, 7)
+    want, _ = oracle_decode_all(data)
+    with codec.Decoder(data, num_threads=2) as dec:
+        assert (dec.width(), dec.height(), dec.framerate()) == (96, 64, 30)
+        first = []
+        for _ in range(3):
+            assert dec.advance_frame(lambda fr: first.append(tuple(p.copy() for p in fr)))
+        dec.reset()                                                  # src/dec.rs:148: rewind only
+        again = []
+        while dec.advance_frame(lambda fr: again.append(tuple(p.copy() for p in fr))):
+            pass
+        same_frames(first, want[:3])
+        same_frames(again, want)                                     # the stream starts with a key frame
+        dec.reset()
+        # advance_delta: 2.5 frame times -> two frames now, the third with the next half
+        frames = []
+        assert dec.advance_delta(2.5 / 30.0, lambda fr: frames.append(1))
+        assert len(frames) == 2
+        assert dec.advance_delta(0.5 / 30.0 + 1e-9, lambda fr: frames.append(1))
+        assert len(frames) == 3
+        assert dec.advance_delta(100.0, lambda fr: frames.append(1)) is False    # runs into EOF
+        assert len(frames) == len(want)
+
+
+@pytest.mark.parametrize("threads,ahead", [(1, 1), (4, 6), (8, 3)])
+def test_decoder_result_does_not_depend_on_read_ahead(threads, ahead):
+    data, _ = oracle_stream(176, 144, 14, 4, 5, 11)
+    want, want_fb = oracle_decode_all(data)
+    got, fb = gpu_decode_all(data, num_threads=threads, read_ahead=ahead)
+    same_frames(got, want)
+    assert np.array_equal(fb, want_fb)
+
+
+def test_decoder_errors():
+    data, _ = oracle_stream(96, 64, 6, 3, 3, 5)
+    with pytest.raises(codec.DecodeError) as e:
+        codec.Decoder(b"XXXXXXXX" + data[8:])
+    assert e.value.kind == "FormatError"
+    with pytest.raises(codec.DecodeError) as e:
+        codec.Decoder(data[:200])
+    assert e.value.kind == "IOError"
+    # cut inside the 4th frame's payload: three frames decode, then an IOError (read_exact fails, src/dec.rs:192/205)
+    info, _ = codec.parse_header(data)
+    pk, _ = codec.index_packets(data, info.first_packet)
+    cut = pk[3][2] + pk[3][1] // 2
+    want, _ = oracle_decode_all(data)
+    with codec.Decoder(data[:cut], num_threads=2) as dec:
+        got = []
+        for _ in range(3):
+            assert dec.advance_frame(lambda fr: got.append(tuple(p.copy() for p in fr)))
+        same_frames(got, want[:3])
+        with pytest.raises(codec.DecodeError) as e:
+            dec.advance_frame(lambda fr: None)
+        assert e.value.kind == "IOError"
+    # stream without its EOF packet: all frames, then the read of the next packet header fails
+    with codec.Decoder(data[:-5], num_threads=2) as dec:
+        n = 0
+        for _ in range(len(want)):
+            assert dec.advance_frame(lambda fr: None)
+            n += 1
+        with pytest.raises(codec.DecodeError):
+            dec.advance_frame(lambda fr: None)
+    # corrupt payload of frame 2 (flip bytes in the token stream): an error or a different picture, never a crash;
+    # later key frames still decode
+    bad = bytearray(data)
+    p2 = pk[1][2]
+    for i in range(30, 60):
+        bad[p2 + i] ^= 0xFF
+    with codec.Decoder(bytes(bad), num_threads=2) as dec:
+        for _ in range(len(want)):
+            try:
+                if not dec.advance_frame(lambda fr: None):
+                    break
+            except PfvError:
+                pass
+
+
+@pytest.mark.parametrize("size,quality,kind,n,key", [((96, 64), 3, "moving", 10, 4), ((130, 70), 5, "moving", 7, 3),
+                                                     ((64, 48), 10, "random", 5, 2), ((176, 144), 0, "moving", 5, 5),
+                                                     ((64, 64), 5, "static", 4, 4), ((320, 240), 2, "moving", 8, 60)])
+def test_encoder_stream_is_byte_identical_to_oracle_encoder(size, quality, kind, n, key):
+    w, h = size
+    drop = (5,) if n > 6 else ()
+    want, _ = oracle_stream(w, h, n, quality, key, 2468, kind=kind, drop_at=drop)
+    sv = SynthVideo(w, h, 2468, kind=kind)
+    with codec.Encoder(w, h, 30, quality, num_threads=3) as enc:
+        for t in range(n):
+            if t in drop:
+                enc.encode_dropframe()
+            elif t % key == 0:
+                enc.encode_iframe(sv.frame(t))
+            else:
+                enc.encode_pframe(sv.frame(t))
+        enc.finish()
+        mine = enc.bytes()
+        prev = enc.prev_frame()
+        with pytest.raises(PfvError):                                # assert!(!self.finished)
+            enc.encode_iframe(sv.frame(0))
+        with pytest.raises(PfvError):
+            enc.finish()
+    assert mine == want
+    _, fb = oracle_decode_all(want)
+    assert np.array_equal(prev, fb)                                  # closed loop: encoder recon == decoder picture
+
+
+def test_encoder_argument_errors():
+    with pytest.raises(PfvError):
+        codec.Encoder(64, 48, 30, 11)                                # assert!(quality >= 0 && quality <= 10)
+    with pytest.raises(PfvError):
+        codec.Encoder(63, 48, 30, 5)                                 # odd size (src/frame.rs:13)
+    with codec.Encoder(64, 48, 30, 5) as enc:
+        with pytest.raises(PfvError):
+            enc.encode_iframe((np.zeros((48, 32), np.uint8), np.zeros((24, 32), np.uint8), np.zeros((24, 32), np.uint8)))
+        assert enc.bytes()[:8] == b"PFVIDEO\0"
+    # close() without finish() still terminates the stream (Drop, src/enc.rs:28-34) - nothing to observe but no hang
+
+
+def test_round_trip_1080p_encoder_to_decoder():
+    """Full-size property: our Encoder's stream decodes (our Decoder) to exactly the encoder's own reconstruction,
+    frame after frame (closed loop, src/enc.rs:85/135), and the oracle agrees on a sample frame."""
+    w, h = 1920, 1080
+    sv = SynthVideo(w, h, 31337)
+    recon = []
+    with codec.Encoder(w, h, 30, 5, num_threads=4) as enc:
+        for t in range(5):
+            (enc.encode_iframe if t == 0 else enc.encode_pframe)(sv.frame(t))
+            recon.append(enc.prev_frame())
+        enc.finish()
+        data = enc.bytes()
+    got, fb = gpu_decode_all(data, num_threads=4)
+    assert len(got) == 5 and np.array_equal(fb, recon[-1])
+    og = pfvo.geometry_for(w, h)
+    for fr, rec in zip(got, recon):
+        y, u, v = pfvo.crop_frame(og, rec)
+        assert np.array_equal(fr[0], y) and np.array_equal(fr[1], u) and np.array_equal(fr[2], v)
+    want, want_fb = oracle_decode_all(data)
+    assert np.array_equal(want_fb, fb)

@@ -11,9 +11,9 @@ echo "== bench"; timeout 900 python bench.py 2> $OUT/bench_$TAG.err | tee $OUT/b
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --cpu-budget 0.5 > $OUT/ncu_launch_$TAG.log 2>&1
-for K in decode_i_sb decode_kernel encode_p_kernel; do
-  WL=decode_i_1080p; [ $K = decode_kernel ] && WL=decode_p_1080p; [ $K = encode_p_kernel ] && WL=encode_p_1080p
-  SK=6; [ $K = decode_i_sb ] && SK=3
+for K in ${KERNELS:-decode_i_stream mc_copy residual_sb encode_p_kernel}; do
+  WL=decode_i_1080p; SK=3
+  case $K in mc_copy*|residual_sb*|decode_p*) WL=decode_p_1080p; SK=6;; encode_p*) WL=encode_p_1080p; SK=6;; esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s $SK -c 2 -f -o $OUT/prof_${K}_$TAG \
       python bench.py --workload $WL --steps 2 --warmup 3 --extras 0 --cpu-budget 0.2 > $OUT/ncu_full_${K}_$TAG.log 2>&1
 done
