@@ -245,3 +245,20 @@ def test_round_trip_1080p_encoder_to_decoder():
         assert np.array_equal(fr[0], y) and np.array_equal(fr[1], u) and np.array_equal(fr[2], v)
     want, want_fb = oracle_decode_all(data)
     assert np.array_equal(want_fb, fb)
+
+
+def test_gop_sharded_gpu_decode_equals_whole_stream():
+    """The multi-GPU partitioning (shard.py) with the GPU Decoder as the per-rank worker: every GOP decoded from its
+    own sub-stream in its own context, merged by display index, equals the whole-stream decode (no collective)."""
+    from pretty_fast_video_b200 import shard
+    data, _ = oracle_stream(176, 144, 17, 3, 4, 31, drop_at=(6,))
+    whole, _ = gpu_decode_all(data, num_threads=2)
+    world = 3
+    merged = []
+    for rank in range(world):
+        info, gops, mine = shard.plan(data, rank, world)
+        for g in mine:
+            part, _ = gpu_decode_all(shard.substream(data, info.first_packet, g), num_threads=2)
+            assert len(part) == g.nframes
+            merged += [(g.first_frame + i, fr) for i, fr in enumerate(part)]
+    same_frames(shard.gather_ordered(merged), whole)
