@@ -353,8 +353,53 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
         e2e = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "jobs_per_submit": chunk,
                "pcie_gbs_each_way": [h2d / e_max / 1e6, d2h / e_max / 1e6]}
-        # spot check: what came back is what the device holds (decoded planes of the last frame, lane 0)
         eng2.close()
+
+        # ---- the same with the sparse coefficient transport (pfv_decode_submit_sparse): tokens cross PCIe ----
+        from pretty_fast_video_b200 import codec
+        from pretty_fast_video_b200.engine import SparseDecodeJob
+        toks = [[codec.dense_to_tokens(hc[k, l], st.nb) for l in range(L)] for k in range(G)]
+        ntok_total = sum(t[1].size for row in toks for t in row)
+        tarena = PinnedArena(4 * ntok_total + G * L * (4 * (st.nb + 1) + 512) + 4096)
+        ptoks = []
+        for k in range(G):
+            row = []
+            for l in range(L):
+                mo = tarena.take((st.nb + 1,), np.uint32); mo[...] = toks[k][l][0]
+                tk = tarena.take((max(1, toks[k][l][1].size),), np.uint32); tk[:toks[k][l][1].size] = toks[k][l][1]
+                row.append((mo, tk[:toks[k][l][1].size]))
+            ptoks.append(row)
+        del toks
+        eng3 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
+        cur3 = [2 * i for i in range(L)]
+        tabs3 = []
+        for rep in range(2):
+            for k in range(G):
+                jobs = []
+                for lane in range(L):
+                    dst = cur3[lane] ^ 1
+                    jobs.append(SparseDecodeJob(PFV_FRAME_I if k == 0 else PFV_FRAME_P, dst, ptoks[k][lane][0], ptoks[k][lane][1],
+                                                (0, 1, 1) if k == 0 else (2, 3, 3), ref_slot=cur3[lane],
+                                                hdr=hh[k, lane] if k else None, out=outs(k, lane)))
+                    cur3[lane] = dst
+                tabs3.append([(eng3.build_sparse_decode_jobs(jobs[i:i + chunk]), jobs[i:i + chunk]) for i in range(0, L, chunk)])
+        ph3 = [0]
+
+        def step_sparse():
+            base = (ph3[0] % 2) * G
+            for k in range(G):
+                for arr, jobs in tabs3[base + k]:
+                    eng3.decode_submit_sparse(jobs, prebuilt=arr)
+            ph3[0] += 1
+
+        s_max, _ = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
+        h2d_s = int(4 * ntok_total + nframes * 4 * (st.nb + 1) + (G - 1) * L * st.nb * 4)
+        e2e["sparse"] = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
+                         "h2d_bytes_per_step": h2d_s, "d2h_bytes_per_step": d2h,
+                         "nonzero_coefficients_per_frame": ntok_total / nframes,
+                         "note": "pfv_decode_submit_sparse: (position,value) tokens over PCIe, dense layout rebuilt on the GPU"}
+        eng3.close()
+        tarena.close()
         out_arena.close()
 
     nframes = G * L
@@ -441,6 +486,57 @@ def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
     return dict(max_ms=max_ms, my_ms=my_ms, frames=G * L, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e)
 
 
+def run_decoder_stream(torch, dist, budget_s, nthreads):
+    """Stream level, the reference's own public API: pfv_rs::dec::Decoder::advance_frame over an in-memory .pfv
+    (what src/lib.rs:310-335 test_decode_speed_2 times).  The stream is made with the engine's Encoder on the GPU;
+    the timed region is container parse + entropy decode (host pool) + H2D tokens + kernels + D2H pictures."""
+    from pretty_fast_video_b200 import codec
+    from pretty_fast_video_b200.synth import SynthVideo
+    w, h, gop, ngop = 1920, 1080, 15, 4
+    sv = SynthVideo(w, h, 0x50465602)
+    with codec.Encoder(w, h, 30, 5, num_threads=nthreads, device=torch.cuda.current_device()) as enc:
+        for t in range(gop * ngop):
+            (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(sv.frame(t % gop + (t // gop) * 3))
+        enc.finish()
+        data = enc.bytes()
+    nfr = gop * ngop
+
+    def one_pass():
+        n = 0
+        with codec.Decoder(data, num_threads=nthreads, device=torch.cuda.current_device(), read_ahead=6) as dec:
+            t0 = time.perf_counter()
+            while dec.advance_frame(lambda fr: None):
+                n += 1
+            dt = time.perf_counter() - t0
+        assert n == nfr
+        return dt
+
+    one_pass()
+    times = [one_pass() for _ in range(3)]
+    gpu_fps = nfr / min(times)
+    # the oracle's Decoder on the same bytes (entropy + MB loops, nthreads OpenMP threads for the MB loops)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pfvo
+    done, t_used = 0, 0.0
+    while t_used < budget_s:
+        dec = pfvo.Decoder(data, nthreads=nthreads)
+        t0 = time.perf_counter()
+        k = 0
+        while k < 15:
+            more, fr = dec.advance_frame()
+            if not more:
+                break
+            k += 1
+        t_used += time.perf_counter() - t0
+        done += k
+        dec.close()
+    return {"value": gpu_fps, "unit": "frames/s", "frames": nfr, "stream_bytes": len(data), "host_threads": nthreads,
+            "note": "Decoder.advance_frame over an in-memory 1920x1080 .pfv (1 key frame / 15): entropy decode on the host pool, "
+                    "sparse tokens H2D, kernels, pictures D2H",
+            "cpu_baseline": {"value": done / t_used, "unit": "frames/s", "cores": nthreads, "kind": "port",
+                             "sample": f"{done} frames of the same stream through the oracle Decoder (entropy + MB loops) in {t_used:.1f} s"}}
+
+
 # ----------------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py touches oracle/)
 # ----------------------------------------------------------------------------------------------------
@@ -502,8 +598,13 @@ def reference_arm(args):
     cfg = WORKLOADS[args.workload]
     t_all = time.perf_counter()
     vals = []
+    # one step = the same number of frames the GPU arm decodes per step (a bounded sample: the distinct frames
+    # are cycled), capped so that the whole run stays within a few minutes
+    per_step = cfg["frames"] if cfg["gop"] == 1 else cfg["gops"] * cfg["gop"]
+    distinct = 4 if cfg["gop"] == 1 else min(cfg["gop"], 6)
+    reps = max(1, min(per_step // distinct, 64))
     for i in range(args.warmup + args.steps):
-        fps, sample, nb = cpu_port_leg(args.workload, budget_s=1e9, nthreads=nthreads, reps=2)
+        fps, sample, nb = cpu_port_leg(args.workload, budget_s=1e9, nthreads=nthreads, reps=reps)
         if i >= args.warmup:
             vals.append(fps)
         if time.perf_counter() - t_all > 240:
@@ -512,9 +613,10 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "1080p decode frames/sec" if "1080p" in args.workload else "decode frames/sec",
         "value": v, "unit": "frames/s", "mb_per_s": v * nb, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-        "ms_per_step": 1e3 * 2 * (4 if cfg["gop"] == 1 else 6) / v, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * reps * distinct / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"]},
+        "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"],
+                   "frames_per_step": reps * distinct, "gop": cfg["gop"]},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C restatement of the reference algorithm (oracle/); the Rust crate cannot be built here (no cargo/rustc)",
@@ -614,6 +716,10 @@ def main():
                     extras[wl]["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": cs}
                 except Exception as ex:                      # an extra must never lose the headline line
                     extras[wl] = {"error": repr(ex)}
+            try:
+                extras["decoder_stream_1080p"] = run_decoder_stream(torch, dist, min(args.cpu_budget, 6.0), nthreads)
+            except Exception as ex:
+                extras["decoder_stream_1080p"] = {"error": repr(ex)}
             line["extras"] = extras
     if dist.rank == 0:
         print(json.dumps(line))

@@ -188,10 +188,15 @@ struct pfv_ctx {
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
     int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "tma" (default), 3 "sbw", 1 "sb" (dense), 2 "warp"
-    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "two" (default), 1 "stream", 3 "sbw", 2 "warp"
+    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "win" (default: TMA window copy + list-driven persistent residual), 7 "winll" (list-free residual),
+                                           // 6 "tma" (per-macroblock TMA boxes),
+                                           // 5 "two" (cp.async copy),
+                                           // 4 "two1" (first pair), 1 "stream", 3 "sbw", 2 "warp"
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
-    CUtensorMap tm_luma{}, tm_chroma{};
+    CUtensorMap tm_luma{}, tm_chroma{};          // encode-P search window boxes
+    CUtensorMap tm_mb_luma{}, tm_mb_chroma{};    // decode-P predictor boxes (32 x 16, 16-byte aligned in x)
+    CUtensorMap tm_win_luma{}, tm_win_chroma{};  // decode-P windows of 8 x 4 macroblocks (176 x 94)
     bool have_tma = false;
     char tma_err[160] = "";
 };
@@ -213,14 +218,22 @@ int build_tensor_maps(pfv_ctx *c)
     }
     EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
     const pfv_geometry &g = c->geo;
-    const cuuint32_t box[4] = {WIN_W, WIN_H, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const char *promo_env = getenv("PFV_TMA_L2PROMO");
+    for (int which = 0; which < 3; which++) {
+    const CUtensorMapL2promotion promo = which == 1 && promo_env ? (CUtensorMapL2promotion)atoi(promo_env) : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    // which == 1: the aligned 32 x 16 box that covers a motion-compensated 16 x 16 block (mc_copy3_kernel)
+    // which == 2: the window of every possible predictor of 8 x 4 macroblocks (mc_copy4_kernel)
+    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : (which == 1 ? 32u : 176u),
+                               which == 0 ? (cuuint32_t)WIN_H : (which == 1 ? 16u : 94u), 1, 1};
+    CUtensorMap *out_l = which == 0 ? &c->tm_luma : (which == 1 ? &c->tm_mb_luma : &c->tm_win_luma);
+    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : (which == 1 ? &c->tm_mb_chroma : &c->tm_win_chroma);
     {   // luma: (x, y, 1, slot)
         const cuuint64_t dims[4] = {g.pw, g.ph, 1, c->nslots};
         const cuuint64_t strides[3] = {g.pw, c->slot_stride, c->slot_stride};
-        CUresult r = encode(&c->tm_luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->d_pool, dims, strides, box, estr,
+        CUresult r = encode(out_l, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->d_pool, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             snprintf(c->tma_err, sizeof(c->tma_err), "cuTensorMapEncodeTiled(luma) -> CUresult %d", (int)r);
             return -1;
@@ -230,13 +243,14 @@ int build_tensor_maps(pfv_ctx *c)
         const cuuint64_t nc = (cuuint64_t)g.cpw * g.cph;
         const cuuint64_t dims[4] = {g.cpw, g.cph, 2, c->nslots};
         const cuuint64_t strides[3] = {g.cpw, nc, c->slot_stride};
-        CUresult r = encode(&c->tm_chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->d_pool + (size_t)g.pw * g.ph, dims,
+        CUresult r = encode(out_c, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, c->d_pool + (size_t)g.pw * g.ph, dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             snprintf(c->tma_err, sizeof(c->tma_err), "cuTensorMapEncodeTiled(chroma) -> CUresult %d", (int)r);
             return -1;
         }
+    }
     }
     c->have_tma = true;
     return 0;
@@ -411,7 +425,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
         c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : (strcmp(v, "sbw") == 0 ? 3 : 0));
-    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : (strcmp(v, "stream") == 0 ? 1 : 0));
+    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : (strcmp(v, "stream") == 0 ? 1 : (strcmp(v, "two1") == 0 ? 4 : (strcmp(v, "two") == 0 ? 5 : (strcmp(v, "tma") == 0 ? 6 : (strcmp(v, "winll") == 0 ? 7 : 0))))));
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -726,6 +740,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         }
         d.dst = slot_ptr(c, j.dst_slot);
         d.ref = j.kind == PFV_FRAME_P ? slot_ptr(c, j.ref_slot) : nullptr;
+        d.ref_slot = j.kind == PFV_FRAME_P ? (int32_t)j.ref_slot : 0;
         for (int p = 0; p < 3; p++) d.qt[p] = c->d_qt + j.qidx[p];
     }
     {
@@ -787,11 +802,25 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                 CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
             } else if (c->decode_p_variant == 1) {
                 CU_TRY(launch_decode_p_stream(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
+            } else if ((c->decode_p_variant == 0 || c->decode_p_variant == 7) && c->have_tma) {
+                const uint32_t k0 = a - n_i;
+                CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)(b - a) * 4 * sizeof(uint32_t), c->s_compute));
+                CU_TRY(launch_decode_p_two_pass4(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
+                                                 c->d_pcount + (size_t)k0 * 4, c->decode_p_variant == 7, c->d_err, c->tm_win_luma,
+                                                 c->tm_win_chroma, c->s_compute));
+                c->launches++;
             } else {
                 const uint32_t k0 = a - n_i;
                 CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)(b - a) * 4 * sizeof(uint32_t), c->s_compute));
-                CU_TRY(launch_decode_p_two_pass(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
-                                                c->d_pcount + (size_t)k0 * 4, c->d_err, c->s_compute));
+                if (c->decode_p_variant == 4)
+                    CU_TRY(launch_decode_p_two_pass(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
+                                                    c->d_pcount + (size_t)k0 * 4, c->d_err, c->s_compute));
+                else if (c->decode_p_variant != 6 || !c->have_tma)
+                    CU_TRY(launch_decode_p_two_pass2(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
+                                                     c->d_pcount + (size_t)k0 * 4, c->d_err, c->s_compute));
+                else
+                    CU_TRY(launch_decode_p_two_pass3(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
+                                                     c->d_pcount + (size_t)k0 * 4, c->d_err, c->tm_mb_luma, c->tm_mb_chroma, c->s_compute));
                 c->launches++;
             }
             c->launches++;

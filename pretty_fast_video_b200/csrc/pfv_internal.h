@@ -42,6 +42,7 @@ struct DecJob {
     uint8_t         *dst;     // frame slot
     const uint8_t   *ref;     // frame slot (P only)
     const QTables   *qt[3];   // per plane
+    int32_t          ref_slot; // the same slot as an index (TMA coordinate of mc_copy3_kernel)
 };
 
 // sparse coefficient transport (pfv_decode_submit_sparse): one frame's token lists and where to expand them
@@ -98,6 +99,13 @@ cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t
 cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_decode_p_two_pass(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
                                      uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s);
+cudaError_t launch_decode_p_two_pass2(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
+                                      uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s);
+cudaError_t launch_decode_p_two_pass3(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
+                                      uint32_t *d_lists, uint32_t *d_counts, int *d_err,
+                                      const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s);
+cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
+                                      bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s);
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);

@@ -102,11 +102,12 @@ def test_decode_pframe_matches_oracle(size, mode):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", ["tma", "stream", "sbw", "sb", "warp"])
-def test_decode_kernel_variants_agree(variant, monkeypatch):
+@pytest.mark.parametrize("ivar,pvar", [("tma", "win"), ("tma", "winll"), ("tma", "tma"), ("sbw", "two"), ("sb", "two1"), ("warp", "stream"), ("tma", "sbw"),
+                                       ("tma", "warp")])
+def test_decode_kernel_variants_agree(ivar, pvar, monkeypatch):
     """The earlier kernels stay selectable (PFV_DECODE_*_VARIANT) and agree with the default ones."""
-    monkeypatch.setenv("PFV_DECODE_I_VARIANT", variant)
-    monkeypatch.setenv("PFV_DECODE_P_VARIANT", "two" if variant == "tma" else variant)
+    monkeypatch.setenv("PFV_DECODE_I_VARIANT", ivar)
+    monkeypatch.setenv("PFV_DECODE_P_VARIANT", pvar)
     w, h = 208, 112
     rng = np.random.default_rng(99)
     qt, _ = make_qtables(4)
@@ -125,6 +126,37 @@ def test_decode_kernel_variants_agree(variant, monkeypatch):
         e.sync()
         assert np.array_equal(e.slot_read(0), want0)
         assert np.array_equal(e.slot_read(1), want1)
+
+
+@pytest.mark.parametrize("pvar", ["win", "winll", "tma", "two", "two1", "stream", "sbw", "warp"])
+def test_decode_pframe_long_motion_vectors(pvar, monkeypatch):
+    """The stream format carries 7-bit vectors (src/dec.rs:367-368) and the reference decoder follows any vector that
+    stays inside the padded plane (src/common.rs:255-261), also ones its own encoder (|mv| <= 15) never emits."""
+    monkeypatch.setenv("PFV_DECODE_P_VARIANT", pvar)
+    w, h = 400, 240
+    rng = np.random.default_rng(17)
+    qt, _ = make_qtables(5)
+    og = pfvo.geometry_for(w, h)
+    hdr = np.zeros((og.nb, 4), np.uint8)
+    mv = hdr[:, :2].view(np.int8)
+    idx = 0
+    for (pw, ph) in ((og.pw, og.ph), (og.cpw, og.cph), (og.cpw, og.cph)):
+        for by in range(ph // 16):
+            for bx in range(pw // 16):
+                mv[idx, 0] = rng.integers(max(-64, -bx * 16), min(63, pw - 16 - bx * 16) + 1)
+                mv[idx, 1] = rng.integers(max(-64, -by * 16), min(63, ph - 16 - by * 16) + 1)
+                hdr[idx, 2] = rng.random() < 0.4
+                idx += 1
+    coeff = rand_coeffs(rng, og.nb, "mixed")
+    coeff.reshape(-1, 256)[hdr[:, 2] == 0] = 0
+    ref = rng.integers(0, 256, pfvo.frame_init(og).size).astype(np.uint8)
+    want = ref.copy()
+    pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdr, coeff, want)
+    with Engine(w, h, qt, nslots=2, max_jobs=1) as e:
+        e.slot_write(0, ref)
+        e.decode_submit([DecodeJob(PFV_FRAME_P, 1, coeff, (2, 3, 3), ref_slot=0, hdr=hdr)])
+        e.sync()
+        assert np.array_equal(e.slot_read(1), want)
 
 
 def test_decode_pframe_all_skipped_is_a_copy():
