@@ -492,18 +492,19 @@ def run_decoder_stream(torch, dist, budget_s, nthreads):
     the timed region is container parse + entropy decode (host pool) + H2D tokens + kernels + D2H pictures."""
     from pretty_fast_video_b200 import codec
     from pretty_fast_video_b200.synth import SynthVideo
-    w, h, gop, ngop = 1920, 1080, 15, 4
+    w, h, gop, ngop = 1920, 1080, 15, 16
     sv = SynthVideo(w, h, 0x50465602)
+    src = [sv.frame(t) for t in range(gop + 3 * 3)]              # GOP g starts 3 frames later in the sequence (g mod 4)
     with codec.Encoder(w, h, 30, 5, num_threads=nthreads, device=torch.cuda.current_device()) as enc:
         for t in range(gop * ngop):
-            (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(sv.frame(t % gop + (t // gop) * 3))
+            (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(src[t % gop + ((t // gop) % 4) * 3])
         enc.finish()
         data = enc.bytes()
     nfr = gop * ngop
 
     def one_pass():
         n = 0
-        with codec.Decoder(data, num_threads=nthreads, device=torch.cuda.current_device(), read_ahead=6) as dec:
+        with codec.Decoder(data, num_threads=nthreads, device=torch.cuda.current_device()) as dec:
             t0 = time.perf_counter()
             while dec.advance_frame(lambda fr: None):
                 n += 1

@@ -190,7 +190,7 @@ typedef struct pfv_decode_job_sparse {
 int  pfv_decode_submit_sparse(pfv_ctx *ctx, const pfv_decode_job_sparse *jobs, uint32_t njobs);
 
 /* Every *_submit (and pfv_slot_read_visible) call takes the next submit id (1, 2, ...).  pfv_ctx_wait_submit blocks
- * until the device-to-host copies of that submit have landed (it must be one of the 8 most recent ids); unlike
+ * until the device-to-host copies of that submit have landed (it must be one of the 64 most recent ids); unlike
  * pfv_sync it does not wait for later submits, which is what a read-ahead decoder needs. */
 uint64_t pfv_ctx_last_submit_id(const pfv_ctx *ctx);
 int      pfv_ctx_wait_submit(pfv_ctx *ctx, uint64_t submit_id);

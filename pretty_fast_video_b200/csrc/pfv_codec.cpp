@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -61,6 +62,24 @@ struct Huffman {
     int8_t   sym[31];
     int      root = -1;
     uint8_t  lut[1 << LUT_BITS];   // (len << 4) | symbol, 0 = longer than LUT_BITS
+    // a token is two symbols back to back (run length, value size: src/dec.rs:262-275); when both codes fit the
+    // window one lookup resolves the pair: run | size << 4 | total length << 8, 0 = take the two-step path
+    uint16_t pair[1 << LUT_BITS];
+
+    void build_pairs()
+    {
+        for (uint32_t b = 0; b < (1u << LUT_BITS); b++) {
+            pair[b] = 0;
+            const uint8_t e1 = lut[b];
+            if (!e1) continue;
+            const uint32_t l1 = e1 >> 4;
+            const uint8_t e2 = lut[b >> l1];
+            if (!e2) continue;
+            const uint32_t l2 = e2 >> 4;
+            if (l1 + l2 > (uint32_t)LUT_BITS) continue;              // the second code would need bits the index does not hold
+            pair[b] = (uint16_t)((e1 & 15u) | ((e2 & 15u) << 4) | ((l1 + l2) << 8));
+        }
+    }
 
     void build(const uint8_t table[16])
     {
@@ -232,26 +251,28 @@ extern "C" int pfv_packet_decode(const pfv_geometry *g, uint32_t kind, const uin
     const uint32_t nb = g->nb;
     uint32_t ntok = 0;
 
-    // one (run, size[, value]) token; returns false on a malformed stream
+    h.build_pairs();
+    // one (run, size[, value]) token out of ONE 57-bit window; returns false on a malformed stream
     auto token = [&](uint32_t &run, int &size, int32_t &value) -> bool {
-        if (h.nsym == 0) return false;                              // empty tree: reference hits unreachable!()
-        if (h.only >= 0) {                                          // zero-length codes
+        uint64_t w = br.peek();
+        uint32_t used;
+        const uint16_t pe = h.pair[w & ((1u << LUT_BITS) - 1)];
+        if (pe) {
+            run = pe & 15u; size = (pe >> 4) & 15; used = pe >> 8;
+        } else if (h.only >= 0) {                                   // zero-length codes
             if (h.only == 0) return false;                           // (0, 0) forever: the reference would never return
-            run = (uint32_t)h.only; size = h.only;
-        }
-        else {
-            uint64_t w = br.peek();
+            run = (uint32_t)h.only; size = h.only; used = 0;
+        } else {
+            if (h.nsym == 0) return false;                          // empty tree: reference hits unreachable!()
             int s1, s2;
             const int l1 = huff_symbol(h, w, s1);
             if (l1 < 0) return false;
-            w >>= l1;
-            const int l2 = huff_symbol(h, w, s2);
+            const int l2 = huff_symbol(h, w >> l1, s2);
             if (l2 < 0) return false;
-            br.pos += (uint64_t)(l1 + l2);
-            run = (uint32_t)s1; size = s2;
+            run = (uint32_t)s1; size = s2; used = (uint32_t)(l1 + l2);
         }
-        value = 0;
-        if (size > 0) value = sign_extend(br.take(size), size);      // read_signed::<i16>(size), src/dec.rs:286
+        value = size > 0 ? sign_extend((uint32_t)(w >> used) & ((1u << size) - 1u), size) : 0;   // read_signed::<i16>(size), src/dec.rs:286
+        br.pos += used + (uint32_t)size;                            // <= 15 + 15 + 15 bits: inside the window
         return !br.overrun();
     };
 
@@ -571,7 +592,14 @@ struct pfv_decoder {
     double delta_accum = 0.0;
     uint64_t epoch = 0;            // bumped by reset(): results of older entropy jobs are dropped
     size_t ysz = 0, csz = 0;
+    double t_prof[5] = {0, 0, 0, 0, 0};   // PFV_TRACE: seconds in schedule / wait entropy+submit / wait GPU / refill / entropy jobs
+    uint64_t n_prof = 0;
 };
+
+static inline double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static void decoder_entropy_job(pfv_decoder *d, DecWork *w)
 {
@@ -580,11 +608,14 @@ static void decoder_entropy_job(pfv_decoder *d, DecWork *w)
     uint32_t *mb_off = static_cast<uint32_t *>(w->meta.p);
     pfv_mbhdr *hdr = reinterpret_cast<pfv_mbhdr *>(mb_off + nb + 1);
     uint32_t ntok = 0;
+    const double t0 = now_s();
     int rc = pfv_packet_decode(&d->geo, w->kind, d->data + pk.payload, pk.len, w->qidx, hdr, mb_off,
                                static_cast<uint32_t *>(w->tok.p), (uint32_t)(w->tok.bytes / 4), &ntok);
+    const double t1 = now_s();
     if (rc) snprintf(w->err, sizeof(w->err), "%s", pfv_last_error());
     {
         std::lock_guard<std::mutex> l(d->m);
+        d->t_prof[4] += t1 - t0;
         w->status = rc;
         w->ntok = ntok;
         w->state = W_READY;
@@ -629,7 +660,10 @@ static int decoder_schedule(pfv_decoder *d)
 static int decoder_submit_ready(pfv_decoder *d, DecWork *must)
 {
     for (DecWork *w : d->inflight) {
-        if (w->state == W_SUBMITTED) continue;
+        if (w->state == W_SUBMITTED) {
+            if (w == must) must = nullptr;                          // went out with an earlier refill: nothing to wait for
+            continue;
+        }
         {
             std::unique_lock<std::mutex> l(d->m);
             if (w->state != W_READY) {
@@ -704,13 +738,30 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
         d->packets.resize(n);
         d->truncated = trunc != 0;
     }
-    d->depth = read_ahead ? read_ahead : 6;
-    if (d->depth > 6) d->depth = 6;                                  // pfv_ctx_wait_submit reaches 8 submits back
+    // default: enough frames in flight to keep every entropy thread busy plus a few on the GPU
+    d->depth = read_ahead ? read_ahead : std::max<uint32_t>(6, (num_threads ? num_threads : 1) + 4);
+    if (d->depth > 48) d->depth = 48;                                // pfv_ctx_wait_submit reaches 64 submits back
     d->nslots = d->depth + 3;
     rc = pfv_ctx_create(device, d->info.width, d->info.height, reinterpret_cast<const int32_t(*)[64]>(qt.data()),
                         d->info.num_qtables, d->nslots, 1, nullptr, &d->ctx);
     if (rc) return rc;
-    for (uint32_t i = 0; i < d->depth + 1; i++) d->work.emplace_back(new DecWork());
+    // pinned buffers are sized once, from the largest frame packet of the stream (cudaHostAlloc costs milliseconds:
+    // never on the per-frame path).  Token capacity: an emitted token costs at least 3 bits when the tree has two or
+    // more symbols, and a one-symbol tree emits none.
+    uint32_t max_len = 0;
+    for (const pfv_packet &pk : d->packets)
+        if ((pk.type == 1 || pk.type == 2) && pk.len > max_len) max_len = pk.len;
+    const uint64_t tok_cap = std::min<uint64_t>((uint64_t)d->geo.nb * 256, (uint64_t)max_len * 8 / 3 + 1);
+    for (uint32_t i = 0; i < d->depth + 1; i++) {
+        std::unique_ptr<DecWork> w(new DecWork());
+        if ((rc = w->tok.reserve((size_t)tok_cap * 4)) ||
+            (rc = w->meta.reserve(((size_t)d->geo.nb + 1) * 4 + (size_t)d->geo.nb * sizeof(pfv_mbhdr))) ||
+            (rc = w->out.reserve(d->ysz + 2 * d->csz))) {
+            pfv_ctx_destroy(d->ctx);
+            return rc;
+        }
+        d->work.push_back(std::move(w));
+    }
     d->pool.reset(new Pool(num_threads ? num_threads : 1));
     *out = d.release();
     return PFV_OK;
@@ -732,6 +783,10 @@ extern "C" void pfv_decoder_close(pfv_decoder *d)
 {
     if (!d) return;
     decoder_drain(d);
+    if (getenv("PFV_TRACE") && d->n_prof)
+        fprintf(stderr, "[pfv_decoder] %llu frames; per frame us: schedule %.0f, wait entropy + submit %.0f, wait GPU %.0f, refill %.0f; entropy job %.0f\n",
+                (unsigned long long)d->n_prof, 1e6 * d->t_prof[0] / d->n_prof, 1e6 * d->t_prof[1] / d->n_prof,
+                1e6 * d->t_prof[2] / d->n_prof, 1e6 * d->t_prof[3] / d->n_prof, 1e6 * d->t_prof[4] / d->n_prof);
     d->pool.reset();
     if (d->ctx) pfv_ctx_destroy(d->ctx);
     delete d;
@@ -776,8 +831,10 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
         if (pk.type != 1 && pk.type != 2) { d->cursor++; if (d->sched < d->cursor) d->sched = d->cursor; continue; }  // src/dec.rs:216-219
         break;
     }
+    const double t0 = now_s();
     int rc = decoder_schedule(d);
     if (rc) return rc;
+    const double t1 = now_s();
     if (d->inflight.empty() || d->inflight.front()->packet != d->cursor)
         return set_error(PFV_ERR_STATE, "internal: read-ahead queue out of step with the cursor");
     DecWork *w = d->inflight.front();
@@ -789,8 +846,10 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
         d->sched = d->cursor;
         return rc;
     }
+    const double t2 = now_s();
     rc = pfv_ctx_wait_submit(d->ctx, w->submit_id);
     if (rc) return rc;
+    const double t3 = now_s();
     d->inflight.pop_front();
     d->delivered = w;
     d->delivered_slot = w->slot;
@@ -800,6 +859,8 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
     if (rc) return rc;
     rc = decoder_submit_ready(d, nullptr);
     if (rc) return rc;
+    const double t4 = now_s();
+    d->t_prof[0] += t1 - t0; d->t_prof[1] += t2 - t1; d->t_prof[2] += t3 - t2; d->t_prof[3] += t4 - t3; d->n_prof++;
     if (got_frame) *got_frame = 1;
     const uint8_t *base = static_cast<const uint8_t *>(w->out.p);
     if (y) *y = base;

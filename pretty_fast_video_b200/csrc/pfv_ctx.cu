@@ -145,7 +145,7 @@ extern "C" void pfv_host_free(void *p)
 namespace {
 
 constexpr int STAGES = 2;        // staging ring depth: H2D of submit n+1 overlaps the kernels of submit n
-constexpr int D2H_RING = 8;      // D2H completion events kept for slot-reuse ordering
+constexpr int D2H_RING = 64;     // D2H completion events kept for slot-reuse ordering and pfv_ctx_wait_submit
 
 struct Stage {
     int16_t   *d_coeff = nullptr;    // max_jobs * nb * 256

@@ -311,9 +311,12 @@ mc_copy2_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McT
     }
 }
 
+#ifndef RS2_CTAS_PER_SM
+#define RS2_CTAS_PER_SM 3    // 4 (128 registers, predictor fetched after the transform) measured slower: 37 vs 28 us
+#endif
 // Persistent residual kernel: chunk = 32 consecutive entries of one (frame, plane) list; CTA c takes chunks
 // c, c + gridDim.x, ...  The chunk table (prefix over njobs * 3 lists) is rebuilt by every CTA from the counts.
-__global__ void __launch_bounds__(SB_THREADS, 3)
+__global__ void __launch_bounds__(SB_THREADS, RS2_CTAS_PER_SM)
 residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs, uint32_t njobs,
                     const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts)
 {
@@ -353,7 +356,7 @@ residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
         uint32_t col;
         const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
         uint8_t *dst = job.dst + pl.off + (size_t)(row * 16u + (uint32_t)(sb >> 1) * 8u) * pl.pw + col * 16u + (uint32_t)(sb & 1) * 8u;
-        uint2 prev[8];                                        // the predictor mc_copy2_kernel stored here
+        uint2 prev[8];                                        // the predictor the copy kernel stored here
 #pragma unroll
         for (int r = 0; r < 8; ++r) prev[r] = __ldcg(reinterpret_cast<const uint2 *>(dst + (size_t)r * pl.pw));
 
@@ -684,9 +687,21 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
         return __ldg(reinterpret_cast<const uint32_t *>(jobs[it.job].hdr) + pl.mb_base + row * pl.bw + col);
     };
 
+    // coded macroblocks of this warp's tile -> the (frame, plane) list.  The atomic that reserves the list range is issued
+    // one window AHEAD of its use, so its round trip hides behind a whole iteration.
+    auto reserve = [&](const Item &it, uint32_t hw, uint32_t &vote) -> uint32_t {
+        const bool coded = !(hw & 0x80000000u) && ((hw >> 16) & 0xffu) != 0u && (lane & 3u) == 0u;
+        vote = __ballot_sync(0xffffffffu, coded);
+        uint32_t base = 0;
+        if (vote && lane == 0) base = atomicAdd(&counts[it.job * 4u + it.p], (uint32_t)__popc(vote));
+        return base;
+    };
+
     Item cur = decode_item(blockIdx.x);
     if (threadIdx.x == 0) issue(cur, 0);
     uint32_t hw_cur = load_hw(cur);
+    uint32_t vote = 0;
+    uint32_t list_base = reserve(cur, hw_cur, vote);
     uint32_t k = 0;
 #pragma unroll 1
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x, ++k) {
@@ -699,6 +714,8 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
             if (threadIdx.x == 0) issue(nxt, st ^ 1u);       // that stage was released by the barrier at the end of the previous iteration
             hw_next = load_hw(nxt);
         }
+        uint32_t vote_next = 0, list_base_next = 0;
+        if (nxt_i < nitems) list_base_next = reserve(nxt, hw_next, vote_next);
         {
             const uint32_t bar = mc3_smem(&sm.bar[st]);
             const uint32_t parity = (k >> 1) & 1u;
@@ -711,12 +728,6 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
             }
         }
-        // coded macroblocks of this warp's tile -> the (frame, plane) list.  The atomic is issued BEFORE the copy and its
-        // result is used after it, so its round trip hides behind the copy.
-        const bool coded = !(hw_cur & 0x80000000u) && ((hw_cur >> 16) & 0xffu) != 0u && (lane & 3u) == 0u;
-        const uint32_t vote = __ballot_sync(0xffffffffu, coded);
-        uint32_t list_base = 0;
-        if (vote && lane == 0) list_base = atomicAdd(&counts[cur.job * 4u + cur.p], (uint32_t)__popc(vote));
         if (!(hw_cur & 0x80000000u)) {
             const PlaneGeom &pl = plane(cur.p);
             const uint32_t rg = lane & 3u, mb = lane >> 2;
@@ -765,6 +776,7 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
         }
         if (vote) {
             list_base = __shfl_sync(0xffffffffu, list_base, 0);
+            const bool coded = !(hw_cur & 0x80000000u) && ((hw_cur >> 16) & 0xffu) != 0u && (lane & 3u) == 0u;
             if (coded) {
                 const PlaneGeom &pl = plane(cur.p);
                 const uint32_t lm = (cur.gy * MC4_ROWS + warp) * pl.bw + cur.tx * 8u + (lane >> 2);
@@ -774,6 +786,8 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
         __syncthreads();                                      // the whole CTA is done with this stage
         cur = nxt;
         hw_cur = hw_next;
+        vote = vote_next;
+        list_base = list_base_next;
     }
 }
 
@@ -926,7 +940,7 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
     }
     if (!listless) {
         uint32_t ctas = P.cta_total * njobs;                  // worst case: every macroblock coded
-        if (ctas > 148u * 3u) ctas = 148u * 3u;
+        if (ctas > 148u * RS2_CTAS_PER_SM) ctas = 148u * RS2_CTAS_PER_SM;
         residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts);
         return cudaGetLastError();
     }
