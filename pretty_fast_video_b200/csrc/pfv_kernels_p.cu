@@ -697,25 +697,29 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
         return base;
     };
 
+    // Software pipeline over windows i (being copied), i+1 (TMA in flight, list range being reserved) and i+2 (headers
+    // being loaded): no load or atomic is consumed in the iteration that issues it.
     Item cur = decode_item(blockIdx.x);
     if (threadIdx.x == 0) issue(cur, 0);
     uint32_t hw_cur = load_hw(cur);
     uint32_t vote = 0;
     uint32_t list_base = reserve(cur, hw_cur, vote);
+    Item nxt = cur;
+    uint32_t hw_next = 0x80000000u;
+    if (blockIdx.x + gridDim.x < nitems) { nxt = decode_item(blockIdx.x + gridDim.x); hw_next = load_hw(nxt); }
     uint32_t k = 0;
 #pragma unroll 1
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x, ++k) {
         const uint32_t st = k & 1u;
-        const uint32_t nxt_i = it + gridDim.x;
-        Item nxt = cur;
-        uint32_t hw_next = 0x80000000u;
-        if (nxt_i < nitems) {
-            nxt = decode_item(nxt_i);
-            if (threadIdx.x == 0) issue(nxt, st ^ 1u);       // that stage was released by the barrier at the end of the previous iteration
-            hw_next = load_hw(nxt);
-        }
+        const bool has_next = it + gridDim.x < nitems;
         uint32_t vote_next = 0, list_base_next = 0;
-        if (nxt_i < nitems) list_base_next = reserve(nxt, hw_next, vote_next);
+        if (has_next) {
+            if (threadIdx.x == 0) issue(nxt, st ^ 1u);       // that stage was released by the barrier at the end of the previous iteration
+            list_base_next = reserve(nxt, hw_next, vote_next);
+        }
+        Item nn = nxt;
+        uint32_t hw_nn = 0x80000000u;
+        if (it + 2 * gridDim.x < nitems) { nn = decode_item(it + 2 * gridDim.x); hw_nn = load_hw(nn); }
         {
             const uint32_t bar = mc3_smem(&sm.bar[st]);
             const uint32_t parity = (k >> 1) & 1u;
@@ -784,8 +788,8 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
             }
         }
         __syncthreads();                                      // the whole CTA is done with this stage
-        cur = nxt;
-        hw_cur = hw_next;
+        cur = nxt; hw_cur = hw_next;
+        nxt = nn; hw_next = hw_nn;
         vote = vote_next;
         list_base = list_base_next;
     }
@@ -911,7 +915,8 @@ residual_sb3_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
 // contiguous chunk ranges balance badly when the coded macroblocks cluster), false with the list-driven persistent
 // residual_sb2_kernel (the default).
 cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
-                                      bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s)
+                                      bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
+                                      cudaEvent_t after_copy)
 {
     static bool attr_done = false;
     const int mc_smem = (int)sizeof(Mc4Smem);
@@ -937,6 +942,7 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
         mc_copy4_kernel<<<ctas, MC4_ROWS * 32, mc_smem, s>>>(g, W, d_jobs, njobs, d_lists, d_counts, d_err, tm_luma, tm_chroma);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        if (after_copy && (e = cudaEventRecord(after_copy, s)) != cudaSuccess) return e;
     }
     if (!listless) {
         uint32_t ctas = P.cta_total * njobs;                  // worst case: every macroblock coded

@@ -59,6 +59,25 @@ pub struct pfv_encode_job {
     pub coeff_out: *mut i16,
 }
 
+/// pfv_decode_job_sparse: what the entropy loops of dec.rs:261-296 / :378-417 produce before the dense scatter
+#[repr(C)]
+pub struct pfv_decode_job_sparse {
+    pub kind: u32,
+    pub flags: u32,
+    pub dst_slot: u32,
+    pub ref_slot: u32,
+    pub qidx: [u8; 3],
+    pub reserved: u8,
+    pub hdr: *const pfv_mbhdr,
+    pub mb_off: *const u32,      // nb + 1 offsets into tok
+    pub tok: *const u32,         // (position << 16) | (value as u16)
+    pub ntok: u32,
+    pub reserved2: u32,
+    pub out_y: *mut u8,
+    pub out_u: *mut u8,
+    pub out_v: *mut u8,
+}
+
 pub enum pfv_ctx {}
 
 pub const PFV_FRAME_I: u32 = 1;
@@ -76,6 +95,9 @@ extern "C" {
     pub fn pfv_slot_reset(ctx: *mut pfv_ctx, slot: u32) -> c_int;
     pub fn pfv_slot_read_visible(ctx: *mut pfv_ctx, slot: u32, y: *mut u8, u: *mut u8, v: *mut u8) -> c_int;
     pub fn pfv_decode_submit(ctx: *mut pfv_ctx, jobs: *const pfv_decode_job, njobs: u32) -> c_int;
+    pub fn pfv_decode_submit_sparse(ctx: *mut pfv_ctx, jobs: *const pfv_decode_job_sparse, njobs: u32) -> c_int;
+    pub fn pfv_ctx_last_submit_id(ctx: *const pfv_ctx) -> u64;
+    pub fn pfv_ctx_wait_submit(ctx: *mut pfv_ctx, submit_id: u64) -> c_int;
     pub fn pfv_encode_submit(ctx: *mut pfv_ctx, jobs: *const pfv_encode_job, njobs: u32) -> c_int;
     pub fn pfv_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn pfv_host_free(p: *mut c_void);
@@ -126,6 +148,21 @@ impl CudaPlanes {
             out_y: std::ptr::null_mut(), out_u: std::ptr::null_mut(), out_v: std::ptr::null_mut(),
         };
         check(unsafe { pfv_decode_submit(self.ctx, &job, 1) })?;
+        self.cur ^= 1;
+        check(unsafe { pfv_sync(self.ctx) })
+    }
+
+    /// Sparse variant of `decode_iframe` / `decode_pframe`: the caller's entropy loop pushes
+    /// `((out_idx & 255) << 16) | (coeff as u16 as u32)` into `tok` and bumps `mb_off[(out_idx >> 8) + 1..]`
+    /// instead of writing `coefficients[out_idx] = coeff` (dec.rs:288, :410); 10-20x fewer bytes cross PCIe.
+    pub fn decode_sparse(&mut self, kind: u32, hdr: &[pfv_mbhdr], mb_off: &[u32], tok: &[u32], qidx: [u8; 3]) -> io::Result<()> {
+        let job = pfv_decode_job_sparse {
+            kind, flags: 0, dst_slot: self.cur ^ 1, ref_slot: self.cur, qidx, reserved: 0,
+            hdr: if kind == PFV_FRAME_P { hdr.as_ptr() } else { std::ptr::null() },
+            mb_off: mb_off.as_ptr(), tok: tok.as_ptr(), ntok: tok.len() as u32, reserved2: 0,
+            out_y: std::ptr::null_mut(), out_u: std::ptr::null_mut(), out_v: std::ptr::null_mut(),
+        };
+        check(unsafe { pfv_decode_submit_sparse(self.ctx, &job, 1) })?;
         self.cur ^= 1;
         check(unsafe { pfv_sync(self.ctx) })
     }
