@@ -34,8 +34,10 @@
 #include <vector>
 
 #include "pfv_internal.h"
+#include "pfv_pool.h"
 
 using pfv::set_error;
+using pfv::Pool;
 
 namespace {
 
@@ -487,46 +489,6 @@ extern "C" int pfv_packet_encode(const pfv_geometry *g, uint32_t kind, const pfv
 // a small fixed pool of host threads
 // ---------------------------------------------------------------------------------------------------
 namespace {
-
-class Pool {
-public:
-    explicit Pool(unsigned n)
-    {
-        if (n == 0) n = 1;
-        for (unsigned i = 0; i < n; i++) th_.emplace_back([this] { run(); });
-    }
-    ~Pool()
-    {
-        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
-        cv_.notify_all();
-        for (auto &t : th_) t.join();
-    }
-    void post(std::function<void()> f)
-    {
-        { std::lock_guard<std::mutex> l(m_); q_.push_back(std::move(f)); }
-        cv_.notify_one();
-    }
-private:
-    void run()
-    {
-        for (;;) {
-            std::function<void()> f;
-            {
-                std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [this] { return stop_ || !q_.empty(); });
-                if (q_.empty()) return;
-                f = std::move(q_.front());
-                q_.pop_front();
-            }
-            f();
-        }
-    }
-    std::mutex m_;
-    std::condition_variable cv_;
-    std::deque<std::function<void()>> q_;
-    std::vector<std::thread> th_;
-    bool stop_ = false;
-};
 
 struct Pinned {
     void  *p = nullptr;

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "pfv_internal.h"
+#include "pfv_pool.h"
 
 using namespace pfv;
 
@@ -157,6 +158,8 @@ struct Stage {
     uint32_t  *d_mboff = nullptr;    // max_jobs * (nb + 1)
     SparseJob *d_sjobs = nullptr;    // max_jobs
     SparseJob *h_sjobs = nullptr;    // pinned mirror
+    uint32_t  *h_tok = nullptr;      // host compaction of dense host buffers: max_jobs * nb * 128 tokens, pinned (lazily allocated)
+    uint32_t  *h_mboff = nullptr;    // max_jobs * (nb + 1), pinned
     cudaEvent_t ev_h2d = nullptr;    // job table + inputs are on the device
     cudaEvent_t ev_kernel = nullptr; // kernels that read/write the stage's device buffers are done
     cudaEvent_t ev_d2h = nullptr;    // copies out of the stage's device buffers are done (encode)
@@ -179,6 +182,11 @@ struct pfv_ctx {
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaStream_t s_aux = nullptr;          // second compute stream: decode-P parts alternate between s_compute and s_aux
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int host_compact = 0;                  // PFV_HOST_COMPACT=1: compact dense host coefficients to tokens on a host pool before the
+                                           // copy.  Off by default: on the bench box (16 host threads) scanning 6.27 MB per 1080p
+                                           // frame cost ~1 ms per frame per thread and halved e2e (7.9 k -> 3.9 k frames/s); hosts
+                                           // that can, hand over tokens directly (pfv_decode_submit_sparse: 13 k frames/s)
+    Pool *pool = nullptr;                  // host threads for the compaction (created on first use)
     int p_split = 1;                       // PFV_DECODE_P_SPLIT: parts a batch of P frames is cut into, alternating between two
                                            // streams.  Measured on B200 (1080p, 32 frames per batch): 1 -> 0.48 of roofline,
                                            // 2 -> 0.43, 4 -> 0.41, 8 -> 0.33: the kernels do not overlap usefully, kept as a knob
@@ -327,6 +335,51 @@ int ensure_sparse_staging(pfv_ctx *c)
     return PFV_OK;
 }
 
+int ensure_compact_staging(pfv_ctx *c)
+{
+    if (c->st[0].h_tok) return PFV_OK;
+    for (int i = 0; i < STAGES; i++) {
+        Stage &s = c->st[i];
+        CU_TRY(cudaHostAlloc(&s.h_tok, (size_t)c->max_jobs * c->geo.nb * 128 * sizeof(uint32_t), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&s.h_mboff, (size_t)c->max_jobs * (c->geo.nb + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+    }
+    if (!c->pool) {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char *v = getenv("PFV_HOST_THREADS")) n = (unsigned)atoi(v);
+        n = n < 1 ? 1 : (n > 16 ? 16 : n);
+        c->pool = new (std::nothrow) Pool(n);
+        if (!c->pool) return fail(PFV_ERR_NOMEM, "out of host memory");
+    }
+    return PFV_OK;
+}
+
+// Dense coefficients of one frame -> the token form of pfv_decode_submit_sparse, on the host.  The dense array the
+// reference hands to the macroblock loops is >90 % zeros on real streams, so scanning it here (32 bytes per test) and
+// sending only the non-zero coefficients over PCIe is several times cheaper than copying it.  Returns the token count,
+// or UINT32_MAX when the frame is too dense for `cap` tokens (then the dense copy is used).
+uint32_t compact_dense(const int16_t *coeff, const pfv_mbhdr *hdr, uint32_t nb, uint32_t *mb_off, uint32_t *tok, uint32_t cap)
+{
+    uint32_t n = 0;
+    mb_off[0] = 0;
+    for (uint32_t m = 0; m < nb; m++) {
+        if (!hdr || hdr[m].has_coeff) {                             // skipped P macroblocks are never read (src/dec.rs:381)
+            if (n + 256 > cap) return UINT32_MAX;
+            const int16_t *c = coeff + (size_t)m * 256;
+            for (uint32_t i = 0; i < 256; i += 16) {
+                uint64_t w[4];
+                memcpy(w, c + i, 32);
+                if ((w[0] | w[1] | w[2] | w[3]) == 0) continue;
+                for (uint32_t k = 0; k < 16; k++) {
+                    const int16_t v = c[i + k];
+                    if (v) tok[n++] = ((i + k) << 16) | (uint32_t)(uint16_t)v;
+                }
+            }
+        }
+        mb_off[m + 1] = n;
+    }
+    return n;
+}
+
 int ensure_src_staging(pfv_ctx *c)
 {
     if (c->st[0].d_src) return PFV_OK;
@@ -364,6 +417,8 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
         cudaFree(s.d_tok); cudaFree(s.d_mboff); cudaFree(s.d_sjobs);
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
         if (s.h_sjobs) cudaFreeHost(s.h_sjobs);
+        if (s.h_tok) cudaFreeHost(s.h_tok);
+        if (s.h_mboff) cudaFreeHost(s.h_mboff);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
@@ -376,6 +431,7 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->s_aux) { cudaStreamSynchronize(c->s_aux); cudaStreamDestroy(c->s_aux); }
+    delete c->pool;
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_compute && c->own_compute) cudaStreamDestroy(c->s_compute);
@@ -405,6 +461,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char *v = getenv("PFV_DECODE_P_SPLIT")) c->p_split = atoi(v) > 0 ? atoi(v) : 1;
+    if (const char *v = getenv("PFV_HOST_COMPACT")) c->host_compact = atoi(v) != 0;
     if (ext_stream) {
         c->s_compute = (cudaStream_t)ext_stream;
         c->own_compute = false;
@@ -684,14 +741,45 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                     return fail(PFV_ERR_BAD_ARG, "jobs %u and %u of one submit are dependent (ref_slot == dst_slot)", i, k);
 
     CU_TRY(cudaSetDevice(c->device));
-    if (any_sparse) {
+    bool any_dense_host = false;
+    if (c->host_compact)
+        for (uint32_t i = 0; i < njobs; i++) any_dense_host |= !jobs[i].sparse && !(jobs[i].flags & PFV_JOB_DEVICE_PTRS);
+    if (any_sparse || any_dense_host) {
         int rc = ensure_sparse_staging(c);
+        if (rc) return rc;
+    }
+    if (any_dense_host) {
+        int rc = ensure_compact_staging(c);
         if (rc) return rc;
     }
     const uint64_t id = ++c->submit_id;
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));     // device buffers of this stage are free again
+
+    // dense HOST coefficients: compact them to tokens on the host pool (the stage's pinned token buffers are free: the
+    // H2D copies that read them were waited for above) and carry on as sparse jobs
+    std::vector<DecIn> compacted;
+    if (any_dense_host) {
+        compacted.assign(jobs, jobs + njobs);
+        const uint32_t cap = g.nb * 128u;
+        std::vector<uint32_t> counts(njobs, UINT32_MAX);
+        parallel_for(*c->pool, njobs, [&](unsigned i) {
+            const DecIn &j = compacted[i];
+            if (j.sparse || (j.flags & PFV_JOB_DEVICE_PTRS)) return;
+            counts[i] = compact_dense(j.coeff, j.kind == PFV_FRAME_P ? j.hdr : nullptr, g.nb,
+                                      st.h_mboff + (size_t)i * (g.nb + 1), st.h_tok + (size_t)i * cap, cap);
+        });
+        for (uint32_t i = 0; i < njobs; i++) {
+            if (counts[i] == UINT32_MAX) continue;              // sparse already, device resident, or too dense: unchanged
+            DecIn &j = compacted[i];
+            j.sparse = true;
+            j.mb_off = st.h_mboff + (size_t)i * (g.nb + 1);
+            j.tok = st.h_tok + (size_t)i * cap;
+            j.ntok = counts[i];
+        }
+        jobs = compacted.data();
+    }
 
     // job table: I jobs first, then P jobs, each kind sorted by q-index triple: jobs that share a triple form
     // one launch (the sub-block kernels take the dequantiser tables as kernel parameters)

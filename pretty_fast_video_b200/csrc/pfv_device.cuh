@@ -189,16 +189,19 @@ __device__ __forceinline__ uint2 pack_row_u8(const int (&y)[8])
     return o;
 }
 
-// src/common.rs:98-104: out = clamp(prev + (d - 128) * 2, 0, 255), d = clamp(y, 0, 255)
+// src/common.rs:98-104: out = clamp(prev + (d - 128) * 2, 0, 255), d = clamp(y, 0, 255).
+// d is clamped and packed four at a time by the saturating pack (I2IP); prev + 2 d - 256 is then two byte dot
+// products per pixel (IDP.4A with one-hot constants picks the byte and scales it) - no per-byte shifts and masks.
 __device__ __forceinline__ uint2 apply_residual_row(const int (&y)[8], uint2 prev)
 {
+    const uint32_t d_lo = pack4_sat_u8(y[0], y[1], y[2], y[3]);
+    const uint32_t d_hi = pack4_sat_u8(y[4], y[5], y[6], y[7]);
     int o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int d = min(max(y[k], 0), 255);
-        const uint32_t pw = (k < 4) ? prev.x : prev.y;
-        const int p = (int)((pw >> (8 * (k & 3))) & 0xffu);
-        o[k] = p + (d - 128) * 2;
+        const uint32_t dw = (k < 4) ? d_lo : d_hi, pw = (k < 4) ? prev.x : prev.y;
+        const uint32_t t = __dp4a(dw, 2u << (8 * (k & 3)), (uint32_t)-256);
+        o[k] = (int)__dp4a(pw, 1u << (8 * (k & 3)), t);
     }
     uint2 r;
     r.x = pack4_sat_u8(o[0], o[1], o[2], o[3]);

@@ -42,6 +42,8 @@ __device__ __forceinline__ void idct8x8_regs(int (&m)[64])
     }
 }
 
+// The two int16 halves of a word are sign-extended by IDP.2A (a 16x8-bit dot product with the constant bytes (1, 0)):
+// it issues on the multiply pipe, where the transform kernels have slack, instead of PRMT/SHF on the ALU pipe.
 __device__ __forceinline__ void unpack_dequant(const uint4 (&raw)[8], const int32_t *deq, int (&m)[64])
 {
     constexpr int zz[64] = PFV_ZIGZAG_INIT;
@@ -49,7 +51,7 @@ __device__ __forceinline__ void unpack_dequant(const uint4 (&raw)[8], const int3
     for (int s = 0; s < 64; ++s) {
         const uint4 &q = raw[s >> 3];
         const uint32_t w = ((s >> 1) & 3) == 0 ? q.x : ((s >> 1) & 3) == 1 ? q.y : ((s >> 1) & 3) == 2 ? q.z : q.w;
-        const int c = (s & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xffffu);
+        const int c = (s & 1) ? __dp2a_hi((int)w, 0x01000000, 0) : __dp2a_lo((int)w, 0x00000001, 0);
         m[zz[s]] = c * deq[s];                               // src/dct.rs:78-83 (tables by scan position)
     }
 }

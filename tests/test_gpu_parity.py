@@ -159,6 +159,38 @@ def test_decode_pframe_long_motion_vectors(pvar, monkeypatch):
         assert np.array_equal(e.slot_read(1), want)
 
 
+@pytest.mark.parametrize("compact", ["0", "1"])
+@pytest.mark.parametrize("mode", ["small", "mixed", "full"])
+def test_host_compaction_of_dense_buffers_is_transparent(compact, mode, monkeypatch):
+    """pfv_decode_submit with dense HOST buffers: the engine may compact them to tokens on the host before the copy
+    (PFV_HOST_COMPACT=1, off by default; too-dense frames go as they are) - same pictures either way."""
+    monkeypatch.setenv("PFV_HOST_COMPACT", compact)
+    w, h = 336, 208
+    rng = np.random.default_rng(5)
+    qt, _ = make_qtables(6)
+    og = pfvo.geometry_for(w, h)
+    jobs_i = [rand_coeffs(rng, og.nb, mode) for _ in range(3)]
+    hdrs = [rand_headers(rng, og) for _ in range(3)]
+    jobs_p = []
+    for hd in hdrs:
+        c = rand_coeffs(rng, og.nb, mode)
+        # garbage in the coefficients of skipped macroblocks must never be read (src/dec.rs:381)
+        c.reshape(-1, 256)[hd[:, 2] == 0] = 12345
+        jobs_p.append(c)
+    with Engine(w, h, qt, nslots=6, max_jobs=3) as e:
+        e.decode_submit([DecodeJob(PFV_FRAME_I, 2 * i, jobs_i[i], (0, 1, 1)) for i in range(3)])
+        e.decode_submit([DecodeJob(PFV_FRAME_P, 2 * i + 1, jobs_p[i], (2, 3, 3), ref_slot=2 * i, hdr=hdrs[i]) for i in range(3)])
+        e.sync()
+        for i in range(3):
+            want = pfvo.frame_init(og)
+            pfvo.decode_iframe_coeffs(og, qt, (0, 1, 1), jobs_i[i], want)
+            assert np.array_equal(e.slot_read(2 * i), want)
+            cz = jobs_p[i].copy()
+            cz.reshape(-1, 256)[hdrs[i][:, 2] == 0] = 0
+            pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdrs[i], cz, want)
+            assert np.array_equal(e.slot_read(2 * i + 1), want)
+
+
 def test_decode_pframe_all_skipped_is_a_copy():
     w, h = 320, 240
     qt, _ = make_qtables(5)
