@@ -281,28 +281,61 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
 
     // src/common.rs:154-204, iteratively.  The centre of each level after the first is the previous
     // level's winner, whose error is already known (the reference recomputes the identical number).
+    //
+    // One pass per level evaluates all 8 neighbours at once: lane = (candidate g = lane >> 2, quarter q = lane & 3),
+    // candidate g in the reference's visiting order (my outer, mx inner, centre skipped, :168-179), the lane owns
+    // macroblock rows q, q+4, q+8, q+12 (16 pixels each).  The 4 partial sums of a candidate meet by two xor-shuffles;
+    // the winner is ONE redux.min over (ssd << 3 | g): the smallest error, and among equal errors the earliest
+    // candidate - exactly what the sequential strict `<` of :189 selects.  Candidates outside the plane (:171,:182)
+    // get the key 0xffffffff.  (The first version looped over the candidates with the whole warp on each one:
+    // ~30 instructions per candidate, 1 300 per macroblock; this is ~100 per level.)
     int cx = bx, cy = by;                                              // current centre, plane coords
     uint32_t best = warp_ssd(s, lds_u8x8_unaligned(win, (uint32_t)(wy0 * WIN_W + wx0)));
+    const int g8 = lane >> 2, q4 = lane & 3;
+    const int mxg = (g8 == 0 || g8 == 3 || g8 == 5) ? -1 : ((g8 == 1 || g8 == 6) ? 0 : 1);
+    const int myg = g8 < 3 ? -1 : (g8 < 5 ? 0 : 1);
+    uint4 srow[4];                                                     // source rows q, q+4, q+8, q+12 out of the (sub-block, row) layout
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int R = q4 + 4 * i;
+        const int l0 = ((R >> 3) * 2) * 8 + (R & 7);                   // lane holding columns 0..7 of row R; +8: columns 8..15
+        srow[i].x = __shfl_sync(FULL, s.x, l0);
+        srow[i].y = __shfl_sync(FULL, s.y, l0);
+        srow[i].z = __shfl_sync(FULL, s.x, l0 + 8);
+        srow[i].w = __shfl_sync(FULL, s.y, l0 + 8);
+    }
 #pragma unroll 1
     for (int step = 8; step >= 1; step >>= 1) {
-        int bdx = 0, bdy = 0;
-#pragma unroll 1
-        for (int my = -1; my <= 1; ++my) {
-            const int oy = cy + my * step;
-            if (oy < 0 || oy > max_y) continue;                        // src/common.rs:171
+        const int ox = cx + mxg * step, oy = cy + myg * step;
+        const bool valid = ox >= 0 && ox <= max_x && oy >= 0 && oy <= max_y;
+        // window offset of row q of the candidate block; invalid candidates still lie inside the (zero-filled) window
+        const uint32_t base = (uint32_t)((15 + q4 + (oy - by)) * WIN_W + 16 + warp * 16 + (ox - bx));
+        const uint32_t sh = (base & 3u) * 8u;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(win + (base & ~3u));
+        uint32_t acc = 0;
 #pragma unroll
-            for (int mx = -1; mx <= 1; ++mx) {
-                if (my == 0 && mx == 0) continue;
-                const int ox = cx + mx * step;
-                if (ox < 0 || ox > max_x) continue;                    // src/common.rs:182
-                const uint32_t off = (uint32_t)((wy0 + (oy - by)) * WIN_W + wx0 + (ox - bx));
-                const uint32_t e = warp_ssd(s, lds_u8x8_unaligned(win, off));
-                if (e < best) {                                        // strict, src/common.rs:189
-                    best = e;
-                    bdx = mx * step;
-                    bdy = my * step;
-                }
-            }
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t *w = wp + i * (4 * WIN_W / 4);
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+            const uint32_t d0 = __vabsdiffu4(srow[i].x, __funnelshift_r(w0, w1, sh));
+            const uint32_t d1 = __vabsdiffu4(srow[i].y, __funnelshift_r(w1, w2, sh));
+            const uint32_t d2 = __vabsdiffu4(srow[i].z, __funnelshift_r(w2, w3, sh));
+            const uint32_t d3 = __vabsdiffu4(srow[i].w, __funnelshift_r(w3, w4, sh));
+            acc = __dp4a(d0, d0, acc);
+            acc = __dp4a(d1, d1, acc);
+            acc = __dp4a(d2, d2, acc);
+            acc = __dp4a(d3, d3, acc);
+        }
+        acc += __shfl_xor_sync(FULL, acc, 1);
+        acc += __shfl_xor_sync(FULL, acc, 2);
+        const uint32_t key = valid ? ((acc << 3) | (uint32_t)g8) : 0xffffffffu;
+        const uint32_t kmin = __reduce_min_sync(FULL, key);
+        int bdx = 0, bdy = 0;
+        if (kmin != 0xffffffffu && (kmin >> 3) < best) {               // strict, src/common.rs:189
+            best = kmin >> 3;
+            const int src_lane = (int)(kmin & 7u) * 4;
+            bdx = __shfl_sync(FULL, mxg, src_lane) * step;
+            bdy = __shfl_sync(FULL, myg, src_lane) * step;
         }
         cx += bdx;
         cy += bdy;
