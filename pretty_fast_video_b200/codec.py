@@ -120,6 +120,10 @@ class Decoder:
         _check_dec(N.lib().pfv_decoder_open(self._buf.ctypes.data, self._buf.size, device, num_threads, read_ahead,
                                             C.byref(self._d)))
         self._w, self._h = self.width(), self.height()
+        self._cache = {}
+        self._got, self._y, self._u, self._v = C.c_int(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._adv = N.lib().pfv_decoder_advance_frame
+        self._args = (self._d, C.byref(self._got), C.byref(self._y), C.byref(self._u), C.byref(self._v))
 
     def width(self) -> int:
         return int(N.lib().pfv_decoder_width(self._d))
@@ -134,18 +138,22 @@ class Decoder:
         _check_dec(N.lib().pfv_decoder_reset(self._d))
 
     def _views(self, y, u, v) -> Frame:
-        w, h = self._w, self._h
-        mk = lambda p, n, shape: np.ctypeslib.as_array((C.c_uint8 * n).from_address(p)).reshape(shape)
-        return (mk(y, w * h, (h, w)), mk(u, (w // 2) * (h // 2), (h // 2, w // 2)), mk(v, (w // 2) * (h // 2), (h // 2, w // 2)))
+        # the decoder hands out pointers into a small ring of pinned pictures: build the numpy views once per buffer
+        fr = self._cache.get(y)
+        if fr is None:
+            w, h = self._w, self._h
+            mk = lambda p, n, shape: np.ctypeslib.as_array((C.c_uint8 * n).from_address(p)).reshape(shape)
+            fr = (mk(y, w * h, (h, w)), mk(u, (w // 2) * (h // 2), (h // 2, w // 2)), mk(v, (w // 2) * (h // 2), (h // 2, w // 2)))
+            self._cache[y] = fr
+        return fr
 
     def advance_frame(self, onvideo: Callable[[Frame], None]) -> bool:
         """Ok(true) / Ok(false) of src/dec.rs:169-224; onvideo gets views valid until the next call."""
-        got = C.c_int()
-        y, u, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        rc = N.lib().pfv_decoder_advance_frame(self._d, C.byref(got), C.byref(y), C.byref(u), C.byref(v))
-        _check_dec(rc)
-        if got.value:
-            onvideo(self._views(y.value, u.value, v.value))
+        rc = self._adv(*self._args)
+        if rc < 0:
+            _check_dec(rc)
+        if self._got.value:
+            onvideo(self._views(self._y.value, self._u.value, self._v.value))
         return rc == 1
 
     def advance_delta(self, delta: float, onvideo: Callable[[Frame], None]) -> bool:
