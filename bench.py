@@ -538,6 +538,31 @@ def run_decoder_stream(torch, dist, budget_s, nthreads):
                              "sample": f"{done} frames of the same stream through the oracle Decoder (entropy + MB loops) in {t_used:.1f} s"}}
 
 
+def run_format_steps(torch, dist, stream, steps):
+    """the colour/format kernels next to the path, device resident: 64 decoded 1080p slots -> packed RGB
+    (save_frame, src/lib.rs:365-395) through pfv_slot_convert_rgb, one launch per picture."""
+    from pretty_fast_video_b200 import Engine, make_qtables
+    w, h, n = 1920, 1080, 64
+    qt, _ = make_qtables(5)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    eng = Engine(w, h, qt, nslots=n, max_jobs=1, device=torch.cuda.current_device(), stream=stream.cuda_stream)
+    fb = eng.geometry.frame_bytes
+    rng = np.random.default_rng(3)
+    for sl in range(n):
+        eng.slot_write(sl, rng.integers(0, 256, fb, dtype=np.uint8))
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+
+    def step():
+        for sl in range(n):
+            eng.slot_convert_rgb(sl, out[sl].data_ptr())
+
+    ms, _ = time_steps(torch, dist, stream, step, eng.sync, steps, 3)
+    eng.close()
+    alg = n * (w * h + 2 * (w // 2) * (h // 2) + w * h * 3)       # planes read once, RGB written once
+    return {"value": n / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "launches_per_step": n,
+            "achieved_gbs": alg / (ms * 1e-3) / 1e9, "note": "yuv420_to_rgb_kernel, one launch per 1080p picture (launch bound)"}
+
+
 # ----------------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py touches oracle/)
 # ----------------------------------------------------------------------------------------------------
@@ -697,11 +722,11 @@ def main():
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
         if args.extras:
             extras = {}
-            for wl in ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p"):
+            for wl in ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p", "decode_p_4k"):
                 if wl == args.workload:
                     continue
                 try:
-                    x = run(wl, max(3, args.steps // 4), 3)
+                    x = run(wl, max(3, args.steps // 4), 3, do_e2e=(wl != "decode_p_4k"))
                     xs = x["st"]
                     extras[wl] = {
                         "value": x["frames"] / (x["max_ms"] * 1e-3), "unit": "frames/s",
@@ -713,10 +738,14 @@ def main():
                         "achieved_gbs": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9,
                         "e2e": x["e2e"],
                     }
-                    cf, cs, _ = cpu_port_leg(wl, min(args.cpu_budget, 6.0), nthreads)
+                    cf, cs, _ = cpu_port_leg(wl, min(args.cpu_budget, 3.0 if wl == "decode_p_4k" else 6.0), nthreads)
                     extras[wl]["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": cs}
                 except Exception as ex:                      # an extra must never lose the headline line
                     extras[wl] = {"error": repr(ex)}
+            try:
+                extras["rgb_out_1080p"] = run_format_steps(torch, dist, stream, max(3, args.steps // 4))
+            except Exception as ex:
+                extras["rgb_out_1080p"] = {"error": repr(ex)}
             try:
                 extras["decoder_stream_1080p"] = run_decoder_stream(torch, dist, min(args.cpu_budget, 6.0), nthreads)
             except Exception as ex:

@@ -75,8 +75,12 @@ enum { PFV_FRAME_I = 1, PFV_FRAME_P = 2 };
 
 /* job.flags */
 enum {
-    PFV_JOB_DEVICE_PTRS = 1u   /* hdr/coeff/src pointers are DEVICE pointers already resident in HBM
+    PFV_JOB_DEVICE_PTRS = 1u,  /* hdr/coeff/src pointers are DEVICE pointers already resident in HBM
                                   (no H2D is issued; out pointers, if non-NULL, are still host)       */
+    PFV_JOB_SRC_RGB = 2u       /* encode jobs: src_y points at packed RGB8 (w*h*3 bytes), src_u/src_v are
+                                  ignored; the engine converts on the device exactly like the reference's
+                                  load_frame + VideoFrame::from_planes (src/lib.rs:337-363, src/frame.rs:51-60,
+                                  reduce src/common.rs:523-536)                                        */
 };
 
 /*
@@ -158,6 +162,13 @@ int  pfv_slot_write(pfv_ctx *ctx, uint32_t slot, const uint8_t *frame_in);
 int  pfv_slot_read_visible(pfv_ctx *ctx, uint32_t slot, uint8_t *y, uint8_t *u, uint8_t *v);
 /* device address of a slot's padded frame, for consumers that keep frames on the GPU                        */
 int  pfv_slot_device_ptr(pfv_ctx *ctx, uint32_t slot, void **out);
+/* Colour / format steps next to the path: the visible crop of a slot (src/dec.rs:195-197) as packed
+ * RGB8, w*h*3 bytes, converted on the device exactly like the reference's save_frame (src/lib.rs:365-395: chroma
+ * `double`d, src/common.rs:538-556; JPEG YCbCr in f32; `as u8`).  pfv_slot_read_rgb copies it to host memory
+ * (asynchronous, D2H stream, like pfv_slot_read_visible); pfv_slot_convert_rgb leaves it in device memory the caller
+ * owns ("decode straight into a game-ready texture", README.md:20), ordered on the compute stream. */
+int  pfv_slot_read_rgb(pfv_ctx *ctx, uint32_t slot, uint8_t *rgb_host);
+int  pfv_slot_convert_rgb(pfv_ctx *ctx, uint32_t slot, void *rgb_device);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Jobs of one call must be independent (no job's ref_slot is another job's dst_slot); calls are

@@ -594,6 +594,69 @@ void pfvo_crop_frame(const pfvo_geometry *g, const uint8_t *frame, uint8_t *y, u
 }
 
 /* ------------------------------------------------------------------------------------
+ * colour / format helpers next to the path
+ * ---------------------------------------------------------------------------------- */
+/* Rust `f as u8`: truncation toward zero, saturating, NaN -> 0. */
+static uint8_t f32_as_u8(float f)
+{
+    if (!(f > 0.0f)) return 0;
+    if (f >= 255.0f) return 255;
+    return (uint8_t)(int)f;
+}
+
+/* common.rs:523-536 */
+void pfvo_plane_reduce(const uint8_t *src, int w, int h, uint8_t *dst)
+{
+    const int nw = w / 2, nh = h / 2;
+    for (int iy = 0; iy < nh; iy++)
+        for (int ix = 0; ix < nw; ix++) dst[ix + iy * nw] = src[ix * 2 + (iy * 2) * w];
+}
+
+/* common.rs:538-556 */
+void pfvo_plane_double(const uint8_t *src, int w, int h, uint8_t *dst)
+{
+    const int nw = w * 2;
+    for (int iy = 0; iy < h; iy++)
+        for (int ix = 0; ix < w; ix++) {
+            const uint8_t px = src[ix + iy * w];
+            const int d = ix * 2 + (iy * 2) * nw;
+            dst[d] = px; dst[d + 1] = px; dst[d + nw] = px; dst[d + nw + 1] = px;
+        }
+}
+
+/* lib.rs:337-363 load_frame (f32, evaluated left to right, `as u8`) + frame.rs:51-60 from_planes (reduce) */
+void pfvo_rgb_to_yuv420(const uint8_t *rgb, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    uint8_t *uf = (uint8_t *)malloc((size_t)w * h), *vf = (uint8_t *)malloc((size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const float r = (float)rgb[3 * i], g = (float)rgb[3 * i + 1], b = (float)rgb[3 * i + 2];
+        const float fy = (0.299f * r) + (0.587f * g) + (0.114f * b);
+        const float fu = 128.0f - (0.168736f * r) - (0.331264f * g) + (0.5f * b);
+        const float fv = 128.0f + (0.5f * r) - (0.418688f * g) - (0.081312f * b);
+        y[i] = f32_as_u8(fy); uf[i] = f32_as_u8(fu); vf[i] = f32_as_u8(fv);
+    }
+    pfvo_plane_reduce(uf, w, h, u);
+    pfvo_plane_reduce(vf, w, h, v);
+    free(uf); free(vf);
+}
+
+/* lib.rs:365-395 save_frame: double() the chroma planes, f32 conversion, `as u8` */
+void pfvo_yuv420_to_rgb(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h, uint8_t *rgb)
+{
+    uint8_t *uf = (uint8_t *)malloc((size_t)w * h), *vf = (uint8_t *)malloc((size_t)w * h);
+    pfvo_plane_double(u, w / 2, h / 2, uf);
+    pfvo_plane_double(v, w / 2, h / 2, vf);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const float fy = (float)y[i], fu = (float)uf[i] - 128.0f, fv = (float)vf[i] - 128.0f;
+        const float r = fy + (1.402f * fv);
+        const float g = fy - (0.344136f * fu) - (0.714136f * fv);
+        const float b = fy + (1.772f * fu);
+        rgb[3 * i] = f32_as_u8(r); rgb[3 * i + 1] = f32_as_u8(g); rgb[3 * i + 2] = f32_as_u8(b);
+    }
+    free(uf); free(vf);
+}
+
+/* ------------------------------------------------------------------------------------
  * growable byte buffer + LSB-first bit writer/reader
  * (bitstream-io 1.6.0 LittleEndian semantics as used at the call sites in SURVEY §8c)
  * ---------------------------------------------------------------------------------- */

@@ -113,6 +113,13 @@ void   pfvo_encode_pframe_coeffs(const pfvo_geometry *g, const int32_t (*qtables
 /* dec.rs:195-197: crop the padded state into tight planes. */
 void   pfvo_crop_frame(const pfvo_geometry *g, const uint8_t *frame, uint8_t *y, uint8_t *u, uint8_t *v);
 
+/* --- colour / format helpers next to the path ------------------------ */
+void pfvo_plane_reduce(const uint8_t *src, int w, int h, uint8_t *dst);                       /* common.rs:523-536 */
+void pfvo_plane_double(const uint8_t *src, int w, int h, uint8_t *dst);                       /* common.rs:538-556 */
+/* rgb: packed w*h*3; y: w*h; u,v: (w/2)*(h/2) */
+void pfvo_rgb_to_yuv420(const uint8_t *rgb, int w, int h, uint8_t *y, uint8_t *u, uint8_t *v);   /* lib.rs:337-363 + frame.rs:51-60 */
+void pfvo_yuv420_to_rgb(const uint8_t *y, const uint8_t *u, const uint8_t *v, int w, int h, uint8_t *rgb);   /* lib.rs:365-395 */
+
 /* --- entropy layer (rle.rs, huffman.rs) and container (enc.rs:190-481, dec.rs) ----- */
 typedef struct pfvo_encoder pfvo_encoder;
 typedef struct pfvo_decoder pfvo_decoder;

@@ -177,3 +177,31 @@ def block_search(src, ref, rw, rh, cx, cy, step):  # common.rs:154-204; src = 25
         dx2, dy2, e2 = block_search(src, ref, rw, rh, cx + best_dx, cy + best_dy, step // 2)
         return best_dx + dx2, best_dy + dy2, e2
     return best_dx, best_dy, best
+
+
+# --- colour / format helpers; numpy float32 keeps the reference's f32 evaluation order -------------
+def f32_as_u8(f):  # Rust `as u8`: truncation toward zero, saturating
+    import numpy as np
+    return np.clip(np.trunc(f), 0, 255).astype(np.uint8)
+
+
+def rgb_to_yuv420(rgb):  # lib.rs:337-363 + frame.rs:51-60 (reduce: common.rs:523-536); rgb = uint8[h, w, 3]
+    import numpy as np
+    f = np.float32
+    r, g, b = (rgb[..., i].astype(f) for i in range(3))
+    y = (f(0.299) * r) + (f(0.587) * g) + (f(0.114) * b)
+    u = f(128.0) - (f(0.168736) * r) - (f(0.331264) * g) + (f(0.5) * b)
+    v = f(128.0) + (f(0.5) * r) - (f(0.418688) * g) - (f(0.081312) * b)
+    return f32_as_u8(y), f32_as_u8(u)[::2, ::2].copy(), f32_as_u8(v)[::2, ::2].copy()
+
+
+def yuv420_to_rgb(y, u, v):  # lib.rs:365-395 (double: common.rs:538-556)
+    import numpy as np
+    f = np.float32
+    uf = np.repeat(np.repeat(u, 2, 0), 2, 1).astype(f) - f(128.0)
+    vf = np.repeat(np.repeat(v, 2, 0), 2, 1).astype(f) - f(128.0)
+    fy = y.astype(f)
+    r = fy + (f(1.402) * vf)
+    g = fy - (f(0.344136) * uf) - (f(0.714136) * vf)
+    b = fy + (f(1.772) * uf)
+    return np.stack([f32_as_u8(r), f32_as_u8(g), f32_as_u8(b)], -1)

@@ -26,6 +26,7 @@ PFV_ERR_STATE = -9
 PFV_FRAME_I = 1
 PFV_FRAME_P = 2
 PFV_JOB_DEVICE_PTRS = 1
+PFV_JOB_SRC_RGB = 2
 
 
 class PfvError(RuntimeError):
@@ -102,6 +103,8 @@ SYMBOLS = {
     "pfv_slot_write": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "pfv_slot_read_visible": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfv_slot_device_ptr": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "pfv_slot_read_rgb": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "pfv_slot_convert_rgb": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "pfv_decode_submit": (C.c_int, [C.c_void_p, C.POINTER(DecodeJob), C.c_uint32]),
     "pfv_encode_submit": (C.c_int, [C.c_void_p, C.POINTER(EncodeJob), C.c_uint32]),
     "pfv_decode_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(DecodeJobSparse), C.c_uint32]),

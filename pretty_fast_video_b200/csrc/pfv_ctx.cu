@@ -158,6 +158,7 @@ struct Stage {
     uint32_t  *d_mboff = nullptr;    // max_jobs * (nb + 1)
     SparseJob *d_sjobs = nullptr;    // max_jobs
     SparseJob *h_sjobs = nullptr;    // pinned mirror
+    uint8_t   *d_rgb_src = nullptr;  // encode jobs with PFV_JOB_SRC_RGB: max_jobs * w*h*3 (lazily allocated)
     uint32_t  *h_tok = nullptr;      // host compaction of dense host buffers: max_jobs * nb * 128 tokens, pinned (lazily allocated)
     uint32_t  *h_mboff = nullptr;    // max_jobs * (nb + 1), pinned
     cudaEvent_t ev_h2d = nullptr;    // job table + inputs are on the device
@@ -182,6 +183,8 @@ struct pfv_ctx {
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaStream_t s_aux = nullptr;          // second compute stream: decode-P parts alternate between s_compute and s_aux
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint8_t *d_rgb = nullptr;              // pfv_slot_read_rgb: device staging of one packed RGB picture (lazily allocated)
+    cudaEvent_t ev_rgb = nullptr;          // the last D2H copy out of d_rgb
     int host_compact = 0;                  // PFV_HOST_COMPACT=1: compact dense host coefficients to tokens on a host pool before the
                                            // copy.  Off by default: on the bench box (16 host threads) scanning 6.27 MB per 1080p
                                            // frame cost ~1 ms per frame per thread and halved e2e (7.9 k -> 3.9 k frames/s); hosts
@@ -414,7 +417,7 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     for (int i = 0; i < STAGES; i++) {
         Stage &s = c->st[i];
         cudaFree(s.d_coeff); cudaFree(s.d_hdr); cudaFree(s.d_src); cudaFree(s.d_jobs);
-        cudaFree(s.d_tok); cudaFree(s.d_mboff); cudaFree(s.d_sjobs);
+        cudaFree(s.d_tok); cudaFree(s.d_mboff); cudaFree(s.d_sjobs); cudaFree(s.d_rgb_src);
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
         if (s.h_sjobs) cudaFreeHost(s.h_sjobs);
         if (s.h_tok) cudaFreeHost(s.h_tok);
@@ -432,6 +435,8 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->s_aux) { cudaStreamSynchronize(c->s_aux); cudaStreamDestroy(c->s_aux); }
     delete c->pool;
+    cudaFree(c->d_rgb);
+    if (c->ev_rgb) cudaEventDestroy(c->ev_rgb);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_compute && c->own_compute) cudaStreamDestroy(c->s_compute);
@@ -678,6 +683,46 @@ extern "C" int pfv_slot_read_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint
     if (rc) return rc;
     CU_TRY(cudaEventRecord(ev, c->s_d2h));
     c->slot_last_d2h[slot] = id;
+    return PFV_OK;
+}
+
+// save_frame (src/lib.rs:365-395) of a slot's visible crop, on stream s, into device memory
+static int convert_rgb(pfv_ctx *c, uint32_t slot, uint8_t *d_out, cudaStream_t s)
+{
+    const pfv_geometry &g = c->geo;
+    const uint8_t *base = slot_ptr(c, slot);
+    const size_t ny = (size_t)g.pw * g.ph, nc = (size_t)g.cpw * g.cph;
+    CU_TRY(launch_yuv420_to_rgb(base, base + ny, base + ny + nc, g.width, g.height, g.pw, g.cpw, d_out, s));
+    c->launches++;
+    return PFV_OK;
+}
+
+extern "C" int pfv_slot_convert_rgb(pfv_ctx *c, uint32_t slot, void *rgb_device)
+{
+    if (!c || slot >= c->nslots || !rgb_device) return fail(PFV_ERR_BAD_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(c->device));
+    return convert_rgb(c, slot, static_cast<uint8_t *>(rgb_device), c->s_compute);
+}
+
+extern "C" int pfv_slot_read_rgb(pfv_ctx *c, uint32_t slot, uint8_t *rgb_host)
+{
+    if (!c || slot >= c->nslots || !rgb_host) return fail(PFV_ERR_BAD_ARG, "bad argument");
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->geo.width * c->geo.height * 3;
+    if (!c->d_rgb) {
+        CU_TRY(cudaMalloc(&c->d_rgb, bytes));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_rgb, cudaEventDisableTiming));
+    }
+    const uint64_t id = ++c->submit_id;
+    cudaEvent_t ev = c->ev_d2h_ring[id % D2H_RING];
+    CU_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_rgb, 0));    // the previous picture has left the staging buffer
+    int rc = convert_rgb(c, slot, c->d_rgb, c->s_compute);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(ev, c->s_compute));
+    CU_TRY(cudaStreamWaitEvent(c->s_d2h, ev, 0));
+    CU_TRY(cudaMemcpyAsync(rgb_host, c->d_rgb, bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+    CU_TRY(cudaEventRecord(c->ev_rgb, c->s_d2h));
+    CU_TRY(cudaEventRecord(ev, c->s_d2h));
     return PFV_OK;
 }
 
@@ -1028,12 +1073,14 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
     if (njobs > c->max_jobs) return fail(PFV_ERR_BAD_ARG, "%u jobs > max_jobs %u", njobs, c->max_jobs);
     if (c->nq < 4) return fail(PFV_ERR_BAD_ARG, "an encoder context needs the 4 q-tables of src/enc.rs:48-51");
     const pfv_geometry &g = c->geo;
-    bool any_p = false;
+    bool any_p = false, any_rgb = false;
     for (uint32_t i = 0; i < njobs; i++) {
         const pfv_encode_job &j = jobs[i];
         if (j.kind != PFV_FRAME_I && j.kind != PFV_FRAME_P) return fail(PFV_ERR_BAD_ARG, "job %u: bad kind %u", i, j.kind);
         if (j.dst_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: dst_slot %u out of range", i, j.dst_slot);
-        if (!j.src_y || !j.src_u || !j.src_v || !j.coeff_out) return fail(PFV_ERR_BAD_ARG, "job %u: NULL plane or coeff_out", i);
+        const bool rgb = (j.flags & PFV_JOB_SRC_RGB) != 0;
+        any_rgb |= rgb;
+        if (!j.src_y || (!rgb && (!j.src_u || !j.src_v)) || !j.coeff_out) return fail(PFV_ERR_BAD_ARG, "job %u: NULL plane or coeff_out", i);
         if (j.kind == PFV_FRAME_P) {
             any_p = true;
             if (j.ref_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: ref_slot %u out of range", i, j.ref_slot);
@@ -1055,12 +1102,17 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
         int rc = ensure_src_staging(c);
         if (rc) return rc;
     }
+    const size_t rgb_bytes = (size_t)g.width * g.height * 3;
+    if (any_rgb && !c->st[0].d_rgb_src)
+        for (int i = 0; i < STAGES; i++) CU_TRY(cudaMalloc(&c->st[i].d_rgb_src, rgb_bytes * c->max_jobs));
     const uint64_t id = ++c->submit_id;
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));
 
     EncJob *tab = static_cast<EncJob *>(st.h_jobs);
+    struct RgbConv { const uint8_t *rgb; uint8_t *planes; };
+    std::vector<RgbConv> conv;
     std::vector<uint32_t> order;
     order.reserve(njobs);
     uint32_t n_i = 0;
@@ -1073,7 +1125,20 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
         const pfv_encode_job &j = jobs[order[k]];
         EncJob &d = tab[k];
         const bool dev = (j.flags & PFV_JOB_DEVICE_PTRS) != 0;
-        if (dev) {
+        if (j.flags & PFV_JOB_SRC_RGB) {
+            // load_frame + from_planes on the device: RGB in (host: copied; device: used in place), tight planes out
+            uint8_t *s = st.d_src + (size_t)k * c->src_stride;
+            const uint8_t *d_rgb = j.src_y;
+            if (!dev) {
+                uint8_t *stage_rgb = st.d_rgb_src + (size_t)k * rgb_bytes;
+                CU_TRY(cudaMemcpyAsync(stage_rgb, j.src_y, rgb_bytes, cudaMemcpyHostToDevice, c->s_h2d));
+                d_rgb = stage_rgb;
+            }
+            conv.push_back({d_rgb, s});
+            for (int p = 0; p < 3; p++) d.src[p] = s + c->src_off[p];
+            if (dev) { d.coeff = j.coeff_out; d.hdr = j.hdr_out; }
+            else { d.coeff = st.d_coeff + (size_t)k * coeff_elems; d.hdr = st.d_hdr + (size_t)k * g.nb; }
+        } else if (dev) {
             d.src[0] = j.src_y; d.src[1] = j.src_u; d.src[2] = j.src_v;
             d.coeff = j.coeff_out;
             d.hdr = j.hdr_out;
@@ -1109,6 +1174,11 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
         if (rc) return rc;
     }
     CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
+    for (const RgbConv &rc : conv) {
+        CU_TRY(launch_rgb_to_yuv420(rc.rgb, g.width, g.height, rc.planes + c->src_off[0], rc.planes + c->src_off[1],
+                                    rc.planes + c->src_off[2], c->s_compute));
+        c->launches++;
+    }
     const EncJob *d_tab = static_cast<const EncJob *>(st.d_jobs);
     if (n_i) { CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, c->s_compute)); c->launches++; }
     if (njobs - n_i) {

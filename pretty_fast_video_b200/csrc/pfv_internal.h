@@ -110,6 +110,9 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);
+cudaError_t launch_rgb_to_yuv420(const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, cudaStream_t s);
+cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, uint32_t w, uint32_t h, uint32_t pw,
+                                 uint32_t cpw, uint8_t *d_rgb, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, cudaStream_t s);
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,

@@ -105,12 +105,13 @@ class SparseDecodeJob:
 class EncodeJob:
     kind: int
     dst_slot: int
-    src: Sequence[Buf]             # (y, u, v) tight planes
+    src: Optional[Sequence[Buf]]   # (y, u, v) tight planes, or None when `rgb` is given
     coeff_out: Buf
     ref_slot: int = 0
     px_err: float = 0.0
     hdr_out: Buf = None
     device_ptrs: bool = False
+    rgb: Buf = None                # packed RGB8 [h, w, 3] source: converted on the device (PFV_JOB_SRC_RGB)
 
 
 class Engine:
@@ -165,7 +166,11 @@ class Engine:
             a.kind, a.dst_slot, a.ref_slot = j.kind, j.dst_slot, j.ref_slot
             a.flags = N.PFV_JOB_DEVICE_PTRS if j.device_ptrs else 0
             a.px_err = j.px_err
-            a.src_y, a.src_u, a.src_v = (_addr(b) for b in j.src)
+            if j.rgb is not None:
+                a.flags |= N.PFV_JOB_SRC_RGB
+                a.src_y = _addr(j.rgb)
+            else:
+                a.src_y, a.src_u, a.src_v = (_addr(b) for b in j.src)
             a.hdr_out, a.coeff_out = _addr(j.hdr_out), _addr(j.coeff_out)
         return arr
 
@@ -226,6 +231,17 @@ class Engine:
         N.check(N.lib().pfv_slot_read_visible(self._ctx, slot, y.ctypes.data, u.ctypes.data, v.ctypes.data))
         self.sync()
         return y, u, v
+
+    def slot_read_rgb(self, slot: int) -> np.ndarray:
+        """Visible crop of a slot as packed RGB8 [h, w, 3], converted on the device (save_frame, src/lib.rs:365-395)."""
+        g = self.geometry
+        rgb = np.empty((g.height, g.width, 3), np.uint8)
+        N.check(N.lib().pfv_slot_read_rgb(self._ctx, slot, rgb.ctypes.data))
+        self.sync()
+        return rgb
+
+    def slot_convert_rgb(self, slot: int, device_ptr: int):
+        N.check(N.lib().pfv_slot_convert_rgb(self._ctx, slot, device_ptr))
 
     def slot_device_ptr(self, slot: int) -> int:
         p = C.c_void_p()

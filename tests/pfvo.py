@@ -147,6 +147,21 @@ def crop_frame(g, frame):
     return y, u, v
 
 
+def rgb_to_yuv420(rgb):
+    h, w, _ = rgb.shape
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    y = np.zeros((h, w), np.uint8); u = np.zeros((h // 2, w // 2), np.uint8); v = np.zeros((h // 2, w // 2), np.uint8)
+    lib().pfvo_rgb_to_yuv420(_p(rgb), w, h, _p(y), _p(u), _p(v))
+    return y, u, v
+
+
+def yuv420_to_rgb(y, u, v):
+    h, w = y.shape
+    rgb = np.zeros((h, w, 3), np.uint8)
+    lib().pfvo_yuv420_to_rgb(_p(np.ascontiguousarray(y)), _p(np.ascontiguousarray(u)), _p(np.ascontiguousarray(v)), w, h, _p(rgb))
+    return rgb
+
+
 class Encoder:
     """pfv_rs::enc::Encoder restated (oracle)."""
 
