@@ -334,18 +334,41 @@ residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
     const uint32_t total = pre[nl];
     const int sb = (int)(threadIdx.x & 3u);
 
-#pragma unroll 1
-    for (uint32_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    // chunk -> (frame, plane, list entry of this thread); ok = the entry exists
+    struct Loc { uint32_t j, p, e; bool ok; };
+    auto locate = [&](uint32_t chunk) {
+        Loc r = {0u, 0u, 0u, false};
+        if (chunk >= total) return r;
         uint32_t lo = 0, hi = nl;                             // largest i with pre[i] <= chunk
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (pre[mid] <= chunk) lo = mid; else hi = mid;
         }
-        const uint32_t j = lo / 3u, p = lo - j * 3u;
+        r.j = lo / 3u; r.p = lo - r.j * 3u;
+        r.e = (chunk - pre[lo]) * SB_MBS_PER_CTA + (threadIdx.x >> 2);
+        r.ok = r.e < counts[r.j * 4u + r.p];
+        return r;
+    };
+    auto list_entry = [&](const Loc &l) -> uint32_t {
+        const PlaneGeom &pl = l.p == 0 ? P.g.pl[0] : (l.p == 1 ? P.g.pl[1] : P.g.pl[2]);
+        return l.ok ? lists[(size_t)l.j * P.g.nb + pl.mb_base + l.e] : 0u;
+    };
+    // Software pipeline: the list entry of the NEXT chunk is loaded while this one is transformed, and its
+    // coefficient line is prefetched into L2 as soon as the entry is known, so the next iteration's loads find
+    // their data on chip (ncu: this kernel spent a third of its time on exposed DRAM latency at 10 warps per SM).
+    Loc cur = locate(blockIdx.x);
+    uint32_t lm_cur = list_entry(cur);
+#pragma unroll 1
+    for (uint32_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        const Loc nxt = locate(chunk + gridDim.x);
+        const uint32_t lm_next = list_entry(nxt);
+        const Loc here = cur;
+        const uint32_t lm = lm_cur;
+        cur = nxt;
+        lm_cur = lm_next;
+        if (!here.ok) continue;
+        const uint32_t j = here.j, p = here.p;
         const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
-        const uint32_t e = (chunk - pre[lo]) * SB_MBS_PER_CTA + (threadIdx.x >> 2);
-        if (e >= counts[j * 4u + p]) continue;
-        const uint32_t lm = lists[(size_t)j * P.g.nb + pl.mb_base + e];
         const DecJob &job = jobs[j];
         const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
 
@@ -364,6 +387,11 @@ residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
         ac |= raw[0].y | raw[0].z | raw[0].w;
 #pragma unroll
         for (int k = 1; k < 8; ++k) ac |= raw[k].x | raw[k].y | raw[k].z | raw[k].w;
+        if (nxt.ok) {
+            const PlaneGeom &pn = nxt.p == 0 ? P.g.pl[0] : (nxt.p == 1 ? P.g.pl[1] : P.g.pl[2]);
+            const void *nsrc = jobs[nxt.j].coeff + ((size_t)(pn.mb_base + lm_next) * 256 + sb * 64);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc));
+        }
         if (ac == 0u) {
             // DC only: both IDCT passes collapse to the DC term (see pfv_sb.cuh), one clamped delta for the sub-block
             const int c0 = (int)(int16_t)(raw[0].x & 0xffffu);
@@ -657,9 +685,11 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
 
     struct Item { uint32_t job, p, gy, tx; };
     auto decode_item = [&](uint32_t it) {
+        // frame-interleaved order: CTAs that run at the same time work on DIFFERENT frames, so their list-count atomics
+        // hit njobs * 3 different addresses instead of the same handful
         Item r;
-        r.job = it / W.total;
-        const uint32_t wi = it - r.job * W.total;
+        const uint32_t wi = it / njobs;
+        r.job = it - wi * njobs;
         r.p = (wi >= W.base[1] ? 1u : 0u) + (wi >= W.base[2] ? 1u : 0u);
         const uint32_t li = wi - (r.p == 0 ? W.base[0] : (r.p == 1 ? W.base[1] : W.base[2]));
         const uint32_t txs = r.p == 0 ? W.tiles_x[0] : (r.p == 1 ? W.tiles_x[1] : W.tiles_x[2]);
