@@ -515,6 +515,17 @@ def run_decoder_stream(torch, dist, budget_s, nthreads):
     one_pass()
     times = [one_pass() for _ in range(3)]
     gpu_fps = nfr / min(times)
+    # the mirror image: Encoder.encode_iframe / encode_pframe over the same source frames -> .pfv bytes
+    def enc_pass(n):
+        with codec.Encoder(w, h, 30, 5, num_threads=nthreads, device=torch.cuda.current_device()) as enc:
+            t0 = time.perf_counter()
+            for t in range(n):
+                (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(src[t % gop + ((t // gop) % 4) * 3])
+            enc.finish()
+            enc.bytes()
+            return time.perf_counter() - t0
+    enc_pass(gop)
+    enc_fps = 4 * gop / min(enc_pass(4 * gop) for _ in range(2))
     # the oracle's Decoder on the same bytes (entropy + MB loops, nthreads OpenMP threads for the MB loops)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import pfvo
@@ -531,7 +542,22 @@ def run_decoder_stream(torch, dist, budget_s, nthreads):
         t_used += time.perf_counter() - t0
         done += k
         dec.close()
+    og = pfvo.geometry_for(w, h)
+    e_done, e_used = 0, 0.0
+    while e_used < budget_s / 2:
+        oenc = pfvo.Encoder(w, h, 30, 5, nthreads=nthreads)
+        t0 = time.perf_counter()
+        for t in range(6):
+            y_, u_, v_ = src[t]
+            (oenc.encode_iframe if t == 0 else oenc.encode_pframe)(y_, u_, v_)
+        e_used += time.perf_counter() - t0
+        e_done += 6
+        oenc.close()
     return {"value": gpu_fps, "unit": "frames/s", "frames": nfr, "stream_bytes": len(data), "host_threads": nthreads,
+            "encoder": {"value": enc_fps, "unit": "frames/s", "note": "Encoder.encode_iframe/encode_pframe (1 key frame / 15) to .pfv bytes: "
+                        "planes H2D, kernels (full block search), coefficients D2H, entropy coding on the host pool",
+                        "cpu_baseline": {"value": e_done / e_used, "unit": "frames/s", "cores": nthreads, "kind": "port",
+                                         "sample": f"{e_done} frames (1 key + 5 P) through the oracle Encoder in {e_used:.1f} s"}},
             "note": "Decoder.advance_frame over an in-memory 1920x1080 .pfv (1 key frame / 15): entropy decode on the host pool, "
                     "sparse tokens H2D, kernels, pictures D2H",
             "cpu_baseline": {"value": done / t_used, "unit": "frames/s", "cores": nthreads, "kind": "port",
