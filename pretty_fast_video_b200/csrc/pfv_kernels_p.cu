@@ -312,7 +312,7 @@ mc_copy2_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McT
 }
 
 #ifndef RS2_CTAS_PER_SM
-#define RS2_CTAS_PER_SM 3    // 4 (128 registers, predictor fetched after the transform) measured slower: 37 vs 28 us
+#define RS2_CTAS_PER_SM 4    // 3 -> 4 (128 registers, no spills): 25.4 -> 24.3 us per 32 frames
 #endif
 // Persistent residual kernel: chunk = 32 consecutive entries of one (frame, plane) list; CTA c takes chunks
 // c, c + gridDim.x, ...  The chunk table (prefix over njobs * 3 lists) is rebuilt by every CTA from the counts.
@@ -392,20 +392,11 @@ residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
             const void *nsrc = jobs[nxt.j].coeff + ((size_t)(pn.mb_base + lm_next) * 256 + sb * 64);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc));
         }
-        if (ac == 0u) {
-            // DC only: both IDCT passes collapse to the DC term (see pfv_sb.cuh), one clamped delta for the sub-block
-            const int c0 = (int)(int16_t)(raw[0].x & 0xffffu);
-            if (c0 == 0) continue;                            // d = 128, delta = 0: the predictor stands
-            const int v = (c0 * deq[0] + (128 << 8)) >> 8;
-            const int delta = (min(max(v, 0), 255) - 128) * 2;    // src/common.rs:101
-            const uint32_t pos4 = (uint32_t)max(delta, 0) * 0x01010101u;
-            const uint32_t neg4 = (uint32_t)min(max(-delta, 0), 255) * 0x01010101u;
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw),
-                       make_uint2(add_delta_sat4(prev[r].x, pos4, neg4), add_delta_sat4(prev[r].y, pos4, neg4)));
-            continue;
-        }
+        // A sub-block without AC terms would collapse to one clamped delta (see pfv_sb.cuh), but its lane sits in a warp
+        // whose other lanes run the full transform anyway (ncu: the 267-instruction shortcut was taken by ~2 lanes in 75 %
+        // of the warp passes = 11 % of all issue slots for nothing).  Only a warp with no AC terms at all, and a lane with
+        // nothing to add, leave early; the transform of a DC-only block gives the same pixels.
+        if (__ballot_sync(__activemask(), ac != 0u) == 0u && (raw[0].x & 0xffffu) == 0u) continue;
         int m[64];
         unpack_dequant(raw, deq, m);
         idct8x8_regs(m);
