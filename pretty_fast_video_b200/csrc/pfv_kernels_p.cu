@@ -23,6 +23,9 @@
 
 namespace pfv {
 
+static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, const uint32_t *d_lists,
+                                   const uint32_t *d_counts, cudaStream_t s);
+
 constexpr int MC_WARPS = 8;
 
 // lane = (macroblock of the tile) * 4 + row group; a lane moves rows rg, rg+4, rg+8, rg+12 of its macroblock, so
@@ -965,12 +968,7 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
         if (e != cudaSuccess) return e;
         if (after_copy && (e = cudaEventRecord(after_copy, s)) != cudaSuccess) return e;
     }
-    if (!listless) {
-        uint32_t ctas = P.cta_total * njobs;                  // worst case: every macroblock coded
-        if (ctas > 148u * RS2_CTAS_PER_SM) ctas = 148u * RS2_CTAS_PER_SM;
-        residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts);
-        return cudaGetLastError();
-    }
+    if (!listless) return launch_residual(P, d_jobs, njobs, d_lists, d_counts, s);
     uint32_t cpf = 0;
     for (int p = 0; p < 3; p++) cpf += (g.pl[p].bw * g.pl[p].bh + RS3_CHUNK - 1) / RS3_CHUNK;
     const uint32_t total = cpf * njobs;
@@ -978,6 +976,143 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
     const uint32_t per_cta = (total + resident - 1) / resident;
     const uint32_t ctas = (total + per_cta - 1) / per_cta;
     residual_sb3_kernel<<<ctas, SB_THREADS, 0, s>>>(P, d_jobs, njobs, per_cta);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------
+// residual pass with sub-block compaction (PFV_RESIDUAL_VARIANT=4; NOT the default: measured 27.4 us against 22.4 us
+// for residual_sb2_kernel per 32 frames - the shared-memory round trip and the three CTA barriers per step cost more
+// than the idle lanes they remove).  ncu's source view of residual_sb2_kernel: the transform body
+// ran with 21 of 32 lanes on average - a third of the sub-blocks of coded macroblocks carry no coefficient at all and
+// their lanes just idle through ~1 700 instructions.  Here a CTA takes 64 listed macroblocks per step, every thread
+// looks at two sub-blocks, the ones with any coefficient are appended to a shared-memory ring (warp-aggregated
+// shared-memory atomic, 128-byte entries, chunk order swizzled like the decode-I ring), and only as many warps as
+// there are entries run the transform.  Empty sub-blocks need nothing: the copy kernel already stored the predictor.
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t RS4_MBS = 64;                              // listed macroblocks per CTA step (256 sub-blocks)
+struct __align__(16) Rs4Smem {
+    uint4    coef[RS4_MBS * 4 * 8];                           // entry s keeps 16-byte chunk k at [s*8 + (k ^ (s & 7))]
+    uint32_t id[RS4_MBS * 4];                                 // (macroblock inside the plane << 2) | sub-block
+    uint32_t n;
+};
+
+__global__ void __launch_bounds__(SB_THREADS, 4)
+residual_sb4_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs, uint32_t njobs,
+                    const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts)
+{
+    extern __shared__ __align__(16) unsigned char rs4_raw[];
+    Rs4Smem &sm = *reinterpret_cast<Rs4Smem *>(rs4_raw);
+    uint32_t *pre = reinterpret_cast<uint32_t *>(rs4_raw + sizeof(Rs4Smem));   // njobs * 3 + 1
+    const uint32_t nl = njobs * 3u;
+    for (uint32_t i = threadIdx.x; i < nl; i += SB_THREADS) {
+        const uint32_t j = i / 3u, p = i - j * 3u;
+        pre[i + 1] = (counts[j * 4u + p] + RS4_MBS - 1) / RS4_MBS;
+    }
+    if (threadIdx.x == 0) { pre[0] = 0; sm.n = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (uint32_t i = 0; i < nl; ++i) pre[i + 1] += pre[i];
+    __syncthreads();
+    const uint32_t total = pre[nl];
+    const uint32_t lane = threadIdx.x & 31u;
+    const int sb = (int)(threadIdx.x & 3u);
+
+#pragma unroll 1
+    for (uint32_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        uint32_t lo = 0, hi = nl;                             // largest i with pre[i] <= chunk
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pre[mid] <= chunk) lo = mid; else hi = mid;
+        }
+        const uint32_t j = lo / 3u, p = lo - j * 3u;
+        const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+        const DecJob &job = jobs[j];
+        const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
+        const uint32_t cnt = counts[j * 4u + p];
+        const uint32_t e0 = (chunk - pre[lo]) * RS4_MBS;
+
+        // ---- A: look at two sub-blocks per thread, queue the ones that carry coefficients ----
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t e = e0 + (uint32_t)half * (SB_THREADS / 4) + (threadIdx.x >> 2);
+            bool need = false;
+            uint4 raw[8];
+            uint32_t lm = 0;
+            if (e < cnt) {
+                lm = lists[(size_t)j * P.g.nb + pl.mb_base + e];
+                const uint4 *src = reinterpret_cast<const uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) raw[k] = __ldcs(src + k);
+                uint32_t any = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) any |= raw[k].x | raw[k].y | raw[k].z | raw[k].w;
+                need = any != 0u;
+            }
+            const uint32_t vote = __ballot_sync(0xffffffffu, need);
+            uint32_t base = 0;
+            if (vote && lane == 0) base = atomicAdd(&sm.n, (uint32_t)__popc(vote));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need) {
+                const uint32_t slot = base + (uint32_t)__popc(vote & ((1u << lane) - 1u));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sm.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = raw[k];
+                sm.id[slot] = (lm << 2) | (uint32_t)sb;
+            }
+        }
+        __syncthreads();
+        const uint32_t n = sm.n;
+        __syncthreads();
+        if (threadIdx.x == 0) sm.n = 0;                       // next step's appends come after the barrier below
+
+        // ---- B: full warps over the queued sub-blocks ----
+#pragma unroll 1
+        for (uint32_t slot = threadIdx.x; slot < n; slot += SB_THREADS) {
+            uint4 r2[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r2[k] = sm.coef[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
+            const uint32_t id = sm.id[slot];
+            const uint32_t lm = id >> 2, s2 = id & 3u;
+            uint32_t col;
+            const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+            uint8_t *dst = job.dst + pl.off + (size_t)(row * 16u + (s2 >> 1) * 8u) * pl.pw + col * 16u + (s2 & 1u) * 8u;
+            uint2 prev[8];                                    // the predictor the copy kernel stored here
+#pragma unroll
+            for (int r = 0; r < 8; ++r) prev[r] = __ldcg(reinterpret_cast<const uint2 *>(dst + (size_t)r * pl.pw));
+            int m[64];
+            unpack_dequant(r2, deq, m);
+            idct8x8_regs(m);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = m[r * 8 + i];
+                __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), apply_residual_row(y, prev[r]));   // src/common.rs:277
+            }
+        }
+        __syncthreads();                                      // the ring may be refilled
+    }
+}
+
+static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, const uint32_t *d_lists,
+                                   const uint32_t *d_counts, cudaStream_t s)
+{
+    static const int v_env = getenv("PFV_RESIDUAL_VARIANT") ? atoi(getenv("PFV_RESIDUAL_VARIANT")) : 2;
+    if (v_env != 4) {
+        uint32_t ctas = P.cta_total * njobs;                  // worst case: every macroblock coded
+        if (ctas > 148u * RS2_CTAS_PER_SM) ctas = 148u * RS2_CTAS_PER_SM;
+        residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts);
+        return cudaGetLastError();
+    }
+    static bool attr_done = false;
+    const size_t smem = sizeof(Rs4Smem) + (njobs * 3 + 1) * sizeof(uint32_t);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(residual_sb4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    uint32_t ctas = (P.cta_total * njobs + 1) / 2;
+    if (ctas > 148u * 4u) ctas = 148u * 4u;
+    residual_sb4_kernel<<<ctas, SB_THREADS, smem, s>>>(P, d_jobs, njobs, d_lists, d_counts);
     return cudaGetLastError();
 }
 

@@ -191,6 +191,26 @@ def test_host_compaction_of_dense_buffers_is_transparent(compact, mode, monkeypa
             assert np.array_equal(e.slot_read(2 * i + 1), want)
 
 
+def test_residual_kernel_variants_agree(monkeypatch):
+    """PFV_RESIDUAL_VARIANT=4 (sub-block compaction in shared memory) gives the pictures of the default kernel."""
+    monkeypatch.setenv("PFV_RESIDUAL_VARIANT", "4")
+    w, h = 400, 240
+    rng = np.random.default_rng(23)
+    qt, _ = make_qtables(5)
+    og = pfvo.geometry_for(w, h)
+    hdr = rand_headers(rng, og)
+    coeff = rand_coeffs(rng, og.nb, "mixed")
+    coeff.reshape(-1, 256)[hdr[:, 2] == 0] = 0
+    ref = rng.integers(0, 256, pfvo.frame_init(og).size).astype(np.uint8)
+    want = ref.copy()
+    pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdr, coeff, want)
+    with Engine(w, h, qt, nslots=2, max_jobs=1) as e:
+        e.slot_write(0, ref)
+        e.decode_submit([DecodeJob(PFV_FRAME_P, 1, coeff, (2, 3, 3), ref_slot=0, hdr=hdr)])
+        e.sync()
+        assert np.array_equal(e.slot_read(1), want)
+
+
 def test_decode_pframe_all_skipped_is_a_copy():
     w, h = 320, 240
     qt, _ = make_qtables(5)
