@@ -516,14 +516,16 @@ namespace {
 enum { W_FREE = 0, W_QUEUED, W_READY, W_SUBMITTED };
 
 struct DecWork {
-    Pinned   tok, meta, out;       // tokens | mb_off + headers | decoded visible planes
+    Pinned   meta, out;            // mb_off | headers | tokens (adjacent: one H2D copy per frame) ; decoded planes
     uint32_t ntok = 0, kind = 0;
     uint8_t  qidx[3] = {0, 0, 0};
     int      state = W_FREE;       // guarded by pfv_decoder::m
     int      status = PFV_OK;
     char     err[256] = "";
     uint64_t submit_id = 0;
-    uint32_t slot = 0;
+    uint32_t slot = 0;             // the frame slot this work item owns (fixed: 1 + its index)
+    uint32_t ref_slot = 0;         // P: slot of the previous frame of the stream (Decoder.framebuffer at that point)
+    uint32_t chain = 0;            // frames between two key frames form a chain; different chains are independent
     uint32_t packet = 0;           // index into packets
     uint64_t epoch = 0;
 };
@@ -548,13 +550,16 @@ struct pfv_decoder {
     uint32_t sched = 0;            // next packet to consider for read-ahead
     std::deque<DecWork *> inflight;   // frames scheduled (entropy queued or later), in stream order
     DecWork *delivered = nullptr;  // the picture handed out by the previous call
-    uint32_t fb_slot = 0;          // slot that holds Decoder.framebuffer (last submitted frame)
-    uint32_t delivered_slot = 0;   // slot of the last picture handed out
+    uint32_t fb_slot = 0;          // slot that holds Decoder.framebuffer for the next frame to be SCHEDULED
+    uint32_t delivered_slot = 0;   // slot of the last picture handed out (slot 0 = the blank initial framebuffer)
+    uint32_t chain = 0;            // chain number of the last scheduled frame
+    uint32_t lanes = 4;            // jobs per submit: frames of up to this many chains (GOPs) go out together
     bool eof = false;
     double delta_accum = 0.0;
     uint64_t epoch = 0;            // bumped by reset(): results of older entropy jobs are dropped
     size_t ysz = 0, csz = 0;
-    double t_prof[5] = {0, 0, 0, 0, 0};   // PFV_TRACE: seconds in schedule / wait entropy+submit / wait GPU / refill / entropy jobs
+    size_t off_u = 0, off_v = 0;   // where the U and V pictures sit in a work item's pinned picture buffer
+    double t_prof[7] = {0, 0, 0, 0, 0, 0, 0};   // PFV_TRACE: seconds in schedule / wait entropy+submit / wait GPU / refill / entropy jobs / cv wait / submit call
     uint64_t n_prof = 0;
 };
 
@@ -569,10 +574,11 @@ static void decoder_entropy_job(pfv_decoder *d, DecWork *w)
     const uint32_t nb = d->geo.nb;
     uint32_t *mb_off = static_cast<uint32_t *>(w->meta.p);
     pfv_mbhdr *hdr = reinterpret_cast<pfv_mbhdr *>(mb_off + nb + 1);
+    uint32_t *tok = mb_off + (nb + 1) + nb;
     uint32_t ntok = 0;
     const double t0 = now_s();
-    int rc = pfv_packet_decode(&d->geo, w->kind, d->data + pk.payload, pk.len, w->qidx, hdr, mb_off,
-                               static_cast<uint32_t *>(w->tok.p), (uint32_t)(w->tok.bytes / 4), &ntok);
+    int rc = pfv_packet_decode(&d->geo, w->kind, d->data + pk.payload, pk.len, w->qidx, hdr, mb_off, tok,
+                               (uint32_t)(w->meta.bytes / 4 - (2 * (size_t)nb + 1)), &ntok);
     const double t1 = now_s();
     if (rc) snprintf(w->err, sizeof(w->err), "%s", pfv_last_error());
     {
@@ -599,13 +605,15 @@ static int decoder_schedule(pfv_decoder *d)
         // token capacity: an emitted token costs at least 3 bits when the tree has two or more symbols, and a
         // one-symbol tree emits none
         const uint64_t cap = std::min<uint64_t>((uint64_t)d->geo.nb * 256, (uint64_t)pk.len * 8 / 3 + 1);
-        int rc = w->tok.reserve((size_t)cap * 4);
+        int rc = w->meta.reserve((2 * (size_t)d->geo.nb + 1 + (size_t)cap) * 4);
         if (rc) return rc;
-        rc = w->meta.reserve(((size_t)d->geo.nb + 1) * 4 + (size_t)d->geo.nb * sizeof(pfv_mbhdr));
-        if (rc) return rc;
-        rc = w->out.reserve(d->ysz + 2 * d->csz);
+        rc = w->out.reserve(d->geo.frame_bytes);
         if (rc) return rc;
         w->kind = pk.type == 1 ? PFV_FRAME_I : PFV_FRAME_P;
+        if (w->kind == PFV_FRAME_I) d->chain++;                      // a key frame depends on nothing: new chain
+        w->chain = d->chain;
+        w->ref_slot = d->fb_slot;                                   // the previous frame of the stream (src/dec.rs:425-432)
+        d->fb_slot = w->slot;
         w->packet = d->sched;
         w->status = PFV_OK;
         w->err[0] = 0;
@@ -618,50 +626,80 @@ static int decoder_schedule(pfv_decoder *d)
     return PFV_OK;
 }
 
-// submit, in stream order, every scheduled frame whose entropy decode is done; `must` = wait for this one
+// Submit scheduled frames whose entropy decode is done.  Frames of one chain (key frame + the P frames behind it) go
+// out in stream order, one per submit; frames of DIFFERENT chains are independent, so one submit carries the next
+// frame of up to `lanes` chains - that divides the per-submit cost (a dozen CUDA calls) by the number of GOPs in
+// flight.  `must` (the next picture to hand out) is waited for; everything else only goes if it is ready.
 static int decoder_submit_ready(pfv_decoder *d, DecWork *must)
 {
-    for (DecWork *w : d->inflight) {
-        if (w->state == W_SUBMITTED) {
-            if (w == must) must = nullptr;                          // went out with an earlier refill: nothing to wait for
-            continue;
-        }
-        {
-            std::unique_lock<std::mutex> l(d->m);
-            if (w->state != W_READY) {
-                if (!must) return PFV_OK;
-                d->cv.wait(l, [w] { return w->state == W_READY; });
+    const uint32_t nb = d->geo.nb;
+    for (int round = 0; round < 64; round++) {
+        std::vector<DecWork *> batch;
+        std::vector<uint32_t> closed;                                // chains that cannot contribute (another) frame to this batch
+        auto is_closed = [&](uint32_t c) { return std::find(closed.begin(), closed.end(), c) != closed.end(); };
+        for (DecWork *w : d->inflight) {
+            if (w->state == W_SUBMITTED) {
+                if (w == must) must = nullptr;                      // went out with an earlier refill: nothing to wait for
+                continue;
             }
+            if (is_closed(w->chain)) continue;
+            closed.push_back(w->chain);                             // at most one frame per chain and submit, in order
+            {
+                std::unique_lock<std::mutex> l(d->m);
+                if (w->state != W_READY) {
+                    if (w != must) continue;
+                    const double tw = now_s();
+                    d->cv.wait(l, [w] { return w->state == W_READY; });
+                    d->t_prof[5] += now_s() - tw;
+                }
+            }
+            if (w->status != PFV_OK) {
+                if (w == must) return set_error(w->status, "%s", w->err);
+                continue;                                           // reported when the cursor reaches it
+            }
+            for (int p = 0; p < 3; p++)
+                if (w->qidx[p] >= d->info.num_qtables) {
+                    w->status = PFV_ERR_BAD_STREAM;
+                    snprintf(w->err, sizeof(w->err), "q-table index %u >= %u (src/dec.rs:244-246 would panic)", w->qidx[p], d->info.num_qtables);
+                    break;
+                }
+            if (w->status != PFV_OK) {
+                if (w == must) return set_error(w->status, "%s", w->err);
+                continue;
+            }
+            batch.push_back(w);
+            if (batch.size() == d->lanes) break;
         }
-        if (w->status != PFV_OK) {
-            if (w == must) return set_error(w->status, "%s", w->err);
-            return PFV_OK;                                          // reported when the cursor reaches it
+        if (batch.empty()) break;
+        pfv_decode_job_sparse jobs[8];
+        for (size_t i = 0; i < batch.size(); i++) {
+            DecWork *w = batch[i];
+            pfv_decode_job_sparse &j = jobs[i];
+            memset(&j, 0, sizeof(j));
+            j.kind = w->kind;
+            j.ref_slot = w->ref_slot;
+            j.dst_slot = w->slot;
+            memcpy(j.qidx, w->qidx, 3);
+            j.mb_off = static_cast<const uint32_t *>(w->meta.p);
+            j.hdr = reinterpret_cast<const pfv_mbhdr *>(j.mb_off + nb + 1);
+            j.tok = j.mb_off + (nb + 1) + nb;
+            j.ntok = w->ntok;
+            j.out_y = static_cast<uint8_t *>(w->out.p);
+            j.out_u = j.out_y + d->off_u;
+            j.out_v = j.out_y + d->off_v;
         }
-        const uint32_t nb = d->geo.nb;
-        pfv_decode_job_sparse j;
-        memset(&j, 0, sizeof(j));
-        j.kind = w->kind;
-        j.ref_slot = d->fb_slot;
-        j.dst_slot = (d->fb_slot + 1) % d->nslots;                   // at most `depth` < nslots - 1 frames run ahead of the
-                                                                     // returned picture, so its slot is never overwritten
-        memcpy(j.qidx, w->qidx, 3);
-        j.mb_off = static_cast<const uint32_t *>(w->meta.p);
-        j.hdr = reinterpret_cast<const pfv_mbhdr *>(j.mb_off + nb + 1);
-        j.tok = static_cast<const uint32_t *>(w->tok.p);
-        j.ntok = w->ntok;
-        j.out_y = static_cast<uint8_t *>(w->out.p);
-        j.out_u = j.out_y + d->ysz;
-        j.out_v = j.out_u + d->csz;
-        for (int p = 0; p < 3; p++)
-            if (j.qidx[p] >= d->info.num_qtables)
-                return set_error(PFV_ERR_BAD_STREAM, "q-table index %u >= %u (src/dec.rs:244-246 would panic)", j.qidx[p], d->info.num_qtables);
-        int rc = pfv_decode_submit_sparse(d->ctx, &j, 1);
+        const double ts = now_s();
+        int rc = pfv_decode_submit_sparse(d->ctx, jobs, (uint32_t)batch.size());
+        d->t_prof[6] += now_s() - ts;
         if (rc) return rc;
-        w->submit_id = pfv_ctx_last_submit_id(d->ctx);
-        w->slot = j.dst_slot;
-        d->fb_slot = j.dst_slot;
-        { std::lock_guard<std::mutex> l(d->m); w->state = W_SUBMITTED; }
-        if (w == must) must = nullptr;
+        const uint64_t id = pfv_ctx_last_submit_id(d->ctx);
+        for (DecWork *w : batch) {
+            w->submit_id = id;
+            std::lock_guard<std::mutex> l(d->m);
+            w->state = W_SUBMITTED;
+            if (w == must) must = nullptr;
+        }
+        if (!must) break;                                           // one batch per call unless the needed picture is still behind
     }
     return PFV_OK;
 }
@@ -686,6 +724,15 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
     pfv_geometry_for(d->info.width, d->info.height, &d->geo);
     d->ysz = (size_t)d->geo.width * d->geo.height;
     d->csz = (size_t)d->geo.cwidth * d->geo.cheight;
+    // When no row is padded the pictures are kept in the slot's own layout (Y | U | V with their padding ROWS in
+    // between): the engine then moves all three with one copy.  Otherwise tight planes back to back.
+    if (d->geo.pw == d->geo.width && d->geo.cpw == d->geo.cwidth) {
+        d->off_u = (size_t)d->geo.pw * d->geo.ph;
+        d->off_v = d->off_u + (size_t)d->geo.cpw * d->geo.cph;
+    } else {
+        d->off_u = d->ysz;
+        d->off_v = d->ysz + d->csz;
+    }
     // packet index: O(1) per packet, no entropy decoding (src/dec.rs:179-180)
     {
         uint32_t cap = 1024, n = 0;
@@ -701,11 +748,11 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
         d->truncated = trunc != 0;
     }
     // default: enough frames in flight to keep every entropy thread busy plus a few on the GPU
-    d->depth = read_ahead ? read_ahead : std::max<uint32_t>(6, (num_threads ? num_threads : 1) + 4);
+    d->depth = read_ahead ? read_ahead : std::max<uint32_t>(6, 2 * (num_threads ? num_threads : 1) + 4);
     if (d->depth > 48) d->depth = 48;                                // pfv_ctx_wait_submit reaches 64 submits back
-    d->nslots = d->depth + 3;
+    d->nslots = d->depth + 2;                                        // slot 0: the blank initial framebuffer; then one per work item
     rc = pfv_ctx_create(device, d->info.width, d->info.height, reinterpret_cast<const int32_t(*)[64]>(qt.data()),
-                        d->info.num_qtables, d->nslots, 1, nullptr, &d->ctx);
+                        d->info.num_qtables, d->nslots, d->lanes, nullptr, &d->ctx);
     if (rc) return rc;
     // pinned buffers are sized once, from the largest frame packet of the stream (cudaHostAlloc costs milliseconds:
     // never on the per-frame path).  Token capacity: an emitted token costs at least 3 bits when the tree has two or
@@ -716,12 +763,12 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
     const uint64_t tok_cap = std::min<uint64_t>((uint64_t)d->geo.nb * 256, (uint64_t)max_len * 8 / 3 + 1);
     for (uint32_t i = 0; i < d->depth + 1; i++) {
         std::unique_ptr<DecWork> w(new DecWork());
-        if ((rc = w->tok.reserve((size_t)tok_cap * 4)) ||
-            (rc = w->meta.reserve(((size_t)d->geo.nb + 1) * 4 + (size_t)d->geo.nb * sizeof(pfv_mbhdr))) ||
-            (rc = w->out.reserve(d->ysz + 2 * d->csz))) {
+        if ((rc = w->meta.reserve((2 * (size_t)d->geo.nb + 1 + (size_t)tok_cap) * 4)) ||
+            (rc = w->out.reserve(d->geo.frame_bytes))) {
             pfv_ctx_destroy(d->ctx);
             return rc;
         }
+        w->slot = i + 1;
         d->work.push_back(std::move(w));
     }
     d->pool.reset(new Pool(num_threads ? num_threads : 1));
@@ -746,9 +793,10 @@ extern "C" void pfv_decoder_close(pfv_decoder *d)
     if (!d) return;
     decoder_drain(d);
     if (getenv("PFV_TRACE") && d->n_prof)
-        fprintf(stderr, "[pfv_decoder] %llu frames; per frame us: schedule %.0f, wait entropy + submit %.0f, wait GPU %.0f, refill %.0f; entropy job %.0f\n",
+        fprintf(stderr, "[pfv_decoder] %llu frames; per frame us: schedule %.0f, wait entropy + submit %.0f, wait GPU %.0f, refill %.0f; entropy job %.0f; of which cv wait %.0f, submit call %.0f\n",
                 (unsigned long long)d->n_prof, 1e6 * d->t_prof[0] / d->n_prof, 1e6 * d->t_prof[1] / d->n_prof,
-                1e6 * d->t_prof[2] / d->n_prof, 1e6 * d->t_prof[3] / d->n_prof, 1e6 * d->t_prof[4] / d->n_prof);
+                1e6 * d->t_prof[2] / d->n_prof, 1e6 * d->t_prof[3] / d->n_prof, 1e6 * d->t_prof[4] / d->n_prof,
+                1e6 * d->t_prof[5] / d->n_prof, 1e6 * d->t_prof[6] / d->n_prof);
     d->pool.reset();
     if (d->ctx) pfv_ctx_destroy(d->ctx);
     delete d;
@@ -778,11 +826,6 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
     if (!d) return set_error(PFV_ERR_BAD_ARG, "NULL decoder");
     if (got_frame) *got_frame = 0;
     if (d->eof) return 0;                                            // src/dec.rs:171-173
-    if (d->delivered) {                                              // the previous picture's buffer may be reused now
-        std::lock_guard<std::mutex> l(d->m);
-        d->delivered->state = W_FREE;
-        d->delivered = nullptr;
-    }
     for (;;) {
         if (d->cursor >= d->packets.size())
             return set_error(PFV_ERR_IO, "stream ends without an EOF packet%s (src/dec.rs:179-180 read fails)",
@@ -802,11 +845,20 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
     DecWork *w = d->inflight.front();
     rc = decoder_submit_ready(d, w);
     if (rc) {
-        // the failing frame is consumed, like a reference decode that returned Err after reading the packet
+        // the failing frame is consumed, like a reference decode that returned Err after reading the packet; the
+        // framebuffer stays what the last returned picture left there
         decoder_drain(d);
+        d->fb_slot = d->delivered_slot;
         d->cursor++;
         d->sched = d->cursor;
         return rc;
+    }
+    if (d->delivered) {
+        // The previous picture's buffers may be reused now - not earlier: its slot is the reference of the frame that
+        // has just been submitted.
+        std::lock_guard<std::mutex> l(d->m);
+        d->delivered->state = W_FREE;
+        d->delivered = nullptr;
     }
     const double t2 = now_s();
     rc = pfv_ctx_wait_submit(d->ctx, w->submit_id);
@@ -826,8 +878,8 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
     if (got_frame) *got_frame = 1;
     const uint8_t *base = static_cast<const uint8_t *>(w->out.p);
     if (y) *y = base;
-    if (u) *u = base + d->ysz;
-    if (v) *v = base + d->ysz + d->csz;
+    if (u) *u = base + d->off_u;
+    if (v) *v = base + d->off_v;
     return 1;
 }
 
@@ -881,6 +933,7 @@ struct pfv_encoder {
     std::deque<std::shared_ptr<OutPacket>> pending;   // packets in stream order, not yet appended to `stream`
     std::vector<uint8_t> stream;                      // the writer W
     uint32_t prev_slot = 0;
+    uint32_t max_pending = 4;
     bool finished = false;
     size_t ysz = 0, csz = 0;
 };
@@ -920,7 +973,8 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
     pfv_ctx_geometry(e->ctx, &e->geo);
     e->ysz = (size_t)e->geo.width * e->geo.height;
     e->csz = (size_t)e->geo.cwidth * e->geo.cheight;
-    const uint32_t depth = 4;
+    // frames in flight: one per entropy thread plus two on the GPU (pfv_ctx_wait_submit reaches 64 submits back)
+    const uint32_t depth = std::min<uint32_t>(std::max<uint32_t>(num_threads, 2) + 2, 32);
     for (uint32_t i = 0; i < depth; i++) {
         std::unique_ptr<EncWork> w(new EncWork());
         if ((rc = w->src.reserve(e->ysz + 2 * e->csz)) || (rc = w->coeff.reserve((size_t)e->geo.nb * 512)) ||
@@ -931,6 +985,7 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
         e->work.push_back(std::move(w));
     }
     e->pool.reset(new Pool(num_threads ? std::min<uint32_t>(num_threads, depth) : 1));
+    e->max_pending = depth;
     // write_header, src/enc.rs:190-219
     std::vector<uint8_t> &s = e->stream;
     s.insert(s.end(), kMagic, kMagic + 8);

@@ -145,7 +145,7 @@ extern "C" void pfv_host_free(void *p)
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int STAGES = 2;        // staging ring depth: H2D of submit n+1 overlaps the kernels of submit n
+constexpr int STAGES = 4;        // staging ring depth: H2D of submit n+1 overlaps the kernels of submit n
 constexpr int D2H_RING = 64;     // D2H completion events kept for slot-reuse ordering and pfv_ctx_wait_submit
 
 struct Stage {
@@ -154,8 +154,8 @@ struct Stage {
     uint8_t   *d_src = nullptr;      // max_jobs * src_stride (encode only, lazily allocated)
     void      *d_jobs = nullptr;     // max_jobs * max(sizeof(DecJob), sizeof(EncJob))
     void      *h_jobs = nullptr;     // pinned mirror of d_jobs
-    uint32_t  *d_tok = nullptr;      // sparse transport: max_jobs * nb * 256 tokens (lazily allocated)
-    uint32_t  *d_mboff = nullptr;    // max_jobs * (nb + 1)
+    uint32_t  *d_pack = nullptr;     // sparse transport, per job slot: [mb_off (nb+1) | headers (nb) | tokens (nb*256)], lazily
+                                     // allocated; a caller that keeps the three arrays adjacent gets ONE copy per frame
     SparseJob *d_sjobs = nullptr;    // max_jobs
     SparseJob *h_sjobs = nullptr;    // pinned mirror
     uint8_t   *d_rgb_src = nullptr;  // encode jobs with PFV_JOB_SRC_RGB: max_jobs * w*h*3 (lazily allocated)
@@ -175,6 +175,7 @@ struct pfv_ctx {
     uint32_t nq = 0, nslots = 0, max_jobs = 0;
     size_t slot_stride = 0;          // frame_bytes rounded up to 256
     size_t src_stride = 0;           // per-job source staging (encode)
+    size_t pack_words = 0;           // per-job sparse staging in 32-bit words: (nb+1) + nb + nb*256, rounded to 16 bytes
     uint32_t src_off[3] = {0, 0, 0};
     uint8_t *d_pool = nullptr;
     QTables *d_qt = nullptr;
@@ -327,11 +328,10 @@ int init_slot(pfv_ctx *c, uint32_t slot, cudaStream_t s)
 
 int ensure_sparse_staging(pfv_ctx *c)
 {
-    if (c->st[0].d_tok) return PFV_OK;
+    if (c->st[0].d_pack) return PFV_OK;
     for (int i = 0; i < STAGES; i++) {
         Stage &s = c->st[i];
-        CU_TRY(cudaMalloc(&s.d_tok, (size_t)c->max_jobs * c->geo.nb * 256 * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&s.d_mboff, (size_t)c->max_jobs * (c->geo.nb + 1) * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&s.d_pack, (size_t)c->max_jobs * c->pack_words * sizeof(uint32_t)));
         CU_TRY(cudaMalloc(&s.d_sjobs, sizeof(SparseJob) * c->max_jobs));
         CU_TRY(cudaHostAlloc(&s.h_sjobs, sizeof(SparseJob) * c->max_jobs, cudaHostAllocDefault));
     }
@@ -417,7 +417,7 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     for (int i = 0; i < STAGES; i++) {
         Stage &s = c->st[i];
         cudaFree(s.d_coeff); cudaFree(s.d_hdr); cudaFree(s.d_src); cudaFree(s.d_jobs);
-        cudaFree(s.d_tok); cudaFree(s.d_mboff); cudaFree(s.d_sjobs); cudaFree(s.d_rgb_src);
+        cudaFree(s.d_pack); cudaFree(s.d_sjobs); cudaFree(s.d_rgb_src);
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
         if (s.h_sjobs) cudaFreeHost(s.h_sjobs);
         if (s.h_tok) cudaFreeHost(s.h_tok);
@@ -459,6 +459,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     c->src_off[1] = (c->geo.width * c->geo.height + 15u) & ~15u;
     c->src_off[2] = (c->src_off[1] + c->geo.cwidth * c->geo.cheight + 15u) & ~15u;
     c->src_stride = ((size_t)c->src_off[2] + (size_t)c->geo.cwidth * c->geo.cheight + 255) & ~(size_t)255;
+    c->pack_words = (((size_t)c->geo.nb + 1) + c->geo.nb + (size_t)c->geo.nb * 256 + 3) & ~(size_t)3;
 
     CU_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
@@ -653,6 +654,12 @@ static int copy_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint8_t *u, uint8
     const pfv_geometry &g = c->geo;
     const uint8_t *base = slot_ptr(c, slot);
     const size_t ny = (size_t)g.pw * g.ph, nc = (size_t)g.cpw * g.cph;
+    if (y && u && v && g.pw == g.width && g.cpw == g.cwidth && u == y + ny && v == u + nc) {
+        // rows are not padded and the caller's three planes sit where the slot's do: the visible planes are prefixes
+        // of the padded ones, one copy moves them all (the few padding rows between them ride along)
+        CU_TRY(cudaMemcpyAsync(y, base, ny + nc + (size_t)g.cwidth * g.cheight, cudaMemcpyDeviceToHost, s));
+        return PFV_OK;
+    }
     if (y) {
         if (g.pw == g.width) CU_TRY(cudaMemcpyAsync(y, base, (size_t)g.width * g.height, cudaMemcpyDeviceToHost, s));
         else CU_TRY(cudaMemcpy2DAsync(y, g.width, base, g.pw, g.width, g.height, cudaMemcpyDeviceToHost, s));
@@ -860,15 +867,28 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
             d.hdr = j.hdr;
         } else {
             if (j.sparse) {
-                uint32_t *d_tok = st.d_tok + (size_t)k * coeff_elems;
-                uint32_t *d_mboff = st.d_mboff + (size_t)k * (g.nb + 1);
-                if (j.ntok) CU_TRY(cudaMemcpyAsync(d_tok, j.tok, (size_t)j.ntok * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
-                CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, (size_t)(g.nb + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
+                uint32_t *d_mboff = st.d_pack + (size_t)k * c->pack_words;
+                uint32_t *d_shdr = d_mboff + (g.nb + 1);
+                uint32_t *d_tok = d_shdr + g.nb;
+                const uint32_t *h_hdr32 = reinterpret_cast<const uint32_t *>(j.hdr);
+                if (h_hdr32 && h_hdr32 == j.mb_off + (g.nb + 1) && (j.ntok == 0 || j.tok == h_hdr32 + g.nb)) {
+                    // mb_off | headers | tokens adjacent in host memory: one copy
+                    CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, ((size_t)(g.nb + 1) + g.nb + j.ntok) * sizeof(uint32_t),
+                                           cudaMemcpyHostToDevice, c->s_h2d));
+                } else {
+                    if (j.ntok) CU_TRY(cudaMemcpyAsync(d_tok, j.tok, (size_t)j.ntok * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
+                    CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, (size_t)(g.nb + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
+                    if (j.kind == PFV_FRAME_P)
+                        CU_TRY(cudaMemcpyAsync(d_shdr, j.hdr, (size_t)g.nb * sizeof(pfv_mbhdr), cudaMemcpyHostToDevice, c->s_h2d));
+                }
                 SparseJob &sj = st.h_sjobs[nsparse++];
                 sj.mb_off = d_mboff;
                 sj.tok = d_tok;
-                sj.hdr = j.kind == PFV_FRAME_P ? d_hdr : nullptr;
+                sj.hdr = j.kind == PFV_FRAME_P ? reinterpret_cast<const pfv_mbhdr *>(d_shdr) : nullptr;
                 sj.coeff = d_coeff;
+                d.coeff = d_coeff;
+                d.hdr = sj.hdr;
+                goto job_common;
             } else if (run_elems && j.coeff == run_src + run_elems && d_coeff == run_dst + run_elems) {
                 run_elems += coeff_elems;
             } else {
@@ -883,6 +903,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                 d.hdr = d_hdr;
             }
         }
+    job_common:
         d.dst = slot_ptr(c, j.dst_slot);
         d.ref = j.kind == PFV_FRAME_P ? slot_ptr(c, j.ref_slot) : nullptr;
         d.ref_slot = j.kind == PFV_FRAME_P ? (int32_t)j.ref_slot : 0;
