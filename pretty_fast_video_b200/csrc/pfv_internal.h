@@ -88,6 +88,8 @@ enum { ERRBIT_BAD_MV = 1 };
 constexpr int WIN_W = 176;
 constexpr int WIN_H = 46;
 constexpr int WIN_BYTES = WIN_W * WIN_H;
+constexpr int WINP_W = 188;                  // re-pitched window: 47 words per row (odd: rows spread over all banks)
+constexpr int WINP_BYTES = WINP_W * WIN_H;
 
 // records the calling thread's error text (pfv_last_error) and returns `code`
 int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));

@@ -217,7 +217,13 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
                 const QTables *__restrict__ qt,
                 const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
 {
-    __shared__ __align__(128) uint8_t win[WIN_BYTES + 16];
+    __shared__ __align__(128) uint8_t stage[WIN_BYTES];                // where the TMA box lands (row pitch 176 B)
+    // The search reads 32 different window rows per instruction.  With the 16-byte granular pitch of the TMA box
+    // (44 words) those rows fall on only 8 bank groups: 2.5 wavefronts per LDS whatever the lane -> row mapping.  The box
+    // is therefore re-pitched once per tile to 47 words (188 B): consecutive rows then start 15 banks apart and the
+    // same reads take 1.25 wavefronts (simulated over all search states; ncu: the data pipe was at 80 %, half of it
+    // bank conflicts).
+    __shared__ __align__(16) uint8_t win[WINP_BYTES + 16];
     __shared__ WarpScratch scratch[WARPS_PER_CTA];
     __shared__ __align__(8) uint64_t bar;
 
@@ -243,7 +249,7 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_u32(win)), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(bar_a)
+            ::"r"(smem_u32(stage)), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(bar_a)
             : "memory");
     }
 
@@ -273,6 +279,15 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
                 : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
         }
     }
+    {   // re-pitch the window: 46 rows x 44 words -> pitch 47 words
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(stage);
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(win);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)(WIN_H * (WIN_W / 4)); i += WARPS_PER_CTA * 32) {
+            const uint32_t row = i / (WIN_W / 4), col = i - row * (WIN_W / 4);
+            dst32[row * (WINP_W / 4) + col] = src32[i];
+        }
+    }
+    __syncthreads();
     if (!active) return;
 
     // window coordinates of this lane's 8 pixels for motion (0,0)
@@ -284,20 +299,20 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
     //
     // One pass per level evaluates all 8 neighbours at once: lane = (candidate g = lane >> 2, quarter q = lane & 3),
     // candidate g in the reference's visiting order (my outer, mx inner, centre skipped, :168-179), the lane owns
-    // macroblock rows q, q+4, q+8, q+12 (16 pixels each).  The 4 partial sums of a candidate meet by two xor-shuffles;
+    // macroblock rows 4q .. 4q+3 (16 pixels each).  The 4 partial sums of a candidate meet by two xor-shuffles;
     // the winner is ONE redux.min over (ssd << 3 | g): the smallest error, and among equal errors the earliest
     // candidate - exactly what the sequential strict `<` of :189 selects.  Candidates outside the plane (:171,:182)
     // get the key 0xffffffff.  (The first version looped over the candidates with the whole warp on each one:
     // ~30 instructions per candidate, 1 300 per macroblock; this is ~100 per level.)
     int cx = bx, cy = by;                                              // current centre, plane coords
-    uint32_t best = warp_ssd(s, lds_u8x8_unaligned(win, (uint32_t)(wy0 * WIN_W + wx0)));
+    uint32_t best = warp_ssd(s, lds_u8x8_unaligned(win, (uint32_t)(wy0 * WINP_W + wx0)));
     const int g8 = lane >> 2, q4 = lane & 3;
     const int mxg = (g8 == 0 || g8 == 3 || g8 == 5) ? -1 : ((g8 == 1 || g8 == 6) ? 0 : 1);
     const int myg = g8 < 3 ? -1 : (g8 < 5 ? 0 : 1);
-    uint4 srow[4];                                                     // source rows q, q+4, q+8, q+12 out of the (sub-block, row) layout
+    uint4 srow[4];                                                     // source rows 4q .. 4q+3 out of the (sub-block, row) layout
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int R = q4 + 4 * i;
+        const int R = 4 * q4 + i;
         const int l0 = ((R >> 3) * 2) * 8 + (R & 7);                   // lane holding columns 0..7 of row R; +8: columns 8..15
         srow[i].x = __shfl_sync(FULL, s.x, l0);
         srow[i].y = __shfl_sync(FULL, s.y, l0);
@@ -309,13 +324,13 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         const int ox = cx + mxg * step, oy = cy + myg * step;
         const bool valid = ox >= 0 && ox <= max_x && oy >= 0 && oy <= max_y;
         // window offset of row q of the candidate block; invalid candidates still lie inside the (zero-filled) window
-        const uint32_t base = (uint32_t)((15 + q4 + (oy - by)) * WIN_W + 16 + warp * 16 + (ox - bx));
+        const uint32_t base = (uint32_t)((15 + 4 * q4 + (oy - by)) * WINP_W + 16 + warp * 16 + (ox - bx));
         const uint32_t sh = (base & 3u) * 8u;
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(win + (base & ~3u));
         uint32_t acc = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t *w = wp + i * (4 * WIN_W / 4);
+            const uint32_t *w = wp + i * (WINP_W / 4);
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
             const uint32_t d0 = __vabsdiffu4(srow[i].x, __funnelshift_r(w0, w1, sh));
             const uint32_t d1 = __vabsdiffu4(srow[i].y, __funnelshift_r(w1, w2, sh));
@@ -341,7 +356,7 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         cy += bdy;
     }
     const int mvx = cx - bx, mvy = cy - by;                            // |mv| <= 15
-    const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((wy0 + mvy) * WIN_W + wx0 + mvx));
+    const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((wy0 + mvy) * WINP_W + wx0 + mvx));
     const bool coded = !((float)best <= job.min_err);                  // src/common.rs:221
 
     const uint32_t m = pl.mb_base + trow * pl.bw + (uint32_t)(bx >> 4);
