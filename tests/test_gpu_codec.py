@@ -262,3 +262,28 @@ def test_gop_sharded_gpu_decode_equals_whole_stream():
             assert len(part) == g.nframes
             merged += [(g.first_frame + i, fr) for i, fr in enumerate(part)]
     same_frames(shard.gather_ordered(merged), whole)
+
+
+def test_decoder_reproduces_the_committed_golden_stream():
+    """tests/golden/stream_96x64_q3.npz (made by tests/golden/make_golden.py, frozen): the GPU Decoder yields the
+    per-frame SHA-256 digests stored with the stream, and the GPU Encoder re-creates the stored bytes."""
+    import hashlib
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "stream_96x64_q3.npz"))
+    data = g["stream"].tobytes()
+    got, _ = gpu_decode_all(data, num_threads=2)
+    sums = [hashlib.sha256(b"".join(p.tobytes() for p in fr)).hexdigest() for fr in got if fr is not None]
+    assert sums == [s for s in g["sha256"]]
+    assert [fr is None for fr in got].count(True) == 1              # the drop frame at t = 5
+    sv = SynthVideo(96, 64, 77)
+    with codec.Encoder(96, 64, 24, 3, num_threads=2) as enc:
+        for t in range(int(g["nframes"])):
+            if t % 4 == 0:
+                enc.encode_iframe(sv.frame(t))
+            elif t == 5:
+                enc.encode_dropframe()
+            else:
+                enc.encode_pframe(sv.frame(t))
+        enc.finish()
+        assert enc.bytes() == data
