@@ -256,6 +256,8 @@ int pfv_packet_decode(const pfv_geometry *g, uint32_t kind, const uint8_t *paylo
 int pfv_packet_encode(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff,
                       uint8_t *out, size_t cap, size_t *len_out);
 size_t pfv_packet_encode_bound(const pfv_geometry *g);   /* a capacity that always suffices */
+/* the largest number of tokens pfv_packet_decode can emit for this payload (<= nb*256): sizes tok_out */
+uint32_t pfv_packet_token_bound(const pfv_geometry *g, const uint8_t *payload, size_t len);
 
 /* -- Decoder (src/dec.rs) -------------------------------------------------------------------------------------- */
 typedef struct pfv_decoder pfv_decoder;

@@ -121,6 +121,7 @@ SYMBOLS = {
     "pfv_packet_encode": (C.c_int, [C.POINTER(Geometry), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_size_t)]),
     "pfv_packet_encode_bound": (C.c_size_t, [C.POINTER(Geometry)]),
+    "pfv_packet_token_bound": (C.c_uint32, [C.POINTER(Geometry), C.c_void_p, C.c_size_t]),
     "pfv_decoder_open": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "pfv_decoder_close": (None, [C.c_void_p]),
     "pfv_decoder_width": (C.c_uint32, [C.c_void_p]),

@@ -71,7 +71,7 @@ def decode_packet(geo: N.Geometry, kind: int, payload: bytes):
     qidx = np.zeros(3, np.uint8)
     hdr = np.zeros((nb, 4), np.uint8)
     mb_off = np.zeros(nb + 1, np.uint32)
-    cap = min(nb * 256, buf.size * 8 // 3 + 1)
+    cap = int(N.lib().pfv_packet_token_bound(C.byref(geo), buf.ctypes.data, buf.size))
     tok = np.zeros(max(cap, 1), np.uint32)
     ntok = C.c_uint32()
     _check_dec(N.lib().pfv_packet_decode(C.byref(geo), kind, buf.ctypes.data, buf.size, qidx.ctypes.data, hdr.ctypes.data,

@@ -171,6 +171,20 @@ inline int huff_symbol(const Huffman &h, uint64_t w, int &symbol)
     return l;
 }
 
+// Upper bound of the tokens a payload can emit.  A token that carries a value costs its two codes plus `size` >= 1
+// value bits: at least 3 bits when the tree has two or more symbols (every code is then >= 1 bit long).  A tree with
+// a single symbol s has zero-length codes: every token is (run s, size s) and costs s bits.
+uint64_t token_bound(const uint8_t *payload, size_t len, uint32_t nb)
+{
+    const uint64_t all = (uint64_t)nb * 256;
+    if (len < 19) return 1;
+    int nsym = 0, only = 0;
+    for (int i = 0; i < 16; i++) if (payload[i]) { nsym++; only = i; }
+    const uint64_t bits = (uint64_t)(len - 19) * 8;
+    const uint64_t bound = nsym >= 2 ? bits / 3 + 1 : (nsym == 1 && only > 0 ? bits / (uint64_t)only + 1 : 1);
+    return std::min(all, bound);
+}
+
 struct PlaneDims { uint32_t pw, ph, bw, bh; };
 
 void plane_dims(const pfv_geometry &g, PlaneDims out[3])
@@ -463,6 +477,12 @@ int encode_packet(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, co
 
 }  // namespace
 
+extern "C" uint32_t pfv_packet_token_bound(const pfv_geometry *g, const uint8_t *payload, size_t len)
+{
+    if (!g || !payload) return 0;
+    return (uint32_t)token_bound(payload, len, g->nb);
+}
+
 extern "C" size_t pfv_packet_encode_bound(const pfv_geometry *g)
 {
     if (!g) return 0;
@@ -604,7 +624,7 @@ static int decoder_schedule(pfv_decoder *d)
         if (!w) break;
         // token capacity: an emitted token costs at least 3 bits when the tree has two or more symbols, and a
         // one-symbol tree emits none
-        const uint64_t cap = std::min<uint64_t>((uint64_t)d->geo.nb * 256, (uint64_t)pk.len * 8 / 3 + 1);
+        const uint64_t cap = token_bound(d->data + pk.payload, pk.len, d->geo.nb);
         int rc = w->meta.reserve((2 * (size_t)d->geo.nb + 1 + (size_t)cap) * 4);
         if (rc) return rc;
         rc = w->out.reserve(d->geo.frame_bytes);
@@ -757,10 +777,10 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
     // pinned buffers are sized once, from the largest frame packet of the stream (cudaHostAlloc costs milliseconds:
     // never on the per-frame path).  Token capacity: an emitted token costs at least 3 bits when the tree has two or
     // more symbols, and a one-symbol tree emits none.
-    uint32_t max_len = 0;
+    uint64_t tok_cap = 1;
     for (const pfv_packet &pk : d->packets)
-        if ((pk.type == 1 || pk.type == 2) && pk.len > max_len) max_len = pk.len;
-    const uint64_t tok_cap = std::min<uint64_t>((uint64_t)d->geo.nb * 256, (uint64_t)max_len * 8 / 3 + 1);
+        if ((pk.type == 1 || pk.type == 2) && pk.len > 0)
+            tok_cap = std::max(tok_cap, token_bound(data + pk.payload, pk.len, d->geo.nb));
     for (uint32_t i = 0; i < d->depth + 1; i++) {
         std::unique_ptr<DecWork> w(new DecWork());
         if ((rc = w->meta.reserve((2 * (size_t)d->geo.nb + 1 + (size_t)tok_cap) * 4)) ||

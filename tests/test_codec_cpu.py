@@ -203,3 +203,57 @@ def test_dense_token_helpers_are_inverse():
     c[rng.random(nb * 256) < 0.9] = 0
     mb_off, tok = codec.dense_to_tokens(c, nb)
     assert np.array_equal(codec.tokens_to_dense(nb, mb_off, tok), c)
+
+
+def test_entropy_decoder_survives_corrupted_payloads():
+    """Mutated and truncated payloads: pfv_packet_decode returns an error or a (different) token list, never crashes,
+    never loops forever, never writes outside its buffers (the reference would panic / return io::Error)."""
+    from pretty_fast_video_b200 import PfvError
+    rng = np.random.default_rng(2024)
+    w, h = 96, 64
+    data, seam = oracle_stream(w, h, 4, 3, 2, 55)
+    info, qt, pk, _ = frame_packets(data)
+    geo = geometry_for(w, h)
+    frames = [(t, l, p) for t, l, p in pk if t != 0 and l > 0]
+    outcomes = {"ok": 0, "err": 0}
+    for t, l, p in frames:
+        fk = PFV_FRAME_I if t == 1 else PFV_FRAME_P
+        good = bytearray(data[p:p + l])
+        for trial in range(150):
+            bad = bytearray(good)
+            mode = trial % 3
+            if mode == 0:                                            # flip a few bytes anywhere (incl. the weight table)
+                for _ in range(int(rng.integers(1, 6))):
+                    bad[int(rng.integers(0, len(bad)))] ^= int(rng.integers(1, 256))
+            elif mode == 1:                                          # truncate
+                bad = bad[:int(rng.integers(0, len(bad)))]
+            else:                                                    # random weight table, payload kept
+                bad[:16] = bytes(rng.integers(0, 256, 16, dtype=np.uint8))
+            try:
+                qidx, hdr, mb_off, tok = codec.decode_packet(geo, fk, bytes(bad))
+                assert mb_off[0] == 0 and mb_off[-1] == tok.size and (np.diff(mb_off.astype(np.int64)) >= 0).all()
+                assert ((tok >> 16) < 256).all()
+                outcomes["ok"] += 1
+            except PfvError:
+                outcomes["err"] += 1
+    assert outcomes["err"] > 0 and outcomes["ok"] + outcomes["err"] == 150 * len(frames)
+
+
+def test_single_symbol_tree_is_decodable():
+    """A frame whose tokens are all (run 1, size 1): the weight table has one entry, both codes have length zero
+    (src/huffman.rs:125-131), every token costs one value bit.  Legal, and far more tokens per byte than usual."""
+    geo = geometry_for(16, 16)
+    nb = geo.nb
+    # every second coefficient is -1 or 0 (size 1 holds only 0 / -1): position pattern z v z v ...
+    rng = np.random.default_rng(3)
+    vals = -rng.integers(0, 2, nb * 128).astype(np.int16)
+    coeff = np.zeros(nb * 256, np.int16)
+    coeff[1::2] = vals
+    # payload by hand: table with weight only for symbol 1, qidx, then nb*128 value bits LSB-first
+    bits = (vals != 0).astype(np.uint8)
+    body = np.packbits(bits, bitorder="little").tobytes()
+    table = bytes([0, 200] + [0] * 14)
+    payload = table + bytes([0, 1, 1]) + body
+    qidx, _, mb_off, tok = codec.decode_packet(geo, PFV_FRAME_I, payload)
+    assert tok.size == nb * 128                                      # zero-valued tokens are kept: they occupy a position
+    assert np.array_equal(codec.tokens_to_dense(nb, mb_off, tok), coeff)
