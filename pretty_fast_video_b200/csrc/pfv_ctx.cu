@@ -191,6 +191,7 @@ struct pfv_ctx {
                                            // frame cost ~1 ms per frame per thread and halved e2e (7.9 k -> 3.9 k frames/s); hosts
                                            // that can, hand over tokens directly (pfv_decode_submit_sparse: 13 k frames/s)
     Pool *pool = nullptr;                  // host threads for the compaction (created on first use)
+    bool pcount_clean = false;             // the last residual kernel left d_pcount[0 .. 4*njobs) zeroed
     int p_split = 1;                       // PFV_DECODE_P_SPLIT: parts a batch of P frames is cut into, alternating between two
                                            // streams.  Measured on B200 (1080p, 32 frames per batch): 1 -> 0.48 of roofline,
                                            // 2 -> 0.43, 4 -> 0.41, 8 -> 0.33: the kernels do not overlap usefully, kept as a knob
@@ -505,7 +506,8 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
     CU_TRY(cudaMalloc(&c->d_plist, (size_t)c->max_jobs * c->geo.nb * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&c->d_pcount, (size_t)c->max_jobs * 4 * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&c->d_pcount, ((size_t)c->max_jobs * 4 + 4) * sizeof(uint32_t)));   // + the residual kernel's "CTAs done" counter
+    CU_TRY(cudaMemset(c->d_pcount, 0, ((size_t)c->max_jobs * 4 + 4) * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_err, sizeof(int)));
     CU_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
     CU_TRY(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocDefault));
@@ -975,7 +977,12 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                 //   s_compute: copy0 | resid0 | copy2 | resid2          s_aux:        | copy1  | resid1 | copy3 | resid3
                 // Measured slower than one pair of launches over the whole batch (see p_split), so the default is 1.
                 const uint32_t k0 = a - n_i, n = b - a;
-                CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)n * 4 * sizeof(uint32_t), c->s_compute));
+                // list counts: cleared by the previous residual kernel itself when the whole group goes out as one pair of
+                // launches on the default kernels (self_clear); otherwise by a memset node here
+                const bool self_clear = c->p_split <= 1 && c->decode_p_variant == 0 && k0 == 0 && c->pcount_clean;
+                if (!self_clear)
+                    CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)n * 4 * sizeof(uint32_t), c->s_compute));
+                c->pcount_clean = c->p_split <= 1 && c->decode_p_variant == 0 && k0 == 0 && n == njobs - n_i;
                 uint32_t parts = (uint32_t)c->p_split;
                 if (parts > n / 2) parts = n / 2;                   // at least 2 frames per part
                 if (parts < 1) parts = 1;
@@ -986,7 +993,8 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                     if (i == 1) CU_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
                     CU_TRY(launch_decode_p_two_pass4(P, d_tab + a + lo, hi - lo, c->d_plist + (size_t)(k0 + lo) * c->geo.nb,
                                                      c->d_pcount + (size_t)(k0 + lo) * 4, c->decode_p_variant == 7, c->d_err,
-                                                     c->tm_win_luma, c->tm_win_chroma, st_i, i == 0 && parts > 1 ? c->ev_fork : nullptr));
+                                                     c->tm_win_luma, c->tm_win_chroma, st_i, i == 0 && parts > 1 ? c->ev_fork : nullptr,
+                                                     c->pcount_clean ? c->d_pcount + (size_t)c->max_jobs * 4 : nullptr));
                     c->launches += 2;
                 }
                 if (parts > 1) {

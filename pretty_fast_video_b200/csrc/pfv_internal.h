@@ -108,7 +108,7 @@ cudaError_t launch_decode_p_two_pass3(const SbParams &P, const DecJob *d_jobs, u
                                       const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s);
 cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
                                       bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
-                                      cudaEvent_t after_copy);
+                                      cudaEvent_t after_copy, uint32_t *d_done);
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);

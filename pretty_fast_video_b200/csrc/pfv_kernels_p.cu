@@ -24,7 +24,7 @@
 namespace pfv {
 
 static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, const uint32_t *d_lists,
-                                   const uint32_t *d_counts, cudaStream_t s);
+                                   uint32_t *d_counts, uint32_t *d_done, cudaStream_t s);
 
 constexpr int MC_WARPS = 8;
 
@@ -321,7 +321,7 @@ mc_copy2_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McT
 // c, c + gridDim.x, ...  The chunk table (prefix over njobs * 3 lists) is rebuilt by every CTA from the counts.
 __global__ void __launch_bounds__(SB_THREADS, RS2_CTAS_PER_SM)
 residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs, uint32_t njobs,
-                    const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts)
+                    const uint32_t *__restrict__ lists, uint32_t *__restrict__ counts, uint32_t *__restrict__ done)
 {
     extern __shared__ uint32_t pre[];                         // njobs * 3 + 1
     const uint32_t nl = njobs * 3u;
@@ -409,6 +409,21 @@ residual_sb2_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = m[r * 8 + i];
             __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), apply_residual_row(y, prev[r]));   // src/common.rs:277
+        }
+    }
+    // The last CTA to finish clears the list counts for the next batch (done != nullptr): saves the memset node the
+    // host would otherwise put in front of every copy kernel.
+    if (done) {
+        __shared__ uint32_t last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last) {
+            for (uint32_t i = threadIdx.x; i < njobs * 4u; i += SB_THREADS) counts[i] = 0u;
+            if (threadIdx.x == 0) *done = 0u;
         }
     }
 }
@@ -624,7 +639,7 @@ cudaError_t launch_decode_p_two_pass3(const SbParams &P, const DecJob *d_jobs, u
     }
     uint32_t ctas = P.cta_total * njobs;                      // worst case: every macroblock coded
     if (ctas > 148u * 3u) ctas = 148u * 3u;
-    residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts);
+    residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts, nullptr);
     return cudaGetLastError();
 }
 
@@ -940,7 +955,7 @@ residual_sb3_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
 // residual_sb2_kernel (the default).
 cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
                                       bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
-                                      cudaEvent_t after_copy)
+                                      cudaEvent_t after_copy, uint32_t *d_done)
 {
     static bool attr_done = false;
     const int mc_smem = (int)sizeof(Mc4Smem);
@@ -968,7 +983,7 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
         if (e != cudaSuccess) return e;
         if (after_copy && (e = cudaEventRecord(after_copy, s)) != cudaSuccess) return e;
     }
-    if (!listless) return launch_residual(P, d_jobs, njobs, d_lists, d_counts, s);
+    if (!listless) return launch_residual(P, d_jobs, njobs, d_lists, d_counts, d_done, s);
     uint32_t cpf = 0;
     for (int p = 0; p < 3; p++) cpf += (g.pl[p].bw * g.pl[p].bh + RS3_CHUNK - 1) / RS3_CHUNK;
     const uint32_t total = cpf * njobs;
@@ -1093,14 +1108,15 @@ residual_sb4_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict
     }
 }
 
+// d_done != nullptr: the kernel clears d_counts when it is done (the caller then skips its memset)
 static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, const uint32_t *d_lists,
-                                   const uint32_t *d_counts, cudaStream_t s)
+                                   uint32_t *d_counts, uint32_t *d_done, cudaStream_t s)
 {
     static const int v_env = getenv("PFV_RESIDUAL_VARIANT") ? atoi(getenv("PFV_RESIDUAL_VARIANT")) : 2;
     if (v_env != 4) {
         uint32_t ctas = P.cta_total * njobs;                  // worst case: every macroblock coded
         if (ctas > 148u * RS2_CTAS_PER_SM) ctas = 148u * RS2_CTAS_PER_SM;
-        residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts);
+        residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts, d_done);
         return cudaGetLastError();
     }
     static bool attr_done = false;
@@ -1113,7 +1129,9 @@ static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint
     uint32_t ctas = (P.cta_total * njobs + 1) / 2;
     if (ctas > 148u * 4u) ctas = 148u * 4u;
     residual_sb4_kernel<<<ctas, SB_THREADS, smem, s>>>(P, d_jobs, njobs, d_lists, d_counts);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && d_done) e = cudaMemsetAsync(d_counts, 0, (size_t)njobs * 4 * sizeof(uint32_t), s);   // this variant does not clear them itself
+    return e;
 }
 
 cudaError_t launch_decode_p_two_pass2(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
@@ -1145,7 +1163,7 @@ cudaError_t launch_decode_p_two_pass2(const SbParams &P, const DecJob *d_jobs, u
     }
     uint32_t ctas = P.cta_total * njobs;                      // worst case: every macroblock coded
     if (ctas > 148u * 3u) ctas = 148u * 3u;
-    residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts);
+    residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts, nullptr);
     return cudaGetLastError();
 }
 
