@@ -91,6 +91,17 @@ constexpr int WIN_BYTES = WIN_W * WIN_H;
 constexpr int WINP_W = 188;                  // re-pitched window: 47 words per row (odd: rows spread over all banks)
 constexpr int WINP_BYTES = WINP_W * WIN_H;
 
+// true the first time it is called with the calling thread's current device (per-device one-time setup such as
+// cudaFuncSetAttribute; a race between two host threads only repeats the setup)
+inline bool first_use_on_device(bool (&done)[64])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 // records the calling thread's error text (pfv_last_error) and returns `code`
 int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 

@@ -612,12 +612,11 @@ cudaError_t launch_decode_p_two_pass3(const SbParams &P, const DecJob *d_jobs, u
                                       uint32_t *d_lists, uint32_t *d_counts, int *d_err,
                                       const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s)
 {
-    static bool attr_done = false;
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const int mc_smem = (int)sizeof(Mc3Smem);
-    if (!attr_done) {
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(mc_copy3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mc_smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const FrameGeom &g = P.g;
     McTiles T;
@@ -957,12 +956,11 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
                                       bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
                                       cudaEvent_t after_copy, uint32_t *d_done)
 {
-    static bool attr_done = false;
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const int mc_smem = (int)sizeof(Mc4Smem);
-    if (!attr_done) {
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(mc_copy4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mc_smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const FrameGeom &g = P.g;
     McWin W;
@@ -1119,12 +1117,11 @@ static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint
         residual_sb2_kernel<<<ctas, SB_THREADS, (njobs * 3 + 1) * sizeof(uint32_t), s>>>(P, d_jobs, njobs, d_lists, d_counts, d_done);
         return cudaGetLastError();
     }
-    static bool attr_done = false;
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const size_t smem = sizeof(Rs4Smem) + (njobs * 3 + 1) * sizeof(uint32_t);
-    if (!attr_done) {
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(residual_sb4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     uint32_t ctas = (P.cta_total * njobs + 1) / 2;
     if (ctas > 148u * 4u) ctas = 148u * 4u;
@@ -1137,12 +1134,11 @@ static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint
 cudaError_t launch_decode_p_two_pass2(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
                                       uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s)
 {
-    static bool attr_done = false;
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const int mc_smem = MC2_WARPS * 2 * MC2_BUF;
-    if (!attr_done) {
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(mc_copy2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mc_smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const FrameGeom &g = P.g;
     McTiles T;

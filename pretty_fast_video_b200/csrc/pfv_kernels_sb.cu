@@ -707,12 +707,11 @@ cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint
 // Job coefficient pointers must be 16-byte aligned (bulk copies); pfv_decode_submit checks.
 cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(StreamSmem));
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     sbw_split(P, njobs, 6u * 148u * 12u, 16u);               // ~6 waves of 148 SMs x 12 resident warps
     dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);
@@ -722,12 +721,11 @@ cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t nj
 
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(decode_p_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(PStreamSmem));
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     sbw_split(P, njobs, 6u * 148u * 8u, 16u);                 // ~6 waves of 148 SMs x 8 resident warps
     dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);

@@ -447,3 +447,35 @@ def test_full_size_1080p_properties():
         e.sync()
         assert np.array_equal(e.slot_read(2), e.slot_read(0))
         assert np.array_equal(e.slot_read(3), e.slot_read(1))
+
+
+def test_contexts_on_two_devices_in_one_process():
+    """One process may own contexts on several GPUs (the sharded path normally uses one process per GPU): per-device
+    kernel attributes, pools and streams must not leak between them."""
+    from pretty_fast_video_b200 import _native as N
+    if N.lib().pfv_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h = 336, 208
+    rng = np.random.default_rng(41)
+    qt, _ = make_qtables(5)
+    og = pfvo.geometry_for(w, h)
+    ci = rand_coeffs(rng, og.nb, "mixed")
+    hdr = rand_headers(rng, og)
+    cp = rand_coeffs(rng, og.nb, "mixed")
+    cp.reshape(-1, 256)[hdr[:, 2] == 0] = 0
+    want0 = pfvo.frame_init(og)
+    pfvo.decode_iframe_coeffs(og, qt, (0, 1, 1), ci, want0)
+    want1 = want0.copy()
+    pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdr, cp, want1)
+    engines = [Engine(w, h, qt, nslots=2, max_jobs=1, device=d) for d in (1, 0, 1)]
+    try:
+        for e in engines:
+            e.decode_submit([DecodeJob(PFV_FRAME_I, 0, ci, (0, 1, 1))])
+        for e in engines:
+            e.decode_submit([DecodeJob(PFV_FRAME_P, 1, cp, (2, 3, 3), ref_slot=0, hdr=hdr)])
+        for e in engines:
+            e.sync()
+            assert np.array_equal(e.slot_read(0), want0) and np.array_equal(e.slot_read(1), want1)
+    finally:
+        for e in engines:
+            e.close()
