@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # The engine library is built in-tree (__graft_entry__.build()); a checkout without it gets one build attempt
+    # here so that the suites can run.  The PRODUCT never builds or falls back by itself: _native.lib() raises.
+    import subprocess
+    lib = os.path.join(ROOT, "pretty_fast_video_b200", "libpfv_b200.so")
+    if not os.path.exists(lib):
+        subprocess.call(["make", "-C", os.path.join(ROOT, "pretty_fast_video_b200", "csrc")])
 
 
 def _has_gpu():
