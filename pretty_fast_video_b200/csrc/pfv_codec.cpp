@@ -953,7 +953,6 @@ struct pfv_encoder {
     std::deque<std::shared_ptr<OutPacket>> pending;   // packets in stream order, not yet appended to `stream`
     std::vector<uint8_t> stream;                      // the writer W
     uint32_t prev_slot = 0;
-    uint32_t max_pending = 4;
     bool finished = false;
     size_t ysz = 0, csz = 0;
 };
@@ -1005,7 +1004,6 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
         e->work.push_back(std::move(w));
     }
     e->pool.reset(new Pool(num_threads ? std::min<uint32_t>(num_threads, depth) : 1));
-    e->max_pending = depth;
     // write_header, src/enc.rs:190-219
     std::vector<uint8_t> &s = e->stream;
     s.insert(s.end(), kMagic, kMagic + 8);

@@ -287,3 +287,26 @@ def test_decoder_reproduces_the_committed_golden_stream():
                 enc.encode_pframe(sv.frame(t))
         enc.finish()
         assert enc.bytes() == data
+
+
+def test_unknown_packets_are_skipped_and_p_first_streams_decode():
+    """src/dec.rs:216-219: a packet of an unknown type is skipped over by its length.  And a stream whose first picture
+    is a P frame decodes against the blank initial framebuffer (Y = 0, U = V = 128, src/frame.rs:38-43)."""
+    data, _ = oracle_stream(96, 64, 6, 3, 3, 9)
+    info, _ = codec.parse_header(data)
+    pk, _ = codec.index_packets(data, info.first_packet)
+    junk = bytes([7]) + (11).to_bytes(4, "little") + bytes(range(11))
+    cut = pk[2][2] - 5                                               # in front of the third frame packet
+    spliced = data[:cut] + junk + data[cut:]
+    want, want_fb = oracle_decode_all(spliced)
+    got, fb = gpu_decode_all(spliced, num_threads=2)
+    same_frames(got, want)
+    assert np.array_equal(fb, want_fb)
+    base, _ = oracle_decode_all(data)
+    same_frames(got, base)                                           # the junk packet changes nothing
+    # drop the leading key frame: the stream now starts with two P frames
+    headless = data[:info.first_packet] + data[pk[1][2] - 5:]
+    want, want_fb = oracle_decode_all(headless)
+    got, fb = gpu_decode_all(headless, num_threads=2)
+    same_frames(got, want)
+    assert np.array_equal(fb, want_fb)
