@@ -501,13 +501,14 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
         c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : (strcmp(v, "sbw") == 0 ? 3 : 0));
-    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : (strcmp(v, "stream") == 0 ? 1 : (strcmp(v, "two1") == 0 ? 4 : (strcmp(v, "two") == 0 ? 5 : (strcmp(v, "tma") == 0 ? 6 : (strcmp(v, "winll") == 0 ? 7 : 0))))));
+    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : (strcmp(v, "stream") == 0 ? 1 : (strcmp(v, "two1") == 0 ? 4 : (strcmp(v, "two") == 0 ? 5 : (strcmp(v, "tma") == 0 ? 6 : (strcmp(v, "winll") == 0 ? 7 : (strcmp(v, "live") == 0 ? 8 : 0)))))));
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
     CU_TRY(cudaMalloc(&c->d_plist, (size_t)c->max_jobs * c->geo.nb * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&c->d_pcount, ((size_t)c->max_jobs * 4 + 4) * sizeof(uint32_t)));   // + the residual kernel's "CTAs done" counter
-    CU_TRY(cudaMemset(c->d_pcount, 0, ((size_t)c->max_jobs * 4 + 4) * sizeof(uint32_t)));
+    // list counts | "CTAs done" counter (4 words) | live mode: windows done per frame | chunk tickets per frame
+    CU_TRY(cudaMalloc(&c->d_pcount, ((size_t)c->max_jobs * 6 + 4) * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(c->d_pcount, 0, ((size_t)c->max_jobs * 6 + 4) * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_err, sizeof(int)));
     CU_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
     CU_TRY(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocDefault));
@@ -598,6 +599,9 @@ extern "C" int pfv_sync(pfv_ctx *c)
         *c->h_err = 0;
         CU_TRY(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->s_compute));
         CU_TRY(cudaStreamSynchronize(c->s_compute));
+        if (bits & ERRBIT_TIMEOUT)
+            return fail(PFV_ERR_CUDA, "decode-P live mode: the residual kernel waited ~0.2 s for a frame the copy kernel never finished "
+                                      "(the two kernels were not co-resident?); pictures of that batch are incomplete");
         if (bits & ERRBIT_BAD_MV)
             return fail(PFV_ERR_BAD_MV, "a motion vector pointed outside the padded plane (src/common.rs:258-259); "
                                         "the co-located block was used instead");
@@ -970,19 +974,28 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                 CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
             } else if (c->decode_p_variant == 1) {
                 CU_TRY(launch_decode_p_stream(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
-            } else if ((c->decode_p_variant == 0 || c->decode_p_variant == 7) && c->have_tma) {
-                // Optional (PFV_DECODE_P_SPLIT > 1): the copy kernel is memory bound and light on registers, the residual
-                // kernel ALU bound and heavy on them, and the jobs of a batch are independent, so the batch can be cut into
-                // parts that alternate between two streams, the second stream starting one copy kernel late:
-                //   s_compute: copy0 | resid0 | copy2 | resid2          s_aux:        | copy1  | resid1 | copy3 | resid3
-                // Measured slower than one pair of launches over the whole batch (see p_split), so the default is 1.
+            } else if (c->decode_p_variant == 8 && c->have_tma && a == n_i && b == njobs) {
+                // "live": copy and residual kernels side by side on two streams (see launch_decode_p_live)
+                if (!c->pcount_clean) {
+                    CU_TRY(cudaMemsetAsync(c->d_pcount, 0, ((size_t)c->max_jobs * 6 + 4) * sizeof(uint32_t), c->s_compute));
+                    c->pcount_clean = true;
+                }
+                CU_TRY(cudaEventRecord(c->ev_fork, c->s_compute));
+                CU_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+                CU_TRY(launch_decode_p_live(sb_params(order[a]), d_tab + a, b - a, c->d_plist, c->d_pcount,
+                                            c->d_pcount + (size_t)c->max_jobs * 4, c->max_jobs, c->d_err, c->tm_win_luma, c->tm_win_chroma,
+                                            c->s_compute, c->s_aux));
+                CU_TRY(cudaEventRecord(c->ev_join, c->s_aux));
+                CU_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_join, 0));
+                c->launches++;
+            } else if ((c->decode_p_variant == 0 || c->decode_p_variant == 7 || c->decode_p_variant == 8) && c->have_tma) {
                 const uint32_t k0 = a - n_i, n = b - a;
                 // list counts: cleared by the previous residual kernel itself when the whole group goes out as one pair of
                 // launches on the default kernels (self_clear); otherwise by a memset node here
-                const bool self_clear = c->p_split <= 1 && c->decode_p_variant == 0 && k0 == 0 && c->pcount_clean;
+                const bool self_clear = c->p_split <= 1 && (c->decode_p_variant == 0 || c->decode_p_variant == 8) && k0 == 0 && c->pcount_clean;
                 if (!self_clear)
                     CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)n * 4 * sizeof(uint32_t), c->s_compute));
-                c->pcount_clean = c->p_split <= 1 && c->decode_p_variant == 0 && k0 == 0 && n == njobs - n_i;
+                c->pcount_clean = c->p_split <= 1 && (c->decode_p_variant == 0 || c->decode_p_variant == 8) && k0 == 0 && n == njobs - n_i;
                 uint32_t parts = (uint32_t)c->p_split;
                 if (parts > n / 2) parts = n / 2;                   // at least 2 frames per part
                 if (parts < 1) parts = 1;

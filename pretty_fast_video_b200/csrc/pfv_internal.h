@@ -81,7 +81,7 @@ struct McTiles {
 };
 
 // error bits the kernels OR into the context's device error word
-enum { ERRBIT_BAD_MV = 1 };
+enum { ERRBIT_BAD_MV = 1, ERRBIT_TIMEOUT = 2 };
 
 // search window of an encode-P tile: 16 px left margin + 8 macroblocks + 15 px right margin, rounded so the
 // row pitch (44 words) spreads the eight rows of a sub-block over distinct banks; 15 + 16 + 15 rows.
@@ -120,6 +120,9 @@ cudaError_t launch_decode_p_two_pass3(const SbParams &P, const DecJob *d_jobs, u
 cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
                                       bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
                                       cudaEvent_t after_copy, uint32_t *d_done);
+cudaError_t launch_decode_p_live(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
+                                 uint32_t *d_ctl, uint32_t max_jobs, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
+                                 cudaStream_t s_copy, cudaStream_t s_resid);
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);

@@ -676,7 +676,8 @@ struct McWin {                                                // window items of
 __global__ void __launch_bounds__(MC4_ROWS * 32)
 mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McWin W, const DecJob *__restrict__ jobs,
                 uint32_t njobs, uint32_t *__restrict__ lists, uint32_t *__restrict__ counts, int *__restrict__ err,
-                const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
+                const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma,
+                uint32_t *__restrict__ jobdone)
 {
     extern __shared__ __align__(128) unsigned char mc4_raw[];
     Mc4Smem &sm = *reinterpret_cast<Mc4Smem *>(mc4_raw);
@@ -695,9 +696,12 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
     auto decode_item = [&](uint32_t it) {
         // frame-interleaved order: CTAs that run at the same time work on DIFFERENT frames, so their list-count atomics
         // hit njobs * 3 different addresses instead of the same handful
+        // (live mode, jobdone != nullptr: frame-major instead, so that frames complete one after the other and the
+        // residual kernel running next to this one can start on frame 0 while the later frames are still copied)
         Item r;
-        const uint32_t wi = it / njobs;
-        r.job = it - wi * njobs;
+        uint32_t wi;
+        if (jobdone) { r.job = it / W.total; wi = it - r.job * W.total; }
+        else { wi = it / njobs; r.job = it - wi * njobs; }
         r.p = (wi >= W.base[1] ? 1u : 0u) + (wi >= W.base[2] ? 1u : 0u);
         const uint32_t li = wi - (r.p == 0 ? W.base[0] : (r.p == 1 ? W.base[1] : W.base[2]));
         const uint32_t txs = r.p == 0 ? W.tiles_x[0] : (r.p == 1 ? W.tiles_x[1] : W.tiles_x[2]);
@@ -825,7 +829,9 @@ mc_copy4_kernel(const __grid_constant__ FrameGeom g, const __grid_constant__ McW
                 lists[(size_t)cur.job * g.nb + pl.mb_base + list_base + (uint32_t)__popc(vote & ((1u << lane) - 1u))] = lm;
             }
         }
+        if (jobdone) __threadfence();                         // this thread's stores of the window are visible device-wide ...
         __syncthreads();                                      // the whole CTA is done with this stage
+        if (jobdone && threadIdx.x == 0) atomicAdd(&jobdone[cur.job], 1u);   // ... before the window is counted as done
         cur = nxt; hw_cur = hw_next;
         nxt = nn; hw_next = hw_nn;
         vote = vote_next;
@@ -976,7 +982,7 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
         uint32_t ctas = njobs * W.total;
         const uint32_t resident = 148u * (uint32_t)(cps_env > 0 ? cps_env : 6);
         if (ctas > resident) ctas = resident;
-        mc_copy4_kernel<<<ctas, MC4_ROWS * 32, mc_smem, s>>>(g, W, d_jobs, njobs, d_lists, d_counts, d_err, tm_luma, tm_chroma);
+        mc_copy4_kernel<<<ctas, MC4_ROWS * 32, mc_smem, s>>>(g, W, d_jobs, njobs, d_lists, d_counts, d_err, tm_luma, tm_chroma, nullptr);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (after_copy && (e = cudaEventRecord(after_copy, s)) != cudaSuccess) return e;
@@ -1129,6 +1135,135 @@ static cudaError_t launch_residual(const SbParams &P, const DecJob *d_jobs, uint
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && d_done) e = cudaMemsetAsync(d_counts, 0, (size_t)njobs * 4 * sizeof(uint32_t), s);   // this variant does not clear them itself
     return e;
+}
+
+// -------------------------------------------------------------------------------------------------
+// "live" decode-P: the copy kernel and the residual kernel run AT THE SAME TIME on two streams and share the SMs
+// (copy: 32 registers, memory bound; residual: 128 registers, issue bound).  The copy kernel walks the frames one
+// after the other and counts finished windows per frame (jobdone); a residual CTA waits until a frame is complete,
+// then takes 32-macroblock chunks of its lists from a per-frame ticket counter until there are none left, and moves
+// on to the next frame.  Grids are sized so that both kernels are resident together (4 + 2 CTAs per SM); the wait is
+// bounded: a frame that does not complete within ~0.2 s flags ERRBIT_TIMEOUT instead of hanging the GPU.
+// The last residual CTA clears every counter for the next batch.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 2)
+residual_live_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs, uint32_t njobs,
+                     const uint32_t *lists, uint32_t *counts, uint32_t *jobdone, uint32_t *rtake, uint32_t *done,
+                     uint32_t windows_per_job, int *__restrict__ err)
+{
+    __shared__ uint32_t s_chunk, s_ok;
+    const int sb = (int)(threadIdx.x & 3u);
+#pragma unroll 1
+    for (uint32_t j = 0; j < njobs; ++j) {
+        if (threadIdx.x == 0) {
+            uint32_t spins = 0, ok = 1;
+            while (ld_acquire_u32(&jobdone[j]) < windows_per_job) {
+                __nanosleep(100);
+                if (++spins > 2000000u) { atomicOr(err, ERRBIT_TIMEOUT); ok = 0; break; }
+            }
+            s_ok = ok;
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        const uint32_t c0 = __ldcg(&counts[j * 4u + 0]), c1 = __ldcg(&counts[j * 4u + 1]), c2 = __ldcg(&counts[j * 4u + 2]);
+        const uint32_t n0 = (c0 + SB_MBS_PER_CTA - 1) / SB_MBS_PER_CTA, n1 = (c1 + SB_MBS_PER_CTA - 1) / SB_MBS_PER_CTA,
+                       n2 = (c2 + SB_MBS_PER_CTA - 1) / SB_MBS_PER_CTA;
+        const uint32_t total = n0 + n1 + n2;
+        const DecJob &job = jobs[j];
+#pragma unroll 1
+        for (;;) {
+            __syncthreads();                                  // everyone has read the previous ticket
+            if (threadIdx.x == 0) s_chunk = atomicAdd(&rtake[j], 1u);
+            __syncthreads();
+            const uint32_t chunk = s_chunk;
+            if (chunk >= total) break;
+            const uint32_t p = (chunk >= n0 ? 1u : 0u) + (chunk >= n0 + n1 ? 1u : 0u);
+            const uint32_t cbase = p == 0 ? 0u : (p == 1 ? n0 : n0 + n1), cnt = p == 0 ? c0 : (p == 1 ? c1 : c2);
+            const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+            const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
+            const uint32_t e = (chunk - cbase) * SB_MBS_PER_CTA + (threadIdx.x >> 2);
+            if (e >= cnt) continue;
+            const uint32_t lm = __ldcg(&lists[(size_t)j * P.g.nb + pl.mb_base + e]);
+            const uint4 *src = reinterpret_cast<const uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64));
+            uint4 raw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) raw[k] = __ldcs(src + k);
+            uint32_t col;
+            const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+            uint8_t *dst = job.dst + pl.off + (size_t)(row * 16u + (uint32_t)(sb >> 1) * 8u) * pl.pw + col * 16u + (uint32_t)(sb & 1) * 8u;
+            uint2 prev[8];                                    // the predictor the copy kernel stored here
+#pragma unroll
+            for (int r = 0; r < 8; ++r) prev[r] = __ldcg(reinterpret_cast<const uint2 *>(dst + (size_t)r * pl.pw));
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) any |= raw[k].x | raw[k].y | raw[k].z | raw[k].w;
+            if (__ballot_sync(__activemask(), any != 0u) == 0u) continue;   // nothing to add in this whole warp
+            int m[64];
+            unpack_dequant(raw, deq, m);
+            idct8x8_regs(m);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = m[r * 8 + i];
+                __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), apply_residual_row(y, prev[r]));   // src/common.rs:277
+            }
+        }
+    }
+    // the last CTA to leave clears the counters of this batch
+    __shared__ uint32_t last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last) {
+        for (uint32_t i = threadIdx.x; i < njobs * 4u; i += SB_THREADS) counts[i] = 0u;
+        for (uint32_t i = threadIdx.x; i < njobs; i += SB_THREADS) { jobdone[i] = 0u; rtake[i] = 0u; }
+        if (threadIdx.x == 0) *done = 0u;
+    }
+}
+
+// ctl: [done (4 words) | jobdone (max_jobs) | rtake (max_jobs)], zero on entry and on exit
+cudaError_t launch_decode_p_live(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
+                                 uint32_t *d_ctl, uint32_t max_jobs, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
+                                 cudaStream_t s_copy, cudaStream_t s_resid)
+{
+    static bool attr_done[64] = {};
+    const int mc_smem = (int)sizeof(Mc4Smem);
+    if (first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(mc_copy4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mc_smem);
+        if (e != cudaSuccess) return e;
+    }
+    const FrameGeom &g = P.g;
+    McWin W;
+    uint32_t t = 0;
+    for (int p = 0; p < 3; p++) {
+        W.base[p] = t;
+        W.tiles_x[p] = (g.pl[p].bw + 7u) / 8u;
+        t += W.tiles_x[p] * ((g.pl[p].bh + MC4_ROWS - 1) / MC4_ROWS);
+    }
+    W.total = t;
+    static const int cc_env = getenv("PFV_LIVE_COPY_CTAS") ? atoi(getenv("PFV_LIVE_COPY_CTAS")) : 0;
+    static const int rc_env = getenv("PFV_LIVE_RESID_CTAS") ? atoi(getenv("PFV_LIVE_RESID_CTAS")) : 0;
+    uint32_t *jobdone = d_ctl + 4, *rtake = d_ctl + 4 + max_jobs;
+    uint32_t ctas = njobs * W.total;
+    const uint32_t copy_res = 148u * (uint32_t)(cc_env > 0 ? cc_env : 4);
+    if (ctas > copy_res) ctas = copy_res;
+    mc_copy4_kernel<<<ctas, MC4_ROWS * 32, mc_smem, s_copy>>>(g, W, d_jobs, njobs, d_lists, d_counts, d_err, tm_luma, tm_chroma, jobdone);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint32_t rctas = 148u * (uint32_t)(rc_env > 0 ? rc_env : 2);
+    residual_live_kernel<<<rctas, SB_THREADS, 0, s_resid>>>(P, d_jobs, njobs, d_lists, d_counts, jobdone, rtake, d_ctl, W.total, d_err);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_decode_p_two_pass2(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,

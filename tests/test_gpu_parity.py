@@ -102,7 +102,7 @@ def test_decode_pframe_matches_oracle(size, mode):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("ivar,pvar", [("tma", "win"), ("tma", "winll"), ("tma", "tma"), ("sbw", "two"), ("sb", "two1"), ("warp", "stream"), ("tma", "sbw"),
+@pytest.mark.parametrize("ivar,pvar", [("tma", "win"), ("tma", "live"), ("tma", "winll"), ("tma", "tma"), ("sbw", "two"), ("sb", "two1"), ("warp", "stream"), ("tma", "sbw"),
                                        ("tma", "warp")])
 def test_decode_kernel_variants_agree(ivar, pvar, monkeypatch):
     """The earlier kernels stay selectable (PFV_DECODE_*_VARIANT) and agree with the default ones."""
@@ -128,7 +128,7 @@ def test_decode_kernel_variants_agree(ivar, pvar, monkeypatch):
         assert np.array_equal(e.slot_read(1), want1)
 
 
-@pytest.mark.parametrize("pvar", ["win", "winll", "tma", "two", "two1", "stream", "sbw", "warp"])
+@pytest.mark.parametrize("pvar", ["win", "live", "winll", "tma", "two", "two1", "stream", "sbw", "warp"])
 def test_decode_pframe_long_motion_vectors(pvar, monkeypatch):
     """The stream format carries 7-bit vectors (src/dec.rs:367-368) and the reference decoder follows any vector that
     stays inside the padded plane (src/common.rs:255-261), also ones its own encoder (|mv| <= 15) never emits."""
@@ -189,6 +189,35 @@ def test_host_compaction_of_dense_buffers_is_transparent(compact, mode, monkeypa
             cz.reshape(-1, 256)[hdrs[i][:, 2] == 0] = 0
             pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdrs[i], cz, want)
             assert np.array_equal(e.slot_read(2 * i + 1), want)
+
+
+def test_live_mode_batches_match_oracle(monkeypatch):
+    """PFV_DECODE_P_VARIANT=live: copy and residual kernels run concurrently, frames complete one after the other;
+    a chain of batched P submits must still give the oracle's pictures."""
+    monkeypatch.setenv("PFV_DECODE_P_VARIANT", "live")
+    w, h = 400, 240
+    rng = np.random.default_rng(77)
+    qt, _ = make_qtables(5)
+    og = pfvo.geometry_for(w, h)
+    L, T = 5, 4
+    state = [rng.integers(0, 256, pfvo.frame_init(og).size).astype(np.uint8) for _ in range(L)]
+    with Engine(w, h, qt, nslots=2 * L, max_jobs=L) as e:
+        for l in range(L):
+            e.slot_write(2 * l, state[l])
+        cur = [2 * l for l in range(L)]
+        for t in range(T):
+            jobs = []
+            for l in range(L):
+                hdr = rand_headers(rng, og, p_coded=0.3 + 0.1 * l)
+                coeff = rand_coeffs(rng, og.nb, "mixed")
+                coeff.reshape(-1, 256)[hdr[:, 2] == 0] = 0
+                pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdr, coeff, state[l])
+                jobs.append(DecodeJob(PFV_FRAME_P, cur[l] ^ 1, coeff, (2, 3, 3), ref_slot=cur[l], hdr=hdr))
+                cur[l] ^= 1
+            e.decode_submit(jobs)
+        e.sync()
+        for l in range(L):
+            assert np.array_equal(e.slot_read(cur[l]), state[l])
 
 
 def test_residual_kernel_variants_agree(monkeypatch):

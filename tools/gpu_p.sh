@@ -2,7 +2,7 @@
 # decode-P iteration: parity tests that touch decode-P, then the P workload with the v1 and v2 kernels, launch list
 TAG=${1:-p}
 OUT=gpurun_out; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_codec.py -x -q -k "pframe or long_motion or variants or stream or batched or decoder or sparse or full_size" 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_codec.py -x -q -k "pframe or long_motion or live or variants or stream or batched or decoder or sparse or full_size" 2>&1 | tail -5
 for V in ${VARIANTS:-win winll two1}; do
   echo "== PFV_DECODE_P_VARIANT=$V"
   PFV_DECODE_P_VARIANT=$V timeout 300 python bench.py --workload decode_p_1080p --extras 0 --cpu-budget 0.1 --steps 10 --e2e 0 2>/dev/null | python -c "
