@@ -81,3 +81,12 @@ def test_product_does_not_reach_into_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pfv_oracle" not in text and "pfvo" not in text and "oracle/" not in text, os.path.join(dirpath, f)
+
+
+def test_cpp_example_builds_and_links_against_the_abi():
+    """examples/decode_speed.cpp (the reference's test_decode_speed_2, src/lib.rs:310-335, on the C ABI) compiles and
+    links; without arguments it prints its usage (no GPU needed for that)."""
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(ROOT, "examples", "decode_speed")], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

@@ -310,3 +310,24 @@ def test_unknown_packets_are_skipped_and_p_first_streams_decode():
     got, fb = gpu_decode_all(headless, num_threads=2)
     same_frames(got, want)
     assert np.array_equal(fb, want_fb)
+
+
+def test_cpp_decode_speed_example_on_the_test2_geometry(tmp_path):
+    """examples/decode_speed.cpp = src/lib.rs:310-335 (test_decode_speed_2) on the C ABI: 512x384, 161 frames, fps 30,
+    quality 2, a key frame every 60 (the parameters of test_encode_2, src/lib.rs:271-292).  The stream it writes is
+    also decoded by the oracle and by the Python mirror: same pictures."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "examples")], stdout=subprocess.DEVNULL)
+    exe = os.path.join(root, "examples", "decode_speed")
+    path = str(tmp_path / "test2_like.pfv")
+    subprocess.check_call([exe, "--make", path, "512", "384", "161"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([exe, path, "3", "6"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert [l.split()[1] for l in out if l.startswith("Decoded")] == ["161"] * 3
+    data = open(path, "rb").read()
+    want, want_fb = oracle_decode_all(data)
+    got, fb = gpu_decode_all(data, num_threads=4)
+    assert len(want) == 161
+    same_frames(got, want)
+    assert np.array_equal(fb, want_fb)
