@@ -14,13 +14,13 @@ with codec.Encoder(w, h, 30, 5, num_threads=16) as enc:
     enc.finish()
     data = enc.bytes()
     print("encoder: %.0f fps" % (gop * ngop / (time.perf_counter() - t0)))
-for threads in (16, 8):
+for threads, ahead in ((16, 0), (16, 48), (16, 24), (12, 48)):
     for rep in range(2):
-        dec = codec.Decoder(data, num_threads=threads)
+        dec = codec.Decoder(data, num_threads=threads, read_ahead=ahead)
         t1 = time.perf_counter()
         n = 0
         while dec.advance_frame(lambda fr: None):
             n += 1
         dt = time.perf_counter() - t1
         dec.close()
-        print("threads %d: %d frames in %.1f ms = %.0f fps" % (threads, n, dt * 1e3, n / dt))
+        print("threads %d ahead %d: %d frames in %.1f ms = %.0f fps" % (threads, ahead, n, dt * 1e3, n / dt))
