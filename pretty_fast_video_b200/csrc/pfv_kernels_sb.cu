@@ -270,14 +270,20 @@ decode_sbw_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__
 // of decode_sbw_kernel<false> lacked (ncu: 25 % issue utilisation, long-scoreboard stalls, 45 % DRAM).
 // Lanes read their 128 B from the stage with the chunk order rotated by (lane & 7) so the 128-byte-strided
 // reads are bank-conflict free; the rotation is undone by address arithmetic when an entry is queued.
-constexpr int STG_STAGES = 2;
 constexpr int STG_TILE_BYTES = 8 * 512;
 
-struct __align__(128) StreamSmem {
-    uint4    stage[SBW_WARPS][STG_STAGES][STG_TILE_BYTES / 16];
-    uint4    coef[SBW_WARPS][SBW_RING * 8];
-    uint32_t id[SBW_WARPS][SBW_RING];
-    uint64_t bar[SBW_WARPS][STG_STAGES];
+// STAGES tiles in flight per warp, RING queue slots per warp.  <2, 64> (the default): the queue always has room for a
+// whole tile (31 carried + 32 new).  <3, 48> and <3, 40> (PFV_DECODE_I_STAGES=3 / 4): a third tile in flight per warp
+// inside the same 3-CTAs-per-SM shared-memory budget; the queue may then be too small for a tile's general
+// sub-blocks, in which case the ones that do not fit wait for a transform pass and are re-read from the stage (kept
+// until then).  Measured on the config-2 stream: 0.81 of roofline for <2, 64> against 0.63 / 0.61 - textured regions
+// are dense, so the overflow path is taken all the time there; kept selectable, parity-tested, not used.
+template <int STAGES, int RING>
+struct __align__(128) StreamSmemT {
+    uint4    stage[SBW_WARPS][STAGES][STG_TILE_BYTES / 16];
+    uint4    coef[SBW_WARPS][RING * 8];
+    uint32_t id[SBW_WARPS][RING];
+    uint64_t bar[SBW_WARPS][STAGES];
     uint32_t left_head[SBW_WARPS], left_cnt[SBW_WARPS];
 };
 
@@ -304,6 +310,9 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+template <int RING>
+__device__ __forceinline__ uint32_t ring_slot(uint32_t u) { return (RING & (RING - 1)) == 0 ? (u & (uint32_t)(RING - 1)) : (u % (uint32_t)RING); }
+
 __device__ __forceinline__ void transform_entry_i(const uint4 *coef, const uint32_t *idv, uint32_t slot, const DecJob &job,
                                                   const PlaneGeom &pl, const int32_t *deq)
 {
@@ -324,11 +333,12 @@ __device__ __forceinline__ void transform_entry_i(const uint4 *coef, const uint3
     }
 }
 
+template <int STAGES, int RING>
 __global__ void __launch_bounds__(SBW_WARPS * 32, 3)
 decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+    StreamSmemT<STAGES, RING> &sm = *reinterpret_cast<StreamSmemT<STAGES, RING> *>(smem_raw);
 
     const uint32_t cta = blockIdx.x;
     const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
@@ -349,16 +359,16 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
     auto issue = [&](uint32_t i) {                            // lane 0 only: tile (tile_begin + i) into stage i % STAGES
         const uint32_t tile = tile_begin + i;
         const uint32_t mbs = min(8u, nmb - tile * 8u);
-        bulk_load(sm.stage[warp][i % STG_STAGES], plane_coeff + (size_t)tile * STG_TILE_BYTES, mbs * 512u,
-                  &sm.bar[warp][i % STG_STAGES]);
+        bulk_load(sm.stage[warp][i % STAGES], plane_coeff + (size_t)tile * STG_TILE_BYTES, mbs * 512u,
+                  &sm.bar[warp][i % STAGES]);
     };
     if (lane == 0) {
 #pragma unroll
-        for (int s2 = 0; s2 < STG_STAGES; ++s2)
+        for (int s2 = 0; s2 < STAGES; ++s2)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bar[warp][s2])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
-        for (uint32_t i = 0; i < STG_STAGES; ++i)
+        for (uint32_t i = 0; i < (uint32_t)STAGES; ++i)
             if (i < ntl) issue(i);
     }
     __syncwarp();
@@ -369,15 +379,13 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
         const uint32_t tile = tile_begin + i;
         const uint32_t lm = tile * 8u + (lane >> 2);
         const bool valid = lm < nmb;
-        const uint4 *stg = sm.stage[warp][i % STG_STAGES];
+        const uint4 *stg = sm.stage[warp][i % STAGES];
 
         // ---- A: take this lane's 128 B out of the stage (chunk k ^ rot lands in raw[k]) ----
-        bar_wait(&sm.bar[warp][i % STG_STAGES], (i / STG_STAGES) & 1u);
+        bar_wait(&sm.bar[warp][i % STAGES], (i / STAGES) & 1u);
         uint4 raw[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) raw[k] = stg[lane * 8u + ((uint32_t)k ^ rot)];
-        __syncwarp();                                         // every lane has read: the stage may be refilled
-        if (lane == 0 && i + STG_STAGES < ntl) issue(i + STG_STAGES);
 
         uint32_t ac = 0u, w0 = 0u;                            // w0: the word that holds the DC coefficient (chunk 0)
 #pragma unroll
@@ -387,14 +395,19 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
             ac |= (is0 ? (raw[k].x & 0xffff0000u) : raw[k].x) | raw[k].y | raw[k].z | raw[k].w;
         }
         const bool general = valid && ac != 0u;
-        const uint32_t vote = __ballot_sync(0xffffffffu, general);
-        if (general) {
-            const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+        const uint32_t vote = __ballot_sync(0xffffffffu, general);  // (also: every lane has read the stage)
+        const uint32_t n = (uint32_t)__popc(vote), rank = (uint32_t)__popc(vote & ((1u << lane) - 1u));
+        const uint32_t room = (uint32_t)RING - (tail - head);
+        const bool overflow = RING < 63 && n > room;          // compile-time false for the 64-slot queue
+        if (!overflow && lane == 0 && i + STAGES < ntl) issue(i + STAGES);   // the stage may be refilled
+        const bool fits = general && (!overflow || rank < room);
+        if (fits) {
+            const uint32_t slot = ring_slot<RING>(tail + rank);
             const uint32_t y = rot ^ (slot & 7u);             // raw[k] is chunk k ^ rot; the ring keeps chunk j at j ^ (slot & 7)
 #pragma unroll
             for (int k = 0; k < 8; ++k) ring[slot * 8u + ((uint32_t)k ^ y)] = raw[k];
             ring_id[slot] = (lm << 2) | (uint32_t)sb;
-        } else if (valid) {
+        } else if (valid && !general) {
             const int c0 = (int)(int16_t)(w0 & 0xffffu);
             const int v = (c0 * deq[0] + (128 << 8)) >> 8;   // both passes collapse to the DC term
             const uint32_t dc4 = pack4_sat_u8(v, v, v, v);
@@ -402,12 +415,32 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
 #pragma unroll
             for (int r = 0; r < 8; ++r) __stcg(reinterpret_cast<uint2 *>(w.dst + (size_t)r * pl.pw), make_uint2(dc4, dc4));
         }
-        tail += (uint32_t)__popc(vote);
-        __syncwarp();
+        if (overflow) {
+            // the queue is full (RING entries): transform 32 of them, then queue the sub-blocks that had to wait,
+            // re-reading them from the stage, and only then let the stage go
+            tail += room;
+            __syncwarp();
+            transform_entry_i(ring, ring_id, ring_slot<RING>(head + lane), job, pl, deq);
+            head += 32u;
+            __syncwarp();
+            if (general && rank >= room) {
+                const uint32_t slot = ring_slot<RING>(tail + (rank - room));
+                const uint32_t y = rot ^ (slot & 7u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ring[slot * 8u + ((uint32_t)k ^ y)] = stg[lane * 8u + ((uint32_t)k ^ rot)];
+                ring_id[slot] = (lm << 2) | (uint32_t)sb;
+            }
+            tail += n - room;
+            __syncwarp();
+            if (lane == 0 && i + STAGES < ntl) issue(i + STAGES);
+        } else {
+            tail += n;
+            __syncwarp();
+        }
 
         // ---- B: a full warp of queued sub-blocks ----
         if (tail - head >= 32u) {
-            transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job, pl, deq);
+            transform_entry_i(ring, ring_id, ring_slot<RING>(head + lane), job, pl, deq);
             head += 32u;
             __syncwarp();
         }
@@ -427,7 +460,7 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
             int w = 0;
 #pragma unroll
             for (int k = 1; k < SBW_WARPS; ++k) w += e >= pre[k] ? 1 : 0;
-            transform_entry_i(sm.coef[w], sm.id[w], (sm.left_head[w] + (e - pre[w])) & (SBW_RING - 1), job, pl, deq);
+            transform_entry_i(sm.coef[w], sm.id[w], ring_slot<RING>(sm.left_head[w] + (e - pre[w])), job, pl, deq);
         }
     }
 }
@@ -705,18 +738,27 @@ cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint
 }
 
 // Job coefficient pointers must be 16-byte aligned (bulk copies); pfv_decode_submit checks.
-cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
+template <int STAGES, int RING>
+static cudaError_t launch_decode_i_stream_t(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
     static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
+    const int smem = (int)sizeof(StreamSmemT<STAGES, RING>);
     if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(StreamSmem));
+        cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel<STAGES, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     sbw_split(P, njobs, 6u * 148u * 12u, 16u);               // ~6 waves of 148 SMs x 12 resident warps
     dim3 grid(P.cta_total, njobs, 1), block(SBW_WARPS * 32, 1, 1);
-    decode_i_stream_kernel<<<grid, block, sizeof(StreamSmem), s>>>(P, d_jobs);
+    decode_i_stream_kernel<STAGES, RING><<<grid, block, smem, s>>>(P, d_jobs);
     return cudaGetLastError();
+}
+
+cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
+{
+    static const int stages_env = getenv("PFV_DECODE_I_STAGES") ? atoi(getenv("PFV_DECODE_I_STAGES")) : 2;
+    if (stages_env == 3) return launch_decode_i_stream_t<3, 48>(P, d_jobs, njobs, s);
+    if (stages_env == 4) return launch_decode_i_stream_t<3, 40>(P, d_jobs, njobs, s);
+    return launch_decode_i_stream_t<2, 64>(P, d_jobs, njobs, s);
 }
 
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s)
