@@ -481,6 +481,48 @@ def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
                "d2h_bytes_per_step": int(nframes * st.nb * 512 + (G - 1) * L * st.nb * 4), "jobs_per_submit": chunk}
         eng2.close()
         oa.close()
+
+        # ---- the same through the sparse encode seam (pfv_encode_submit_sparse): the run-length pass runs on the device and
+        # the device itself stores each frame's RLE sequence into pinned host memory ----
+        from pretty_fast_video_b200 import _native as N
+        from pretty_fast_video_b200.engine import SparseEncodeJob
+        cap = st.nb * 64                                            # entries per frame; the overflow flag is checked below
+        eng3 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
+        sa = PinnedArena(G * L * (cap * 4 + st.nb * 4 + 1024) + 8192)
+        ot = sa.take((G, L, cap), np.uint32)
+        os_ = sa.take((G, L, 64), np.uint32)
+        oh3 = sa.take((G, L, st.nb, 4), np.uint8)
+        cur = [2 * i for i in range(L)]
+        tabs3 = []
+        for rep in range(2):
+            for k in range(G):
+                jobs = []
+                for lane in range(L):
+                    b = hs[k, lane].ctypes.data
+                    dst = cur[lane] ^ 1
+                    jobs.append(SparseEncodeJob(PFV_FRAME_I if k == 0 else PFV_FRAME_P, dst, (b, b + ysz, b + ysz + csz), ot[k, lane],
+                                                os_[k, lane], tok_cap=cap, ref_slot=cur[lane], px_err=st.px_err, hdr_out=oh3[k, lane]))
+                    cur[lane] = dst
+                tabs3.append([(eng3.build_sparse_encode_jobs(jobs[i:i + chunk]), jobs[i:i + chunk]) for i in range(0, L, chunk)])
+        ph3 = [0]
+
+        def step_sparse():
+            base = (ph3[0] % 2) * G
+            for k in range(G):
+                for arr, jobs in tabs3[base + k]:
+                    eng3.encode_submit_sparse(jobs, prebuilt=arr)
+            ph3[0] += 1
+
+        s_max, _ = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
+        ntok = os_[:, :, N.PFV_TOKSTATS_NTOK].astype(np.int64)
+        assert not (os_[:, :, N.PFV_TOKSTATS_FLAGS] != 0).any(), "token buffer overflow in the sparse encode leg"
+        e2e["sparse"] = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
+                         "h2d_bytes_per_step": int(nframes * (ysz + 2 * csz)),
+                         "d2h_bytes_per_step": int(ntok.sum() * 4 + nframes * N.PFV_TOKSTATS_WORDS * 4 + (G - 1) * L * st.nb * 4),
+                         "rle_entries_per_frame": float(ntok.mean()),
+                         "note": "pfv_encode_submit_sparse: run-length pass on the GPU, RLE sequence stored by the device into pinned host memory"}
+        eng3.close()
+        sa.close()
     coded = st.coded[1:]
     alg = L * st.nb * MB_BYTES_ENC_I + int(coded.sum()) * MB_BYTES_ENC_P_CODED + int((~coded).sum()) * MB_BYTES_ENC_P_SKIP
     return dict(max_ms=max_ms, my_ms=my_ms, frames=G * L, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e)

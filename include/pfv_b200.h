@@ -200,6 +200,41 @@ typedef struct pfv_decode_job_sparse {
 } pfv_decode_job_sparse;
 int  pfv_decode_submit_sparse(pfv_ctx *ctx, const pfv_decode_job_sparse *jobs, uint32_t njobs);
 
+/*
+ * Sparse ENCODE transport (SURVEY §8 f2 "on encode" + f4 "GPU-side RLE").  Same work as pfv_encode_submit, but what
+ * comes back is the frame's RLE sequence instead of nb*256 dense coefficients: the run-length pass of
+ * rle_encode (src/rle.rs:9-39, called per macroblock by src/enc.rs:256-262 / :370-378) and the symbol count of
+ * update_table (src/rle.rs:41-47) run on the device.  tok_out[i] = run | size << 4 | uint16(value) << 16 is one
+ * RLESequence {num_zeroes, coeff_size, coeff} (src/rle.rs:3-7), in stream order (macroblocks in frame order, P
+ * macroblocks without coefficients contribute nothing).  stats_out receives PFV_TOKSTATS_WORDS words:
+ *   [0..15]  how often each num_zeroes symbol occurs      [16..31] how often each coeff_size symbol occurs
+ *   [PFV_TOKSTATS_NTOK]  entries the frame produced       [PFV_TOKSTATS_FLAGS]  PFV_TOKFLAG_* bits
+ * which is everything rle_create_huffman (src/rle.rs:49-66) and the bit writer need: pfv_packet_encode_tokens turns
+ * (hdr, tok, stats) into the packet pfv_packet_encode would have produced from the dense coefficients.
+ * tok_out, stats_out and mb_off_out (optional: nb+1 offsets of each macroblock's entries) are written by the device
+ * itself with exactly the bytes the frame needs, so they must be device-accessible: pinned host memory
+ * (pfv_host_alloc, cudaHostAlloc, cudaHostRegister) or device memory.  Pageable memory is refused (PFV_ERR_BAD_ARG).
+ * nb*256 entries always suffice; a smaller tok_cap that overflows stores tok_cap entries and sets PFV_TOKFLAG_OVERFLOW.
+ */
+#define PFV_TOKSTATS_WORDS   36u
+#define PFV_TOKSTATS_NTOK    32u
+#define PFV_TOKSTATS_FLAGS   33u
+#define PFV_TOKFLAG_OVERFLOW 1u     /* the frame produced more than tok_cap entries                                  */
+#define PFV_TOKFLAG_RANGE    2u     /* a coefficient needs more than 15 bits: not representable (src/rle.rs:24, :43) */
+typedef struct pfv_encode_job_sparse {
+    uint32_t kind;             /* PFV_FRAME_I or PFV_FRAME_P                                         */
+    uint32_t flags;            /* PFV_JOB_SRC_RGB, PFV_JOB_DEVICE_PTRS (sources and hdr_out on the device) */
+    uint32_t dst_slot, ref_slot;
+    float    px_err;
+    uint32_t tok_cap;          /* capacity of tok_out in entries                                     */
+    const uint8_t *src_y, *src_u, *src_v;
+    pfv_mbhdr *hdr_out;        /* P: nb headers (any host memory, or device with PFV_JOB_DEVICE_PTRS) */
+    uint32_t  *mb_off_out;     /* optional, nb + 1                                                   */
+    uint32_t  *tok_out;        /* tok_cap entries                                                    */
+    uint32_t  *stats_out;      /* PFV_TOKSTATS_WORDS words                                           */
+} pfv_encode_job_sparse;
+int  pfv_encode_submit_sparse(pfv_ctx *ctx, const pfv_encode_job_sparse *jobs, uint32_t njobs);
+
 /* Every *_submit (and pfv_slot_read_visible) call takes the next submit id (1, 2, ...).  pfv_ctx_wait_submit blocks
  * until the device-to-host copies of that submit have landed (it must be one of the 64 most recent ids); unlike
  * pfv_sync it does not wait for later submits, which is what a read-ahead decoder needs. */
@@ -256,6 +291,14 @@ int pfv_packet_decode(const pfv_geometry *g, uint32_t kind, const uint8_t *paylo
 int pfv_packet_encode(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff,
                       uint8_t *out, size_t cap, size_t *len_out);
 size_t pfv_packet_encode_bound(const pfv_geometry *g);   /* a capacity that always suffices */
+/* The same packet from the sparse encode seam: tok/stats as pfv_encode_submit_sparse delivers them (the Huffman tree
+ * comes from the two histograms, src/rle.rs:49-66; the payload size is known before the first bit is written). */
+int pfv_packet_encode_tokens(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const uint32_t *tok,
+                             const uint32_t *stats, uint8_t *out, size_t cap, size_t *len_out);
+/* Host restatement of the device tokenizer (the run-length pass alone): dense coefficients -> tok/stats/mb_off in
+ * the format above.  What a host without the sparse seam runs before pfv_packet_encode_tokens; mb_off_out may be NULL. */
+int pfv_packet_tokenize(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff,
+                        uint32_t *tok_out, uint32_t tok_cap, uint32_t *mb_off_out, uint32_t *stats_out);
 /* the largest number of tokens pfv_packet_decode can emit for this payload (<= nb*256): sizes tok_out */
 uint32_t pfv_packet_token_bound(const pfv_geometry *g, const uint8_t *payload, size_t len);
 

@@ -1351,6 +1351,24 @@ void pfvo_decoder_free(pfvo_decoder *d)
     free(d->qtables); free(d->framebuffer); free(d->coeffs); free(d->hdrs); free(d);
 }
 
+/* rle.rs:9-39 + rle.rs:41-47 as a callable: the RLE sequence of `data` (one call per macroblock, enc.rs:256-262 / :370-378) and,
+ * added to table[16], its symbol counts.  Returns the sequence length; writes at most cap entries. */
+size_t pfvo_rle_encode(const int16_t *data, size_t n, uint8_t *num_zeroes, uint8_t *coeff_size, int16_t *coeff, size_t cap,
+                       int32_t table[16])
+{
+    rle_vec seq = {0};
+    rle_encode(&seq, data, n);
+    if (table) update_table(table, seq.p, seq.len);
+    for (size_t i = 0; i < seq.len && i < cap; i++) {
+        num_zeroes[i] = seq.p[i].num_zeroes;
+        coeff_size[i] = seq.p[i].coeff_size;
+        coeff[i] = seq.p[i].coeff;
+    }
+    size_t len = seq.len;
+    free(seq.p);
+    return len;
+}
+
 /* lib.rs:96-158 / 160-239: the reference's only asserting tests, as a callable */
 long pfvo_entropy_roundtrip(const int16_t *data, size_t n, int16_t *decoded)
 {

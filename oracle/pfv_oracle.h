@@ -159,6 +159,11 @@ void pfvo_decoder_free(pfvo_decoder *d);
  * Returns number of bytes the run coded to, or <0 on mismatch. `decoded` receives the round trip. */
 long pfvo_entropy_roundtrip(const int16_t *data, size_t n, int16_t *decoded);
 
+/* rle_encode (rle.rs:9-39) + update_table (rle.rs:41-47) of one coefficient slice: returns the sequence length, writes at
+ * most cap entries, adds the symbol counts to table[16] (may be NULL). */
+size_t pfvo_rle_encode(const int16_t *data, size_t n, uint8_t *num_zeroes, uint8_t *coeff_size, int16_t *coeff, size_t cap,
+                       int32_t table[16]);
+
 #ifdef __cplusplus
 }
 #endif

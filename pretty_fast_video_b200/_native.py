@@ -72,6 +72,19 @@ class DecodeJobSparse(C.Structure):
     ]
 
 
+class EncodeJobSparse(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("flags", C.c_uint32), ("dst_slot", C.c_uint32), ("ref_slot", C.c_uint32),
+        ("px_err", C.c_float), ("tok_cap", C.c_uint32),
+        ("src_y", C.c_void_p), ("src_u", C.c_void_p), ("src_v", C.c_void_p),
+        ("hdr_out", C.c_void_p), ("mb_off_out", C.c_void_p), ("tok_out", C.c_void_p), ("stats_out", C.c_void_p),
+    ]
+
+
+PFV_TOKSTATS_WORDS, PFV_TOKSTATS_NTOK, PFV_TOKSTATS_FLAGS = 36, 32, 33
+PFV_TOKFLAG_OVERFLOW, PFV_TOKFLAG_RANGE = 1, 2
+
+
 class StreamInfo(C.Structure):
     _fields_ = [("version", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("framerate", C.c_uint32),
                 ("num_qtables", C.c_uint32), ("first_packet", C.c_uint64)]
@@ -108,6 +121,7 @@ SYMBOLS = {
     "pfv_decode_submit": (C.c_int, [C.c_void_p, C.POINTER(DecodeJob), C.c_uint32]),
     "pfv_encode_submit": (C.c_int, [C.c_void_p, C.POINTER(EncodeJob), C.c_uint32]),
     "pfv_decode_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(DecodeJobSparse), C.c_uint32]),
+    "pfv_encode_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(EncodeJobSparse), C.c_uint32]),
     "pfv_ctx_last_submit_id": (C.c_uint64, [C.c_void_p]),
     "pfv_ctx_wait_submit": (C.c_int, [C.c_void_p, C.c_uint64]),
     "pfv_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
@@ -121,6 +135,10 @@ SYMBOLS = {
     "pfv_packet_encode": (C.c_int, [C.POINTER(Geometry), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                     C.POINTER(C.c_size_t)]),
     "pfv_packet_encode_bound": (C.c_size_t, [C.POINTER(Geometry)]),
+    "pfv_packet_encode_tokens": (C.c_int, [C.POINTER(Geometry), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_size_t, C.POINTER(C.c_size_t)]),
+    "pfv_packet_tokenize": (C.c_int, [C.POINTER(Geometry), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                      C.c_void_p, C.c_void_p]),
     "pfv_packet_token_bound": (C.c_uint32, [C.POINTER(Geometry), C.c_void_p, C.c_size_t]),
     "pfv_decoder_open": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "pfv_decoder_close": (None, [C.c_void_p]),

@@ -109,6 +109,33 @@ def encode_packet(geo: N.Geometry, kind: int, coeff: np.ndarray, hdr: Optional[n
     return out[:n.value].tobytes()
 
 
+def tokenize(geo: N.Geometry, kind: int, coeff: np.ndarray, hdr: Optional[np.ndarray] = None, tok_cap: Optional[int] = None):
+    """Host run-length pass (rle_encode, src/rle.rs:9-39, per macroblock): dense coefficients -> (tok, stats, mb_off) in the
+    format of the sparse encode seam.  tok[i] = run | size << 4 | uint16(value) << 16."""
+    c = np.ascontiguousarray(coeff, np.int16)
+    h = np.ascontiguousarray(hdr, np.uint8) if hdr is not None else None
+    cap = geo.nb * 256 if tok_cap is None else int(tok_cap)
+    tok = np.empty(max(cap, 1), np.uint32)
+    stats = np.zeros(N.PFV_TOKSTATS_WORDS, np.uint32)
+    mb_off = np.zeros(geo.nb + 1, np.uint32)
+    N.check(N.lib().pfv_packet_tokenize(C.byref(geo), kind, h.ctypes.data if h is not None else None, c.ctypes.data,
+                                        tok.ctypes.data, cap, mb_off.ctypes.data, stats.ctypes.data))
+    return tok[:min(int(stats[N.PFV_TOKSTATS_NTOK]), cap)], stats, mb_off
+
+
+def encode_packet_tokens(geo: N.Geometry, kind: int, tok: np.ndarray, stats: np.ndarray, hdr: Optional[np.ndarray] = None) -> bytes:
+    """Entropy-codes one frame from the sparse encode seam (RLE sequence + symbol statistics) -> packet bytes."""
+    t = np.ascontiguousarray(tok, np.uint32)
+    st = np.ascontiguousarray(stats, np.uint32)
+    h = np.ascontiguousarray(hdr, np.uint8) if hdr is not None else None
+    cap = N.lib().pfv_packet_encode_bound(C.byref(geo))
+    out = np.empty(cap, np.uint8)
+    n = C.c_size_t()
+    N.check(N.lib().pfv_packet_encode_tokens(C.byref(geo), kind, h.ctypes.data if h is not None else None, t.ctypes.data,
+                                             st.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
 # ---- Decoder -------------------------------------------------------------------------------------------
 Frame = Tuple[np.ndarray, np.ndarray, np.ndarray]
 

@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -413,19 +414,20 @@ struct BitWriter {
     }
 };
 
-// Encodes into `out` (resized); returns PFV_OK or an error.  scratch is reused across calls by the caller.
-int encode_packet(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff, std::vector<uint32_t> &scratch,
-                  std::vector<uint8_t> &out)
+// The packet from one frame's RLE sequence and symbol statistics (the sparse encode seam, pfv_encode_submit_sparse):
+// tree from the histograms, exact size first, then the bits.
+int encode_packet_tokens(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, const uint32_t *tok, const uint32_t *stats,
+                         std::vector<uint8_t> &out)
 {
     const uint32_t nb = g.nb;
-    uint32_t hist[16] = {0};
-    scratch.resize((size_t)nb * 256);
-    uint32_t *tok = scratch.data();
-    size_t ntok = 0;
-    for (uint32_t m = 0; m < nb; m++) {
-        if (kind == PFV_FRAME_P && !hdr[m].has_coeff) continue;      // subblocks: None (src/enc.rs:357-358)
-        ntok += rle_macroblock(coeff + (size_t)m * 256, tok + ntok, hist);
-    }
+    const size_t ntok = stats[PFV_TOKSTATS_NTOK];
+    if (stats[PFV_TOKSTATS_FLAGS] & PFV_TOKFLAG_OVERFLOW)
+        return set_error(PFV_ERR_BAD_ARG, "the frame produced %zu RLE entries, more than the token buffer holds", ntok);
+    if (stats[PFV_TOKSTATS_FLAGS] & PFV_TOKFLAG_RANGE)
+        return set_error(PFV_ERR_BAD_ARG, "a coefficient needs more than 15 bits: not representable (src/rle.rs:24, :43)");
+    // update_table counts both symbols of an entry into one table (src/rle.rs:41-47)
+    uint32_t hist[16];
+    for (int i = 0; i < 16; i++) hist[i] = stats[i] + stats[16 + i];
     // rle_create_huffman (src/rle.rs:49-66): weights normalised to u8, i32 arithmetic
     int32_t mx = 0;
     for (int i = 0; i < 16; i++) mx = std::max(mx, (int32_t)hist[i]);
@@ -440,14 +442,27 @@ int encode_packet(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, co
     }
     Huffman h;
     h.build(table);
-    // exact payload size
+    // exact payload size: every symbol costs its code, every entry its `size` value bits
     uint64_t bits = 19 * 8;
     if (kind == PFV_FRAME_P)
         for (uint32_t m = 0; m < nb; m++) bits += (hdr[m].mx != 0 || hdr[m].my != 0) ? 16 : 2;
-    for (size_t i = 0; i < ntok; i++) {
-        const uint32_t t = tok[i], run = t & 15u, size = (t >> 4) & 31u;
-        if (size > 15) return set_error(PFV_ERR_BAD_ARG, "coefficient %d needs %u bits: not representable (src/rle.rs:24, :43)", (int)(int16_t)(t >> 16), size);
-        bits += h.len[run] + h.len[size] + size;
+    for (int i = 0; i < 16; i++) bits += (uint64_t)hist[i] * h.len[i] + (uint64_t)stats[16 + i] * (uint32_t)i;
+    // one table lookup per entry: both codes concatenated, indexed by the entry's low byte (run | size << 4)
+    uint32_t pair_val[256];
+    uint8_t  pair_len[256], pair_bits[256];
+    for (uint32_t b = 0; b < 256; b++) {
+        const uint32_t run = b & 15u, size = b >> 4;
+        pair_val[b] = h.val[run] | (h.val[size] << h.len[run]);
+        pair_len[b] = (uint8_t)(h.len[run] + h.len[size]);
+        pair_bits[b] = (uint8_t)(pair_len[b] + size);
+    }
+    {   // the statistics must describe this very sequence: the buffer below is sized from them
+        uint64_t seq_bits = 0, sym_bits = 0;
+        for (size_t i = 0; i < ntok; i++) seq_bits += pair_bits[tok[i] & 255u];
+        for (int i = 0; i < 16; i++) sym_bits += (uint64_t)hist[i] * h.len[i] + (uint64_t)stats[16 + i] * (uint32_t)i;
+        if (seq_bits != sym_bits)
+            return set_error(PFV_ERR_BAD_ARG, "RLE entries and their statistics disagree (%llu bits against %llu)",
+                             (unsigned long long)seq_bits, (unsigned long long)sym_bits);
     }
     const size_t payload = (size_t)((bits + 7) / 8);
     out.resize(5 + payload + 8);                                     // +8: the writer stores 4 bytes at a time
@@ -465,14 +480,62 @@ int encode_packet(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, co
             if (has_mvec) bw.put(((uint32_t)hdr[m].mx & 127u) | (((uint32_t)hdr[m].my & 127u) << 7), 14);
         }
     for (size_t i = 0; i < ntok; i++) {                              // src/enc.rs:301-315, :455-466
-        const uint32_t t = tok[i], run = t & 15u, size = (t >> 4) & 15u;
-        bw.put(h.val[run] | (h.val[size] << h.len[run]), h.len[run] + h.len[size]);
+        const uint32_t t = tok[i], b = t & 255u, size = b >> 4;
+        // code pair (<= 30 bits) and value bits (<= 15) leave the 64-bit window room: one put each
+        bw.put(pair_val[b], pair_len[b]);
         if (size) bw.put((t >> 16) & ((1u << size) - 1u), (int)size);
     }
     uint8_t *end = bw.finish();
     if ((size_t)(end - &out[5]) != payload) return set_error(PFV_ERR_STATE, "internal: packet size mismatch");
     out.resize(5 + payload);
     return PFV_OK;
+}
+
+// Run-length pass on the host: what the device tokenizer (pfv_kernels_tok.cu) emits, from dense coefficients.
+int tokenize_frame(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff, uint32_t *tok, size_t cap,
+                   uint32_t *mb_off, uint32_t *stats)
+{
+    const uint32_t nb = g.nb;
+    uint32_t hist[16] = {0}, sizes[16] = {0};
+    size_t ntok = 0;
+    uint32_t flags = 0;
+    uint32_t local[256 + 32];
+    for (uint32_t m = 0; m < nb; m++) {
+        if (mb_off) mb_off[m] = (uint32_t)ntok;
+        if (kind == PFV_FRAME_P && !hdr[m].has_coeff) continue;      // subblocks: None (src/enc.rs:357-358)
+        const uint32_t n = rle_macroblock(coeff + (size_t)m * 256, local, hist);
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t size = (local[i] >> 4) & 31u;
+            if (size > 15) flags |= PFV_TOKFLAG_RANGE;
+            sizes[size & 15u]++;
+            if (ntok + i < cap) tok[ntok + i] = local[i];
+        }
+        ntok += n;
+    }
+    if (mb_off) mb_off[nb] = (uint32_t)ntok;
+    if (ntok > cap) flags |= PFV_TOKFLAG_OVERFLOW;
+    memset(stats, 0, PFV_TOKSTATS_WORDS * sizeof(uint32_t));
+    for (int i = 0; i < 16; i++) { stats[16 + i] = sizes[i]; stats[i] = hist[i] - sizes[i]; }   // rle_macroblock counts both symbols into hist
+    stats[PFV_TOKSTATS_NTOK] = (uint32_t)ntok;
+    stats[PFV_TOKSTATS_FLAGS] = flags;
+    return PFV_OK;
+}
+
+// Encodes into `out` (resized); returns PFV_OK or an error.  scratch is reused across calls by the caller.
+int encode_packet(const pfv_geometry &g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff, std::vector<uint32_t> &scratch,
+                  std::vector<uint8_t> &out)
+{
+    scratch.resize((size_t)g.nb * 256);
+    uint32_t stats[PFV_TOKSTATS_WORDS];
+    int rc = tokenize_frame(g, kind, hdr, coeff, scratch.data(), scratch.size(), nullptr, stats);
+    if (rc) return rc;
+    if (stats[PFV_TOKSTATS_FLAGS] & PFV_TOKFLAG_RANGE) {
+        for (size_t i = 0; i < stats[PFV_TOKSTATS_NTOK]; i++)
+            if (((scratch[i] >> 4) & 31u) > 15)
+                return set_error(PFV_ERR_BAD_ARG, "coefficient %d needs %u bits: not representable (src/rle.rs:24, :43)",
+                                 (int)(int16_t)(scratch[i] >> 16), (scratch[i] >> 4) & 31u);
+    }
+    return encode_packet_tokens(g, kind, hdr, scratch.data(), stats, out);
 }
 
 }  // namespace
@@ -503,6 +566,30 @@ extern "C" int pfv_packet_encode(const pfv_geometry *g, uint32_t kind, const pfv
     memcpy(out, pkt.data(), pkt.size());
     *len_out = pkt.size();
     return PFV_OK;
+}
+
+extern "C" int pfv_packet_encode_tokens(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const uint32_t *tok,
+                                        const uint32_t *stats, uint8_t *out, size_t cap, size_t *len_out)
+{
+    if (!g || !tok || !stats || !out || !len_out) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    if (kind != PFV_FRAME_I && kind != PFV_FRAME_P) return set_error(PFV_ERR_BAD_ARG, "bad kind %u", kind);
+    if (kind == PFV_FRAME_P && !hdr) return set_error(PFV_ERR_BAD_ARG, "P frames need headers");
+    std::vector<uint8_t> pkt;
+    int rc = encode_packet_tokens(*g, kind, hdr, tok, stats, pkt);
+    if (rc) return rc;
+    if (pkt.size() > cap) return set_error(PFV_ERR_NOMEM, "packet of %zu bytes does not fit %zu", pkt.size(), cap);
+    memcpy(out, pkt.data(), pkt.size());
+    *len_out = pkt.size();
+    return PFV_OK;
+}
+
+extern "C" int pfv_packet_tokenize(const pfv_geometry *g, uint32_t kind, const pfv_mbhdr *hdr, const int16_t *coeff,
+                                   uint32_t *tok_out, uint32_t tok_cap, uint32_t *mb_off_out, uint32_t *stats_out)
+{
+    if (!g || !coeff || !tok_out || !stats_out) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    if (kind != PFV_FRAME_I && kind != PFV_FRAME_P) return set_error(PFV_ERR_BAD_ARG, "bad kind %u", kind);
+    if (kind == PFV_FRAME_P && !hdr) return set_error(PFV_ERR_BAD_ARG, "P frames need headers");
+    return tokenize_frame(*g, kind, hdr, coeff, tok_out, tok_cap, mb_off_out, stats_out);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -926,14 +1013,17 @@ extern "C" int pfv_decoder_advance_delta(pfv_decoder *d, double delta, pfv_onvid
 namespace {
 
 struct EncWork {
-    Pinned   src, coeff, hdr;
+    Pinned   src, coeff, hdr;      // coeff: the RLE sequence + statistics (sparse seam, default) or nb*256 dense coefficients
+    std::vector<uint8_t> packet;   // the finished packet; the buffer is reused frame after frame (a fresh 100+ KB vector per frame
+                                   // means an mmap/munmap pair per frame, and every munmap interrupts all threads of the process)
     uint32_t kind = 0;
     uint64_t submit_id = 0;
-    bool     busy = false;         // guarded by pfv_encoder::m
+    bool     busy = false;         // guarded by pfv_encoder::m; released once the packet has been appended to the stream
 };
 
 struct OutPacket {
-    std::vector<uint8_t> bytes;
+    EncWork *work = nullptr;       // frame packets: bytes are in work->packet
+    std::vector<uint8_t> bytes;    // literal packets (drop frame, eof)
     bool ready = false;
     int  status = PFV_OK;
     char err[256] = "";
@@ -947,6 +1037,8 @@ struct pfv_encoder {
     pfv_geometry geo{};
     pfv_ctx *ctx = nullptr;
     std::unique_ptr<Pool> pool;
+    std::unique_ptr<Pool> copy_pool;                  // helpers for the copy of the caller's planes into pinned memory
+    unsigned copy_helpers = 0;
     std::vector<std::unique_ptr<EncWork>> work;
     std::mutex m;
     std::condition_variable cv;
@@ -954,24 +1046,84 @@ struct pfv_encoder {
     std::vector<uint8_t> stream;                      // the writer W
     uint32_t prev_slot = 0;
     bool finished = false;
+    bool dense = false;            // PFV_ENCODER_DENSE=1: the dense seam (pfv_encode_submit + host run-length pass)
+    bool trace = false;            // PFV_TRACE=1: where the calling thread spends its time, printed at close
+    double t_flush = 0, t_wait = 0, t_copy = 0, t_submit = 0;
+    uint64_t n_frames = 0;
     size_t ysz = 0, csz = 0;
 };
+
+// The caller's planes may be reused as soon as encode_*frame returns (the reference borrows them for the call only), so they are
+// copied into pinned memory first.  One thread moves ~8-10 GB/s, which at 1080p (3.1 MB) is the slowest step of the whole
+// call; large frames are therefore copied in 256 KB pieces by the calling thread and a few helpers.
+static void encoder_copy_planes(pfv_encoder *e, uint8_t *dst, const uint8_t *y, const uint8_t *u, const uint8_t *v)
+{
+    struct Seg { uint8_t *d; const uint8_t *s; size_t n; };
+    const Seg planes[3] = {{dst, y, e->ysz}, {dst + e->ysz, u, e->csz}, {dst + e->ysz + e->csz, v, e->csz}};
+    const size_t total = e->ysz + 2 * e->csz;
+    if (!e->copy_pool || total < ((size_t)1 << 20)) {
+        for (const Seg &p : planes) memcpy(p.d, p.s, p.n);
+        return;
+    }
+    constexpr size_t PIECE = (size_t)256 << 10;
+    std::vector<Seg> segs;
+    for (const Seg &p : planes)
+        for (size_t o = 0; o < p.n; o += PIECE) segs.push_back({p.d + o, p.s + o, std::min(PIECE, p.n - o)});
+    std::atomic<size_t> next{0};
+    std::atomic<unsigned> done{0};
+    auto work = [&] {
+        for (;;) {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= segs.size()) break;
+            memcpy(segs[i].d, segs[i].s, segs[i].n);
+        }
+    };
+    const unsigned helpers = e->copy_helpers;
+    for (unsigned i = 0; i < helpers; i++)
+        e->copy_pool->post([&] { work(); done.fetch_add(1, std::memory_order_release); });
+    work();
+    while (done.load(std::memory_order_acquire) != helpers) std::this_thread::yield();
+}
 
 // append finished packets, in order; wait_all = block until everything submitted so far is in `stream`
 static int encoder_flush(pfv_encoder *e, bool wait_all)
 {
-    std::unique_lock<std::mutex> l(e->m);
-    while (!e->pending.empty()) {
-        std::shared_ptr<OutPacket> p = e->pending.front();
-        if (!p->ready) {
-            if (!wait_all) break;
-            e->cv.wait(l, [&p] { return p->ready; });
+    // finished packets leave the queue under the lock; their bytes are appended outside it (the entropy threads take the same
+    // lock when they finish a frame)
+    std::vector<std::shared_ptr<OutPacket>> ready;
+    {
+        std::unique_lock<std::mutex> l(e->m);
+        while (!e->pending.empty()) {
+            std::shared_ptr<OutPacket> p = e->pending.front();
+            if (!p->ready) {
+                if (!wait_all) break;
+                e->cv.wait(l, [&p] { return p->ready; });
+            }
+            e->pending.pop_front();
+            ready.push_back(std::move(p));
         }
-        e->pending.pop_front();
-        if (p->status != PFV_OK) return set_error(p->status, "%s", p->err);
-        e->stream.insert(e->stream.end(), p->bytes.begin(), p->bytes.end());
     }
-    return PFV_OK;
+    size_t add = 0;
+    int rc = PFV_OK;
+    for (auto &p : ready) {
+        if (p->status != PFV_OK && rc == PFV_OK) rc = set_error(p->status, "%s", p->err);
+        add += p->work ? p->work->packet.size() : p->bytes.size();
+    }
+    if (rc == PFV_OK) {
+        if (e->stream.size() + add > e->stream.capacity())
+            e->stream.reserve(std::max(e->stream.capacity() * 2, e->stream.size() + add + ((size_t)1 << 20)));
+        for (auto &p : ready) {
+            const std::vector<uint8_t> &b = p->work ? p->work->packet : p->bytes;
+            e->stream.insert(e->stream.end(), b.begin(), b.end());
+        }
+    }
+    bool released = false;
+    {
+        std::lock_guard<std::mutex> l(e->m);
+        for (auto &p : ready) if (p->work) { p->work->busy = false; released = true; }
+    }
+    if (released) e->cv.notify_all();
+    return rc;
 }
 
 extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framerate, int quality, uint32_t num_threads, int device,
@@ -992,11 +1144,20 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
     pfv_ctx_geometry(e->ctx, &e->geo);
     e->ysz = (size_t)e->geo.width * e->geo.height;
     e->csz = (size_t)e->geo.cwidth * e->geo.cheight;
-    // frames in flight: one per entropy thread plus two on the GPU (pfv_ctx_wait_submit reaches 64 submits back)
-    const uint32_t depth = std::min<uint32_t>(std::max<uint32_t>(num_threads, 2) + 2, 32);
+    // frames in flight: one per entropy thread, two on the GPU, two finished and waiting to be appended (a work item is held
+    // until then); pfv_ctx_wait_submit reaches 64 submits back
+    const uint32_t depth = std::min<uint32_t>(std::max<uint32_t>(num_threads, 2) + 4, 32);
+    {
+        const char *env = getenv("PFV_ENCODER_DENSE");
+        e->dense = env && atoi(env) != 0;
+        env = getenv("PFV_TRACE");
+        e->trace = env && atoi(env) != 0;
+    }
+    // sparse seam: nb*256 entries always suffice (an entry consumes at least one coefficient), + the statistics block
+    const size_t out_bytes = e->dense ? (size_t)e->geo.nb * 512 : ((size_t)e->geo.nb * 256 + PFV_TOKSTATS_WORDS) * sizeof(uint32_t);
     for (uint32_t i = 0; i < depth; i++) {
         std::unique_ptr<EncWork> w(new EncWork());
-        if ((rc = w->src.reserve(e->ysz + 2 * e->csz)) || (rc = w->coeff.reserve((size_t)e->geo.nb * 512)) ||
+        if ((rc = w->src.reserve(e->ysz + 2 * e->csz)) || (rc = w->coeff.reserve(out_bytes)) ||
             (rc = w->hdr.reserve((size_t)e->geo.nb * sizeof(pfv_mbhdr)))) {
             pfv_ctx_destroy(e->ctx);
             return rc;
@@ -1004,6 +1165,8 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
         e->work.push_back(std::move(w));
     }
     e->pool.reset(new Pool(num_threads ? std::min<uint32_t>(num_threads, depth) : 1));
+    e->copy_helpers = num_threads >= 2 ? std::min<uint32_t>(num_threads - 1, 3) : 0;
+    if (e->copy_helpers) e->copy_pool.reset(new Pool(e->copy_helpers));
     // write_header, src/enc.rs:190-219
     std::vector<uint8_t> &s = e->stream;
     s.insert(s.end(), kMagic, kMagic + 8);
@@ -1022,48 +1185,77 @@ static int encoder_frame(pfv_encoder *e, uint32_t kind, const uint8_t *y, const 
     if (!e) return set_error(PFV_ERR_BAD_ARG, "NULL encoder");
     if (e->finished) return set_error(PFV_ERR_STATE, "encoder is finished (assert!(!self.finished), src/enc.rs:80,130)");
     if (!y || !u || !v) return set_error(PFV_ERR_BAD_ARG, "NULL plane");
-    int rc = encoder_flush(e, false);
-    if (rc) return rc;
+    const double t0 = e->trace ? now_s() : 0;
+    int rc = PFV_OK;
+    double t1 = 0;
     EncWork *w = nullptr;
-    {
+    for (;;) {
+        // a work item is free again once its packet has been appended, which only this thread does: append what is ready,
+        // and if every item is still in flight wait for the oldest packet
+        rc = encoder_flush(e, false);
+        if (rc) return rc;
+        if (e->trace && t1 == 0) t1 = now_s();
         std::unique_lock<std::mutex> l(e->m);
-        e->cv.wait(l, [e] { for (auto &x : e->work) if (!x->busy) return true; return false; });
         for (auto &x : e->work) if (!x->busy) { w = x.get(); break; }
-        w->busy = true;
+        if (w) { w->busy = true; break; }
+        std::shared_ptr<OutPacket> head = e->pending.front();
+        e->cv.wait(l, [&head] { return head->ready; });
     }
+    const double t2 = e->trace ? now_s() : 0;
     uint8_t *src = static_cast<uint8_t *>(w->src.p);
-    memcpy(src, y, e->ysz);
-    memcpy(src + e->ysz, u, e->csz);
-    memcpy(src + e->ysz + e->csz, v, e->csz);
-    pfv_encode_job j;
-    memset(&j, 0, sizeof(j));
-    j.kind = kind;
-    j.ref_slot = e->prev_slot;
-    j.dst_slot = e->prev_slot ^ 1u;
-    j.px_err = e->px_err;
-    j.src_y = src; j.src_u = src + e->ysz; j.src_v = src + e->ysz + e->csz;
-    j.hdr_out = static_cast<pfv_mbhdr *>(w->hdr.p);
-    j.coeff_out = static_cast<int16_t *>(w->coeff.p);
-    rc = pfv_encode_submit(e->ctx, &j, 1);
+    encoder_copy_planes(e, src, y, u, v);
+    const double t3 = e->trace ? now_s() : 0;
+    const uint32_t dst_slot = e->prev_slot ^ 1u;
+    uint32_t *tok = static_cast<uint32_t *>(w->coeff.p), *stats = tok + (size_t)e->geo.nb * 256;
+    if (e->dense) {
+        pfv_encode_job j;
+        memset(&j, 0, sizeof(j));
+        j.kind = kind;
+        j.ref_slot = e->prev_slot;
+        j.dst_slot = dst_slot;
+        j.px_err = e->px_err;
+        j.src_y = src; j.src_u = src + e->ysz; j.src_v = src + e->ysz + e->csz;
+        j.hdr_out = static_cast<pfv_mbhdr *>(w->hdr.p);
+        j.coeff_out = static_cast<int16_t *>(w->coeff.p);
+        rc = pfv_encode_submit(e->ctx, &j, 1);
+    } else {
+        pfv_encode_job_sparse j;
+        memset(&j, 0, sizeof(j));
+        j.kind = kind;
+        j.ref_slot = e->prev_slot;
+        j.dst_slot = dst_slot;
+        j.px_err = e->px_err;
+        j.src_y = src; j.src_u = src + e->ysz; j.src_v = src + e->ysz + e->csz;
+        j.hdr_out = static_cast<pfv_mbhdr *>(w->hdr.p);
+        j.tok_out = tok;
+        j.tok_cap = e->geo.nb * 256u;
+        j.stats_out = stats;
+        rc = pfv_encode_submit_sparse(e->ctx, &j, 1);
+    }
     if (rc) { std::lock_guard<std::mutex> l(e->m); w->busy = false; return rc; }
-    e->prev_slot = j.dst_slot;                                       // src/enc.rs:95-97, :145-147
+    if (e->trace) {
+        e->t_flush += t1 - t0; e->t_wait += t2 - t1; e->t_copy += t3 - t2; e->t_submit += now_s() - t3;
+        e->n_frames++;
+    }
+    e->prev_slot = dst_slot;                                         // src/enc.rs:95-97, :145-147
     w->kind = kind;
     w->submit_id = pfv_ctx_last_submit_id(e->ctx);
     std::shared_ptr<OutPacket> pkt(new OutPacket());
+    pkt->work = w;
     { std::lock_guard<std::mutex> l(e->m); e->pending.push_back(pkt); }
-    e->pool->post([e, w, pkt] {
+    e->pool->post([e, w, pkt, tok, stats] {
         int rc2 = pfv_ctx_wait_submit(e->ctx, w->submit_id);
         if (rc2 == PFV_OK) {
             static thread_local std::vector<uint32_t> scratch;
-            rc2 = encode_packet(e->geo, w->kind, static_cast<const pfv_mbhdr *>(w->hdr.p), static_cast<const int16_t *>(w->coeff.p),
-                                scratch, pkt->bytes);
+            const pfv_mbhdr *hdr = static_cast<const pfv_mbhdr *>(w->hdr.p);
+            rc2 = e->dense ? encode_packet(e->geo, w->kind, hdr, static_cast<const int16_t *>(w->coeff.p), scratch, w->packet)
+                           : encode_packet_tokens(e->geo, w->kind, hdr, tok, stats, w->packet);
         }
         if (rc2) snprintf(pkt->err, sizeof(pkt->err), "%s", pfv_last_error());
         {
             std::lock_guard<std::mutex> l(e->m);
             pkt->status = rc2;
             pkt->ready = true;
-            w->busy = false;
         }
         e->cv.notify_all();
     });
@@ -1125,7 +1317,13 @@ extern "C" void pfv_encoder_close(pfv_encoder *e)
     if (!e) return;
     if (!e->finished) pfv_encoder_finish(e);                         // Drop, src/enc.rs:28-34
     else encoder_flush(e, true);
+    if (e->trace && e->n_frames)
+        fprintf(stderr, "[pfv encoder] %llu frames, per frame on the calling thread: append packets %.1f us, wait for a free work item "
+                        "%.1f us, copy planes %.1f us, submit %.1f us\n", (unsigned long long)e->n_frames,
+                1e6 * e->t_flush / e->n_frames, 1e6 * e->t_wait / e->n_frames, 1e6 * e->t_copy / e->n_frames,
+                1e6 * e->t_submit / e->n_frames);
     e->pool.reset();
+    e->copy_pool.reset();
     if (e->ctx) { pfv_sync(e->ctx); pfv_ctx_destroy(e->ctx); }
     delete e;
 }

@@ -131,7 +131,7 @@ extern "C" int pfv_host_alloc(void **out, size_t bytes)
 {
     if (!out) return fail(PFV_ERR_BAD_ARG, "pfv_host_alloc: out is NULL");
     *out = nullptr;
-    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));   // reachable by every device (sparse encode seam)
     return PFV_OK;
 }
 
@@ -158,6 +158,9 @@ struct Stage {
                                      // allocated; a caller that keeps the three arrays adjacent gets ONE copy per frame
     SparseJob *d_sjobs = nullptr;    // max_jobs
     SparseJob *h_sjobs = nullptr;    // pinned mirror
+    uint32_t  *d_tokpack = nullptr;  // sparse encode, per job slot: [mb_off (nb+1) | RLE entries (nb*256) | statistics], lazily allocated
+    TokJob    *d_tjobs = nullptr;    // max_jobs
+    TokJob    *h_tjobs = nullptr;    // pinned mirror
     uint8_t   *d_rgb_src = nullptr;  // encode jobs with PFV_JOB_SRC_RGB: max_jobs * w*h*3 (lazily allocated)
     uint32_t  *h_tok = nullptr;      // host compaction of dense host buffers: max_jobs * nb * 128 tokens, pinned (lazily allocated)
     uint32_t  *h_mboff = nullptr;    // max_jobs * (nb + 1), pinned
@@ -418,7 +421,8 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     for (int i = 0; i < STAGES; i++) {
         Stage &s = c->st[i];
         cudaFree(s.d_coeff); cudaFree(s.d_hdr); cudaFree(s.d_src); cudaFree(s.d_jobs);
-        cudaFree(s.d_pack); cudaFree(s.d_sjobs); cudaFree(s.d_rgb_src);
+        cudaFree(s.d_pack); cudaFree(s.d_sjobs); cudaFree(s.d_rgb_src); cudaFree(s.d_tokpack); cudaFree(s.d_tjobs);
+        if (s.h_tjobs) cudaFreeHost(s.h_tjobs);
         if (s.h_jobs) cudaFreeHost(s.h_jobs);
         if (s.h_sjobs) cudaFreeHost(s.h_sjobs);
         if (s.h_tok) cudaFreeHost(s.h_tok);
@@ -526,7 +530,14 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
         CU_TRY(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
     }
-    for (int i = 0; i < D2H_RING; i++) CU_TRY(cudaEventCreateWithFlags(&c->ev_d2h_ring[i], cudaEventDisableTiming));
+    {
+        // pfv_ctx_wait_submit is what a host's entropy threads block in, one thread per frame in flight: they sleep in the driver
+        // (cudaEventBlockingSync) instead of spinning, which on a 16-thread host took the cores the submitting thread needs.
+        // PFV_EVENT_SPIN=1 restores busy-waiting (lowest wake-up latency, one core per waiter).
+        const char *env = getenv("PFV_EVENT_SPIN");
+        const unsigned flags = cudaEventDisableTiming | ((env && atoi(env) != 0) ? 0u : (unsigned)cudaEventBlockingSync);
+        for (int i = 0; i < D2H_RING; i++) CU_TRY(cudaEventCreateWithFlags(&c->ev_d2h_ring[i], flags));
+    }
     CU_TRY(cudaEventCreate(&c->ev_k0));
     CU_TRY(cudaEventCreate(&c->ev_k1));
 
@@ -1108,21 +1119,45 @@ extern "C" int pfv_ctx_wait_submit(pfv_ctx *c, uint64_t id)
 // ---------------------------------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------------------------------
-extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_t njobs)
+namespace {
+
+// one frame of either encode entry point
+struct EncIn {
+    uint32_t kind, flags, dst_slot, ref_slot;
+    float    px_err;
+    const uint8_t *src_y, *src_u, *src_v;
+    pfv_mbhdr *hdr_out;
+    int16_t   *coeff_out;                              // dense seam
+    bool       sparse;                                 // sparse seam: the three below, already as device-accessible addresses
+    uint32_t   tok_cap;
+    uint32_t  *mb_off_out, *tok_out, *stats_out;
+};
+
+// the address the device uses for memory the caller handed in; nullptr if the device cannot reach it (pageable host memory)
+uint32_t *device_view(const void *p)
 {
-    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
-    if (njobs == 0) return PFV_OK;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type == cudaMemoryTypeUnregistered || !a.devicePointer) return nullptr;
+    return static_cast<uint32_t *>(a.devicePointer);
+}
+
+int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
+{
     if (njobs > c->max_jobs) return fail(PFV_ERR_BAD_ARG, "%u jobs > max_jobs %u", njobs, c->max_jobs);
     if (c->nq < 4) return fail(PFV_ERR_BAD_ARG, "an encoder context needs the 4 q-tables of src/enc.rs:48-51");
     const pfv_geometry &g = c->geo;
     bool any_p = false, any_rgb = false;
+    uint32_t n_sparse = 0;
     for (uint32_t i = 0; i < njobs; i++) {
-        const pfv_encode_job &j = jobs[i];
+        const EncIn &j = jobs[i];
         if (j.kind != PFV_FRAME_I && j.kind != PFV_FRAME_P) return fail(PFV_ERR_BAD_ARG, "job %u: bad kind %u", i, j.kind);
         if (j.dst_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: dst_slot %u out of range", i, j.dst_slot);
         const bool rgb = (j.flags & PFV_JOB_SRC_RGB) != 0;
         any_rgb |= rgb;
-        if (!j.src_y || (!rgb && (!j.src_u || !j.src_v)) || !j.coeff_out) return fail(PFV_ERR_BAD_ARG, "job %u: NULL plane or coeff_out", i);
+        n_sparse += j.sparse ? 1u : 0u;
+        if (!j.src_y || (!rgb && (!j.src_u || !j.src_v)) || (!j.sparse && !j.coeff_out))
+            return fail(PFV_ERR_BAD_ARG, "job %u: NULL plane or coeff_out", i);
         if (j.kind == PFV_FRAME_P) {
             any_p = true;
             if (j.ref_slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "job %u: ref_slot %u out of range", i, j.ref_slot);
@@ -1147,6 +1182,15 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
     const size_t rgb_bytes = (size_t)g.width * g.height * 3;
     if (any_rgb && !c->st[0].d_rgb_src)
         for (int i = 0; i < STAGES; i++) CU_TRY(cudaMalloc(&c->st[i].d_rgb_src, rgb_bytes * c->max_jobs));
+    // per job slot of the sparse seam: mb_off (nb+1), RLE entries (nb*256), statistics; every part 16-byte aligned
+    const size_t tp_off_words = ((size_t)g.nb + 1 + 3) & ~(size_t)3;
+    const size_t tp_words = tp_off_words + (size_t)g.nb * 256 + PFV_TOKSTATS_WORDS;
+    if (n_sparse && !c->st[0].d_tokpack)
+        for (int i = 0; i < STAGES; i++) {
+            CU_TRY(cudaMalloc(&c->st[i].d_tokpack, tp_words * sizeof(uint32_t) * c->max_jobs));
+            CU_TRY(cudaMalloc(&c->st[i].d_tjobs, sizeof(TokJob) * c->max_jobs));
+            CU_TRY(cudaHostAlloc(&c->st[i].h_tjobs, sizeof(TokJob) * c->max_jobs, cudaHostAllocDefault));
+        }
     const uint64_t id = ++c->submit_id;
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));
@@ -1163,8 +1207,9 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
 
     const size_t ysz = (size_t)g.width * g.height, csz = (size_t)g.cwidth * g.cheight;
     const size_t coeff_elems = (size_t)g.nb * 256;
+    uint32_t n_tok = 0;
     for (uint32_t k = 0; k < njobs; k++) {
-        const pfv_encode_job &j = jobs[order[k]];
+        const EncIn &j = jobs[order[k]];
         EncJob &d = tab[k];
         const bool dev = (j.flags & PFV_JOB_DEVICE_PTRS) != 0;
         if (j.flags & PFV_JOB_SRC_RGB) {
@@ -1203,8 +1248,22 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
         d.ref = j.kind == PFV_FRAME_P ? slot_ptr(c, j.ref_slot) : nullptr;
         d.ref_slot = j.kind == PFV_FRAME_P ? (int32_t)j.ref_slot : 0;
         d.min_err = j.px_err * j.px_err * 256.0f;                  // src/common.rs:209 (f32, left to right)
+        if (j.sparse) {
+            // the dense coefficients stay in the stage's device buffer; only their RLE sequence leaves the device
+            d.coeff = st.d_coeff + (size_t)k * coeff_elems;
+            TokJob &t = st.h_tjobs[n_tok++];
+            uint32_t *pack = st.d_tokpack + (size_t)k * tp_words;
+            t.coeff = d.coeff;
+            t.hdr = j.kind == PFV_FRAME_P ? d.hdr : nullptr;
+            t.mb_off = pack;
+            t.tok = pack + tp_off_words;
+            t.stats = pack + tp_off_words + (size_t)g.nb * 256;
+            t.out_tok = j.tok_out; t.out_stats = j.stats_out; t.out_mb_off = j.mb_off_out;
+            t.tok_cap = j.tok_cap;
+        }
     }
     CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(EncJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
+    if (n_tok) CU_TRY(cudaMemcpyAsync(st.d_tjobs, st.h_tjobs, sizeof(TokJob) * n_tok, cudaMemcpyHostToDevice, c->s_h2d));
     CU_TRY(cudaEventRecord(st.ev_h2d, c->s_h2d));
 
     CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
@@ -1227,19 +1286,24 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
         CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, c->s_compute));
         c->launches++;
     }
+    if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 3; }
     CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
     c->have_kernel_time = true;
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
 
     bool any_host = false;
     for (uint32_t i = 0; i < njobs; i++) any_host |= (jobs[i].flags & PFV_JOB_DEVICE_PTRS) == 0;
-    if (any_host) {
+    if (any_host || n_tok) {
         CU_TRY(cudaStreamWaitEvent(c->s_d2h, st.ev_kernel, 0));
+        // the device writes each frame's RLE sequence itself (pinned host memory is reached over PCIe): the copy is as
+        // long as the sequence, which no host-issued cudaMemcpyAsync could know at submit time
+        if (n_tok) { CU_TRY(launch_token_store(g.nb, st.d_tjobs, n_tok, c->s_d2h)); c->launches++; }
         for (uint32_t k = 0; k < njobs; k++) {
-            const pfv_encode_job &j = jobs[order[k]];
+            const EncIn &j = jobs[order[k]];
             if (j.flags & PFV_JOB_DEVICE_PTRS) continue;
-            CU_TRY(cudaMemcpyAsync(j.coeff_out, st.d_coeff + (size_t)k * coeff_elems, coeff_elems * sizeof(int16_t),
-                                   cudaMemcpyDeviceToHost, c->s_d2h));
+            if (!j.sparse)
+                CU_TRY(cudaMemcpyAsync(j.coeff_out, st.d_coeff + (size_t)k * coeff_elems, coeff_elems * sizeof(int16_t),
+                                       cudaMemcpyDeviceToHost, c->s_d2h));
             if (j.kind == PFV_FRAME_P)
                 CU_TRY(cudaMemcpyAsync(j.hdr_out, st.d_hdr + (size_t)k * g.nb, (size_t)g.nb * sizeof(pfv_mbhdr),
                                        cudaMemcpyDeviceToHost, c->s_d2h));
@@ -1248,4 +1312,39 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
     CU_TRY(cudaEventRecord(st.ev_d2h, c->s_d2h));
     CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
     return PFV_OK;
+}
+
+}  // namespace
+
+extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_t njobs)
+{
+    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (njobs == 0) return PFV_OK;
+    std::vector<EncIn> in(njobs);
+    for (uint32_t i = 0; i < njobs; i++) {
+        const pfv_encode_job &j = jobs[i];
+        in[i] = EncIn{j.kind, j.flags, j.dst_slot, j.ref_slot, j.px_err, j.src_y, j.src_u, j.src_v, j.hdr_out, j.coeff_out,
+                      false, 0, nullptr, nullptr, nullptr};
+    }
+    return encode_submit_impl(c, in.data(), njobs);
+}
+
+extern "C" int pfv_encode_submit_sparse(pfv_ctx *c, const pfv_encode_job_sparse *jobs, uint32_t njobs)
+{
+    if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
+    if (njobs == 0) return PFV_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    std::vector<EncIn> in(njobs);
+    for (uint32_t i = 0; i < njobs; i++) {
+        const pfv_encode_job_sparse &j = jobs[i];
+        if (!j.tok_out || !j.stats_out) return fail(PFV_ERR_BAD_ARG, "job %u: NULL tok_out or stats_out", i);
+        uint32_t *tok = device_view(j.tok_out), *stats = device_view(j.stats_out);
+        uint32_t *mb_off = j.mb_off_out ? device_view(j.mb_off_out) : nullptr;
+        if (!tok || !stats || (j.mb_off_out && !mb_off))
+            return fail(PFV_ERR_BAD_ARG, "job %u: tok_out / stats_out / mb_off_out must be pinned host memory (pfv_host_alloc) or "
+                                         "device memory: the device stores the RLE sequence itself", i);
+        in[i] = EncIn{j.kind, j.flags, j.dst_slot, j.ref_slot, j.px_err, j.src_y, j.src_u, j.src_v, j.hdr_out, nullptr,
+                      true, j.tok_cap, mb_off, tok, stats};
+    }
+    return encode_submit_impl(c, in.data(), njobs);
 }

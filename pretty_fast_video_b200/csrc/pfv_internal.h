@@ -53,6 +53,19 @@ struct SparseJob {
     int16_t         *coeff;   // nb*256 dense destination, device
 };
 
+// sparse encode transport (pfv_encode_submit_sparse): where one frame's dense coefficients are and where its RLE sequence goes
+struct TokJob {
+    const int16_t   *coeff;      // nb*256, device (what the encode kernels just wrote)
+    const pfv_mbhdr *hdr;        // P: nb headers; I: nullptr
+    uint32_t        *mb_off;     // nb + 1, device staging
+    uint32_t        *tok;        // nb*256, device staging
+    uint32_t        *stats;      // PFV_TOKSTATS_WORDS, device staging
+    uint32_t        *out_tok;    // caller's buffers as device-accessible addresses (pinned host or device memory)
+    uint32_t        *out_stats;
+    uint32_t        *out_mb_off; // may be nullptr
+    uint32_t         tok_cap;
+};
+
 struct EncJob {
     const uint8_t *src[3];    // tight source planes, device
     pfv_mbhdr     *hdr;       // nb, device (P only)
@@ -126,6 +139,8 @@ cudaError_t launch_decode_p_live(const SbParams &P, const DecJob *d_jobs, uint32
 cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);
+cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
+cudaError_t launch_token_store(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_rgb_to_yuv420(const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, cudaStream_t s);
 cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, uint32_t w, uint32_t h, uint32_t pw,
                                  uint32_t cpw, uint8_t *d_rgb, cudaStream_t s);

@@ -114,6 +114,24 @@ class EncodeJob:
     rgb: Buf = None                # packed RGB8 [h, w, 3] source: converted on the device (PFV_JOB_SRC_RGB)
 
 
+@dataclass
+class SparseEncodeJob:
+    """pfv_encode_job_sparse: the frame's RLE sequence comes back instead of dense coefficients.  tok_out / stats_out /
+    mb_off_out must be pinned (PinnedArena) or device memory: the device stores them itself."""
+    kind: int
+    dst_slot: int
+    src: Optional[Sequence[Buf]]
+    tok_out: Buf                   # uint32[tok_cap]: run | size << 4 | uint16(value) << 16
+    stats_out: Buf                 # uint32[PFV_TOKSTATS_WORDS]
+    tok_cap: int = 0               # entries; 0 = tok_out.size
+    ref_slot: int = 0
+    px_err: float = 0.0
+    hdr_out: Buf = None
+    mb_off_out: Buf = None
+    device_ptrs: bool = False
+    rgb: Buf = None
+
+
 class Engine:
     def __init__(self, width: int, height: int, qtables: np.ndarray, nslots: int = 2, max_jobs: int = 1,
                  device: int = 0, stream: Optional[int] = None):
@@ -173,6 +191,27 @@ class Engine:
                 a.src_y, a.src_u, a.src_v = (_addr(b) for b in j.src)
             a.hdr_out, a.coeff_out = _addr(j.hdr_out), _addr(j.coeff_out)
         return arr
+
+    def build_sparse_encode_jobs(self, jobs: Sequence[SparseEncodeJob]):
+        arr = (N.EncodeJobSparse * len(jobs))()
+        for a, j in zip(arr, jobs):
+            a.kind, a.dst_slot, a.ref_slot = j.kind, j.dst_slot, j.ref_slot
+            a.flags = N.PFV_JOB_DEVICE_PTRS if j.device_ptrs else 0
+            a.px_err = j.px_err
+            if j.rgb is not None:
+                a.flags |= N.PFV_JOB_SRC_RGB
+                a.src_y = _addr(j.rgb)
+            else:
+                a.src_y, a.src_u, a.src_v = (_addr(b) for b in j.src)
+            a.hdr_out, a.mb_off_out, a.tok_out, a.stats_out = (_addr(b) for b in (j.hdr_out, j.mb_off_out, j.tok_out, j.stats_out))
+            a.tok_cap = int(j.tok_cap) if j.tok_cap else int(j.tok_out.size)
+        return arr
+
+    def encode_submit_sparse(self, jobs, prebuilt=None):
+        """Sparse encode transport (pfv_encode_submit_sparse): the run-length pass runs on the GPU, only its output crosses PCIe."""
+        arr = prebuilt if prebuilt is not None else self.build_sparse_encode_jobs(jobs)
+        self._keep.append((jobs, arr))
+        N.check(N.lib().pfv_encode_submit_sparse(self._ctx, arr, len(arr)))
 
     def build_sparse_decode_jobs(self, jobs: Sequence[SparseDecodeJob]):
         arr = (N.DecodeJobSparse * len(jobs))()

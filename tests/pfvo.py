@@ -44,6 +44,7 @@ def lib():
         l.pfvo_decoder_framebuffer.restype = C.c_void_p
         l.pfvo_decoder_qtables.restype = C.c_void_p
         l.pfvo_entropy_roundtrip.restype = C.c_long
+        l.pfvo_rle_encode.restype = C.c_size_t
         for n in ("pfvo_dct_scale_factor", "pfvo_q_table_intra", "pfvo_q_table_inter", "pfvo_zigzag", "pfvo_inv_zigzag"):
             getattr(l, n).restype = C.c_void_p
         _lib = l
@@ -282,3 +283,23 @@ def entropy_roundtrip(data):
     out = np.zeros_like(d)
     rc = lib().pfvo_entropy_roundtrip(_p(d), C.c_size_t(d.size), _p(out))
     return rc, out
+
+
+def rle_frame(coeff, coded=None):
+    """rle_encode per macroblock (enc.rs:256-262 / :370-378) over a frame's dense coefficients [nb, 256]; `coded` = per-macroblock
+    has_coeff (P frames, enc.rs:357-358).  Returns (tok, table, mb_off) with tok = run | size << 4 | uint16(value) << 16."""
+    c = np.ascontiguousarray(coeff, np.int16).reshape(-1, 256)
+    nb = c.shape[0]
+    z = np.zeros(256, np.uint8); sz = np.zeros(256, np.uint8); v = np.zeros(256, np.int16)
+    table = np.zeros(16, np.int32)
+    toks, mb_off = [], np.zeros(nb + 1, np.uint32)
+    for m in range(nb):
+        if coded is None or coded[m]:
+            n = lib().pfvo_rle_encode(_p(c[m]), C.c_size_t(256), _p(z), _p(sz), _p(v), C.c_size_t(256), _p(table))
+            assert n <= 256
+            toks.append(z[:n].astype(np.uint32) | (sz[:n].astype(np.uint32) << 4) | (v[:n].view(np.uint16).astype(np.uint32) << 16))
+            mb_off[m + 1] = mb_off[m] + n
+        else:
+            mb_off[m + 1] = mb_off[m]
+    tok = np.concatenate(toks) if toks else np.zeros(0, np.uint32)
+    return tok, table, mb_off

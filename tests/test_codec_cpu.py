@@ -257,3 +257,61 @@ def test_single_symbol_tree_is_decodable():
     qidx, _, mb_off, tok = codec.decode_packet(geo, PFV_FRAME_I, payload)
     assert tok.size == nb * 128                                      # zero-valued tokens are kept: they occupy a position
     assert np.array_equal(codec.tokens_to_dense(nb, mb_off, tok), coeff)
+
+
+# ---- sparse encode seam: host restatement of the device tokenizer + the writer that takes its output -------------------
+@pytest.mark.parametrize("size,quality,kind", [((96, 64), 3, "moving"), ((176, 144), 0, "moving"), ((64, 48), 10, "random")])
+def test_tokenize_matches_oracle_rle_and_packets_are_byte_identical(size, quality, kind):
+    """pfv_packet_tokenize == rle_encode per macroblock + update_table of the oracle (src/rle.rs:9-47); the packet written from
+    (tok, stats) is the oracle's packet byte for byte."""
+    from pretty_fast_video_b200 import _native as N
+    w, h = size
+    data, seam = oracle_stream(w, h, 6, quality, 3, 7, kind=kind)
+    info, qt, pk, _ = frame_packets(data)
+    geo = geometry_for(w, h)
+    frames = [(t, l, p) for t, l, p in pk if t != 0 and l > 0]
+    for (t, l, p), (fk, hdr, coeff) in zip(frames, seam):
+        coded = None if fk == PFV_FRAME_I else np.asarray(hdr).reshape(-1, 4)[:, 2]
+        o_tok, o_table, o_off = pfvo.rle_frame(coeff, coded)
+        tok, stats, mb_off = codec.tokenize(geo, fk, coeff, hdr)
+        assert np.array_equal(tok, o_tok)
+        assert np.array_equal(mb_off, o_off)
+        assert np.array_equal(stats[:16].astype(np.int64) + stats[16:32], o_table)
+        assert int(stats[N.PFV_TOKSTATS_NTOK]) == o_tok.size and int(stats[N.PFV_TOKSTATS_FLAGS]) == 0
+        # per-symbol split: [0..15] = num_zeroes, [16..31] = coeff_size
+        assert np.array_equal(stats[:16], np.bincount(o_tok & 15, minlength=16))
+        assert np.array_equal(stats[16:32], np.bincount((o_tok >> 4) & 15, minlength=16))
+        assert codec.encode_packet_tokens(geo, fk, tok, stats, hdr) == data[p - 5:p + l]
+
+
+def test_tokenize_edge_cases():
+    from pretty_fast_video_b200 import _native as N
+    geo = geometry_for(16, 16)                                        # 3 macroblocks
+    coeff = np.zeros(geo.nb * 256, np.int16)
+    coeff[255] = 7                  # 255 zeros first: 16 escapes + (15, size)
+    coeff[256 + 16] = -1            # run of exactly 16: one escape + (1, size); tail 239 zeros = 15 escapes + (14, 0)
+    # third macroblock all zero: 17 escapes + (1, 0)
+    tok, stats, mb_off = codec.tokenize(geo, PFV_FRAME_I, coeff)
+    o_tok, o_table, o_off = pfvo.rle_frame(coeff)
+    assert np.array_equal(tok, o_tok) and np.array_equal(mb_off, o_off)
+    assert list(np.diff(mb_off)) == [17, 18, 18]
+    assert np.array_equal(stats[:16].astype(np.int64) + stats[16:32], o_table)
+    pkt = codec.encode_packet_tokens(geo, PFV_FRAME_I, tok, stats)
+    assert pkt == codec.encode_packet(geo, PFV_FRAME_I, coeff)
+    _, _, off2, tok2 = codec.decode_packet(geo, PFV_FRAME_I, pkt[5:])
+    assert np.array_equal(codec.tokens_to_dense(geo.nb, off2, tok2), coeff)
+    # a token buffer that is too small and an unrepresentable coefficient are reported, never written
+    t_small, st_small, _ = codec.tokenize(geo, PFV_FRAME_I, coeff, tok_cap=10)
+    assert int(st_small[N.PFV_TOKSTATS_FLAGS]) & N.PFV_TOKFLAG_OVERFLOW and int(st_small[N.PFV_TOKSTATS_NTOK]) == 53
+    with pytest.raises(Exception, match="more than the token buffer"):
+        codec.encode_packet_tokens(geo, PFV_FRAME_I, t_small, st_small)
+    coeff[3] = -16384
+    t_bad, st_bad, _ = codec.tokenize(geo, PFV_FRAME_I, coeff)
+    assert int(st_bad[N.PFV_TOKSTATS_FLAGS]) & N.PFV_TOKFLAG_RANGE
+    with pytest.raises(Exception, match="not representable"):
+        codec.encode_packet_tokens(geo, PFV_FRAME_I, t_bad, st_bad)
+    # statistics that do not describe the sequence are caught by the exact-size check
+    st_wrong = stats.copy()
+    st_wrong[16 + 4] += 1
+    with pytest.raises(Exception, match="disagree"):
+        codec.encode_packet_tokens(geo, PFV_FRAME_I, tok, st_wrong)

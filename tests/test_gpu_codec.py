@@ -6,7 +6,7 @@ import pytest
 import pfvo
 from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine, PfvError, codec, geometry_for, make_qtables
 from pretty_fast_video_b200 import _native as N
-from pretty_fast_video_b200.engine import DecodeJob, SparseDecodeJob
+from pretty_fast_video_b200.engine import DecodeJob, EncodeJob, PinnedArena, SparseDecodeJob, SparseEncodeJob
 from pretty_fast_video_b200.synth import SynthVideo
 from test_codec_cpu import oracle_stream
 
@@ -185,10 +185,143 @@ def test_decoder_errors():
                 pass
 
 
+# ---- sparse encode seam: the run-length pass on the device ---------------------------------------------------------------
+def _sparse_outputs(arena, nb, cap=None):
+    cap = nb * 256 if cap is None else cap
+    return (arena.take((max(cap, 1),), np.uint32), arena.take((N.PFV_TOKSTATS_WORDS,), np.uint32), arena.take((nb + 1,), np.uint32),
+            arena.take((nb, 4), np.uint8))
+
+
+@pytest.mark.parametrize("size", [(16, 16), (64, 48), (50, 38), (512, 384), (1918, 1080)])
+@pytest.mark.parametrize("quality,kind", [(0, "moving"), (5, "moving"), (10, "random"), (5, "static")])
+def test_sparse_encode_matches_oracle_rle(size, quality, kind):
+    """pfv_encode_submit_sparse: the device's RLE sequence, symbol statistics and offsets are rle_encode + update_table
+    (src/rle.rs:9-47) of the oracle's coefficients, for a key frame and the P frame that follows it; the packets written from
+    them are the oracle encoder's packets."""
+    w, h = size
+    if w > 600 and (quality, kind) not in ((5, "moving"), (10, "random")):
+        pytest.skip("large sizes at two settings only")
+    qt, px_err = make_qtables(quality)
+    og = pfvo.geometry_for(w, h)
+    geo = geometry_for(w, h)
+    sv = SynthVideo(w, h, 4242 + quality, kind)
+    f0, f1 = sv.frame(0), sv.frame(1)
+    prev = pfvo.frame_init(og)
+    want_c0 = pfvo.encode_iframe_coeffs(og, qt, *f0, prev)
+    want_h1, want_c1 = pfvo.encode_pframe_coeffs(og, qt, px_err, *f1, prev)
+    arena = PinnedArena(2 * (og.nb * 256 * 4 + og.nb * 8 + 4096) + 65536)
+    tok0, st0, off0, _ = _sparse_outputs(arena, og.nb)
+    tok1, st1, off1, h1 = _sparse_outputs(arena, og.nb)
+    with Engine(w, h, qt, nslots=3) as e:
+        e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_I, 1, f0, tok0, st0, mb_off_out=off0)])
+        e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_P, 2, f1, tok1, st1, ref_slot=1, px_err=px_err, hdr_out=h1, mb_off_out=off1)])
+        e.sync()
+        recon = e.slot_read(2)
+    assert np.array_equal(recon, prev)
+    assert np.array_equal(h1, want_h1)
+    for fk, tok, st, off, want_c, hdr in ((PFV_FRAME_I, tok0, st0, off0, want_c0, None), (PFV_FRAME_P, tok1, st1, off1, want_c1, want_h1)):
+        o_tok, o_table, o_off = pfvo.rle_frame(want_c, None if hdr is None else hdr[:, 2])
+        n = int(st[N.PFV_TOKSTATS_NTOK])
+        assert n == o_tok.size and int(st[N.PFV_TOKSTATS_FLAGS]) == 0
+        assert np.array_equal(tok[:n], o_tok)
+        assert np.array_equal(off, o_off)
+        assert np.array_equal(st[:16], np.bincount(o_tok & 15, minlength=16))
+        assert np.array_equal(st[16:32], np.bincount((o_tok >> 4) & 15, minlength=16))
+        assert np.array_equal(st[:16].astype(np.int64) + st[16:32], o_table)
+        assert codec.encode_packet_tokens(geo, fk, tok[:n], st, hdr) == codec.encode_packet(geo, fk, want_c, hdr)
+    arena.close()
+
+
+def test_sparse_encode_batches_overflow_and_device_outputs():
+    """Several independent frames in one submit (I and P mixed, dense and sparse seams agree); a token buffer that is too small
+    is reported; outputs in device memory work like pinned ones."""
+    import torch
+    w, h, quality = 176, 144, 4
+    qt, px_err = make_qtables(quality)
+    geo = geometry_for(w, h)
+    nb = geo.nb
+    sv = SynthVideo(w, h, 77, "moving")
+    frames = [sv.frame(t) for t in range(4)]
+    arena = PinnedArena(8 * (nb * 256 * 4 + nb * 8 + 4096) + 65536)
+    dense_c = [np.zeros(nb * 256, np.int16) for _ in range(4)]
+    dense_h = [np.zeros((nb, 4), np.uint8) for _ in range(4)]
+    outs = [_sparse_outputs(arena, nb) for _ in range(4)]
+    with Engine(w, h, qt, nslots=10, max_jobs=4) as e:
+        # slot 0 = key frame of frame 0 (reference of every P job below)
+        e.encode_submit([EncodeJob(PFV_FRAME_I, 0, frames[0], dense_c[0])])
+        e.sync()
+        kinds = [PFV_FRAME_I, PFV_FRAME_P, PFV_FRAME_P, PFV_FRAME_I]
+        e.encode_submit([EncodeJob(k, 1 + i, frames[i], dense_c[i], ref_slot=0, px_err=px_err, hdr_out=dense_h[i])
+                         for i, k in enumerate(kinds)])
+        e.sync()
+        want_recon = [e.slot_read(1 + i) for i in range(4)]
+        e.encode_submit_sparse([SparseEncodeJob(k, 5 + i, frames[i], outs[i][0], outs[i][1], ref_slot=0, px_err=px_err,
+                                                hdr_out=outs[i][3], mb_off_out=outs[i][2]) for i, k in enumerate(kinds)])
+        e.sync()
+        for i, k in enumerate(kinds):
+            tok, st, off, hdr = outs[i]
+            assert np.array_equal(e.slot_read(5 + i), want_recon[i])
+            hd = dense_h[i] if k == PFV_FRAME_P else None
+            if hd is not None:
+                assert np.array_equal(hdr, hd)
+            t_tok, t_st, t_off = codec.tokenize(geo, k, dense_c[i], hd)
+            n = int(st[N.PFV_TOKSTATS_NTOK])
+            assert np.array_equal(tok[:n], t_tok) and np.array_equal(st, t_st) and np.array_equal(off, t_off)
+        # too small a buffer: flagged, the first tok_cap entries are still the right ones
+        n_full = int(outs[0][1][N.PFV_TOKSTATS_NTOK])
+        small_tok, small_st, _, _ = _sparse_outputs(arena, nb, cap=n_full // 2)
+        small_tok[:] = 0xdeadbeef
+        guard = arena.take((64,), np.uint32)
+        guard[:] = 0x5a5a5a5a
+        e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_I, 9, frames[0], small_tok, small_st, tok_cap=n_full // 2)])
+        e.sync()
+        assert int(small_st[N.PFV_TOKSTATS_FLAGS]) & N.PFV_TOKFLAG_OVERFLOW and int(small_st[N.PFV_TOKSTATS_NTOK]) == n_full
+        assert np.array_equal(small_tok[:n_full // 2], outs[0][0][:n_full // 2])
+        assert (guard == 0x5a5a5a5a).all()
+        with pytest.raises(PfvError, match="more than the token buffer"):
+            codec.encode_packet_tokens(geo, PFV_FRAME_I, small_tok, small_st)
+        # pageable host memory is refused: the device could not write it
+        with pytest.raises(PfvError, match="pinned"):
+            e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_I, 9, frames[0], np.zeros(nb * 256, np.uint32),
+                                                    np.zeros(N.PFV_TOKSTATS_WORDS, np.uint32))])
+        # device-resident outputs
+        d_tok = torch.zeros(nb * 256, dtype=torch.int32, device="cuda")
+        d_st = torch.zeros(N.PFV_TOKSTATS_WORDS, dtype=torch.int32, device="cuda")
+        e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_I, 9, frames[0], d_tok.data_ptr(), d_st.data_ptr(), tok_cap=nb * 256)])
+        e.sync()
+        assert np.array_equal(d_st.cpu().numpy().view(np.uint32), outs[0][1])
+        assert np.array_equal(d_tok.cpu().numpy().view(np.uint32)[:n_full], outs[0][0][:n_full])
+    arena.close()
+
+
+def test_sparse_encode_of_an_all_zero_frame():
+    """Every macroblock all zeros: 17 escapes + one run entry each (src/rle.rs:31-38), the longest escape chains the tokenizer
+    can meet.  (An unrepresentable coefficient cannot come out of the transform, |c| < 2^14; the RANGE flag is exercised on the
+    host restatement in tests/test_codec_cpu.py.)"""
+    w, h = 64, 48
+    qt, _ = make_qtables(5)
+    geo = geometry_for(w, h)
+    y = np.full((h, w), 128, np.uint8)                               # (px - 128) = 0 everywhere
+    u = np.full((h // 2, w // 2), 128, np.uint8)
+    arena = PinnedArena(geo.nb * 256 * 4 + 65536)
+    tok, st, off, _ = _sparse_outputs(arena, geo.nb)
+    with Engine(w, h, qt) as e:
+        e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_I, 1, (y, u, u), tok, st, mb_off_out=off)])
+        e.sync()
+    want = pfvo.encode_iframe_coeffs(pfvo.geometry_for(w, h), qt, y, u, u, pfvo.frame_init(pfvo.geometry_for(w, h)))
+    o_tok, o_table, o_off = pfvo.rle_frame(want)
+    n = int(st[N.PFV_TOKSTATS_NTOK])
+    assert np.array_equal(tok[:n], o_tok) and np.array_equal(off, o_off)
+    assert np.array_equal(st[:16].astype(np.int64) + st[16:32], o_table)
+    arena.close()
+
+
+@pytest.mark.parametrize("dense", ["0", "1"])
 @pytest.mark.parametrize("size,quality,kind,n,key", [((96, 64), 3, "moving", 10, 4), ((130, 70), 5, "moving", 7, 3),
                                                      ((64, 48), 10, "random", 5, 2), ((176, 144), 0, "moving", 5, 5),
                                                      ((64, 64), 5, "static", 4, 4), ((320, 240), 2, "moving", 8, 60)])
-def test_encoder_stream_is_byte_identical_to_oracle_encoder(size, quality, kind, n, key):
+def test_encoder_stream_is_byte_identical_to_oracle_encoder(size, quality, kind, n, key, dense, monkeypatch):
+    monkeypatch.setenv("PFV_ENCODER_DENSE", dense)                   # both seams: device run-length pass (default) and host
     w, h = size
     drop = (5,) if n > 6 else ()
     want, _ = oracle_stream(w, h, n, quality, key, 2468, kind=kind, drop_at=drop)
