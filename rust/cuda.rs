@@ -78,6 +78,28 @@ pub struct pfv_decode_job_sparse {
     pub out_v: *mut u8,
 }
 
+/// pfv_encode_job_sparse: the frame's RLE sequence (what rle_encode, rle.rs:9-39, pushes) instead of dense coefficients
+#[repr(C)]
+pub struct pfv_encode_job_sparse {
+    pub kind: u32,
+    pub flags: u32,
+    pub dst_slot: u32,
+    pub ref_slot: u32,
+    pub px_err: f32,
+    pub tok_cap: u32,
+    pub src_y: *const u8,
+    pub src_u: *const u8,
+    pub src_v: *const u8,
+    pub hdr_out: *mut pfv_mbhdr,
+    pub mb_off_out: *mut u32,    // optional, nb + 1
+    pub tok_out: *mut u32,       // pinned: run | size << 4 | (coeff as u16) << 16
+    pub stats_out: *mut u32,     // pinned: PFV_TOKSTATS_WORDS
+}
+
+pub const PFV_TOKSTATS_WORDS: usize = 36;
+pub const PFV_TOKSTATS_NTOK: usize = 32;
+pub const PFV_TOKSTATS_FLAGS: usize = 33;
+
 pub enum pfv_ctx {}
 
 pub const PFV_FRAME_I: u32 = 1;
@@ -99,6 +121,7 @@ extern "C" {
     pub fn pfv_ctx_last_submit_id(ctx: *const pfv_ctx) -> u64;
     pub fn pfv_ctx_wait_submit(ctx: *mut pfv_ctx, submit_id: u64) -> c_int;
     pub fn pfv_encode_submit(ctx: *mut pfv_ctx, jobs: *const pfv_encode_job, njobs: u32) -> c_int;
+    pub fn pfv_encode_submit_sparse(ctx: *mut pfv_ctx, jobs: *const pfv_encode_job_sparse, njobs: u32) -> c_int;
     pub fn pfv_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn pfv_host_free(p: *mut c_void);
 }
@@ -182,6 +205,50 @@ impl CudaPlanes {
             hdr_out: hdr_out.as_mut_ptr(), coeff_out: coeff_out.as_mut_ptr(),
         };
         check(unsafe { pfv_encode_submit(self.ctx, &job, 1) })?;
+        self.cur ^= 1;
+        check(unsafe { pfv_sync(self.ctx) })
+    }
+}
+
+/// Pinned output of the sparse encode seam; the device stores into it directly.
+pub struct PinnedTokens {
+    ptr: *mut u32,
+    cap: usize,
+}
+
+impl PinnedTokens {
+    pub fn new(nb: usize) -> io::Result<PinnedTokens> {
+        let cap = nb * 256;                                // an RLE entry consumes at least one coefficient
+        let mut p: *mut c_void = std::ptr::null_mut();
+        check(unsafe { pfv_host_alloc(&mut p, (cap + PFV_TOKSTATS_WORDS) * 4) })?;
+        Ok(PinnedTokens { ptr: p as *mut u32, cap })
+    }
+    pub fn stats(&self) -> &[u32] { unsafe { std::slice::from_raw_parts(self.ptr.add(self.cap), PFV_TOKSTATS_WORDS) } }
+    /// (num_zeroes, coeff_size, coeff) of every RLESequence of the frame, in stream order
+    pub fn entries(&self) -> impl Iterator<Item = (u8, u8, i16)> + '_ {
+        let n = self.stats()[PFV_TOKSTATS_NTOK] as usize;
+        unsafe { std::slice::from_raw_parts(self.ptr, n) }.iter().map(|t| ((t & 15) as u8, ((t >> 4) & 15) as u8, (t >> 16) as u16 as i16))
+    }
+}
+
+impl Drop for PinnedTokens {
+    fn drop(&mut self) { unsafe { pfv_host_free(self.ptr as *mut c_void) } }
+}
+
+impl CudaPlanes {
+    /// Sparse variant of `encode`: replaces enc.rs:84-97 / :134-147 AND the rle_encode + update_table loops of
+    /// write_iframe_packet / write_pframe_packet (enc.rs:256-262, :264-266 / :370-378, :380-382).  After the call
+    /// `out.stats()[0..16] + out.stats()[16..32]` is the `symbol_table` handed to rle_create_huffman and `out.entries()` is the
+    /// concatenation of `block_coeff` in macroblock order.
+    pub fn encode_sparse(&mut self, kind: u32, y: &[u8], u: &[u8], v: &[u8], px_err: f32,
+                         hdr_out: &mut [pfv_mbhdr], out: &mut PinnedTokens) -> io::Result<()> {
+        let job = pfv_encode_job_sparse {
+            kind, flags: 0, dst_slot: self.cur ^ 1, ref_slot: self.cur, px_err, tok_cap: out.cap as u32,
+            src_y: y.as_ptr(), src_u: u.as_ptr(), src_v: v.as_ptr(),
+            hdr_out: hdr_out.as_mut_ptr(), mb_off_out: std::ptr::null_mut(),
+            tok_out: out.ptr, stats_out: unsafe { out.ptr.add(out.cap) },
+        };
+        check(unsafe { pfv_encode_submit_sparse(self.ctx, &job, 1) })?;
         self.cur ^= 1;
         check(unsafe { pfv_sync(self.ctx) })
     }
