@@ -8,6 +8,8 @@
 //
 // One warp = one macroblock (see pfv_device.cuh).  grid.y = job (frame) index, so one launch covers a
 // whole batch of independent frames.
+#include <type_traits>
+
 #include "pfv_internal.h"
 #include "pfv_device.cuh"
 
@@ -279,12 +281,15 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
                 : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
         }
     }
-    {   // re-pitch the window: 46 rows x 44 words -> pitch 47 words
-        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(stage);
+    {   // re-pitch the window: 46 rows x 44 words -> pitch 47 words (one 16-byte load, four word stores per item)
+        const uint4 *src128 = reinterpret_cast<const uint4 *>(stage);
         uint32_t *dst32 = reinterpret_cast<uint32_t *>(win);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)(WIN_H * (WIN_W / 4)); i += WARPS_PER_CTA * 32) {
-            const uint32_t row = i / (WIN_W / 4), col = i - row * (WIN_W / 4);
-            dst32[row * (WINP_W / 4) + col] = src32[i];
+        constexpr uint32_t CHUNKS = WIN_W / 16;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)WIN_H * CHUNKS; i += WARPS_PER_CTA * 32) {
+            const uint32_t row = i / CHUNKS, col = i - row * CHUNKS;
+            const uint4 v = src128[i];
+            uint32_t *d = dst32 + row * (WINP_W / 4) + col * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
     }
     __syncthreads();
@@ -319,8 +324,10 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         srow[i].z = __shfl_sync(FULL, s.x, l0 + 8);
         srow[i].w = __shfl_sync(FULL, s.y, l0 + 8);
     }
-#pragma unroll 1
-    for (int step = 8; step >= 1; step >>= 1) {
+    // Levels 8 and 4 start from a centre that is a multiple of 4 away from the macroblock origin (itself a multiple of 16), so
+    // all their candidates are word aligned in the window: 4 words per row, no funnel shifts.  Levels 2 and 1 are general.
+    auto level = [&](const int step, auto aligned_tag) {
+        constexpr bool ALIGNED = decltype(aligned_tag)::value;
         const int ox = cx + mxg * step, oy = cy + myg * step;
         const bool valid = ox >= 0 && ox <= max_x && oy >= 0 && oy <= max_y;
         // window offset of row q of the candidate block; invalid candidates still lie inside the (zero-filled) window
@@ -331,11 +338,18 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t *w = wp + i * (WINP_W / 4);
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-            const uint32_t d0 = __vabsdiffu4(srow[i].x, __funnelshift_r(w0, w1, sh));
-            const uint32_t d1 = __vabsdiffu4(srow[i].y, __funnelshift_r(w1, w2, sh));
-            const uint32_t d2 = __vabsdiffu4(srow[i].z, __funnelshift_r(w2, w3, sh));
-            const uint32_t d3 = __vabsdiffu4(srow[i].w, __funnelshift_r(w3, w4, sh));
+            uint32_t r0, r1, r2, r3;
+            if (ALIGNED) {
+                r0 = w[0]; r1 = w[1]; r2 = w[2]; r3 = w[3];
+            } else {
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                r0 = __funnelshift_r(w0, w1, sh); r1 = __funnelshift_r(w1, w2, sh);
+                r2 = __funnelshift_r(w2, w3, sh); r3 = __funnelshift_r(w3, w4, sh);
+            }
+            const uint32_t d0 = __vabsdiffu4(srow[i].x, r0);
+            const uint32_t d1 = __vabsdiffu4(srow[i].y, r1);
+            const uint32_t d2 = __vabsdiffu4(srow[i].z, r2);
+            const uint32_t d3 = __vabsdiffu4(srow[i].w, r3);
             acc = __dp4a(d0, d0, acc);
             acc = __dp4a(d1, d1, acc);
             acc = __dp4a(d2, d2, acc);
@@ -354,7 +368,11 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         }
         cx += bdx;
         cy += bdy;
-    }
+    };
+#pragma unroll 1
+    for (int step = 8; step >= 4; step >>= 1) level(step, std::true_type{});
+#pragma unroll 1
+    for (int step = 2; step >= 1; step >>= 1) level(step, std::false_type{});
     const int mvx = cx - bx, mvy = cy - by;                            // |mv| <= 15
     const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((wy0 + mvy) * WINP_W + wx0 + mvx));
     const bool coded = !((float)best <= job.min_err);                  // src/common.rs:221

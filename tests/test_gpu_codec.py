@@ -380,6 +380,33 @@ def test_round_trip_1080p_encoder_to_decoder():
     assert np.array_equal(want_fb, fb)
 
 
+def test_round_trip_4k_p_stream_sharded_like_config5():
+    """BASELINE config 5 at full size (3840x2160 P-frame stream, GOPs sharded): two GOPs encoded on the GPU, each decoded from its
+    own sub-stream (the per-rank unit of shard.py), equal to the whole-stream decode, to the encoder's reconstruction and - for the
+    last frame of the stream - to the oracle decoder."""
+    from pretty_fast_video_b200 import shard
+    w, h, gop = 3840, 2160, 3
+    sv = SynthVideo(w, h, 4711)
+    with codec.Encoder(w, h, 30, 5, num_threads=4) as enc:
+        for t in range(2 * gop):
+            (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(sv.frame(t))
+        last_recon = enc.prev_frame()
+        enc.finish()
+        data = enc.bytes()
+    whole, fb = gpu_decode_all(data, num_threads=4)
+    assert len(whole) == 2 * gop and np.array_equal(fb, last_recon)
+    merged = []
+    for rank in range(2):
+        info, gops, mine = shard.plan(data, rank, 2)
+        assert [g.nframes for g in gops] == [gop, gop] and len(mine) == 1
+        for g in mine:
+            part, _ = gpu_decode_all(shard.substream(data, info.first_packet, g), num_threads=2)
+            merged += [(g.first_frame + i, fr) for i, fr in enumerate(part)]
+    same_frames(shard.gather_ordered(merged), whole)
+    _, want_fb = oracle_decode_all(data)
+    assert np.array_equal(want_fb, fb)
+
+
 def test_gop_sharded_gpu_decode_equals_whole_stream():
     """The multi-GPU partitioning (shard.py) with the GPU Decoder as the per-rank worker: every GOP decoded from its
     own sub-stream in its own context, merged by display index, equals the whole-stream decode (no collective)."""
