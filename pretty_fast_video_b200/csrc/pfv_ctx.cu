@@ -825,6 +825,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));     // device buffers of this stage are free again
+    CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_d2h, 0));        // ... also for an encode submit that used the stage before
 
     // dense HOST coefficients: compact them to tokens on the host pool (the stage's pinned token buffers are free: the
     // H2D copies that read them were waited for above) and carry on as sparse jobs
@@ -1195,6 +1196,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));
+    CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_d2h, 0));           // tok_store_kernel of the stage's previous use reads d_tjobs
 
     EncJob *tab = static_cast<EncJob *>(st.h_jobs);
     struct RgbConv { const uint8_t *rgb; uint8_t *planes; };

@@ -294,6 +294,43 @@ def test_sparse_encode_batches_overflow_and_device_outputs():
     arena.close()
 
 
+def test_interleaved_encode_and_decode_submits_share_the_staging_rings():
+    """One context, 24 submits alternating between the sparse encode seam and the decode seam without a sync in between: every
+    staging stage is reused several times by both kinds (the store kernel of an encode submit and the copies of a decode submit must
+    not overtake each other)."""
+    w, h, quality = 176, 144, 6
+    qt, px_err = make_qtables(quality)
+    geo = geometry_for(w, h)
+    nb = geo.nb
+    sv = SynthVideo(w, h, 1234, "moving")
+    frames = [sv.frame(t) for t in range(12)]
+    arena = PinnedArena(12 * (nb * 256 * 4 + 8192) + 12 * (w * h * 2) + 65536)
+    outs = [_sparse_outputs(arena, nb) for _ in range(12)]
+    pics = [(arena.take((h, w), np.uint8), arena.take((h // 2, w // 2), np.uint8), arena.take((h // 2, w // 2), np.uint8)) for _ in range(12)]
+    dense = []
+    with Engine(w, h, qt, nslots=4) as e:
+        for t in range(12):                                          # the expected coefficients, one frame at a time
+            c = np.zeros(nb * 256, np.int16)
+            e.encode_submit([EncodeJob(PFV_FRAME_I, 0, frames[t], c)])
+            e.sync()
+            dense.append(c)
+        for t in range(12):
+            e.encode_submit_sparse([SparseEncodeJob(PFV_FRAME_I, 1, frames[t], outs[t][0], outs[t][1], mb_off_out=outs[t][2])])
+            e.decode_submit([DecodeJob(PFV_FRAME_I, 2 + (t & 1), dense[t], (0, 1, 1), out=pics[t])])
+        e.sync()
+        for t in range(12):
+            tok, st, off = codec.tokenize(geo, PFV_FRAME_I, dense[t])
+            n = int(outs[t][1][N.PFV_TOKSTATS_NTOK])
+            assert np.array_equal(outs[t][0][:n], tok) and np.array_equal(outs[t][1], st) and np.array_equal(outs[t][2], off)
+        og = pfvo.geometry_for(w, h)
+        for t in (0, 5, 11):
+            fr = pfvo.frame_init(og)
+            pfvo.decode_iframe_coeffs(og, qt, (0, 1, 1), dense[t], fr)
+            y, u, v = pfvo.crop_frame(og, fr)
+            assert np.array_equal(pics[t][0], y) and np.array_equal(pics[t][1], u) and np.array_equal(pics[t][2], v)
+    arena.close()
+
+
 def test_sparse_encode_of_an_all_zero_frame():
     """Every macroblock all zeros: 17 escapes + one run entry each (src/rle.rs:31-38), the longest escape chains the tokenizer
     can meet.  (An unrepresentable coefficient cannot come out of the transform, |c| < 2^14; the RANGE flag is exercised on the
