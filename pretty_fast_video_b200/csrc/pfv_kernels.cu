@@ -214,7 +214,7 @@ __device__ __forceinline__ uint32_t warp_ssd(uint2 src, uint2 ref)
 // window (block_search never moves further than 8+4+2+1 = 15 px, src/common.rs:154-204) is fetched
 // from the reference slot by ONE 4-D TMA box {WIN_W, WIN_H, 1, 1}; the part outside the plane is
 // zero-filled by the TMA unit and never visited (candidates there are skipped, src/common.rs:171,182).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
                 const QTables *__restrict__ qt,
                 const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
