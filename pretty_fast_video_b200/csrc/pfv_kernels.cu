@@ -8,6 +8,7 @@
 //
 // One warp = one macroblock (see pfv_device.cuh).  grid.y = job (frame) index, so one launch covers a
 // whole batch of independent frames.
+#include <cstdlib>
 #include <type_traits>
 
 #include "pfv_internal.h"
@@ -214,7 +215,8 @@ __device__ __forceinline__ uint32_t warp_ssd(uint2 src, uint2 ref)
 // window (block_search never moves further than 8+4+2+1 = 15 px, src/common.rs:154-204) is fetched
 // from the reference slot by ONE 4-D TMA box {WIN_W, WIN_H, 1, 1}; the part outside the plane is
 // zero-filled by the TMA unit and never visited (candidates there are skipped, src/common.rs:171,182).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+template <int CTAS_PER_SM>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
                 const QTables *__restrict__ qt,
                 const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
@@ -442,7 +444,17 @@ cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
                             cudaStream_t s)
 {
     dim3 grid(g.total_tiles, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
-    encode_p_kernel<<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
+    // resident CTAs per SM = the register budget the kernel is compiled for (3: 72 registers ... 6: 40); the kernel is issue
+    // bound with long shared-memory latencies, so more resident warps pay until the register squeeze costs more
+    // measured on 32 x 1080p: 3: 77.5 k, 4: 84.8 k, 5: 81.5 k, 6: 83.2 k frames/s
+    const char *e = getenv("PFV_ENCODE_P_CTAS_PER_SM");
+    const int v = e ? atoi(e) : 0;
+    switch ((v >= 3 && v <= 6) ? v : 4) {
+    case 3: encode_p_kernel<3><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
+    case 5: encode_p_kernel<5><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
+    case 6: encode_p_kernel<6><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
+    default: encode_p_kernel<4><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
+    }
     return cudaGetLastError();
 }
 

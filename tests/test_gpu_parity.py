@@ -336,6 +336,14 @@ def test_encode_pframe_matches_oracle(size, quality, kind):
     assert np.array_equal(got_recon, prev)
 
 
+@pytest.mark.parametrize("ctas", ["3", "5", "6"])
+def test_encode_p_register_budget_variants_agree(ctas, monkeypatch):
+    """PFV_ENCODE_P_CTAS_PER_SM compiles the same kernel for 72 / 64 (default) / 48 / 40 registers: identical results."""
+    monkeypatch.setenv("PFV_ENCODE_P_CTAS_PER_SM", ctas)
+    test_encode_pframe_matches_oracle((512, 384), 5, "moving")
+    test_encode_pframe_matches_oracle((50, 38), 2, "moving")
+
+
 def _oracle_stream(w, h, nframes, quality, key_every, seed, kind="moving"):
     """Encode with the oracle; return per-frame seam data and decoded visible planes."""
     sv = SynthVideo(w, h, seed, kind)
