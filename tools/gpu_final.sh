@@ -18,4 +18,20 @@ for spec in "decode_i:decode_i_stream:decode_i_1080p:3:2" "decode_p:mc_copy4|res
       python bench.py --workload $WL --steps 2 --warmup 3 --extras 0 --cpu-budget 0.1 --e2e 0 > $OUT/ncu_full_${NAME}_$TAG.log 2>&1
   tail -1 $OUT/ncu_full_${NAME}_$TAG.log
 done
+echo "== ncu launch list of the Encoder object (sparse encode seam: encode kernels + tokenizer + store), 1080p, 16 frames"
+cat > /tmp/enc_ll.py <<'PY'
+from pretty_fast_video_b200 import codec
+from pretty_fast_video_b200.synth import SynthVideo
+sv = SynthVideo(1920, 1080, 0x50465602)
+src = [sv.frame(t) for t in range(8)]
+with codec.Encoder(1920, 1080, 30, 5, num_threads=4) as enc:
+    for t in range(16):
+        (enc.encode_iframe if t % 8 == 0 else enc.encode_pframe)(src[t % 8])
+    enc.finish()
+    print(len(enc.bytes()))
+PY
+PYTHONPATH=$PWD timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_enc_$TAG.csv \
+    python /tmp/enc_ll.py > $OUT/ncu_launch_enc_$TAG.log 2>&1
+tail -1 $OUT/ncu_launch_enc_$TAG.log
 ls $OUT | tr '\n' ' '
+
