@@ -597,7 +597,7 @@ def run_decoder_stream(torch, dist, budget_s, nthreads):
         oenc.close()
     return {"value": gpu_fps, "unit": "frames/s", "frames": nfr, "stream_bytes": len(data), "host_threads": nthreads,
             "encoder": {"value": enc_fps, "unit": "frames/s", "note": "Encoder.encode_iframe/encode_pframe (1 key frame / 15) to .pfv bytes: "
-                        "planes H2D, kernels (full block search), coefficients D2H, entropy coding on the host pool",
+                        "planes H2D, kernels (full block search), run-length pass on the GPU, RLE sequence stored into pinned host memory, Huffman + bit packing on the host pool",
                         "cpu_baseline": {"value": e_done / e_used, "unit": "frames/s", "cores": nthreads, "kind": "port",
                                          "sample": f"{e_done} frames (1 key + 5 P) through the oracle Encoder in {e_used:.1f} s"}},
             "note": "Decoder.advance_frame over an in-memory 1920x1080 .pfv (1 key frame / 15): entropy decode on the host pool, "
