@@ -1250,6 +1250,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         d.ref = j.kind == PFV_FRAME_P ? slot_ptr(c, j.ref_slot) : nullptr;
         d.ref_slot = j.kind == PFV_FRAME_P ? (int32_t)j.ref_slot : 0;
         d.min_err = j.px_err * j.px_err * 256.0f;                  // src/common.rs:209 (f32, left to right)
+        d.mb_cnt = nullptr;
         if (j.sparse) {
             // the dense coefficients stay in the stage's device buffer; only their RLE sequence leaves the device
             d.coeff = st.d_coeff + (size_t)k * coeff_elems;
@@ -1258,6 +1259,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
             t.coeff = d.coeff;
             t.hdr = j.kind == PFV_FRAME_P ? d.hdr : nullptr;
             t.mb_off = pack;
+            d.mb_cnt = pack + 1;                                   // the encode kernel leaves each macroblock's entry count here
             t.tok = pack + tp_off_words;
             t.stats = pack + tp_off_words + (size_t)g.nb * 256;
             t.out_tok = j.tok_out; t.out_stats = j.stats_out; t.out_mb_off = j.mb_off_out;
@@ -1288,7 +1290,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, c->s_compute));
         c->launches++;
     }
-    if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 3; }
+    if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 2; }
     CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
     c->have_kernel_time = true;
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));

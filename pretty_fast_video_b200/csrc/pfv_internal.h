@@ -74,6 +74,7 @@ struct EncJob {
     const uint8_t *ref;       // frame slot holding prev_frame (P only)
     int32_t        ref_slot;  // the same slot as an index (TMA coordinate)
     float          min_err;   // px_err*px_err*256 (src/common.rs:209)
+    uint32_t      *mb_cnt;    // sparse encode seam: nb entry counts of rle_encode per macroblock (0 = none), else nullptr
 };
 
 // Parameters of the register-resident sub-block kernels (pfv_kernels_sb.cu): the three per-plane tables of

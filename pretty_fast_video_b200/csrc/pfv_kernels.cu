@@ -13,6 +13,7 @@
 
 #include "pfv_internal.h"
 #include "pfv_device.cuh"
+#include "pfv_tok.cuh"
 
 namespace pfv {
 
@@ -133,7 +134,7 @@ __device__ __forceinline__ int byte_of(uint2 v, int k)
 // encode-I
 // -------------------------------------------------------------------------------------------------
 template <int MPW>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 encode_i_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
                 const QTables *__restrict__ qt)
 {
@@ -169,6 +170,10 @@ encode_i_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         for (int k = 0; k < 8; ++k) scale[k] = c_scaleT[r * 8 + k];
         const uint4 craw = encode_mb_core(ws, lane, gaddr, encM, scale, x);
         __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)m * 256) + lane, craw);
+        if (job.mb_cnt) {                                              // sparse seam: how many RLE entries this macroblock makes
+            const uint32_t n = tok::warp_count(craw, (uint32_t)lane);
+            if (lane == 0) job.mb_cnt[m] = n;
+        }
 
         // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
         int32_t deq[8];
@@ -404,11 +409,17 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         for (int k = 0; k < 8; ++k) scale[k] = c_scaleT[r * 8 + k];
         const uint4 craw = encode_mb_core(ws, lane, gaddr, encM, scale, x);
         __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)m * 256) + lane, craw);
+        if (job.mb_cnt) {                                              // sparse seam: how many RLE entries this macroblock makes
+            const uint32_t n = tok::warp_count(craw, (uint32_t)lane);
+            if (lane == 0) job.mb_cnt[m] = n;
+        }
         int32_t deq[8];
         lane_load8(q->deqT, r, deq);
         int y[8];
         decode_mb_core(ws, lane, gaddr, deq, y);
         out = apply_residual_row(y, prev);                             // src/common.rs:277
+    } else if (job.mb_cnt && lane == 0) {
+        job.mb_cnt[m] = 0;                                             // subblocks: None (src/enc.rs:357-358)
     }
     uint8_t *dst = job.dst + pl.off + (size_t)((uint32_t)by + py) * pl.pw + (uint32_t)bx + px;
     *reinterpret_cast<uint2 *>(dst) = out;

@@ -5,9 +5,11 @@
 // src/rle.rs:41-47) and only then writes bits.  A dense 1080p frame is 6.27 MB of i16 over PCIe and through a host
 // scan; >90 % of it is zeros.  Here the run-length pass runs on the device and only the RLE sequence crosses PCIe:
 //
-//   tok_count_kernel   one warp per macroblock: number of RLE entries it produces
+//   (encode kernels)   count the entries of each macroblock while its coefficients are still in registers (pfv_tok.cuh)
 //   tok_scan_kernel    one CTA per frame: exclusive prefix sum -> mb_off[nb+1]; clears the frame's statistics
-//   tok_emit_kernel    one warp per macroblock: the entries themselves, in stream order, + the two symbol histograms
+//   tok_emit_kernel    a warp takes 8 consecutive macroblocks, skips the ones without coefficients by one ballot over their
+//                      headers, compacts the non-zero coefficients of the others and writes their entries at their final
+//                      offsets, in stream order, + the two symbol histograms
 //   tok_store_kernel   copies exactly `ntok` entries (+ statistics, + mb_off on request) to the caller's buffers with
 //                      16-byte stores; the destination may be pinned HOST memory (zero-copy over PCIe), so the
 //                      transfer size follows the data without a host round trip
@@ -15,90 +17,18 @@
 // Entry format (what pfv_packet_encode_tokens takes): run | size << 4 | uint16(value) << 16, exactly one word per
 // RLESequence {num_zeroes, coeff_size, coeff} (src/rle.rs:3-7).
 #include "pfv_internal.h"
+#include "pfv_tok.cuh"
 
 namespace pfv {
 
-constexpr int TOK_WARPS = 8;
-constexpr unsigned FULL = 0xffffffffu;
+using tok::FULL;
+using tok::escapes_of;
 
-// escapes a zero run of `run` costs before its final entry: `while run > 15 { push(15,0,0); run -= 15 }` (src/rle.rs:18-21)
-__device__ __forceinline__ int escapes_of(int run)
-{
-    return (run - 1) / 15;                                           // run = 0 -> 0 (C division truncates)
-}
-
-struct LaneCoeffs {
-    int      v[8];      // this lane's coefficients: macroblock positions 8*lane .. 8*lane+7
-    uint32_t nz;        // bit k set = v[k] != 0
-    int      prev;      // position of the last non-zero coefficient before 8*lane (-1: none)
-    int      last;      // position of the macroblock's last non-zero coefficient (-1: none), all lanes
-};
-
-__device__ __forceinline__ LaneCoeffs load_lane(const int16_t *__restrict__ mb, uint32_t lane)
-{
-    LaneCoeffs c;
-    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(mb) + lane);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    c.nz = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        c.v[k] = (int)(int16_t)(w[k >> 1] >> (16 * (k & 1)));
-        c.nz |= (c.v[k] != 0 ? 1u : 0u) << k;
-    }
-    int incl = c.nz ? (int)(8u * lane) + (31 - __clz((int)c.nz)) : -1;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, d);
-        if ((int)lane >= d) incl = max(incl, t);
-    }
-    c.prev = __shfl_up_sync(FULL, incl, 1);
-    if (lane == 0) c.prev = -1;
-    c.last = __shfl_sync(FULL, incl, 31);
-    return c;
-}
-
-// RLE entries this lane produces: its non-zero coefficients with the escapes in front of them; lane 31 also owns the
-// tail of the macroblock (src/rle.rs:31-38)
-__device__ __forceinline__ uint32_t lane_count(const LaneCoeffs &c, uint32_t lane)
-{
-    uint32_t n = 0;
-    int p = c.prev;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (c.nz & (1u << k)) {
-            const int pos = (int)(8u * lane) + k;
-            n += 1u + (uint32_t)escapes_of(pos - p - 1);
-            p = pos;
-        }
-    if (lane == 31) {
-        const int run = 255 - c.last;
-        if (run > 0) n += 1u + (uint32_t)escapes_of(run);
-    }
-    return n;
-}
-
-__device__ __forceinline__ bool mb_coded(const TokJob &job, uint32_t m)
-{
-    return job.hdr == nullptr || job.hdr[m].has_coeff != 0;          // subblocks: None writes nothing (src/enc.rs:357-358)
-}
-
-__global__ void __launch_bounds__(TOK_WARPS * 32)
-tok_count_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
-{
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t m = blockIdx.x * TOK_WARPS + warp;
-    if (m >= nb) return;
-    const TokJob job = jobs[blockIdx.y];
-    uint32_t total = 0;
-    if (mb_coded(job, m)) {
-        const LaneCoeffs c = load_lane(job.coeff + (size_t)m * 256, lane);
-        total = __reduce_add_sync(FULL, lane_count(c, lane));
-    }
-    if (lane == 0) job.mb_off[m + 1] = total;
-}
+constexpr int TOK_WARPS = 2;            // no CTA-wide step: a warp that is done gives its slot back (see tok_emit_kernel)
+constexpr uint32_t TOK_CHUNK = 8;       // macroblocks per warp
 
 // mb_off[m+1] holds the count of macroblock m on entry, the inclusive sum on exit; mb_off[0] = 0.
-constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 4;
+constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 12;      // 12 288 counts per iteration: a 1080p frame (12 240) in one
 __global__ void __launch_bounds__(SCAN_THREADS)
 tok_scan_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
 {
@@ -149,68 +79,171 @@ tok_scan_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     if (t == 0) job.stats[PFV_TOKSTATS_NTOK] = carry_s;
 }
 
+// Symbol statistics without contended atomics.  Nearly every entry of a macroblock carries one of two or three symbols (run 0/1,
+// size 2/3), so 32 lanes adding to one shared-memory histogram serialise 32-fold.  Instead a lane counts its own entries of one
+// macroblock in two 64-bit registers (16 bins x 4 bits: a lane makes at most 9 entries per macroblock), folds them after each
+// macroblock into four registers of 8 x 8 bits, and the warp adds those up every <= 16 macroblocks by a reduce-scatter (16
+// shuffles) that leaves word k of the 16 x (2 x 16 bit) totals in lanes 2k, 2k+1; 16 lanes then add two bins each to the
+// frame's counters (only the bins that occurred: a handful per warp).
+struct LaneHist {
+    uint64_t acc[4];     // [0] run bins 0,2,..,14  [1] run bins 1,3,..,15  [2] size bins even  [3] size bins odd; 8 bits each
+};
+
+__device__ __forceinline__ void hist_fold(LaneHist &h, uint64_t r64, uint64_t s64)
+{
+    constexpr uint64_t M = 0x0f0f0f0f0f0f0f0full;
+    h.acc[0] += r64 & M;
+    h.acc[1] += (r64 >> 4) & M;
+    h.acc[2] += s64 & M;
+    h.acc[3] += (s64 >> 4) & M;
+}
+
+__device__ __forceinline__ void hist_flush(LaneHist &h, uint32_t lane, uint32_t *hist)
+{
+    uint32_t w[16];                                                  // word a*4+j: byte 2j of acc[a] | byte 2j+1 << 16
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const uint32_t lo = (uint32_t)h.acc[a], hi = (uint32_t)(h.acc[a] >> 32);
+        w[a * 4 + 0] = __byte_perm(lo, 0u, 0x4140);
+        w[a * 4 + 1] = __byte_perm(lo, 0u, 0x4342);
+        w[a * 4 + 2] = __byte_perm(hi, 0u, 0x4140);
+        w[a * 4 + 3] = __byte_perm(hi, 0u, 0x4342);
+        h.acc[a] = 0;
+    }
+    uint32_t v8[8], v4[4], v2[2];
+    const bool b4 = lane & 16u, b3 = lane & 8u, b2 = lane & 4u, b1 = lane & 2u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = (b4 ? w[8 + i] : w[i]) + __shfl_xor_sync(FULL, b4 ? w[i] : w[8 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v4[i] = (b3 ? v8[4 + i] : v8[i]) + __shfl_xor_sync(FULL, b3 ? v8[i] : v8[4 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) v2[i] = (b2 ? v4[2 + i] : v4[i]) + __shfl_xor_sync(FULL, b2 ? v4[i] : v4[2 + i], 4);
+    uint32_t v = (b1 ? v2[1] : v2[0]) + __shfl_xor_sync(FULL, b1 ? v2[0] : v2[1], 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    if ((lane & 1u) == 0) {                                          // this lane pair holds word k = lane >> 1 = a*4 + j
+        const uint32_t k = lane >> 1, a = k >> 2, j = k & 3u;
+        const uint32_t bin = (a >= 2 ? 16u : 0u) + 4u * j + (a & 1u);   // byte 2j of acc[a] counts bin 2*(2j) + (a & 1)
+        if (v & 0xffffu) atomicAdd(&hist[bin], v & 0xffffu);
+        if (v >> 16) atomicAdd(&hist[bin + 2u], v >> 16);
+    }
+}
+
+// One warp = `chunk` consecutive macroblocks; grid.x = chunks / TOK_WARPS, grid.y = frame.
+//
+// Per macroblock: (1) a lane keeps the non-zero ones of its 8 coefficients and the warp compacts them, in order, into a
+// shared-memory list of (position, value) - one popc, one 5-step scan, <= 8 short predicated stores; (2) the list is walked 32
+// entries at a time, one entry per lane: run = distance to the previous list entry, escapes = (run-1)/15, a second scan turns
+// entries-per-lane into output offsets, and neighbouring lanes write neighbouring words of the sequence.  (The first version
+// let every lane walk its own 8 coefficients with the whole entry logic inside 8 divergent steps: ~800 warp instructions per
+// macroblock, 136 us per 32 P frames; ncu, profiles/README.md.)
 __global__ void __launch_bounds__(TOK_WARPS * 32)
 tok_emit_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
 {
-    __shared__ uint32_t hist[32];                                    // [0..15] num_zeroes symbols, [16..31] coeff_size symbols
-    __shared__ uint32_t bad;
+    // Warps are independent (no CTA barrier, statistics added straight to the frame's counters): with a shared histogram and a
+    // final __syncthreads the fast warps of a CTA sat at the barrier holding their slots (9.6 stalled warps per issue slot,
+    // 84 us per 32 P frames) while the warps with a cluster of coded macroblocks finished.
+    __shared__ uint32_t list[TOK_WARPS][256];                        // (position << 16) | uint16(value), in coefficient order
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (threadIdx.x < 32) hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) bad = 0;
-    __syncthreads();
-    const uint32_t m = blockIdx.x * TOK_WARPS + warp;
     const TokJob job = jobs[blockIdx.y];
-    if (m < nb && mb_coded(job, m)) {
-        const LaneCoeffs c = load_lane(job.coeff + (size_t)m * 256, lane);
-        const uint32_t n = lane_count(c, lane);
-        uint32_t incl = n;
+    // a warp walks its macroblocks one after the other (~0.4 us each): short chunks keep the longest chain short where the
+    // coded macroblocks of a P frame cluster (32 per warp measured 136 us per 32 frames, most of it waiting for the slowest warp)
+    constexpr uint32_t chunk = TOK_CHUNK;
+    const uint32_t m0 = (blockIdx.x * TOK_WARPS + warp) * chunk;
+    if (m0 < nb) {
+        // which of this chunk's macroblocks carry coefficients: `subblocks: None` writes nothing (src/enc.rs:357-358)
+        const uint32_t mine = m0 + lane;
+        const bool in_chunk = lane < chunk && mine < nb;
+        const bool has = in_chunk && (job.hdr == nullptr || job.hdr[mine].has_coeff != 0);
+        uint32_t todo = __ballot_sync(FULL, has);
+        const uint32_t my_off = in_chunk ? job.mb_off[mine] : 0u;    // where each macroblock's entries start
+        uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
+        if (todo) raw_next = __ldcs(reinterpret_cast<const uint4 *>(job.coeff + (size_t)(m0 + (uint32_t)(__ffs((int)todo) - 1)) * 256) + lane);
+        LaneHist lh;
+        lh.acc[0] = lh.acc[1] = lh.acc[2] = lh.acc[3] = 0;
+        uint32_t folded = 0, esc_total = 0, range_bad = 0;
+        uint32_t *L = list[warp];
+        while (todo) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const uint4 raw = raw_next;
+            if (todo)                                                // the next macroblock's coefficients travel while this one is walked
+                raw_next = __ldcs(reinterpret_cast<const uint4 *>(job.coeff + (size_t)(m0 + (uint32_t)(__ffs((int)todo) - 1)) * 256) + lane);
+            // (1) compaction
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            uint32_t nz = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(FULL, incl, d);
-            if ((int)lane >= d) incl += u;
-        }
-        uint32_t *out = job.tok + job.mb_off[m] + (incl - n);
-        int p = c.prev;
-        uint32_t esc_total = 0;
+            for (int k = 0; k < 8; ++k) nz |= (((w[k >> 1] >> (16 * (k & 1))) & 0xffffu) != 0u ? 1u : 0u) << k;
+            const uint32_t cnt = (uint32_t)__popc(nz);
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (c.nz & (1u << k)) {
-                const int pos = (int)(8u * lane) + k;
-                int run = pos - p - 1;
-                const int esc = escapes_of(run);
-                for (int e = 0; e < esc; ++e) *out++ = 15u;          // {15, 0, 0}
-                run -= 15 * esc;
-                esc_total += (uint32_t)esc;
-                const int v = c.v[k];
-                const uint32_t a = (uint32_t)(v < 0 ? -v : v) & 0xffffu;     // val.abs() as u16 (src/rle.rs:23)
-                const uint32_t size = (32u - (uint32_t)__clz((int)a)) + 1u;   // (16 - leading_zeros) + 1 (src/rle.rs:24)
-                if (size > 15u) atomicOr(&bad, PFV_TOKFLAG_RANGE);             // does not fit a 4-bit symbol (src/rle.rs:43)
-                *out++ = (uint32_t)run | (size << 4) | ((uint32_t)(uint16_t)v << 16);
-                atomicAdd(&hist[run], 1u);
-                atomicAdd(&hist[16u + (size & 15u)], 1u);
-                p = pos;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(FULL, incl, d);
+                if ((int)lane >= d) incl += u;
             }
-        if (lane == 31) {
-            int run = 255 - c.last;
-            if (run > 0) {
-                const int esc = escapes_of(run);
-                for (int e = 0; e < esc; ++e) *out++ = 15u;
-                run -= 15 * esc;
-                esc_total += (uint32_t)esc;
-                *out++ = (uint32_t)run;                              // {run, 0, 0} (src/rle.rs:36-38)
-                atomicAdd(&hist[run], 1u);
-                atomicAdd(&hist[16], 1u);
+            const uint32_t T = __shfl_sync(FULL, incl, 31);          // non-zero coefficients of the macroblock
+            uint32_t r = incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (nz & (1u << k)) L[r++] = ((8u * lane + (uint32_t)k) << 16) | ((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            __syncwarp();
+            // (2) entries, 32 list items at a time
+            uint32_t *out = job.tok + __shfl_sync(FULL, my_off, j);
+            uint64_t r64 = 0, s64 = 0;                               // this lane's entries of this macroblock, 16 bins x 4 bits
+            for (uint32_t t0 = 0; t0 < T; t0 += 32u) {
+                const uint32_t i = t0 + lane;
+                const bool act = i < T;
+                const uint32_t e = act ? L[i] : 0u;
+                const int pos = (int)(e >> 16);
+                const int pprev = (act && i > 0u) ? (int)(L[i - 1u] >> 16) : -1;
+                int run = pos - pprev - 1;
+                const int esc = act ? escapes_of(run) : 0;           // `while run > 15 { push(15,0,0); run -= 15 }` (src/rle.rs:18-21)
+                const uint32_t ntk = act ? (uint32_t)esc + 1u : 0u;
+                uint32_t inc2 = ntk;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(FULL, inc2, d);
+                    if ((int)lane >= d) inc2 += u;
+                }
+                if (act) {
+                    uint32_t *o = out + (inc2 - ntk);
+                    for (int q = 0; q < esc; ++q) *o++ = 15u;        // {15, 0, 0}
+                    run -= 15 * esc;
+                    const int v = (int)(int16_t)(e & 0xffffu);
+                    const uint32_t a = (uint32_t)(v < 0 ? -v : v) & 0xffffu;     // val.abs() as u16 (src/rle.rs:23)
+                    const uint32_t size = (32u - (uint32_t)__clz((int)a)) + 1u;   // (16 - leading_zeros) + 1 (src/rle.rs:24)
+                    range_bad |= size > 15u ? PFV_TOKFLAG_RANGE : 0u;              // does not fit a 4-bit symbol (src/rle.rs:43)
+                    *o = (uint32_t)run | (size << 4) | (e << 16);
+                    r64 += 1ull << (run << 2);
+                    s64 += 1ull << ((size & 15u) << 2);
+                    esc_total += (uint32_t)esc;
+                }
+                out += __shfl_sync(FULL, inc2, 31);
             }
+            if (lane == 0) {                                         // the tail of the macroblock (src/rle.rs:31-38)
+                int run = 255 - (T ? (int)(L[T - 1u] >> 16) : -1);
+                if (run > 0) {
+                    const int esc = escapes_of(run);
+                    for (int q = 0; q < esc; ++q) *out++ = 15u;
+                    run -= 15 * esc;
+                    esc_total += (uint32_t)esc;
+                    *out = (uint32_t)run;                            // {run, 0, 0}
+                    r64 += 1ull << (run << 2);
+                    s64 += 1ull;
+                }
+            }
+            __syncwarp();                                            // the list is rewritten by the next macroblock
+            hist_fold(lh, r64, s64);
+            if (++folded == 16u) { hist_flush(lh, lane, job.stats); folded = 0; }   // 16 x 9 entries fit the 8-bit fields
         }
+        if (folded) hist_flush(lh, lane, job.stats);
+        // escapes {15, 0, 0} can come 17 to an entry: counted apart, one add per warp
         esc_total = __reduce_add_sync(FULL, esc_total);
         if (lane == 0 && esc_total) {
-            atomicAdd(&hist[15], esc_total);
-            atomicAdd(&hist[16], esc_total);
+            atomicAdd(job.stats + 15, esc_total);
+            atomicAdd(job.stats + 16, esc_total);
         }
+        if (__any_sync(FULL, range_bad != 0) && lane == 0) atomicOr(job.stats + PFV_TOKSTATS_FLAGS, PFV_TOKFLAG_RANGE);
     }
-    __syncthreads();
-    if (threadIdx.x < 32 && hist[threadIdx.x]) atomicAdd(job.stats + threadIdx.x, hist[threadIdx.x]);
-    if (threadIdx.x == 32 && bad) atomicOr(job.stats + PFV_TOKSTATS_FLAGS, bad);
 }
 
 constexpr int STORE_THREADS = 256;
@@ -239,11 +272,12 @@ tok_store_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     }
 }
 
+// The per-macroblock entry counts are already in mb_off[1..] (written by the encode kernels, EncJob::mb_cnt).
 cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
-    dim3 grid((nb + TOK_WARPS - 1) / TOK_WARPS, njobs, 1), block(TOK_WARPS * 32, 1, 1);
-    tok_count_kernel<<<grid, block, 0, s>>>(nb, d_jobs);
     tok_scan_kernel<<<njobs, SCAN_THREADS, 0, s>>>(nb, d_jobs);
+    const uint32_t chunks = (nb + TOK_CHUNK - 1u) / TOK_CHUNK;
+    dim3 grid((chunks + TOK_WARPS - 1) / TOK_WARPS, njobs, 1), block(TOK_WARPS * 32, 1, 1);
     tok_emit_kernel<<<grid, block, 0, s>>>(nb, d_jobs);
     return cudaGetLastError();
 }
