@@ -16,6 +16,8 @@
 //
 // Entry format (what pfv_packet_encode_tokens takes): run | size << 4 | uint16(value) << 16, exactly one word per
 // RLESequence {num_zeroes, coeff_size, coeff} (src/rle.rs:3-7).
+#include <cstdlib>
+
 #include "pfv_internal.h"
 #include "pfv_tok.cuh"
 
@@ -285,7 +287,9 @@ cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, c
 cudaError_t launch_token_store(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
     // few CTAs: the sink is PCIe (or a neighbouring HBM buffer), and the kernel shares the GPU with the next submit's work
-    dim3 grid(32, njobs, 1);
+    const char *e = getenv("PFV_TOK_STORE_CTAS");
+    const int v = e ? atoi(e) : 0;
+    dim3 grid((v >= 1 && v <= 1024) ? (unsigned)v : 32u, njobs, 1);
     tok_store_kernel<<<grid, STORE_THREADS, 0, s>>>(nb, d_jobs);
     return cudaGetLastError();
 }

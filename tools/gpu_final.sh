@@ -33,5 +33,7 @@ PY
 PYTHONPATH=$PWD timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_enc_$TAG.csv \
     python /tmp/enc_ll.py > $OUT/ncu_launch_enc_$TAG.log 2>&1
 tail -1 $OUT/ncu_launch_enc_$TAG.log
+echo "== device time of the sparse encode seam next to the dense one (32 x 1080p per submit, resident)"
+timeout 300 python tools/exp/tok_cost.py 2>&1 | tail -6 | tee $OUT/tok_cost_$TAG.txt
 ls $OUT | tr '\n' ' '
 
