@@ -567,7 +567,7 @@ def run_decoder_stream(torch, dist, budget_s, nthreads):
             enc.bytes()
             return time.perf_counter() - t0
     enc_pass(gop)
-    enc_fps = 4 * gop / min(enc_pass(4 * gop) for _ in range(2))
+    enc_fps = 8 * gop / min(enc_pass(8 * gop) for _ in range(3))     # best of 3: the calling thread shares the host with 16 workers
     # the oracle's Decoder on the same bytes (entropy + MB loops, nthreads OpenMP threads for the MB loops)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import pfvo

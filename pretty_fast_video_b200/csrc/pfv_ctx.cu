@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "pfv_internal.h"
@@ -189,6 +190,9 @@ struct pfv_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint8_t *d_rgb = nullptr;              // pfv_slot_read_rgb: device staging of one packed RGB picture (lazily allocated)
     cudaEvent_t ev_rgb = nullptr;          // the last D2H copy out of d_rgb
+    bool trace = false;                    // PFV_TRACE=1: host time of the encode submit path, printed at destroy
+    double t_enc_alloc = 0, t_enc_wait = 0, t_enc_copy = 0, t_enc_launch = 0, t_enc_d2h = 0;
+    uint64_t n_enc_submits = 0;
     int host_compact = 0;                  // PFV_HOST_COMPACT=1: compact dense host coefficients to tokens on a host pool before the
                                            // copy.  Off by default: on the bench box (16 host threads) scanning 6.27 MB per 1080p
                                            // frame cost ~1 ms per frame per thread and halved e2e (7.9 k -> 3.9 k frames/s); hosts
@@ -387,6 +391,11 @@ uint32_t compact_dense(const int16_t *coeff, const pfv_mbhdr *hdr, uint32_t nb, 
     return n;
 }
 
+inline double host_now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int ensure_src_staging(pfv_ctx *c)
 {
     if (c->st[0].d_src) return PFV_OK;
@@ -414,6 +423,11 @@ int wait_slot_readers(pfv_ctx *c, const uint32_t *slots, uint32_t n)
 extern "C" void pfv_ctx_destroy(pfv_ctx *c)
 {
     if (!c) return;
+    if (c->trace && c->n_enc_submits)
+        fprintf(stderr, "[pfv ctx] %llu encode submits, host time per submit: staging alloc %.1f us, wait for the stage %.1f us, "
+                        "copies in %.1f us, launches %.1f us, copies out %.1f us\n", (unsigned long long)c->n_enc_submits,
+                1e6 * c->t_enc_alloc / c->n_enc_submits, 1e6 * c->t_enc_wait / c->n_enc_submits, 1e6 * c->t_enc_copy / c->n_enc_submits,
+                1e6 * c->t_enc_launch / c->n_enc_submits, 1e6 * c->t_enc_d2h / c->n_enc_submits);
     cudaSetDevice(c->device);
     if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
@@ -473,6 +487,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char *v = getenv("PFV_DECODE_P_SPLIT")) c->p_split = atoi(v) > 0 ? atoi(v) : 1;
     if (const char *v = getenv("PFV_HOST_COMPACT")) c->host_compact = atoi(v) != 0;
+    if (const char *v = getenv("PFV_TRACE")) c->trace = atoi(v) != 0;
     if (ext_stream) {
         c->s_compute = (cudaStream_t)ext_stream;
         c->own_compute = false;
@@ -1176,6 +1191,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
     // the divisors of the tables an encoder uses must be non-zero (the reference clamps them to >= 1, src/enc.rs:48-51)
 
     CU_TRY(cudaSetDevice(c->device));
+    const double t0 = c->trace ? host_now() : 0;
     {
         int rc = ensure_src_staging(c);
         if (rc) return rc;
@@ -1194,7 +1210,9 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         }
     const uint64_t id = ++c->submit_id;
     Stage &st = c->st[id % STAGES];
+    const double t1 = c->trace ? host_now() : 0;
     CU_TRY(cudaEventSynchronize(st.ev_h2d));
+    const double t2 = c->trace ? host_now() : 0;
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_d2h, 0));           // tok_store_kernel of the stage's previous use reads d_tjobs
 
@@ -1269,6 +1287,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
     CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(EncJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
     if (n_tok) CU_TRY(cudaMemcpyAsync(st.d_tjobs, st.h_tjobs, sizeof(TokJob) * n_tok, cudaMemcpyHostToDevice, c->s_h2d));
     CU_TRY(cudaEventRecord(st.ev_h2d, c->s_h2d));
+    const double t3 = c->trace ? host_now() : 0;
 
     CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
     CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_d2h, 0));       // earlier D2H out of this stage's coeff/hdr buffers
@@ -1294,6 +1313,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
     CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
     c->have_kernel_time = true;
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
+    const double t4 = c->trace ? host_now() : 0;
 
     bool any_host = false;
     for (uint32_t i = 0; i < njobs; i++) any_host |= (jobs[i].flags & PFV_JOB_DEVICE_PTRS) == 0;
@@ -1315,6 +1335,11 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
     }
     CU_TRY(cudaEventRecord(st.ev_d2h, c->s_d2h));
     CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
+    if (c->trace) {
+        const double t5 = host_now();
+        c->t_enc_alloc += t1 - t0; c->t_enc_wait += t2 - t1; c->t_enc_copy += t3 - t2; c->t_enc_launch += t4 - t3; c->t_enc_d2h += t5 - t4;
+        c->n_enc_submits++;
+    }
     return PFV_OK;
 }
 
