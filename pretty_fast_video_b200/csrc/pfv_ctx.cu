@@ -1304,9 +1304,10 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         c->launches++;
     }
     const EncJob *d_tab = static_cast<const EncJob *>(st.d_jobs);
-    if (n_i) { CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, c->s_compute)); c->launches++; }
+    const bool count = n_tok != 0;                                 // an entry point's jobs are all dense or all sparse
+    if (n_i) { CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, count, c->s_compute)); c->launches++; }
     if (njobs - n_i) {
-        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, c->s_compute));
+        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->s_compute));
         c->launches++;
     }
     if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 2; }

@@ -133,7 +133,7 @@ __device__ __forceinline__ int byte_of(uint2 v, int k)
 // -------------------------------------------------------------------------------------------------
 // encode-I
 // -------------------------------------------------------------------------------------------------
-template <int MPW>
+template <int MPW, bool COUNT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 encode_i_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
                 const QTables *__restrict__ qt)
@@ -170,7 +170,7 @@ encode_i_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         for (int k = 0; k < 8; ++k) scale[k] = c_scaleT[r * 8 + k];
         const uint4 craw = encode_mb_core(ws, lane, gaddr, encM, scale, x);
         __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)m * 256) + lane, craw);
-        if (job.mb_cnt) {                                              // sparse seam: how many RLE entries this macroblock makes
+        if (COUNT) {                                                   // sparse seam: how many RLE entries this macroblock makes
             const uint32_t n = tok::warp_count(craw, (uint32_t)lane);
             if (lane == 0) job.mb_cnt[m] = n;
         }
@@ -220,7 +220,7 @@ __device__ __forceinline__ uint32_t warp_ssd(uint2 src, uint2 ref)
 // window (block_search never moves further than 8+4+2+1 = 15 px, src/common.rs:154-204) is fetched
 // from the reference slot by ONE 4-D TMA box {WIN_W, WIN_H, 1, 1}; the part outside the plane is
 // zero-filled by the TMA unit and never visited (candidates there are skipped, src/common.rs:171,182).
-template <int CTAS_PER_SM>
+template <int CTAS_PER_SM, bool COUNT>   // COUNT: sparse encode seam, leave each macroblock's RLE entry count in job.mb_cnt
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs,
                 const QTables *__restrict__ qt,
@@ -409,7 +409,7 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         for (int k = 0; k < 8; ++k) scale[k] = c_scaleT[r * 8 + k];
         const uint4 craw = encode_mb_core(ws, lane, gaddr, encM, scale, x);
         __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)m * 256) + lane, craw);
-        if (job.mb_cnt) {                                              // sparse seam: how many RLE entries this macroblock makes
+        if (COUNT) {                                                   // sparse seam: how many RLE entries this macroblock makes
             const uint32_t n = tok::warp_count(craw, (uint32_t)lane);
             if (lane == 0) job.mb_cnt[m] = n;
         }
@@ -418,7 +418,7 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
         int y[8];
         decode_mb_core(ws, lane, gaddr, deq, y);
         out = apply_residual_row(y, prev);                             // src/common.rs:277
-    } else if (job.mb_cnt && lane == 0) {
+    } else if (COUNT && lane == 0) {
         job.mb_cnt[m] = 0;                                             // subblocks: None (src/enc.rs:357-358)
     }
     uint8_t *dst = job.dst + pl.off + (size_t)((uint32_t)by + py) * pl.pw + (uint32_t)bx + px;
@@ -442,17 +442,18 @@ cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, 
 }
 
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
-                            const QTables *d_qt, cudaStream_t s)
+                            const QTables *d_qt, bool count, cudaStream_t s)
 {
     const uint32_t per_cta = WARPS_PER_CTA * ENC_MPW;
     dim3 grid((g.nb + per_cta - 1) / per_cta, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
-    encode_i_kernel<ENC_MPW><<<grid, block, 0, s>>>(g, d_jobs, d_qt);
+    if (count) encode_i_kernel<ENC_MPW, true><<<grid, block, 0, s>>>(g, d_jobs, d_qt);
+    else       encode_i_kernel<ENC_MPW, false><<<grid, block, 0, s>>>(g, d_jobs, d_qt);
     return cudaGetLastError();
 }
 
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
-                            cudaStream_t s)
+                            bool count, cudaStream_t s)
 {
     dim3 grid(g.total_tiles, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
     // resident CTAs per SM = the register budget the kernel is compiled for (3: 72 registers ... 6: 40); the kernel is issue
@@ -460,12 +461,24 @@ cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
     // measured on 32 x 1080p: 3: 77.5 k, 4: 84.8 k, 5: 81.5 k, 6: 83.2 k frames/s
     const char *e = getenv("PFV_ENCODE_P_CTAS_PER_SM");
     const int v = e ? atoi(e) : 0;
-    switch ((v >= 3 && v <= 6) ? v : 4) {
-    case 3: encode_p_kernel<3><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
-    case 5: encode_p_kernel<5><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
-    case 6: encode_p_kernel<6><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
-    default: encode_p_kernel<4><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma); break;
+    const int ctas = (v >= 3 && v <= 6) ? v : 4;
+#define PFV_ENC_P(C, CNT) encode_p_kernel<C, CNT><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma)
+    if (count) {
+        switch (ctas) {
+        case 3: PFV_ENC_P(3, true); break;
+        case 5: PFV_ENC_P(5, true); break;
+        case 6: PFV_ENC_P(6, true); break;
+        default: PFV_ENC_P(4, true); break;
+        }
+    } else {
+        switch (ctas) {
+        case 3: PFV_ENC_P(3, false); break;
+        case 5: PFV_ENC_P(5, false); break;
+        case 6: PFV_ENC_P(6, false); break;
+        default: PFV_ENC_P(4, false); break;
+        }
     }
+#undef PFV_ENC_P
     return cudaGetLastError();
 }
 
