@@ -205,3 +205,31 @@ def yuv420_to_rgb(y, u, v):  # lib.rs:365-395 (double: common.rs:538-556)
     g = fy - (f(0.344136) * uf) - (f(0.714136) * vf)
     b = fy + (f(1.772) * uf)
     return np.stack([f32_as_u8(r), f32_as_u8(g), f32_as_u8(b)], -1)
+
+
+def rle_encode(data):  # rle.rs:9-39 -> [(num_zeroes, coeff_size, coeff)]
+    out, run = [], 0
+    for val in data:
+        val = int(val)
+        if val == 0:
+            run += 1
+            continue
+        while run > 15:
+            out.append((15, 0, 0))
+            run -= 15
+        c = (-val if val < 0 else val) & 0xffff          # val.abs() as u16 (wraps for i16::MIN)
+        out.append((run, c.bit_length() + 1, val))       # (16 - leading_zeros) + 1
+        run = 0
+    while run > 15:
+        out.append((15, 0, 0))
+        run -= 15
+    if run > 0:
+        out.append((run, 0, 0))
+    return out
+
+
+def update_table(table, seq):  # rle.rs:41-47
+    for z, s, _ in seq:
+        table[z] += 1
+        table[s] += 1
+    return table
