@@ -788,6 +788,10 @@ def main():
         nthreads = os.cpu_count() or 1
         cfps, sample, _ = cpu_port_leg(args.workload, args.cpu_budget, nthreads)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
+        if nthreads > 1 and args.cpu_budget >= 1.0:
+            # the same port on ONE thread (SURVEY 8d quotes the CPU path at 1 thread and at all threads)
+            c1, s1, _ = cpu_port_leg(args.workload, min(args.cpu_budget / 4, 3.0), 1)
+            line["cpu_baseline"]["one_thread"] = {"value": c1, "unit": "frames/s", "cores": 1, "sample": s1}
         if args.extras:
             extras = {}
             for wl in ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p", "decode_p_4k"):
