@@ -90,3 +90,34 @@ def test_cpp_example_builds_and_links_against_the_abi():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
     r = subprocess.run([os.path.join(ROOT, "examples", "decode_speed")], capture_output=True, text=True)
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_cubin_is_sm_100a_and_the_staging_paths_are_tma():
+    """The shipped library carries sm_100a SASS only, and the kernels the design describes as TMA-staged really are:
+    UTMALDG = cp.async.bulk.tensor (encode-P search window, decode-P predictor window), UBLKCP = cp.async.bulk (decode-I tiles),
+    SYNCS = mbarrier completion (B200_PROFILING.md's mnemonics)."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "pretty_fast_video_b200", "libpfv_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    archs = {l.split("=")[1].strip() for l in sass.splitlines() if l.strip().startswith("arch =")}
+    assert archs == {"sm_100a"}
+    body, name = {}, None
+    for l in sass.splitlines():
+        if "Function :" in l:
+            name = l.split("Function :")[1].strip()
+            body[name] = []
+        elif name:
+            body[name].append(l)
+    def has(kernel, mnemonic):
+        hits = [k for k in body if kernel in k]
+        assert hits, kernel
+        return all(any(mnemonic in x for x in body[k]) for k in hits)
+    assert has("encode_p_kernel", "UTMALDG") and has("encode_p_kernel", "SYNCS")
+    assert has("mc_copy4_kernel", "UTMALDG")
+    assert has("decode_i_stream_kernel", "UBLKCP") and has("decode_i_stream_kernel", "SYNCS")
+    for k in ("tok_scan_kernel", "tok_emit_kernel", "tok_store_kernel", "expand_tokens_kernel", "residual_sb2_kernel",
+              "encode_i_kernel", "rgb_to_yuv420_kernel", "yuv420_to_rgb_kernel"):
+        assert any(k in n for n in body), k
