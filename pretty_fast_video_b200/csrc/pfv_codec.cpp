@@ -859,7 +859,9 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
     if (d->depth > 48) d->depth = 48;                                // pfv_ctx_wait_submit reaches 64 submits back
     d->nslots = d->depth + 2;                                        // slot 0: the blank initial framebuffer; then one per work item
     rc = pfv_ctx_create(device, d->info.width, d->info.height, reinterpret_cast<const int32_t(*)[64]>(qt.data()),
-                        d->info.num_qtables, d->nslots, d->lanes, nullptr, &d->ctx);
+                        // q-table indices are u8 in the packets (src/dec.rs:244-246): tables beyond 256 can never be addressed;
+                        // the reference's Decoder::new accepts such a header, so does this one
+                        d->info.num_qtables > 256 ? 256u : d->info.num_qtables, d->nslots, d->lanes, nullptr, &d->ctx);
     if (rc) return rc;
     // pinned buffers are sized once, from the largest frame packet of the stream (cudaHostAlloc costs milliseconds:
     // never on the per-frame path).  Token capacity: an emitted token costs at least 3 bits when the tree has two or

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "pfv_internal.h"
+#include "pfv_dct.cuh"
 #include "pfv_pool.h"
 
 using namespace pfv;
@@ -186,8 +187,6 @@ struct pfv_ctx {
     int *d_err = nullptr;
     int *h_err = nullptr;            // pinned
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
-    cudaStream_t s_aux = nullptr;          // second compute stream: decode-P parts alternate between s_compute and s_aux
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint8_t *d_rgb = nullptr;              // pfv_slot_read_rgb: device staging of one packed RGB picture (lazily allocated)
     cudaEvent_t ev_rgb = nullptr;          // the last D2H copy out of d_rgb
     bool trace = false;                    // PFV_TRACE=1: host time of the encode submit path, printed at destroy
@@ -199,28 +198,28 @@ struct pfv_ctx {
                                            // that can, hand over tokens directly (pfv_decode_submit_sparse: 13 k frames/s)
     Pool *pool = nullptr;                  // host threads for the compaction (created on first use)
     bool pcount_clean = false;             // the last residual kernel left d_pcount[0 .. 4*njobs) zeroed
-    int p_split = 1;                       // PFV_DECODE_P_SPLIT: parts a batch of P frames is cut into, alternating between two
-                                           // streams.  Measured on B200 (1080p, 32 frames per batch): 1 -> 0.48 of roofline,
-                                           // 2 -> 0.43, 4 -> 0.41, 8 -> 0.33: the kernels do not overlap usefully, kept as a knob
     bool own_compute = true;
     Stage st[STAGES];
     cudaEvent_t ev_d2h_ring[D2H_RING]{};
     std::vector<uint64_t> slot_last_d2h;   // submit id (1-based) whose D2H last read the slot; 0 = none
     uint64_t submit_id = 0;
+    uint64_t failed_ring[D2H_RING]{};      // failed_ring[id % D2H_RING] == id: that submit broke off after its id was issued
     uint64_t launches = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     bool have_kernel_time = false;
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
+    std::vector<uint32_t> h_enc_magic;     // nq * 64: quant_magic(q[raster]) by raster position (src/dct.rs:93-95)
+    bool enc_tables_ok = false;            // tables 0..3 exist and every divisor is in 1..65535 (what an encoder needs)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
-    int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "tma" (default), 3 "sbw", 1 "sb" (dense), 2 "warp"
-    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "win" (default: TMA window copy + list-driven persistent residual), 7 "winll" (list-free residual),
-                                           // 6 "tma" (per-macroblock TMA boxes),
-                                           // 5 "two" (cp.async copy),
-                                           // 4 "two1" (first pair), 1 "stream", 3 "sbw", 2 "warp"
+    // One default kernel per path plus independently written second implementations, selectable for the parity tests:
+    int decode_i_variant = 0;              // PFV_DECODE_I_VARIANT: 0 "stream" (default: TMA-staged classify/compact/transform), 1 "sb" (plain
+                                           // thread-per-sub-block), 2 "warp" (first generation, warp per macroblock)
+    int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "fused" (default: warp-specialised copy + residual in one kernel),
+                                           // 1 "win" (window copy kernel + list-driven residual kernel), 2 "warp" (also used without TMA)
+    int encode_i_variant = 0;              // PFV_ENCODE_I_VARIANT: 0 "stream" (default: thread per sub-block), 2 "warp"
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
     CUtensorMap tm_luma{}, tm_chroma{};          // encode-P search window boxes
-    CUtensorMap tm_mb_luma{}, tm_mb_chroma{};    // decode-P predictor boxes (32 x 16, 16-byte aligned in x)
     CUtensorMap tm_win_luma{}, tm_win_chroma{};  // decode-P windows of 8 x 4 macroblocks (176 x 94)
     bool have_tma = false;
     char tma_err[160] = "";
@@ -244,15 +243,13 @@ int build_tensor_maps(pfv_ctx *c)
     EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
     const pfv_geometry &g = c->geo;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const char *promo_env = getenv("PFV_TMA_L2PROMO");
-    for (int which = 0; which < 3; which++) {
-    const CUtensorMapL2promotion promo = which == 1 && promo_env ? (CUtensorMapL2promotion)atoi(promo_env) : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    // which == 1: the aligned 32 x 16 box that covers a motion-compensated 16 x 16 block (mc_copy3_kernel)
-    // which == 2: the window of every possible predictor of 8 x 4 macroblocks (mc_copy4_kernel)
-    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : (which == 1 ? 32u : 176u),
-                               which == 0 ? (cuuint32_t)WIN_H : (which == 1 ? 16u : 94u), 1, 1};
-    CUtensorMap *out_l = which == 0 ? &c->tm_luma : (which == 1 ? &c->tm_mb_luma : &c->tm_win_luma);
-    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : (which == 1 ? &c->tm_mb_chroma : &c->tm_win_chroma);
+    for (int which = 0; which < 2; which++) {
+    const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    // which == 0: the search window of an encode-P tile of 8 macroblocks (176 x 46)
+    // which == 1: the window of every possible predictor of 8 x 4 macroblocks (176 x 94; decode-P)
+    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : 176u, which == 0 ? (cuuint32_t)WIN_H : 94u, 1, 1};
+    CUtensorMap *out_l = which == 0 ? &c->tm_luma : &c->tm_win_luma;
+    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : &c->tm_win_chroma;
     {   // luma: (x, y, 1, slot)
         const cuuint64_t dims[4] = {g.pw, g.ph, 1, c->nslots};
         const cuuint64_t strides[3] = {g.pw, c->slot_stride, c->slot_stride};
@@ -452,12 +449,9 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
-    if (c->s_aux) { cudaStreamSynchronize(c->s_aux); cudaStreamDestroy(c->s_aux); }
     delete c->pool;
     cudaFree(c->d_rgb);
     if (c->ev_rgb) cudaEventDestroy(c->ev_rgb);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_compute && c->own_compute) cudaStreamDestroy(c->s_compute);
     delete c;
 }
@@ -482,10 +476,6 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
 
     CU_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-    CU_TRY(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-    CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    if (const char *v = getenv("PFV_DECODE_P_SPLIT")) c->p_split = atoi(v) > 0 ? atoi(v) : 1;
     if (const char *v = getenv("PFV_HOST_COMPACT")) c->host_compact = atoi(v) != 0;
     if (const char *v = getenv("PFV_TRACE")) c->trace = atoi(v) != 0;
     if (ext_stream) {
@@ -510,6 +500,14 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     for (uint32_t t = 0; t < c->nq; t++)
         for (int i = 0; i < 64; i++)
             c->h_deq_scan[t * 64 + i] = (int32_t)((uint32_t)kScale[i] * (uint32_t)qtables[t][i]);
+    c->h_enc_magic.resize((size_t)c->nq * 64);
+    c->enc_tables_ok = c->nq >= 4;
+    for (uint32_t t = 0; t < c->nq; t++)
+        for (int i = 0; i < 64; i++) {
+            const int32_t q = qtables[t][i];
+            if (t < 4 && (q < 1 || q > QUANT_MAX_DIVISOR)) c->enc_tables_ok = false;
+            c->h_enc_magic[t * 64 + i] = quant_magic(q);
+        }
     {
         uint32_t cta = 0;
         for (int p = 0; p < 3; p++) {
@@ -518,9 +516,9 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
         }
         c->cta_total = cta;
     }
-    if (const char *v = getenv("PFV_DECODE_I_VARIANT"))
-        c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : (strcmp(v, "sbw") == 0 ? 3 : 0));
-    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sbw") == 0 ? 3 : (strcmp(v, "stream") == 0 ? 1 : (strcmp(v, "two1") == 0 ? 4 : (strcmp(v, "two") == 0 ? 5 : (strcmp(v, "tma") == 0 ? 6 : (strcmp(v, "winll") == 0 ? 7 : (strcmp(v, "live") == 0 ? 8 : 0)))))));
+    if (const char *v = getenv("PFV_DECODE_I_VARIANT")) c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : 0);
+    if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "win") == 0 ? 1 : 0);
+    if (const char *v = getenv("PFV_ENCODE_I_VARIANT")) c->encode_i_variant = strcmp(v, "warp") == 0 ? 2 : 0;
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -714,7 +712,7 @@ extern "C" int pfv_slot_read_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint
     CU_TRY(cudaSetDevice(c->device));
     // order after everything submitted so far on the compute stream; takes a submit id of its own so the
     // slot-reuse bookkeeping sees this read
-    const uint64_t id = ++c->submit_id;
+    const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     cudaEvent_t ev = c->ev_d2h_ring[id % D2H_RING];
     CU_TRY(cudaEventRecord(ev, c->s_compute));
     CU_TRY(cudaStreamWaitEvent(c->s_d2h, ev, 0));
@@ -752,7 +750,7 @@ extern "C" int pfv_slot_read_rgb(pfv_ctx *c, uint32_t slot, uint8_t *rgb_host)
         CU_TRY(cudaMalloc(&c->d_rgb, bytes));
         CU_TRY(cudaEventCreateWithFlags(&c->ev_rgb, cudaEventDisableTiming));
     }
-    const uint64_t id = ++c->submit_id;
+    const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     cudaEvent_t ev = c->ev_d2h_ring[id % D2H_RING];
     CU_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_rgb, 0));    // the previous picture has left the staging buffer
     int rc = convert_rgb(c, slot, c->d_rgb, c->s_compute);
@@ -836,7 +834,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         int rc = ensure_compact_staging(c);
         if (rc) return rc;
     }
-    const uint64_t id = ++c->submit_id;
+    const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
     CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));     // device buffers of this stage are free again
@@ -984,79 +982,34 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
             while (b < n_i && qkey(order[b]) == qkey(order[a])) b++;
             const SbParams P = sb_params(order[a]);
             if (c->decode_i_variant == 1) CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
-            else if (c->decode_i_variant == 3) CU_TRY(launch_decode_sbw(false, P, d_tab + a, b - a, c->d_err, c->s_compute));
             else CU_TRY(launch_decode_i_stream(P, d_tab + a, b - a, c->s_compute));
             c->launches++;
             a = b;
         }
     }
-    if (njobs - n_i && c->decode_p_variant == 2) {
+    if (njobs - n_i && (c->decode_p_variant == 2 || !c->have_tma)) {
         CU_TRY(launch_decode(true, c->fg, d_tab + n_i, njobs - n_i, c->d_err, c->s_compute));
         c->launches++;
     } else {
         for (uint32_t a = n_i; a < njobs;) {
             uint32_t b = a + 1;
             while (b < njobs && qkey(order[b]) == qkey(order[a])) b++;
-            if (c->decode_p_variant == 3) {
-                CU_TRY(launch_decode_sbw(true, sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
-            } else if (c->decode_p_variant == 1) {
-                CU_TRY(launch_decode_p_stream(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->s_compute));
-            } else if (c->decode_p_variant == 8 && c->have_tma && a == n_i && b == njobs) {
-                // "live": copy and residual kernels side by side on two streams (see launch_decode_p_live)
-                if (!c->pcount_clean) {
-                    CU_TRY(cudaMemsetAsync(c->d_pcount, 0, ((size_t)c->max_jobs * 6 + 4) * sizeof(uint32_t), c->s_compute));
-                    c->pcount_clean = true;
-                }
-                CU_TRY(cudaEventRecord(c->ev_fork, c->s_compute));
-                CU_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-                CU_TRY(launch_decode_p_live(sb_params(order[a]), d_tab + a, b - a, c->d_plist, c->d_pcount,
-                                            c->d_pcount + (size_t)c->max_jobs * 4, c->max_jobs, c->d_err, c->tm_win_luma, c->tm_win_chroma,
-                                            c->s_compute, c->s_aux));
-                CU_TRY(cudaEventRecord(c->ev_join, c->s_aux));
-                CU_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_join, 0));
+            if (c->decode_p_variant == 0) {
+                CU_TRY(launch_decode_p_fused(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->tm_win_luma, c->tm_win_chroma, c->s_compute));
                 c->launches++;
-            } else if ((c->decode_p_variant == 0 || c->decode_p_variant == 7 || c->decode_p_variant == 8) && c->have_tma) {
+            } else {
                 const uint32_t k0 = a - n_i, n = b - a;
-                // list counts: cleared by the previous residual kernel itself when the whole group goes out as one pair of
-                // launches on the default kernels (self_clear); otherwise by a memset node here
-                const bool self_clear = c->p_split <= 1 && (c->decode_p_variant == 0 || c->decode_p_variant == 8) && k0 == 0 && c->pcount_clean;
+                // list counts: cleared by the previous residual kernel itself when the whole group went out as one pair of
+                // launches (self_clear); otherwise by a memset node here
+                const bool self_clear = k0 == 0 && c->pcount_clean;
                 if (!self_clear)
                     CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)n * 4 * sizeof(uint32_t), c->s_compute));
-                c->pcount_clean = c->p_split <= 1 && (c->decode_p_variant == 0 || c->decode_p_variant == 8) && k0 == 0 && n == njobs - n_i;
-                uint32_t parts = (uint32_t)c->p_split;
-                if (parts > n / 2) parts = n / 2;                   // at least 2 frames per part
-                if (parts < 1) parts = 1;
-                const SbParams P = sb_params(order[a]);
-                for (uint32_t i = 0; i < parts; i++) {
-                    const uint32_t lo = (uint32_t)((uint64_t)n * i / parts), hi = (uint32_t)((uint64_t)n * (i + 1) / parts);
-                    cudaStream_t st_i = (i & 1u) ? c->s_aux : c->s_compute;
-                    if (i == 1) CU_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-                    CU_TRY(launch_decode_p_two_pass4(P, d_tab + a + lo, hi - lo, c->d_plist + (size_t)(k0 + lo) * c->geo.nb,
-                                                     c->d_pcount + (size_t)(k0 + lo) * 4, c->decode_p_variant == 7, c->d_err,
-                                                     c->tm_win_luma, c->tm_win_chroma, st_i, i == 0 && parts > 1 ? c->ev_fork : nullptr,
-                                                     c->pcount_clean ? c->d_pcount + (size_t)c->max_jobs * 4 : nullptr));
-                    c->launches += 2;
-                }
-                if (parts > 1) {
-                    CU_TRY(cudaEventRecord(c->ev_join, c->s_aux));
-                    CU_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_join, 0));
-                }
-                c->launches--;                                      // the common increment below counts one of them
-            } else {
-                const uint32_t k0 = a - n_i;
-                CU_TRY(cudaMemsetAsync(c->d_pcount + (size_t)k0 * 4, 0, (size_t)(b - a) * 4 * sizeof(uint32_t), c->s_compute));
-                if (c->decode_p_variant == 4)
-                    CU_TRY(launch_decode_p_two_pass(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
-                                                    c->d_pcount + (size_t)k0 * 4, c->d_err, c->s_compute));
-                else if (c->decode_p_variant != 6 || !c->have_tma)
-                    CU_TRY(launch_decode_p_two_pass2(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
-                                                     c->d_pcount + (size_t)k0 * 4, c->d_err, c->s_compute));
-                else
-                    CU_TRY(launch_decode_p_two_pass3(sb_params(order[a]), d_tab + a, b - a, c->d_plist + (size_t)k0 * c->geo.nb,
-                                                     c->d_pcount + (size_t)k0 * 4, c->d_err, c->tm_mb_luma, c->tm_mb_chroma, c->s_compute));
-                c->launches++;
+                c->pcount_clean = k0 == 0 && n == njobs - n_i;
+                CU_TRY(launch_decode_p_two_pass4(sb_params(order[a]), d_tab + a, n, c->d_plist + (size_t)k0 * c->geo.nb,
+                                                 c->d_pcount + (size_t)k0 * 4, c->d_err, c->tm_win_luma, c->tm_win_chroma, c->s_compute,
+                                                 c->pcount_clean ? c->d_pcount + (size_t)c->max_jobs * 4 : nullptr));
+                c->launches += 2;
             }
-            c->launches++;
             a = b;
         }
     }
@@ -1081,6 +1034,19 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     return PFV_OK;
 }
 
+// A submit that fails after its id was issued leaves the id without a recorded completion event: mark it, and record
+// the ring event anyway so that a later pfv_ctx_wait_submit(id) neither succeeds on the record of 64 submits ago nor
+// blocks - it reports the failure.
+static int finish_submit(pfv_ctx *c, uint64_t id_before, int rc)
+{
+    const uint64_t id = c->submit_id;
+    if (rc != PFV_OK && id != id_before) {
+        __atomic_store_n(&c->failed_ring[id % D2H_RING], id, __ATOMIC_RELEASE);
+        cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h);
+    }
+    return rc;
+}
+
 extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_t njobs)
 {
     if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
@@ -1096,7 +1062,8 @@ extern "C" int pfv_decode_submit(pfv_ctx *c, const pfv_decode_job *jobs, uint32_
         d.mb_off = nullptr; d.tok = nullptr; d.ntok = 0;
         d.out_y = j.out_y; d.out_u = j.out_u; d.out_v = j.out_v;
     }
-    return decode_submit_impl(c, in.data(), njobs);
+    const uint64_t before = c->submit_id;
+    return finish_submit(c, before, decode_submit_impl(c, in.data(), njobs));
 }
 
 extern "C" int pfv_decode_submit_sparse(pfv_ctx *c, const pfv_decode_job_sparse *jobs, uint32_t njobs)
@@ -1114,7 +1081,8 @@ extern "C" int pfv_decode_submit_sparse(pfv_ctx *c, const pfv_decode_job_sparse 
         d.mb_off = j.mb_off; d.tok = j.tok; d.ntok = j.ntok;
         d.out_y = j.out_y; d.out_u = j.out_u; d.out_v = j.out_v;
     }
-    return decode_submit_impl(c, in.data(), njobs);
+    const uint64_t before = c->submit_id;
+    return finish_submit(c, before, decode_submit_impl(c, in.data(), njobs));
 }
 
 extern "C" uint64_t pfv_ctx_last_submit_id(const pfv_ctx *c) { return c ? __atomic_load_n(&c->submit_id, __ATOMIC_RELAXED) : 0; }
@@ -1127,6 +1095,8 @@ extern "C" int pfv_ctx_wait_submit(pfv_ctx *c, uint64_t id)
     if (id == 0 || id > last) return fail(PFV_ERR_BAD_ARG, "submit id %llu has not been issued", (unsigned long long)id);
     if (id + D2H_RING <= last)
         return fail(PFV_ERR_BAD_ARG, "submit id %llu is older than the %d most recent submits", (unsigned long long)id, D2H_RING);
+    if (__atomic_load_n(&c->failed_ring[id % D2H_RING], __ATOMIC_ACQUIRE) == id)
+        return fail(PFV_ERR_CUDA, "submit %llu failed after it was issued (see the error it returned)", (unsigned long long)id);
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaEventSynchronize(c->ev_d2h_ring[id % D2H_RING]));
     return PFV_OK;
@@ -1188,7 +1158,11 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
                 if (jobs[k].dst_slot == jobs[i].ref_slot)
                     return fail(PFV_ERR_BAD_ARG, "jobs %u and %u of one submit are dependent (ref_slot == dst_slot)", i, k);
     if (any_p && !c->have_tma) return fail(PFV_ERR_CUDA, "encode-P needs TMA tensor maps: %s", c->tma_err);
-    // the divisors of the tables an encoder uses must be non-zero (the reference clamps them to >= 1, src/enc.rs:48-51)
+    // the divisors of the tables an encoder uses must be non-zero (the reference clamps them to >= 1, src/enc.rs:48-51; its
+    // `n / d` would panic on 0, src/dct.rs:95); the quantiser's reciprocal multiply is exact up to 65535
+    if (!c->enc_tables_ok)
+        return fail(PFV_ERR_BAD_ARG, "encoding needs q-tables 0..3 (intra_l, intra_c, inter_l, inter_c) with every divisor in 1..%d",
+                    (int)QUANT_MAX_DIVISOR);
 
     CU_TRY(cudaSetDevice(c->device));
     const double t0 = c->trace ? host_now() : 0;
@@ -1208,7 +1182,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
             CU_TRY(cudaMalloc(&c->st[i].d_tjobs, sizeof(TokJob) * c->max_jobs));
             CU_TRY(cudaHostAlloc(&c->st[i].h_tjobs, sizeof(TokJob) * c->max_jobs, cudaHostAllocDefault));
         }
-    const uint64_t id = ++c->submit_id;
+    const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     Stage &st = c->st[id % STAGES];
     const double t1 = c->trace ? host_now() : 0;
     CU_TRY(cudaEventSynchronize(st.ev_h2d));
@@ -1305,7 +1279,20 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
     }
     const EncJob *d_tab = static_cast<const EncJob *>(st.d_jobs);
     const bool count = n_tok != 0;                                 // an entry point's jobs are all dense or all sparse
-    if (n_i) { CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, count, c->s_compute)); c->launches++; }
+    if (n_i) {
+        if (c->encode_i_variant == 2) {
+            CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, count, c->s_compute));
+        } else {
+            EncSbParams P;
+            P.g = c->fg;
+            for (int t = 0; t < 2; t++) {                              // intra_l, intra_c (src/enc.rs:84-90)
+                memcpy(P.encM[t], &c->h_enc_magic[(size_t)t * 64], 64 * sizeof(uint32_t));
+                memcpy(P.deq[t], &c->h_deq_scan[(size_t)t * 64], 64 * sizeof(int32_t));
+            }
+            CU_TRY(launch_encode_i_stream(P, d_tab, n_i, count, c->s_compute));
+        }
+        c->launches++;
+    }
     if (njobs - n_i) {
         CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->s_compute));
         c->launches++;
@@ -1356,7 +1343,8 @@ extern "C" int pfv_encode_submit(pfv_ctx *c, const pfv_encode_job *jobs, uint32_
         in[i] = EncIn{j.kind, j.flags, j.dst_slot, j.ref_slot, j.px_err, j.src_y, j.src_u, j.src_v, j.hdr_out, j.coeff_out,
                       false, 0, nullptr, nullptr, nullptr};
     }
-    return encode_submit_impl(c, in.data(), njobs);
+    const uint64_t before = c->submit_id;
+    return finish_submit(c, before, encode_submit_impl(c, in.data(), njobs));
 }
 
 extern "C" int pfv_encode_submit_sparse(pfv_ctx *c, const pfv_encode_job_sparse *jobs, uint32_t njobs)
@@ -1376,5 +1364,6 @@ extern "C" int pfv_encode_submit_sparse(pfv_ctx *c, const pfv_encode_job_sparse 
         in[i] = EncIn{j.kind, j.flags, j.dst_slot, j.ref_slot, j.px_err, j.src_y, j.src_u, j.src_v, j.hdr_out, nullptr,
                       true, j.tok_cap, mb_off, tok, stats};
     }
-    return encode_submit_impl(c, in.data(), njobs);
+    const uint64_t before = c->submit_id;
+    return finish_submit(c, before, encode_submit_impl(c, in.data(), njobs));
 }

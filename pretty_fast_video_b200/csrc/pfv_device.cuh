@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pfv_dct.cuh"
+
 namespace pfv {
 
 // ---- per-warp shared scratch -------------------------------------------------------------------
@@ -53,58 +55,6 @@ __constant__ int32_t c_scaleT[64] = {
     34, 39, 35, 28, 34, 28, 35, 39,
     37, 43, 39, 31, 37, 31, 39, 43,
 };
-
-// ---- 1-D transforms ------------------------------------------------------------------------------
-// src/dct.rs:241-293 / :176-239.  Rust's `/` truncates toward zero: x / 2^k = (x + (x < 0 ? 2^k - 1 : 0)) >> k.
-// Written as (x - (2^k - 1) * s) >> k with s = x >> 31 (0 or -1) so that the bias is ONE multiply-add on the FMA
-// pipe (IMAD) instead of a LEA.HI on the ALU pipe, and the sign is shared by the two divisions every operand of the
-// butterflies takes: per operand 3 ALU + 2 FMA instructions instead of 5 ALU.  ncu had the ALU pipe as the busiest
-// unit of every transform kernel (both pipes issue one warp instruction per 2 cycles per sub-partition, and the
-// transforms were 2.2 : 1 ALU : FMA).  `+ - *` wrap like release-mode Rust; the bias never overflows (it is only
-// added to negative values).
-struct Tdiv {
-    int x, s;
-    __device__ __forceinline__ explicit Tdiv(int v) : x(v), s(v >> 31) {}
-    __device__ __forceinline__ int d2() const { return (x - s) >> 1; }
-    __device__ __forceinline__ int d4() const { return (x - 3 * s) >> 2; }
-    __device__ __forceinline__ int d16() const { return (x - 15 * s) >> 4; }
-};
-
-__device__ __forceinline__ void idct8(int (&v)[8])
-{
-    const int c0 = v[0], d4 = v[1], c2 = v[2], d6 = v[3], c1 = v[4], d5 = v[5], c3 = v[6], d7 = v[7];
-    const int c4 = d4, c5 = d5 + d6, c7 = d5 - d6, c6 = d7;
-    const int b4 = c4 + c5, b5 = c4 - c5, b6 = c6 + c7, b7 = c6 - c7;
-    const int b0 = c0 + c1, b1 = c0 - c1;
-    const Tdiv t2(c2), t3(c3), t4(b4), t5(b5), t6(b6), t7(b7);
-    const int b2 = c2 + t2.d4() + t3.d2();
-    const int b3 = t2.d2() - c3 - t3.d4();
-    const int a4 = t7.d4() + b4 + t4.d4() - t4.d16();
-    const int a7 = t4.d4() - b7 - t7.d4() + t7.d16();
-    const int a5 = b5 - b6 + t6.d4() + t6.d16();
-    const int a6 = b6 + b5 - t5.d4() - t5.d16();
-    const int a0 = b0 + b2, a1 = b1 + b3, a2 = b1 - b3, a3 = b0 - b2;
-    v[0] = a0 + a4; v[1] = a1 + a5; v[2] = a2 + a6; v[3] = a3 + a7;
-    v[4] = a3 - a7; v[5] = a2 - a6; v[6] = a1 - a5; v[7] = a0 - a4;
-}
-
-__device__ __forceinline__ void fdct8(int (&v)[8])
-{
-    const int a0 = v[0] + v[7], a1 = v[1] + v[6], a2 = v[2] + v[5], a3 = v[3] + v[4];
-    const int a4 = v[0] - v[7], a5 = v[1] - v[6], a6 = v[2] - v[5], a7 = v[3] - v[4];
-    const int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
-    const int c0 = b0 + b1, c1 = b0 - b1;
-    const Tdiv t2(b2), t3(b3), t4(a4), t5(a5), t6(a6), t7(a7);
-    const int c2 = b2 + t2.d4() + t3.d2();
-    const int c3 = t2.d2() - b3 - t3.d4();
-    const int b4 = t7.d4() + a4 + t4.d4() - t4.d16();
-    const int b7 = t4.d4() - a7 - t7.d4() + t7.d16();
-    const int b5 = a5 + a6 - t6.d4() - t6.d16();
-    const int b6 = a6 - a5 + t5.d4() + t5.d16();
-    const int c4 = b4 + b5, c5 = b4 - b5, c6 = b6 + b7, c7 = b6 - b7;
-    v[0] = c0; v[1] = c4; v[2] = c2; v[3] = c5 - c7;
-    v[4] = c1; v[5] = c5 + c7; v[6] = c3; v[7] = c6;
-}
 
 // d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)   (PTX cvt.pack, SASS I2IP)
 __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c)

@@ -42,7 +42,7 @@ struct DecJob {
     uint8_t         *dst;     // frame slot
     const uint8_t   *ref;     // frame slot (P only)
     const QTables   *qt[3];   // per plane
-    int32_t          ref_slot; // the same slot as an index (TMA coordinate of mc_copy3_kernel)
+    int32_t          ref_slot; // the same slot as an index (TMA coordinate)
 };
 
 // sparse coefficient transport (pfv_decode_submit_sparse): one frame's token lists and where to expand them
@@ -88,11 +88,37 @@ struct SbParams {
     uint32_t  tiles_per_warp; // streaming kernels: consecutive 8-macroblock tiles one warp walks
 };
 
-// mc_copy_kernel: tiles of 8 consecutive macroblocks, never straddling a plane
-struct McTiles {
-    uint32_t base[3];         // first tile of each plane
+// Parameters of the thread-per-sub-block encode kernels (pfv_kernels_enc.cu): the tables of ONE (luma, chroma) pair travel
+// as kernel parameters so that the quantiser's multiplies take them as constant-bank operands.
+struct EncSbParams {
+    FrameGeom g;
+    uint32_t  encM[2][64];    // luma / chroma: quant_magic(q) by RASTER position (src/dct.rs:93-95)
+    int32_t   deq[2][64];     // luma / chroma: SCALE[s]*q[s] by SCAN position (the closed-loop reconstruction)
+    uint32_t  cta_base[3];
+    uint32_t  cta_total;
+    uint32_t  tiles_per_warp;
+};
+
+// decode-P window items of one frame: a window covers 8 x `rows` macroblocks of one plane
+struct McWin {
+    uint32_t base[3];         // first item of each plane
+    uint32_t tiles_x[3];      // windows per row of windows
+    float    rcp_tiles_x[3];
     uint32_t total;
 };
+inline McWin make_mc_windows(const FrameGeom &g, uint32_t rows)
+{
+    McWin W;
+    uint32_t t = 0;
+    for (int p = 0; p < 3; p++) {
+        W.base[p] = t;
+        W.tiles_x[p] = (g.pl[p].bw + 7u) / 8u;
+        W.rcp_tiles_x[p] = 1.0f / (float)W.tiles_x[p];
+        t += W.tiles_x[p] * ((g.pl[p].bh + rows - 1) / rows);
+    }
+    W.total = t;
+    return W;
+}
 
 // error bits the kernels OR into the context's device error word
 enum { ERRBIT_BAD_MV = 1, ERRBIT_TIMEOUT = 2 };
@@ -124,21 +150,15 @@ cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, 
                           int *d_err, cudaStream_t s);
 cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
-cudaError_t launch_decode_p_two_pass(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
-                                     uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s);
-cudaError_t launch_decode_p_two_pass2(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
-                                      uint32_t *d_lists, uint32_t *d_counts, int *d_err, cudaStream_t s);
-cudaError_t launch_decode_p_two_pass3(const SbParams &P, const DecJob *d_jobs, uint32_t njobs,
-                                      uint32_t *d_lists, uint32_t *d_counts, int *d_err,
-                                      const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s);
+// window copy + list-driven residual pass (pfv_kernels_p.cu); d_done != nullptr: the residual kernel clears d_counts itself
 cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
-                                      bool listless, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
-                                      cudaEvent_t after_copy, uint32_t *d_done);
-cudaError_t launch_decode_p_live(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
-                                 uint32_t *d_ctl, uint32_t max_jobs, int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
-                                 cudaStream_t s_copy, cudaStream_t s_resid);
-cudaError_t launch_decode_p_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
-cudaError_t launch_decode_sbw(bool inter, SbParams P, const DecJob *d_jobs, uint32_t njobs, int *d_err, cudaStream_t s);
+                                      int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,
+                                      uint32_t *d_done);
+// the fused warp-specialised decode-P kernel (pfv_kernels_pf.cu)
+cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, int *d_err,
+                                  const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s);
+// completes cta_base / cta_total / tiles_per_warp of the streaming kernels (pfv_kernels_sb.cu)
+void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t waves_x_warps, uint32_t max_tpw);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_token_store(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
@@ -146,6 +166,7 @@ cudaError_t launch_rgb_to_yuv420(const uint8_t *d_rgb, uint32_t w, uint32_t h, u
 cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, uint32_t w, uint32_t h, uint32_t pw,
                                  uint32_t cpw, uint8_t *d_rgb, cudaStream_t s);
 // count: every job of the launch has EncJob::mb_cnt set (sparse encode seam)
+cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, bool count, cudaStream_t s);
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,

@@ -456,29 +456,9 @@ cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
                             bool count, cudaStream_t s)
 {
     dim3 grid(g.total_tiles, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
-    // resident CTAs per SM = the register budget the kernel is compiled for (3: 72 registers ... 6: 40); the kernel is issue
-    // bound with long shared-memory latencies, so more resident warps pay until the register squeeze costs more
-    // measured on 32 x 1080p: 3: 77.5 k, 4: 84.8 k, 5: 81.5 k, 6: 83.2 k frames/s
-    const char *e = getenv("PFV_ENCODE_P_CTAS_PER_SM");
-    const int v = e ? atoi(e) : 0;
-    const int ctas = (v >= 3 && v <= 6) ? v : 4;
-#define PFV_ENC_P(C, CNT) encode_p_kernel<C, CNT><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma)
-    if (count) {
-        switch (ctas) {
-        case 3: PFV_ENC_P(3, true); break;
-        case 5: PFV_ENC_P(5, true); break;
-        case 6: PFV_ENC_P(6, true); break;
-        default: PFV_ENC_P(4, true); break;
-        }
-    } else {
-        switch (ctas) {
-        case 3: PFV_ENC_P(3, false); break;
-        case 5: PFV_ENC_P(5, false); break;
-        case 6: PFV_ENC_P(6, false); break;
-        default: PFV_ENC_P(4, false); break;
-        }
-    }
-#undef PFV_ENC_P
+    // compiled for 4 resident CTAs per SM (64 registers): measured on 32 x 1080p 3: 77.5 k, 4: 84.8 k, 5: 81.5 k, 6: 83.2 k frames/s
+    if (count) encode_p_kernel<4, true><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
+    else       encode_p_kernel<4, false><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,193 @@
+// pfv_kernels_enc.cu — encode-I with one THREAD per 8x8 sub-block (the default for key frames; sm_100a).
+//
+// Encoder::encode_iframe (src/enc.rs:84-97) per plane: encode_plane (src/common.rs:351-386 -> encode_block :141-152 ->
+// encode_subblock :287-298 -> fdct / DctMatrix8x8::encode, src/dct.rs:176-239, :88-99) and then decode_plane of what
+// was just encoded (src/common.rs:423-446), blitted into prev_frame - the closed loop.
+//
+// The first-generation kernel (pfv_kernels.cu, one warp per macroblock, transposes and the zig-zag through shared
+// memory) ran at 0.18 of the HBM roofline.  Here, like the decode side: a thread keeps its sub-block's 64 values in
+// registers, both forward passes and the quantiser run without any exchange, the zig-zag is a compile-time register
+// renaming, the divisors are multipliers in the constant bank.  A warp walks tiles of 8 consecutive macroblocks
+// (lane = macroblock*4 + sub-block): its 8-byte source loads cover full 128-byte lines of the tight source plane (the
+// rows of the next tile are fetched while this one is transformed) and a lane's 8 coefficient stores fill 128
+// contiguous bytes of the dense layout.
+//
+// The reconstruction is the decode-I problem again: a sub-block whose AC terms all quantised to zero reconstructs to
+// one flat value (see pfv_sb.cuh) and is stored on the spot; the others are queued in the warp's shared-memory ring
+// and inverse-transformed 32 at a time by full warps (classify / compact / transform, as decode_i_stream_kernel).
+//
+// COUNT (sparse encode seam): each macroblock's number of RLE entries (rle_encode, src/rle.rs:9-39) is derived from
+// the non-zero masks of its four sub-blocks while they are still in registers (pfv_dct.cuh: sb_runs).
+#include <stdlib.h>
+
+#include "pfv_internal.h"
+#include "pfv_device.cuh"
+#include "pfv_sb.cuh"
+
+namespace pfv {
+
+constexpr int ENC_WARPS = 4;
+
+struct __align__(16) EncStreamSmem {
+    uint4    coef[ENC_WARPS][SBW_RING * 8];
+    uint32_t id[ENC_WARPS][SBW_RING];
+    uint32_t left_head[ENC_WARPS], left_cnt[ENC_WARPS];
+};
+
+// rows y0 .. y0+7, bytes x0 .. x0+7 of a tight vw x vh source plane, padded with the clear colour (src/common.rs:352-356)
+__device__ __forceinline__ void load_src_sb(const uint8_t *__restrict__ src, const PlaneGeom &pl, uint32_t x0, uint32_t y0,
+                                            bool fast, uint2 (&rows)[8])
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t y = y0 + (uint32_t)r;
+        uint2 v = make_uint2(pl.clear4, pl.clear4);
+        if (y < pl.vh && x0 < pl.vw) {
+            const uint8_t *p = src + (size_t)y * pl.vw + x0;
+            if (fast) {
+                v = __ldcs(reinterpret_cast<const uint2 *>(p));   // vw % 8 == 0 and base 8-byte aligned: all 8 bytes exist
+            } else {
+                uint32_t w[2] = {0u, 0u};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t b = (x0 + k < pl.vw) ? (uint32_t)p[k] : (pl.clear4 & 0xffu);
+                    w[k >> 2] |= b << (8 * (k & 3));
+                }
+                v = make_uint2(w[0], w[1]);
+            }
+        }
+        rows[r] = v;
+    }
+}
+
+// the macroblock's RLE entry count from the run bookkeeping of its four sub-blocks (lanes 4m .. 4m+3); every lane of
+// the group gets the result.  Same arithmetic as mb_entry_count (pfv_dct.cuh), the loop over sub-blocks as shuffles.
+__device__ __forceinline__ uint32_t mb_entry_count_lanes(const SbRuns &r, uint32_t sb)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int own_last = r.first >= 0 ? (int)(64u * sb) + r.last : -1;
+    int prev = -1;                                             // last non-zero position before this sub-block
+#pragma unroll
+    for (int d = 1; d <= 3; ++d) {
+        const int t = __shfl_up_sync(FULL, own_last, d, 4);
+        if ((int)sb >= d) prev = max(prev, t);
+    }
+    uint32_t n = r.inner;
+    if (r.first >= 0) n += rle_escapes((int)(64u * sb) + r.first - prev - 1);
+    if (sb == 3u) {
+        const int run = 255 - max(prev, own_last);
+        if (run > 0) n += 1u + rle_escapes(run);
+    }
+    n += __shfl_xor_sync(FULL, n, 1);
+    n += __shfl_xor_sync(FULL, n, 2);
+    return n;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(ENC_WARPS * 32, 4)
+encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__restrict__ jobs)
+{
+    __shared__ EncStreamSmem sm;
+
+    const uint32_t cta = blockIdx.x;
+    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
+    const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+    const uint32_t *encM = p == 0 ? P.encM[0] : P.encM[1];    // intra_l, intra_c (src/enc.rs:84-90)
+    const int32_t *deq = p == 0 ? P.deq[0] : P.deq[1];
+    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * ENC_WARPS + warp) * P.tiles_per_warp;
+    const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
+    const EncJob job = jobs[blockIdx.y];
+    const uint32_t sb = lane & 3u;
+    const uint8_t *src = p == 0 ? job.src[0] : (p == 1 ? job.src[1] : job.src[2]);
+    const bool fast = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
+    uint4 *ring = sm.coef[warp];
+    uint32_t *ring_id = sm.id[warp];
+
+    auto fetch = [&](uint32_t tile, uint2 (&rows)[8]) {
+        const uint32_t lm = min(tile * 8u + (lane >> 2), nmb - 1u);
+        uint32_t col;
+        const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+        load_src_sb(src, pl, col * 16u + (sb & 1u) * 8u, row * 16u + (sb >> 1) * 8u, fast, rows);
+    };
+
+    uint2 nxt[8];
+    if (tile_begin < tile_end) fetch(tile_begin, nxt);
+    uint32_t head = 0, tail = 0;
+#pragma unroll 1
+    for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+        const uint32_t lm = tile * 8u + (lane >> 2);
+        const bool valid = lm < nmb;
+        int x[64];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t wd = k < 4 ? nxt[r].x : nxt[r].y;
+                x[r * 8 + k] = (int)((wd >> (8 * (k & 3))) & 0xffu) * 256 - 32768;   // (p - 128) << 8, src/common.rs:291
+            }
+        }
+        if (tile + 1 < tile_end) fetch(tile + 1, nxt);          // in flight during the transform
+
+        uint32_t w[32];
+        encode_sb_regs(x, encM, w);
+        uint32_t ac = w[0] & 0xffff0000u;
+#pragma unroll
+        for (int i = 1; i < 32; ++i) ac |= w[i];
+        if (valid) {
+            uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64u));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) __stcs(dstc + k, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
+        }
+        if (COUNT) {                                            // sparse seam: how many RLE entries this macroblock makes
+            const uint32_t n = mb_entry_count_lanes(sb_runs(w), sb);
+            if (valid && sb == 0u) job.mb_cnt[pl.mb_base + lm] = n;
+        }
+
+        // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
+        const bool general = valid && ac != 0u;
+        const uint32_t vote = __ballot_sync(0xffffffffu, general);
+        if (general) {
+            const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                ring[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            ring_id[slot] = (lm << 2) | sb;
+        } else if (valid) {
+            store_dc_only(sb_dst(job.dst, pl, lm, (int)sb), pl.pw, (int)(int16_t)(w[0] & 0xffffu), deq[0]);
+        }
+        tail += (uint32_t)__popc(vote);
+        __syncwarp();
+        if (tail - head >= 32u) {
+            transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
+            head += 32u;
+            __syncwarp();
+        }
+    }
+    flush_rings_i<ENC_WARPS>(sm.coef, sm.id, sm.left_head, sm.left_cnt, head, tail, warp, lane, job.dst, pl, deq);
+}
+
+cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s)
+{
+    // ~4 waves of the 148 SMs x 16 resident warps, at most 16 tiles per warp (what is left in a warp's ring at the end
+    // is one partly filled transform pass)
+    uint32_t tiles = 0;
+    for (int p = 0; p < 3; p++) tiles += (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
+    uint32_t tpw = (uint32_t)(((uint64_t)tiles * njobs) / (4u * 148u * 16u));
+    tpw = tpw < 1 ? 1 : (tpw > 16 ? 16 : tpw);
+    P.tiles_per_warp = tpw;
+    uint32_t cta = 0;
+    for (int p = 0; p < 3; p++) {
+        P.cta_base[p] = cta;
+        const uint32_t ntiles = (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
+        cta += (ntiles + ENC_WARPS * tpw - 1) / (ENC_WARPS * tpw);
+    }
+    P.cta_total = cta;
+    dim3 grid(P.cta_total, njobs, 1), block(ENC_WARPS * 32, 1, 1);
+    if (count) encode_i_stream_kernel<true><<<grid, block, 0, s>>>(P, d_jobs);
+    else       encode_i_stream_kernel<false><<<grid, block, 0, s>>>(P, d_jobs);
+    return cudaGetLastError();
+}
+
+}  // namespace pfv

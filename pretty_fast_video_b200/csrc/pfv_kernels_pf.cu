@@ -1,0 +1,358 @@
+// pfv_kernels_pf.cu — decode-P in ONE warp-specialised kernel (the default for P frames; sm_100a).
+//
+// VideoPlane::decode_plane_delta_into (src/common.rs:498-521): every macroblock fetches its motion-compensated
+// predictor from the OLD plane (get_block, :327-339); a coded one adds the decoded residual (decode_block_delta
+// :254-285, apply_residuals :98-104).  The two populations want opposite things: the copy is memory bound and needs
+// few registers, the residual transform is issue bound (exact integer IDCT, ~1 300 instructions per 8x8) and needs
+// 128.  As two kernels (pfv_kernels_p.cu) they run back to back, 40 us + 25 us per 32 x 1080p, and the coded blocks
+// cross L2 twice.  Here a persistent CTA (2 per SM) has two halves that never meet at a CTA barrier:
+//
+//   warps 0-3  COPY.  Per item ONE TMA box: the 176 x 94 window holding every possible predictor (|mv| <= 15,
+//              src/common.rs:154-204) of 8 x 4 macroblocks, three windows in flight.  Warp w owns macroblock row w;
+//              lane = macroblock*4 + row group picks its unaligned rows out of the window.  Skipped macroblocks
+//              (src/common.rs:281-283) go straight to the destination as full 128-byte lines.  A CODED macroblock
+//              is handed over instead: its predictor is written into a slot of a shared-memory ring and its 512 B of
+//              coefficients are fetched into the same slot by one bulk copy (cp.async.bulk), both counted on the slot
+//              group's mbarrier.
+//   warps 4-7  TRANSFORM.  Warp x takes ring groups x, x+4, ... : 8 macroblocks = 32 sub-blocks = one full warp,
+//              whatever windows, planes or frames they came from.  One thread per 8x8 sub-block: dequantise,
+//              register-resident IDCT, residual on the predictor out of the ring, 8 row stores; then the group is
+//              released to the copy half (second mbarrier).
+//
+// A transform lane is (sub-block s = lane >> 3, slot j = lane & 7).  The ring keeps the coefficients of slot j at
+// coef[j * 528] exactly as the bulk copy delivered them (scan order, no re-arranging pass) and the predictor of
+// (s, j) at pred[lane * 80]: with those pitches the 128-bit reads of 8 consecutive lanes fall into 8 different bank
+// groups.  The dequantiser tables are read from shared memory (a group may mix planes, so they cannot be
+// constant-bank operands).
+#include <stdlib.h>
+
+#include "pfv_internal.h"
+#include "pfv_device.cuh"
+#include "pfv_sb.cuh"
+
+namespace pfv {
+
+constexpr int PF_ROWS = 4;                                   // macroblock rows per window = copy warps
+constexpr int PF_WIN_W = 176;                                // 16 + 8*16 + 15, rounded up to 16
+constexpr int PF_WIN_H = PF_ROWS * 16 + 30;
+constexpr int PF_WIN_BYTES = PF_WIN_W * PF_WIN_H;            // 16 544
+constexpr int PF_STAGE = (PF_WIN_BYTES + 127) & ~127;
+constexpr int PF_STAGES = 3;
+constexpr int PF_NG = 8;                                     // ring groups
+constexpr int PF_RING_MB = PF_NG * 8;                        // ring slots (macroblocks)
+constexpr int PF_COEF_PITCH = 528;                           // bytes per slot: 512 + 16 (8 slots -> 8 different bank groups)
+constexpr int PF_PRED_PITCH = 80;                            // bytes per sub-block: 64 + 16
+constexpr int PF_XF_WARPS = 4;
+constexpr int PF_THREADS = (PF_ROWS + PF_XF_WARPS) * 32;
+
+struct __align__(16) PfGroup {
+    unsigned char coef[8 * PF_COEF_PITCH];
+    unsigned char pred[32 * PF_PRED_PITCH];                  // sub-block s of slot j: row r at [(s*8 + j)*80 + r*8]
+    uint4         id[8];                                     // {byte offset of the macroblock in a frame slot, job, plane, valid}
+};
+
+struct __align__(128) PfSmem {
+    unsigned char win[PF_STAGES][PF_STAGE];
+    PfGroup  grp[PF_NG];
+    int32_t  deq[3][64];
+    uint64_t win_full[PF_STAGES];
+    uint64_t grp_full[PF_NG];                                // 8 arrivals (one per slot) + the slots' coefficient bytes
+    uint64_t grp_empty[PF_NG];                               // the transform warp has taken the group into registers
+    uint32_t tail;                                           // ring slots handed out so far
+    volatile uint32_t total_groups;                          // 0xffffffff until the copy half is done
+};
+
+__device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+
+__device__ __forceinline__ void bar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void bar_arrive_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// 16 bytes at byte offset x of a window row (x + 24 <= PF_WIN_W): three 8-byte loads, one select level, four funnel shifts
+__device__ __forceinline__ uint4 win_row16(const unsigned char *row, uint32_t x)
+{
+    const uint2 *q = reinterpret_cast<const uint2 *>(row + (x & ~7u));
+    const uint2 a = q[0], b = q[1], c = q[2];
+    const bool odd = (x & 4u) != 0u;
+    const uint32_t t0 = odd ? a.y : a.x, t1 = odd ? b.x : a.y, t2 = odd ? b.y : b.x, t3 = odd ? c.x : b.y, t4 = odd ? c.y : c.x;
+    const uint32_t sh = (x & 3u) * 8u;
+    uint4 o;
+    o.x = __funnelshift_r(t0, t1, sh);
+    o.y = __funnelshift_r(t1, t2, sh);
+    o.z = __funnelshift_r(t2, t3, sh);
+    o.w = __funnelshift_r(t3, t4, sh);
+    return o;
+}
+
+// the dequantiser out of shared memory (src/dct.rs:78-83, tables by scan position); see unpack_dequant
+__device__ __forceinline__ void unpack_dequant_smem(const uint4 (&raw)[8], const int32_t *deq, int (&m)[64])
+{
+    constexpr int zz[64] = PFV_ZIGZAG_INIT;
+    const int4 *dq = reinterpret_cast<const int4 *>(deq);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int4 d = dq[k];
+        const uint4 &q = raw[k >> 1];
+        const uint32_t w0 = (k & 1) ? q.z : q.x, w1 = (k & 1) ? q.w : q.y;
+        m[zz[4 * k + 0]] = __dp2a_lo((int)w0, 0x00000001, 0) * d.x;
+        m[zz[4 * k + 1]] = __dp2a_hi((int)w0, 0x01000000, 0) * d.y;
+        m[zz[4 * k + 2]] = __dp2a_lo((int)w1, 0x00000001, 0) * d.z;
+        m[zz[4 * k + 3]] = __dp2a_hi((int)w1, 0x01000000, 0) * d.w;
+    }
+}
+
+struct PfPos { uint32_t job, wi; };
+struct PfItem { uint32_t job, p, gy, tx; };
+
+__global__ void __launch_bounds__(PF_THREADS, 2)
+decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant__ McWin W, const DecJob *__restrict__ jobs,
+                      uint32_t njobs, int *__restrict__ err,
+                      const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
+{
+    extern __shared__ __align__(128) unsigned char pf_raw[];
+    PfSmem &sm = *reinterpret_cast<PfSmem *>(pf_raw);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const FrameGeom &g = P.g;
+    const uint32_t nitems = njobs * W.total;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < PF_STAGES; ++s) bar_init(&sm.win_full[s], 1);
+#pragma unroll
+        for (int s = 0; s < PF_NG; ++s) { bar_init(&sm.grp_full[s], 8); bar_init(&sm.grp_empty[s], 1); }
+        sm.tail = 0;
+        sm.total_groups = 0xffffffffu;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = threadIdx.x; i < 3 * 64; i += PF_THREADS) (&sm.deq[0][0])[i] = (&P.deq[0][0])[i];
+    __syncthreads();
+
+    auto plane = [&](uint32_t p) -> const PlaneGeom & { return p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]); };
+
+    if (warp >= PF_ROWS) {
+        // ================================ TRANSFORM half ================================
+        const uint32_t sb = lane >> 3, sj = lane & 7u;
+#pragma unroll 1
+        for (uint32_t G = warp - PF_ROWS;; G += PF_XF_WARPS) {
+            const uint32_t rgp = G % PF_NG, par = (G / PF_NG) & 1u;
+            bool stop = false;
+            while (!bar_try(&sm.grp_full[rgp], par)) {
+                if (sm.total_groups <= G) { stop = true; break; }
+            }
+            if (stop) break;
+            const PfGroup &grp = sm.grp[rgp];
+            const uint4 id = grp.id[sj];
+            uint4 raw[8], pv[4];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) raw[k] = *reinterpret_cast<const uint4 *>(grp.coef + sj * PF_COEF_PITCH + sb * 128u + 16 * k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pv[k] = *reinterpret_cast<const uint4 *>(grp.pred + lane * PF_PRED_PITCH + 16 * k);
+            const uint32_t p = min(id.z, 2u);
+            const int32_t *deq = sm.deq[p];
+            int m[64];
+            unpack_dequant_smem(raw, deq, m);
+            __syncwarp();
+            if (lane == 0) bar_arrive(&sm.grp_empty[rgp]);     // everything of the group is in registers now
+            const bool valid = id.w != 0u;
+            const uint32_t pw = plane(p).pw;
+            uint8_t *dst = nullptr;
+            if (valid) dst = jobs[id.y].dst + id.x + (size_t)((sb >> 1) * 8u) * pw + (sb & 1u) * 8u;
+            idct8x8_regs(m);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = 2 * k + h;
+                    int y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = m[r * 8 + i];
+                    const uint2 o = apply_residual_row(y, h == 0 ? make_uint2(pv[k].x, pv[k].y) : make_uint2(pv[k].z, pv[k].w));   // src/common.rs:277
+                    if (valid) __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pw), o);
+                }
+            }
+        }
+        return;
+    }
+
+    // ==================================== COPY half ====================================
+    const uint32_t G0 = gridDim.x;
+    const uint32_t dj = G0 % njobs, dw = G0 / njobs;
+    auto advance = [&](PfPos &q) {
+        q.job += dj; q.wi += dw;
+        if (q.job >= njobs) { q.job -= njobs; q.wi++; }
+    };
+    auto item_of = [&](const PfPos &q) {
+        // frame-interleaved order: CTAs that run at the same time work on DIFFERENT frames
+        PfItem r;
+        r.job = q.job;
+        r.p = (q.wi >= W.base[1] ? 1u : 0u) + (q.wi >= W.base[2] ? 1u : 0u);
+        const uint32_t li = q.wi - (r.p == 0 ? W.base[0] : (r.p == 1 ? W.base[1] : W.base[2]));
+        const uint32_t txs = r.p == 0 ? W.tiles_x[0] : (r.p == 1 ? W.tiles_x[1] : W.tiles_x[2]);
+        const float rcp = r.p == 0 ? W.rcp_tiles_x[0] : (r.p == 1 ? W.rcp_tiles_x[1] : W.rcp_tiles_x[2]);
+        r.gy = div_small(li, txs, rcp, r.tx);
+        return r;
+    };
+    auto issue = [&](const PfItem &it, uint32_t st) {          // thread 0 only
+        bar_arrive_tx(&sm.win_full[st], (uint32_t)PF_WIN_BYTES);
+        const CUtensorMap *tm = it.p == 0 ? &tm_luma : &tm_chroma;
+        const int cx = (int)it.tx * 128 - 16, cy = (int)it.gy * (PF_ROWS * 16) - 15, cz = it.p == 2 ? 1 : 0, cw = jobs[it.job].ref_slot;
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_addr(sm.win[st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(smem_addr(&sm.win_full[st]))
+            : "memory");
+    };
+    const uint32_t mb = lane >> 2, rg = lane & 3u;
+    // header word of this lane's macroblock (row = gy*4 + warp, column = tx*8 + mb); bit 31 set = no such macroblock
+    auto load_hw = [&](const PfItem &it) -> uint32_t {
+        const PlaneGeom &pl = plane(it.p);
+        const uint32_t row = it.gy * PF_ROWS + warp, col = it.tx * 8u + mb;
+        if (row >= pl.bh || col >= pl.bw) return 0x80000000u;
+        return __ldg(reinterpret_cast<const uint32_t *>(jobs[it.job].hdr) + pl.mb_base + row * pl.bw + col);
+    };
+
+    uint32_t it = blockIdx.x;
+    PfPos pc, pn, pt;
+    pc.wi = it / njobs;
+    pc.job = it - pc.wi * njobs;
+    pn = pc; advance(pn);
+    pt = pc;
+#pragma unroll 1
+    for (uint32_t s = 0; s < (uint32_t)PF_STAGES; ++s) {
+        if (threadIdx.x == 0 && it + s * G0 < nitems) issue(item_of(pt), s);
+        advance(pt);
+    }
+    uint32_t hw_cur = it < nitems ? load_hw(item_of(pc)) : 0x80000000u;
+    uint32_t k = 0;
+#pragma unroll 1
+    for (; it < nitems; it += G0, ++k) {
+        const uint32_t st = k % PF_STAGES;
+        const PfItem cur = item_of(pc);
+        uint32_t hw_next = 0x80000000u;
+        if (it + G0 < nitems) hw_next = load_hw(item_of(pn));
+
+        const PlaneGeom &pl = plane(cur.p);
+        const DecJob &job = jobs[cur.job];
+        const bool exists = !(hw_cur & 0x80000000u);
+        const bool coded = exists && ((hw_cur >> 16) & 0xffu) != 0u;
+        const int bx = (int)(cur.tx * 8u + mb) * 16, by = (int)(cur.gy * PF_ROWS + warp) * 16;
+        int mvx = (int)(int8_t)(hw_cur & 0xffu), mvy = (int)(int8_t)((hw_cur >> 8) & 0xffu);   // src/common.rs:255-256
+        if (exists) {
+            const int sx = bx + mvx, sy = by + mvy;
+            if (sx < 0 || sy < 0 || sx > (int)pl.pw - 16 || sy > (int)pl.ph - 16) {
+                // reference: debug_assert / slice panic (src/common.rs:258-259).  Never follow it: the stream is
+                // flagged bad and the co-located block is used.
+                if (rg == 0) atomicOr(err, ERRBIT_BAD_MV);
+                mvx = 0; mvy = 0;
+            }
+        }
+        // ring slots for this warp's coded macroblocks (one warp-aggregated shared-memory atomic)
+        const uint32_t vote = __ballot_sync(0xffffffffu, coded && rg == 0);
+        uint32_t e = 0;
+        if (vote) {
+            if (lane == 0) e = atomicAdd(&sm.tail, (uint32_t)__popc(vote));
+            e = __shfl_sync(0xffffffffu, e, 0) + (uint32_t)__popc(vote & ((1u << (lane & ~3u)) - 1u));
+        }
+        const uint32_t slot = e % PF_RING_MB, rgp = slot >> 3, sj = slot & 7u;
+        PfGroup &grp = sm.grp[rgp];
+        if (coded) bar_wait(&sm.grp_empty[rgp], ((e / PF_RING_MB) & 1u) ^ 1u);   // the slot's previous tenant has been taken out
+
+        bar_wait(&sm.win_full[st], (k / PF_STAGES) & 1u);
+        if (exists) {
+            uint8_t *dst = job.dst + pl.off + (size_t)((uint32_t)by + rg) * pl.pw + (uint32_t)bx;
+            const bool in_window = mvx >= -16 && mvx <= 15 && mvy >= -15 && mvy <= 15;
+            // Vectors beyond +-15 are legal for the reference decoder (7-bit vectors, src/dec.rs:367-368) but outside the
+            // staged window - its own encoder never searches further (src/common.rs:154-204).  Rare: fetch from global.
+            const uint8_t *gsrc = job.ref + pl.off + (size_t)((uint32_t)(by + mvy) + rg) * pl.pw + (uint32_t)(bx + mvx);
+            const uint32_t wx = (uint32_t)(16 + (int)mb * 16 + mvx), wy = (uint32_t)(15 + (int)warp * 16 + mvy) + rg;
+            const unsigned char *wrow = sm.win[st] + wy * PF_WIN_W;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 o;
+                if (in_window) {
+                    o = win_row16(wrow + i * 4 * PF_WIN_W, wx);
+                } else {
+                    const uint2 a = ldg_u8x8_unaligned(gsrc + (size_t)(4 * i) * pl.pw);
+                    const uint2 b = ldg_u8x8_unaligned(gsrc + (size_t)(4 * i) * pl.pw + 8);
+                    o = make_uint4(a.x, a.y, b.x, b.y);
+                }
+                if (coded) {
+                    // row R = rg + 4i of the macroblock: left half -> sub-block (R >> 3) * 2, right half -> the next one
+                    const uint32_t R = rg + 4u * (uint32_t)i, L = (R >> 3) * 16u + sj;
+                    unsigned char *pp = grp.pred + L * PF_PRED_PITCH + (R & 7u) * 8u;
+                    *reinterpret_cast<uint2 *>(pp) = make_uint2(o.x, o.y);
+                    *reinterpret_cast<uint2 *>(pp + 8 * PF_PRED_PITCH) = make_uint2(o.z, o.w);
+                } else {
+                    __stcg(reinterpret_cast<uint4 *>(dst + (size_t)(4 * i) * pl.pw), o);   // blit_block, src/common.rs:341-349
+                }
+            }
+        }
+        if (coded && rg == 0)
+            grp.id[sj] = make_uint4(pl.off + (uint32_t)by * pl.pw + (uint32_t)bx, cur.job, cur.p, 1u);
+        __syncwarp();                                           // the four lanes of a macroblock have written its predictor
+        if (coded && rg == 0) bar_arrive_tx(&sm.grp_full[rgp], 512u);
+        if (coded && rg == 0) {
+            const uint32_t lm = (cur.gy * PF_ROWS + warp) * pl.bw + cur.tx * 8u + mb;
+            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(pl.mb_base + lm) * 256, 512u, &sm.grp_full[rgp]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PF_ROWS * 32) : "memory");   // the copy half is done with this window stage
+        if (threadIdx.x == 0 && it + PF_STAGES * G0 < nitems) issue(item_of(pt), st);
+        advance(pt);
+        pc = pn; advance(pn);
+        hw_cur = hw_next;
+    }
+
+    // the copy half is done: complete the last, partly filled group with empty slots and tell the transform half where to stop
+    asm volatile("bar.sync 1, %0;" ::"n"(PF_ROWS * 32) : "memory");
+    if (threadIdx.x == 0) {
+        const uint32_t tail = *reinterpret_cast<volatile uint32_t *>(&sm.tail);
+        const uint32_t rem = (8u - (tail & 7u)) & 7u;
+        for (uint32_t q = 0; q < rem; ++q) {
+            const uint32_t e = tail + q, slot = e % PF_RING_MB, rgp = slot >> 3;
+            bar_wait(&sm.grp_empty[rgp], ((e / PF_RING_MB) & 1u) ^ 1u);
+            sm.grp[rgp].id[slot & 7u] = make_uint4(0u, 0u, 0u, 0u);
+            bar_arrive(&sm.grp_full[rgp]);
+        }
+        __threadfence_block();
+        sm.total_groups = (tail + 7u) >> 3;
+    }
+}
+
+cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, int *d_err,
+                                  const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s)
+{
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
+    const int smem = (int)sizeof(PfSmem);
+    if (first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(decode_p_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    const McWin W = make_mc_windows(P.g, PF_ROWS);
+    uint32_t ctas = njobs * W.total;
+    if (ctas > 148u * 2u) ctas = 148u * 2u;
+    decode_p_fused_kernel<<<ctas, PF_THREADS, smem, s>>>(P, W, d_jobs, njobs, d_err, tm_luma, tm_chroma);
+    return cudaGetLastError();
+}
+
+}  // namespace pfv

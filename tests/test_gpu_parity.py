@@ -102,10 +102,10 @@ def test_decode_pframe_matches_oracle(size, mode):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("ivar,pvar", [("tma", "win"), ("tma", "live"), ("tma", "winll"), ("tma", "tma"), ("sbw", "two"), ("sb", "two1"), ("warp", "stream"), ("tma", "sbw"),
-                                       ("tma", "warp")])
+@pytest.mark.parametrize("ivar,pvar", [("stream", "fused"), ("stream", "win"), ("sb", "warp"), ("warp", "win")])
 def test_decode_kernel_variants_agree(ivar, pvar, monkeypatch):
-    """The earlier kernels stay selectable (PFV_DECODE_*_VARIANT) and agree with the default ones."""
+    """One default kernel per path plus independently written second implementations (PFV_DECODE_*_VARIANT): all agree
+    with the oracle."""
     monkeypatch.setenv("PFV_DECODE_I_VARIANT", ivar)
     monkeypatch.setenv("PFV_DECODE_P_VARIANT", pvar)
     w, h = 208, 112
@@ -128,7 +128,7 @@ def test_decode_kernel_variants_agree(ivar, pvar, monkeypatch):
         assert np.array_equal(e.slot_read(1), want1)
 
 
-@pytest.mark.parametrize("pvar", ["win", "live", "winll", "tma", "two", "two1", "stream", "sbw", "warp"])
+@pytest.mark.parametrize("pvar", ["fused", "win", "warp"])
 def test_decode_pframe_long_motion_vectors(pvar, monkeypatch):
     """The stream format carries 7-bit vectors (src/dec.rs:367-368) and the reference decoder follows any vector that
     stays inside the padded plane (src/common.rs:255-261), also ones its own encoder (|mv| <= 15) never emits."""
@@ -191,10 +191,11 @@ def test_host_compaction_of_dense_buffers_is_transparent(compact, mode, monkeypa
             assert np.array_equal(e.slot_read(2 * i + 1), want)
 
 
-def test_live_mode_batches_match_oracle(monkeypatch):
-    """PFV_DECODE_P_VARIANT=live: copy and residual kernels run concurrently, frames complete one after the other;
-    a chain of batched P submits must still give the oracle's pictures."""
-    monkeypatch.setenv("PFV_DECODE_P_VARIANT", "live")
+@pytest.mark.parametrize("pvar", ["fused", "win"])
+def test_chained_batches_of_pframes_match_oracle(pvar, monkeypatch):
+    """A chain of batched P submits (5 lanes x 4 frames, different coded fractions per lane: the fused kernel's ring
+    mixes macroblocks of different frames in one transform pass) gives the oracle's pictures."""
+    monkeypatch.setenv("PFV_DECODE_P_VARIANT", pvar)
     w, h = 400, 240
     rng = np.random.default_rng(77)
     qt, _ = make_qtables(5)
@@ -218,26 +219,6 @@ def test_live_mode_batches_match_oracle(monkeypatch):
         e.sync()
         for l in range(L):
             assert np.array_equal(e.slot_read(cur[l]), state[l])
-
-
-def test_residual_kernel_variants_agree(monkeypatch):
-    """PFV_RESIDUAL_VARIANT=4 (sub-block compaction in shared memory) gives the pictures of the default kernel."""
-    monkeypatch.setenv("PFV_RESIDUAL_VARIANT", "4")
-    w, h = 400, 240
-    rng = np.random.default_rng(23)
-    qt, _ = make_qtables(5)
-    og = pfvo.geometry_for(w, h)
-    hdr = rand_headers(rng, og)
-    coeff = rand_coeffs(rng, og.nb, "mixed")
-    coeff.reshape(-1, 256)[hdr[:, 2] == 0] = 0
-    ref = rng.integers(0, 256, pfvo.frame_init(og).size).astype(np.uint8)
-    want = ref.copy()
-    pfvo.decode_pframe_coeffs(og, qt, (2, 3, 3), hdr, coeff, want)
-    with Engine(w, h, qt, nslots=2, max_jobs=1) as e:
-        e.slot_write(0, ref)
-        e.decode_submit([DecodeJob(PFV_FRAME_P, 1, coeff, (2, 3, 3), ref_slot=0, hdr=hdr)])
-        e.sync()
-        assert np.array_equal(e.slot_read(1), want)
 
 
 def test_decode_pframe_all_skipped_is_a_copy():
@@ -336,12 +317,41 @@ def test_encode_pframe_matches_oracle(size, quality, kind):
     assert np.array_equal(got_recon, prev)
 
 
-@pytest.mark.parametrize("ctas", ["3", "5", "6"])
-def test_encode_p_register_budget_variants_agree(ctas, monkeypatch):
-    """PFV_ENCODE_P_CTAS_PER_SM compiles the same kernel for 72 / 64 (default) / 48 / 40 registers: identical results."""
-    monkeypatch.setenv("PFV_ENCODE_P_CTAS_PER_SM", ctas)
-    test_encode_pframe_matches_oracle((512, 384), 5, "moving")
-    test_encode_pframe_matches_oracle((50, 38), 2, "moving")
+@pytest.mark.parametrize("ivar", ["stream", "warp"])
+def test_encode_i_kernel_variants_agree(ivar, monkeypatch):
+    """PFV_ENCODE_I_VARIANT: the thread-per-sub-block kernel (default) and the first-generation warp-per-macroblock
+    kernel give the oracle's coefficients and reconstruction; a ragged size (padding with the clear colour, planes
+    whose width is not a multiple of 8) and a batch of jobs in one launch."""
+    monkeypatch.setenv("PFV_ENCODE_I_VARIANT", ivar)
+    test_encode_iframe_matches_oracle((50, 38), 2)
+    test_encode_iframe_matches_oracle((512, 384), 5)
+    w, h, n = 336, 208, 5
+    qt, _ = make_qtables(4)
+    og = pfvo.geometry_for(w, h)
+    sv = SynthVideo(w, h, 5, "moving")
+    outs = [np.zeros(og.nb * 256, np.int16) for _ in range(n)]
+    with Engine(w, h, qt, nslots=n, max_jobs=n) as e:
+        e.encode_submit([EncodeJob(PFV_FRAME_I, i, sv.frame(i), outs[i]) for i in range(n)])
+        e.sync()
+        for i in range(n):
+            prev = pfvo.frame_init(og)
+            want = pfvo.encode_iframe_coeffs(og, qt, *sv.frame(i), prev)
+            assert np.array_equal(outs[i], want)
+            assert np.array_equal(e.slot_read(i), prev)
+
+
+def test_encode_rejects_zero_divisors():
+    """The reference's quantiser divides by the table entry (src/dct.rs:95: a zero would panic); Encoder::new clamps its
+    tables to >= 1 (src/enc.rs:48-51).  A context with a zero divisor in tables 0..3 decodes, but refuses to encode."""
+    qt, _ = make_qtables(5)
+    bad = qt.copy()
+    bad[2, 17] = 0
+    y = np.zeros((48, 64), np.uint8); u = np.zeros((24, 32), np.uint8)
+    with Engine(64, 48, bad) as e:
+        with pytest.raises(PfvError):
+            e.encode_submit([EncodeJob(PFV_FRAME_I, 0, (y, u, u), np.zeros(e.geometry.nb * 256, np.int16))])
+        e.decode_submit([DecodeJob(PFV_FRAME_I, 0, np.zeros(e.geometry.nb * 256, np.int16), (0, 1, 1))])
+        e.sync()
 
 
 def _oracle_stream(w, h, nframes, quality, key_every, seed, kind="moving"):
