@@ -7,11 +7,18 @@ A "step" is one pass of the hot path over one batch of synthetic frames.  Worklo
   decode_i_1080p  configs[1]  64 independent 1080p key frames per GPU, one launch per step           (default)
   decode_p_1080p  configs[2]  32 GOPs x 15 frames (1 key frame / 15), frame k of every GOP per launch
   encode_p_1080p  configs[3]  the same GOPs encoded (full SSD block search), frame k of every GOP per launch
-  decode_p_4k     configs[4]  4 GOPs x 15 frames of 3840x2160 per GPU, GOPs sharded over the ranks
+  decode_p_4k     configs[4]  16 GOPs x 15 frames of 3840x2160 per GPU, GOPs sharded over the ranks
+  encode_i_1080p   64 independent 1080p key frames encoded (+ closed-loop reconstruction) per launch
 
 `value`  : whole-job frames/s with the inputs resident in HBM (CUDA events on the launching stream).
-`e2e`    : the same through the C ABI with pinned HOST buffers, H2D of every coefficient/header/source byte and
-           D2H of every decoded plane (or coefficient) inside the timed region.
+`e2e`    : the same through the C ABI with pinned HOST buffers, H2D of every token/header/source byte and D2H of
+           every decoded plane (or RLE entry) inside the timed region.  `e2e.value` is the seam the product's own
+           Decoder / Encoder use (sparse: pfv_decode_submit_sparse / pfv_encode_submit_sparse - the entropy decoder's
+           tokens go up, the device's RLE sequence comes down); `e2e.dense` is the same leg with the reference's dense
+           Vec<i16> seam (pfv_decode_submit / pfv_encode_submit).  `e2e.pcie_ceiling_gbs` is what concurrent pinned
+           cudaMemcpyAsync in both directions reaches on this box with all ranks copying at once.
+`verified`: after every timed leg (outside the timed region) the first and the last job's final frame is read back
+           and compared with the oracle on the same inputs; a mismatch fails the run.
 `roofline`: algorithmic bytes per launch / mean launch time, against MEASURED_PEAKS.json's HBM copy bandwidth.
 `cpu_baseline`: the oracle (plain-C restatement of the reference algorithm, OpenMP over macroblocks like the
            reference's rayon par_iter) on this box's host cores, on a bounded sample.  The Rust reference itself
@@ -46,7 +53,8 @@ WORKLOADS = {
     "decode_i_1080p": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465601),
     "decode_p_1080p": dict(w=1920, h=1080, frames=0, gops=32, gop=15, quality=5, seed=0x50465602),
     "encode_p_1080p": dict(w=1920, h=1080, frames=0, gops=32, gop=15, quality=5, seed=0x50465602),
-    "decode_p_4k": dict(w=3840, h=2160, frames=0, gops=4, gop=15, quality=5, seed=0x50465603),
+    "decode_p_4k": dict(w=3840, h=2160, frames=0, gops=16, gop=15, quality=5, seed=0x50465603),
+    "encode_i_1080p": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465601),
     # stress stream of SURVEY 8d: uniform-random pixels, every sub-block dense (worst case for the decode kernels)
     "decode_i_1080p_dense": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465604, kind="random"),
 }
@@ -61,6 +69,75 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+SEARCH_CANDIDATES_PER_MB = 33   # block_search: the centre + 4 levels x 8 neighbours (src/common.rs:154-204), out-of-plane ones skipped
+DISTINCT_SEQUENCES = 8          # GOP workloads: lane g plays sequence g mod 8 (building 32 distinct 1080p sequences in numpy costs more
+                                # than the whole bench; every lane still has its own buffers in HBM)
+
+
+def config_of(workload):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    cfg = WORKLOADS[workload]
+    per_step = cfg["frames"] if cfg["gop"] == 1 else cfg["gops"] * cfg["gop"]
+    return {"workload": workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"],
+            "frames_per_step_per_gpu": per_step, "gop": cfg["gop"],
+            "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+            "sharding": "frames/GOPs split over ranks, no collective on the data path"}
+
+
+def bind_to_gpu_numa_node(torch, index):
+    """Run this rank's host threads (and, by first touch, its pinned arenas) on the CPUs next to its GPU."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(path + "/numa_node") as f:
+            node = int(f.read().strip())
+        with open(path + "/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "local_cpulist": cpulist, "bound_cpus": len(cpus) if cpus else len(allowed),
+                "host_cpus": len(allowed)}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
+def pcie_ceiling(torch, dist, h2d_bytes, d2h_bytes, seconds=0.4):
+    """What the box gives: every rank at once copies pinned host <-> device in both directions with plain
+    cudaMemcpyAsync on two streams, chunks of the sizes the e2e legs use.  Returns this rank's GB/s (h2d, d2h)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hs = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hd = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    ds = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    dd = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def burst(n):
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                ds.copy_(hs, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hd.copy_(dd, non_blocking=True)
+    burst(4)
+    torch.cuda.synchronize()
+    dist.barrier()
+    n = max(8, int(seconds * 40e9 / max(h2d_bytes, 1)))
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record(s1); e[2].record(s2)
+    burst(n)
+    e[1].record(s1); e[3].record(s2)
+    torch.cuda.synchronize()
+    dist.barrier()
+    return n * h2d_bytes / e[0].elapsed_time(e[1]) / 1e6, n * d2h_bytes / e[2].elapsed_time(e[3]) / 1e6
 
 
 def ncu_traffic(kernel_key):
@@ -182,17 +259,21 @@ class Streams:
         ysz, csz = w * h, (w // 2) * (h // 2)
         self.src_bytes = ysz + 2 * csz
         self.d_src = torch.zeros((self.gop, self.lanes, self.src_bytes), dtype=torch.uint8, device=dev)
-        # I-only workload: every frame of one moving sequence; GOP workloads: lane g = its own sequence
+        # I-only workload: every frame of one moving sequence; GOP workloads: lane g plays sequence g mod DISTINCT_SEQUENCES
+        cache = {}
         for lane in range(self.lanes):
             if self.gop == 1:
                 sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank, kind=cfg.get("kind", "moving")) if lane == 0 else sv
-                frames = [sv.frame(lane)]
+                frames = [np.concatenate([p.ravel() for p in sv.frame(lane)])]
             else:
-                sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank + lane, kind=cfg.get("kind", "moving"))
-                frames = [sv.frame(t) for t in range(self.gop)]
-            for k, (y, u, v) in enumerate(frames):
-                buf = np.concatenate([y.ravel(), u.ravel(), v.ravel()])
+                key = lane % DISTINCT_SEQUENCES
+                if key not in cache:
+                    sv = SynthVideo(w, h, cfg["seed"] + 1000 * rank + key, kind=cfg.get("kind", "moving"))
+                    cache[key] = [np.concatenate([p.ravel() for p in sv.frame(t)]) for t in range(self.gop)]
+                frames = cache[key]
+            for k, buf in enumerate(frames):
                 self.d_src[k, lane].copy_(torch.from_numpy(buf))
+        del cache
         torch.cuda.synchronize()
         cur = [2 * i for i in range(self.lanes)]
         for k in range(self.gop):
@@ -273,6 +354,61 @@ def time_steps(torch, dist, stream, step_fn, sync_fn, steps, warmup, wall=False)
     return dist.max(ms), ms
 
 
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pfvo
+    return pfvo
+
+
+def verify_decode(torch, st: Streams, eng, final_slot_of_lane):
+    """Outside the timed region: the first and the last lane's framebuffer after the last frame of the step against
+    the oracle decoding the same coefficients (the whole GOP chain for P workloads)."""
+    pfvo = _oracle()
+    og = pfvo.geometry_for(st.cfg["w"], st.cfg["h"])
+    nt = min(16, os.cpu_count() or 1)
+    ok = True
+    for lane in sorted({0, st.lanes - 1}):
+        frame = pfvo.frame_init(og)
+        for k in range(st.gop):
+            c = st.d_coeff[k, lane].cpu().numpy()
+            if k == 0:
+                pfvo.decode_iframe_coeffs(og, st.qt, (0, 1, 1), c, frame, nt)
+            else:
+                pfvo.decode_pframe_coeffs(og, st.qt, (2, 3, 3), st.d_hdr[k, lane].cpu().numpy(), c, frame, nt)
+        ok &= bool(np.array_equal(eng.slot_read(final_slot_of_lane(lane)), frame))
+    return ok
+
+
+def verify_encode(torch, st: Streams, eng, final_slot_of_lane, d_c, d_h):
+    """The first and the last lane: headers, coefficients of coded macroblocks and reconstruction of the step's last
+    frame against the oracle encoding the same source planes (the whole GOP chain for P workloads)."""
+    pfvo = _oracle()
+    w, h = st.cfg["w"], st.cfg["h"]
+    og = pfvo.geometry_for(w, h)
+    nt = min(16, os.cpu_count() or 1)
+    ysz, csz = w * h, (w // 2) * (h // 2)
+    ok = True
+    for lane in sorted({0, st.lanes - 1}):
+        prev = pfvo.frame_init(og)
+        hd = None
+        for k in range(st.gop):
+            b = st.d_src[k, lane].cpu().numpy()
+            y, u, v = b[:ysz].reshape(h, w), b[ysz:ysz + csz].reshape(h // 2, w // 2), b[ysz + csz:].reshape(h // 2, w // 2)
+            if k == 0:
+                c = pfvo.encode_iframe_coeffs(og, st.qt, y, u, v, prev, nt)
+            else:
+                hd, c = pfvo.encode_pframe_coeffs(og, st.qt, st.px_err, y, u, v, prev, nt)
+        got_c = d_c[lane].cpu().numpy().reshape(-1, 256)
+        if st.gop == 1:
+            ok &= bool(np.array_equal(got_c, c.reshape(-1, 256)))
+        else:
+            coded = hd[:, 2] != 0
+            ok &= bool(np.array_equal(d_h[lane].cpu().numpy(), hd))
+            ok &= bool(np.array_equal(got_c[coded], c.reshape(-1, 256)[coded]))
+        ok &= bool(np.array_equal(eng.slot_read(final_slot_of_lane(lane)), prev))
+    return ok
+
+
 def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
     from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine
     from pretty_fast_video_b200.engine import DecodeJob
@@ -313,6 +449,8 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
     l0 = eng.launch_count
     max_ms, my_ms = time_steps(torch, dist, stream, step_dev, eng.sync, steps, warmup)
     launches_per_step = (eng.launch_count - l0) // (steps + warmup)
+    last_jobs = tables[((phase[0] - 1) % 2) * G + G - 1][1]
+    verified = verify_decode(torch, st, eng, lambda lane: last_jobs[lane].dst_slot)
     eng.close()
 
     # ---- end to end through host buffers ------------------------------------------------------------
@@ -321,41 +459,36 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
         from pretty_fast_video_b200 import PinnedArena
         arena, hc, hh, hs = st.host()
         chunk = min(L, 8)                                   # jobs per submit: H2D of chunk i+1 overlaps chunk i
-        eng2 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
         ysz, csz = w * h, (w // 2) * (h // 2)
         out_arena = PinnedArena(G * L * (ysz + 2 * csz) + 4096)
         outb = out_arena.take((G, L, ysz + 2 * csz), np.uint8)
+        nframes = G * L
+        d2h = int((ysz + 2 * csz) * nframes)
 
         def outs(k, lane):
             b = outb[k, lane].ctypes.data
             return (b, b + ysz, b + ysz + csz)
 
-        cur2 = [2 * i for i in range(L)]
-        tabs2 = []
-        for rep in range(2):
-            for k in range(G):
-                full, jobs = make_jobs(eng2, k, cur2, lambda k, l: hc[k, l].ctypes.data, lambda k, l: hh[k, l].ctypes.data,
-                                       False, outs)
-                tabs2.append([(eng2.build_decode_jobs(jobs[i:i + chunk]), jobs[i:i + chunk]) for i in range(0, L, chunk)])
-        ph2 = [0]
+        def check_outputs():
+            """the pictures that came back over PCIe (first / last lane, last frame of the GOP) against the oracle"""
+            pfvo = _oracle()
+            og = pfvo.geometry_for(w, h)
+            nt = min(16, os.cpu_count() or 1)
+            ok = True
+            for lane in sorted({0, L - 1}):
+                frame = pfvo.frame_init(og)
+                for k in range(G):
+                    if k == 0:
+                        pfvo.decode_iframe_coeffs(og, st.qt, (0, 1, 1), hc[k, lane], frame, nt)
+                    else:
+                        pfvo.decode_pframe_coeffs(og, st.qt, (2, 3, 3), hh[k, lane], hc[k, lane], frame, nt)
+                y, u, v = pfvo.crop_frame(og, frame)
+                got = outb[G - 1, lane]
+                ok &= bool(np.array_equal(got[:ysz], y.ravel()) and np.array_equal(got[ysz:ysz + csz], u.ravel()) and
+                           np.array_equal(got[ysz + csz:], v.ravel()))
+            return ok
 
-        def step_e2e():
-            base = (ph2[0] % 2) * G
-            for k in range(G):
-                for arr, jobs in tabs2[base + k]:
-                    eng2.decode_submit(jobs, prebuilt=arr)
-            ph2[0] += 1
-
-        e_max, _ = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
-        nframes = G * L
-        h2d = int(st.nb * 512 * nframes + (G - 1) * L * st.nb * 4)
-        d2h = int((ysz + 2 * csz) * nframes)
-        e2e = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "jobs_per_submit": chunk,
-               "pcie_gbs_each_way": [h2d / e_max / 1e6, d2h / e_max / 1e6]}
-        eng2.close()
-
-        # ---- the same with the sparse coefficient transport (pfv_decode_submit_sparse): tokens cross PCIe ----
+        # ---- sparse coefficient transport (pfv_decode_submit_sparse): what the product's Decoder hands over ----
         from pretty_fast_video_b200 import codec
         from pretty_fast_video_b200.engine import SparseDecodeJob
         toks = [[codec.dense_to_tokens(hc[k, l], st.nb) for l in range(L)] for k in range(G)]
@@ -392,14 +525,49 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
                     eng3.decode_submit_sparse(jobs, prebuilt=arr)
             ph3[0] += 1
 
-        s_max, _ = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
         h2d_s = int(4 * ntok_total + nframes * 4 * (st.nb + 1) + (G - 1) * L * st.nb * 4)
-        e2e["sparse"] = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
-                         "h2d_bytes_per_step": h2d_s, "d2h_bytes_per_step": d2h,
-                         "nonzero_coefficients_per_frame": ntok_total / nframes,
-                         "note": "pfv_decode_submit_sparse: (position,value) tokens over PCIe, dense layout rebuilt on the GPU"}
+        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * st.nb * 512, chunk * (ysz + 2 * csz))
+        outb[...] = 0
+        s_max, s_my = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
+        e2e = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
+               "h2d_bytes_per_step": h2d_s, "d2h_bytes_per_step": d2h, "jobs_per_submit": chunk,
+               "seam": "sparse: pfv_decode_submit_sparse - (position,value) tokens over PCIe, dense layout rebuilt on the GPU, pictures back",
+               "nonzero_coefficients_per_frame": ntok_total / nframes,
+               "pcie_gbs_each_way": [h2d_s / s_my / 1e6, d2h / s_my / 1e6],
+               "pcie_ceiling_gbs": [ceil_h2d, ceil_d2h],
+               "frac_of_pcie_ceiling": max(h2d_s / s_my / 1e6 / ceil_h2d, d2h / s_my / 1e6 / ceil_d2h),
+               "verified": check_outputs()}
         eng3.close()
         tarena.close()
+
+        # ---- the reference's dense Vec<i16> seam (pfv_decode_submit) ----
+        eng2 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
+        cur2 = [2 * i for i in range(L)]
+        tabs2 = []
+        for rep in range(2):
+            for k in range(G):
+                full, jobs = make_jobs(eng2, k, cur2, lambda k, l: hc[k, l].ctypes.data, lambda k, l: hh[k, l].ctypes.data,
+                                       False, outs)
+                tabs2.append([(eng2.build_decode_jobs(jobs[i:i + chunk]), jobs[i:i + chunk]) for i in range(0, L, chunk)])
+        ph2 = [0]
+
+        def step_e2e():
+            base = (ph2[0] % 2) * G
+            for k in range(G):
+                for arr, jobs in tabs2[base + k]:
+                    eng2.decode_submit(jobs, prebuilt=arr)
+            ph2[0] += 1
+
+        outb[...] = 0
+        e_max, e_my = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
+        h2d = int(st.nb * 512 * nframes + (G - 1) * L * st.nb * 4)
+        e2e["dense"] = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "pcie_gbs_each_way": [h2d / e_my / 1e6, d2h / e_my / 1e6],
+                        "frac_of_pcie_ceiling": max(h2d / e_my / 1e6 / ceil_h2d, d2h / e_my / 1e6 / ceil_d2h),
+                        "seam": "dense: pfv_decode_submit - the reference's Vec<i16> of nb*256 coefficients over PCIe",
+                        "verified": check_outputs()}
+        eng2.close()
         out_arena.close()
 
     nframes = G * L
@@ -408,7 +576,8 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
     else:
         coded = st.coded[1:]
         alg = L * st.nb * MB_BYTES_DEC_I + int(coded.sum()) * MB_BYTES_DEC_P_CODED + int((~coded).sum()) * MB_BYTES_DEC_P_SKIP
-    return dict(max_ms=max_ms, my_ms=my_ms, frames=nframes, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e)
+    return dict(max_ms=max_ms, my_ms=my_ms, frames=nframes, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e,
+                verified=verified)
 
 
 def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
@@ -453,37 +622,17 @@ def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
     l0 = eng.launch_count
     max_ms, my_ms = time_steps(torch, dist, stream, step_dev, eng.sync, steps, warmup)
     launches_per_step = (eng.launch_count - l0) // (steps + warmup)
+    last_jobs = tabs[((ph[0] - 1) % 2) * G + G - 1][0][1]
+    verified = verify_encode(torch, st, eng, lambda lane: last_jobs[lane].dst_slot, d_c, d_h)
     eng.close()
 
     e2e = None
     if do_e2e:
         arena, hc, hh, hs = st.host()
         chunk = min(L, 8)
-        eng2 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
-        oa = PinnedArena(G * L * (st.nb * 512 + st.nb * 4) + 8192)
-        oc = oa.take((G, L, st.nb * 256), np.int16)
-        oh = oa.take((G, L, st.nb, 4), np.uint8)
-        tabs2 = make_tables(eng2, lambda k, l: hs[k, l].ctypes.data, lambda k, l: oc[k, l].ctypes.data,
-                            lambda k, l: oh[k, l].ctypes.data, False, chunk)
-        ph2 = [0]
-
-        def step_e2e():
-            base = (ph2[0] % 2) * G
-            for k in range(G):
-                for arr, jobs in tabs2[base + k]:
-                    eng2.encode_submit(jobs, prebuilt=arr)
-            ph2[0] += 1
-
-        e_max, _ = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
         nframes = G * L
-        e2e = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
-               "h2d_bytes_per_step": int(nframes * (ysz + 2 * csz)),
-               "d2h_bytes_per_step": int(nframes * st.nb * 512 + (G - 1) * L * st.nb * 4), "jobs_per_submit": chunk}
-        eng2.close()
-        oa.close()
-
-        # ---- the same through the sparse encode seam (pfv_encode_submit_sparse): the run-length pass runs on the device and
-        # the device itself stores each frame's RLE sequence into pinned host memory ----
+        # ---- the sparse encode seam (pfv_encode_submit_sparse): what the product's Encoder uses.  The run-length pass runs
+        # on the device and the device itself stores each frame's RLE sequence into pinned host memory ----
         from pretty_fast_video_b200 import _native as N
         from pretty_fast_video_b200.engine import SparseEncodeJob
         cap = st.nb * 64                                            # entries per frame; the overflow flag is checked below
@@ -513,19 +662,75 @@ def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
                     eng3.encode_submit_sparse(jobs, prebuilt=arr)
             ph3[0] += 1
 
-        s_max, _ = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
+        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * (ysz + 2 * csz), chunk * st.nb * 512)
+        s_max, s_my = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
         ntok = os_[:, :, N.PFV_TOKSTATS_NTOK].astype(np.int64)
         assert not (os_[:, :, N.PFV_TOKSTATS_FLAGS] != 0).any(), "token buffer overflow in the sparse encode leg"
-        e2e["sparse"] = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
-                         "h2d_bytes_per_step": int(nframes * (ysz + 2 * csz)),
-                         "d2h_bytes_per_step": int(ntok.sum() * 4 + nframes * N.PFV_TOKSTATS_WORDS * 4 + (G - 1) * L * st.nb * 4),
-                         "rle_entries_per_frame": float(ntok.mean()),
-                         "note": "pfv_encode_submit_sparse: run-length pass on the GPU, RLE sequence stored by the device into pinned host memory"}
+        # the RLE sequence that came back over PCIe (first / last lane, last frame) against rle_encode of the oracle's coefficients
+        pfvo = _oracle()
+        og = pfvo.geometry_for(w, h)
+        nt = min(16, os.cpu_count() or 1)
+        ok = True
+        for lane in sorted({0, L - 1}):
+            prev = pfvo.frame_init(og)
+            hd = None
+            for k in range(G):
+                b = hs[k, lane]
+                y, u, v = b[:ysz].reshape(h, w), b[ysz:ysz + csz].reshape(h // 2, w // 2), b[ysz + csz:].reshape(h // 2, w // 2)
+                if k == 0:
+                    c = pfvo.encode_iframe_coeffs(og, st.qt, y, u, v, prev, nt)
+                else:
+                    hd, c = pfvo.encode_pframe_coeffs(og, st.qt, st.px_err, y, u, v, prev, nt)
+            o_tok, o_table, _ = pfvo.rle_frame(c, None if G == 1 else hd[:, 2])
+            n = int(os_[G - 1, lane, N.PFV_TOKSTATS_NTOK])
+            ok &= bool(n == o_tok.size and np.array_equal(ot[G - 1, lane, :n], o_tok))
+            ok &= bool(np.array_equal(os_[G - 1, lane, :16].astype(np.int64) + os_[G - 1, lane, 16:32], o_table))
+            if G > 1:
+                ok &= bool(np.array_equal(oh3[G - 1, lane], hd))
+        h2d = int(nframes * (ysz + 2 * csz))
+        d2h_s = int(ntok.sum() * 4 + nframes * N.PFV_TOKSTATS_WORDS * 4 + (G - 1) * L * st.nb * 4)
+        e2e = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_s, "jobs_per_submit": chunk,
+               "rle_entries_per_frame": float(ntok.mean()),
+               "seam": "sparse: pfv_encode_submit_sparse - source planes up, run-length pass on the GPU, RLE sequence stored by the device into pinned host memory",
+               "pcie_gbs_each_way": [h2d / s_my / 1e6, d2h_s / s_my / 1e6], "pcie_ceiling_gbs": [ceil_h2d, ceil_d2h],
+               "frac_of_pcie_ceiling": max(h2d / s_my / 1e6 / ceil_h2d, d2h_s / s_my / 1e6 / ceil_d2h),
+               "verified": ok}
         eng3.close()
         sa.close()
-    coded = st.coded[1:]
-    alg = L * st.nb * MB_BYTES_ENC_I + int(coded.sum()) * MB_BYTES_ENC_P_CODED + int((~coded).sum()) * MB_BYTES_ENC_P_SKIP
-    return dict(max_ms=max_ms, my_ms=my_ms, frames=G * L, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e)
+
+        # ---- the reference's dense seam (pfv_encode_submit): all coefficients come back ----
+        eng2 = Engine(w, h, st.qt, nslots=2 * L, max_jobs=chunk, device=dev_index, stream=stream.cuda_stream)
+        oa = PinnedArena(G * L * (st.nb * 512 + st.nb * 4) + 8192)
+        oc = oa.take((G, L, st.nb * 256), np.int16)
+        oh = oa.take((G, L, st.nb, 4), np.uint8)
+        tabs2 = make_tables(eng2, lambda k, l: hs[k, l].ctypes.data, lambda k, l: oc[k, l].ctypes.data,
+                            lambda k, l: oh[k, l].ctypes.data, False, chunk)
+        ph2 = [0]
+
+        def step_e2e():
+            base = (ph2[0] % 2) * G
+            for k in range(G):
+                for arr, jobs in tabs2[base + k]:
+                    eng2.encode_submit(jobs, prebuilt=arr)
+            ph2[0] += 1
+
+        e_max, e_my = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
+        d2h = int(nframes * st.nb * 512 + (G - 1) * L * st.nb * 4)
+        e2e["dense"] = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "pcie_gbs_each_way": [h2d / e_my / 1e6, d2h / e_my / 1e6],
+                        "frac_of_pcie_ceiling": max(h2d / e_my / 1e6 / ceil_h2d, d2h / e_my / 1e6 / ceil_d2h),
+                        "seam": "dense: pfv_encode_submit - nb*256 int16 coefficients per frame back over PCIe"}
+        eng2.close()
+        oa.close()
+    if G == 1:
+        alg = L * st.nb * MB_BYTES_ENC_I
+    else:
+        coded = st.coded[1:]
+        alg = L * st.nb * MB_BYTES_ENC_I + int(coded.sum()) * MB_BYTES_ENC_P_CODED + int((~coded).sum()) * MB_BYTES_ENC_P_SKIP
+    return dict(max_ms=max_ms, my_ms=my_ms, frames=G * L, alg_bytes=alg, launches_per_step=launches_per_step, e2e=e2e,
+                verified=verified)
 
 
 def run_decoder_stream(torch, dist, budget_s, nthreads):
@@ -684,6 +889,10 @@ def cpu_port_leg(workload, budget_s, nthreads, reps=None):
     return fps, sample, og.nb
 
 
+def metric_name(workload):
+    return "1080p decode frames/sec" if workload.startswith("decode") and "1080p" in workload else f"{workload} frames/sec"
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -705,13 +914,13 @@ def reference_arm(args):
             break
     v = float(np.mean(vals)) if vals else fps
     line = {
-        "impl": "reference", "metric": "1080p decode frames/sec" if "1080p" in args.workload else "decode frames/sec",
+        "impl": "reference", "metric": metric_name(args.workload),
         "value": v, "unit": "frames/s", "mb_per_s": v * nb, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
         "ms_per_step": 1e3 * reps * distinct / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"],
-                   "frames_per_step": reps * distinct, "gop": cfg["gop"]},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "config": config_of(args.workload),
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample,
+                         "frames_per_step": reps * distinct},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C restatement of the reference algorithm (oracle/); the Rust crate cannot be built here (no cargo/rustc)",
     }
@@ -726,7 +935,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="decode_i_1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--extras", type=int, default=1, help="also run the P-stream decode/encode workloads (N=1 only)")
+    ap.add_argument("--extras", type=int, default=1, help="also run the other workloads (N > 1: the resident P-stream legs only)")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--e2e", type=int, default=1, help="0 skips the host-buffer leg (kernel tuning runs only)")
     args = ap.parse_args()
@@ -754,6 +963,7 @@ def main():
         r["st"] = st
         return r
 
+    binding = bind_to_gpu_numa_node(torch, dist.local)
     sampler = ClockSampler(dist.local)
     sampler.start()
     r = run(args.workload, args.steps, args.warmup, bool(args.e2e))
@@ -762,58 +972,78 @@ def main():
     fps = r["frames"] * dist.world / (r["max_ms"] * 1e-3)
     launches = r["launches_per_step"]
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
-    kernel_key = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_stream_kernel",
-                  "decode_p_1080p": "mc_copy_kernel+residual_sb_kernel", "decode_p_4k": "mc_copy_kernel+residual_sb_kernel",
-                  "encode_p_1080p": "encode_p_kernel"}[args.workload]
+    kernel_of = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_stream_kernel",
+                 "decode_p_1080p": "decode_p_fused_kernel", "decode_p_4k": "decode_p_fused_kernel",
+                 "encode_p_1080p": "encode_p_kernel", "encode_i_1080p": "encode_i_stream_kernel"}
+    kernel_key = kernel_of[args.workload]
+
+    def stats_of(xs):
+        return {"mb_per_frame": xs.nb, "coded_mb_fraction_p": xs.coded_frac, "nonzero_mv_fraction_p": xs.mv_nonzero,
+                "ac_subblock_fraction": xs.general_frac,
+                "distinct_sequences": 1 if xs.gop == 1 else min(xs.lanes, DISTINCT_SEQUENCES)}
+
+    verified_all = bool(r["verified"]) and all(bool(x.get("verified", True)) for x in ((r["e2e"] or {}), (r["e2e"] or {}).get("dense", {})))
     line = {
-        "metric": "1080p decode frames/sec" if "decode" in args.workload and "1080p" in args.workload else f"{args.workload} frames/sec",
+        "metric": metric_name(args.workload),
         "value": fps, "unit": "frames/s", "mb_per_s": fps * st.nb,
         "n_gpus": dist.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["max_ms"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": cfg["w"], "height": cfg["h"], "quality": cfg["quality"],
-                   "frames_per_step_per_gpu": r["frames"], "gop": cfg["gop"], "mb_per_frame": st.nb,
-                   "coded_mb_fraction_p": st.coded_frac, "nonzero_mv_fraction_p": st.mv_nonzero,
-                   "ac_subblock_fraction": st.general_frac,
-                   "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
-                   "sharding": "frames/GOPs split over ranks, no collective on the data path"},
+        "config": config_of(args.workload),
+        "workload_stats": stats_of(st),
+        "verified": verified_all,
         "gpu_launches": launches * args.steps,
         "e2e": {k: v for k, v in (r["e2e"] or {}).items()},
         "roofline": {"bound": "hbm", "kernel": kernel_key, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": r["alg_bytes"],
-                     "launches_per_step": launches, "traffic": ncu_traffic(kernel_key)},
+                     "launches_per_step": launches, "traffic": ncu_traffic(kernel_key),
+                     "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload, per launch)"},
         "clocks": clocks,
+        "host_binding": binding,
     }
+    if args.workload.startswith("encode_p"):
+        line["candidate_pixels_per_s"] = fps * st.nb * SEARCH_CANDIDATES_PER_MB * 256
 
+    nthreads = os.cpu_count() or 1
     if dist.world == 1:
-        nthreads = os.cpu_count() or 1
         cfps, sample, _ = cpu_port_leg(args.workload, args.cpu_budget, nthreads)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
         if nthreads > 1 and args.cpu_budget >= 1.0:
             # the same port on ONE thread (SURVEY 8d quotes the CPU path at 1 thread and at all threads)
             c1, s1, _ = cpu_port_leg(args.workload, min(args.cpu_budget / 4, 3.0), 1)
             line["cpu_baseline"]["one_thread"] = {"value": c1, "unit": "frames/s", "cores": 1, "sample": s1}
-        if args.extras:
-            extras = {}
-            for wl in ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p", "decode_p_4k"):
-                if wl == args.workload:
-                    continue
-                try:
-                    x = run(wl, max(3, args.steps // 4), 3, do_e2e=(wl != "decode_p_4k"))
-                    xs = x["st"]
-                    extras[wl] = {
-                        "value": x["frames"] / (x["max_ms"] * 1e-3), "unit": "frames/s",
-                        "mb_per_s": x["frames"] / (x["max_ms"] * 1e-3) * xs.nb, "ms_per_step": x["max_ms"],
-                        "frames_per_step": x["frames"], "launches_per_step": x["launches_per_step"],
-                        "coded_mb_fraction_p": xs.coded_frac, "nonzero_mv_fraction_p": xs.mv_nonzero,
-                        "ac_subblock_fraction": xs.general_frac,
-                        "roofline_frac": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9 / peak,
-                        "achieved_gbs": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9,
-                        "e2e": x["e2e"],
-                    }
+    if args.extras:
+        extras = {}
+        # N > 1 (the scaling run): the P-stream configs ride along, resident legs only, so that BASELINE.json configs[2]
+        # and configs[4] (GOPs sharded over the ranks) sit on the driver's record at every N
+        names = ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p", "encode_i_1080p", "decode_p_4k") if dist.world == 1 \
+            else ("decode_p_1080p", "decode_p_4k")
+        for wl in names:
+            if wl == args.workload:
+                continue
+            try:
+                x = run(wl, max(3, args.steps // 4), 3, do_e2e=(dist.world == 1 and wl != "decode_p_4k"))
+                xs = x["st"]
+                xfps = x["frames"] * dist.world / (x["max_ms"] * 1e-3)
+                extras[wl] = {
+                    "value": xfps, "unit": "frames/s", "mb_per_s": xfps * xs.nb, "ms_per_step": x["max_ms"], "n_gpus": dist.world,
+                    "frames_per_step_per_gpu": x["frames"], "launches_per_step": x["launches_per_step"],
+                    "workload_stats": stats_of(xs), "kernel": kernel_of[wl], "verified": bool(x["verified"]),
+                    "roofline_frac": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9 / peak,
+                    "achieved_gbs": x["alg_bytes"] / (x["my_ms"] * 1e-3) / 1e9,
+                    "traffic": ncu_traffic(kernel_of[wl] + ":" + wl) or ncu_traffic(kernel_of[wl]),
+                    "e2e": x["e2e"],
+                }
+                if wl.startswith("encode_p"):
+                    extras[wl]["candidate_pixels_per_s"] = xfps * xs.nb * SEARCH_CANDIDATES_PER_MB * 256
+                if dist.world == 1:
                     cf, cs, _ = cpu_port_leg(wl, min(args.cpu_budget, 3.0 if wl == "decode_p_4k" else 6.0), nthreads)
                     extras[wl]["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": cs}
-                except Exception as ex:                      # an extra must never lose the headline line
-                    extras[wl] = {"error": repr(ex)}
+                verified_all &= bool(x["verified"]) and all(bool(y.get("verified", True)) for y in ((x["e2e"] or {}), (x["e2e"] or {}).get("dense", {})))
+                del x, xs
+            except Exception as ex:                      # an extra must never lose the headline line
+                extras[wl] = {"error": repr(ex)}
+                verified_all = False
+        if dist.world == 1:
             try:
                 extras["rgb_out_1080p"] = run_format_steps(torch, dist, stream, max(3, args.steps // 4))
             except Exception as ex:
@@ -822,10 +1052,14 @@ def main():
                 extras["decoder_stream_1080p"] = run_decoder_stream(torch, dist, min(args.cpu_budget, 6.0), nthreads)
             except Exception as ex:
                 extras["decoder_stream_1080p"] = {"error": repr(ex)}
-            line["extras"] = extras
+        line["extras"] = extras
+        line["verified"] = verified_all
+    line["verified"] = dist.sum(1.0 if line["verified"] else 0.0) == float(dist.world)     # every rank's legs
     if dist.rank == 0:
         print(json.dumps(line))
     dist.close()
+    if not line["verified"]:
+        raise SystemExit("bench.py: a timed leg's output differs from the oracle (see the \"verified\" keys)")
 
 
 if __name__ == "__main__":
