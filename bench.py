@@ -423,7 +423,8 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
             jobs.append(DecodeJob(PFV_FRAME_I if k == 0 else PFV_FRAME_P, dst, coeff_ptr(k, lane),
                                   (0, 1, 1) if k == 0 else (2, 3, 3), ref_slot=cur[lane],
                                   hdr=hdr_ptr(k, lane) if k else None, device_ptrs=device,
-                                  out=outs(k, lane) if outs else None))
+                                  out=outs(k, lane) if outs else None,
+                                  dense_hint=(k == 0 and st.general_frac > 0.5)))   # the caller knows its content (PFV_JOB_DENSE)
             cur[lane] = dst
         return eng.build_decode_jobs(jobs), jobs
 

@@ -77,10 +77,15 @@ enum { PFV_FRAME_I = 1, PFV_FRAME_P = 2 };
 enum {
     PFV_JOB_DEVICE_PTRS = 1u,  /* hdr/coeff/src pointers are DEVICE pointers already resident in HBM
                                   (no H2D is issued; out pointers, if non-NULL, are still host)       */
-    PFV_JOB_SRC_RGB = 2u       /* encode jobs: src_y points at packed RGB8 (w*h*3 bytes), src_u/src_v are
+    PFV_JOB_SRC_RGB = 2u,      /* encode jobs: src_y points at packed RGB8 (w*h*3 bytes), src_u/src_v are
                                   ignored; the engine converts on the device exactly like the reference's
                                   load_frame + VideoFrame::from_planes (src/lib.rs:337-363, src/frame.rs:51-60,
                                   reduce src/common.rs:523-536)                                        */
+    PFV_JOB_DENSE = 4u         /* decode key-frame jobs, a HINT: most 8x8 sub-blocks of this frame carry AC
+                                  coefficients (the caller's entropy decoder knows: more than ~6 non-zero
+                                  coefficients per sub-block).  Such frames skip the classify/compact staging that
+                                  pays on ordinary streams.  Results never depend on the hint; sparse jobs set it
+                                  themselves from their token count.                                   */
 };
 
 /*

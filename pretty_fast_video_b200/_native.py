@@ -27,6 +27,7 @@ PFV_FRAME_I = 1
 PFV_FRAME_P = 2
 PFV_JOB_DEVICE_PTRS = 1
 PFV_JOB_SRC_RGB = 2
+PFV_JOB_DENSE = 4
 
 
 class PfvError(RuntimeError):

@@ -31,8 +31,20 @@ constexpr int ENC_WARPS = 4;
 struct __align__(16) EncStreamSmem {
     uint4    coef[ENC_WARPS][SBW_RING * 8];
     uint32_t id[ENC_WARPS][SBW_RING];
-    uint32_t left_head[ENC_WARPS], left_cnt[ENC_WARPS];
 };
+
+// 8 bytes of a source row whose plane width is not a multiple of 8 (or whose base is unaligned): byte by byte, padded with the
+// clear colour.  Rare and out of line: the streaming kernel's loop must stay small enough for the instruction cache.
+__device__ __noinline__ uint2 load_src_row_ragged(const uint8_t *__restrict__ p, uint32_t x0, uint32_t vw, uint32_t clear)
+{
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t b = (x0 + k < vw) ? (uint32_t)p[k] : (clear & 0xffu);
+        w[k >> 2] |= b << (8 * (k & 3));
+    }
+    return make_uint2(w[0], w[1]);
+}
 
 // rows y0 .. y0+7, bytes x0 .. x0+7 of a tight vw x vh source plane, padded with the clear colour (src/common.rs:352-356)
 __device__ __forceinline__ void load_src_sb(const uint8_t *__restrict__ src, const PlaneGeom &pl, uint32_t x0, uint32_t y0,
@@ -44,17 +56,8 @@ __device__ __forceinline__ void load_src_sb(const uint8_t *__restrict__ src, con
         uint2 v = make_uint2(pl.clear4, pl.clear4);
         if (y < pl.vh && x0 < pl.vw) {
             const uint8_t *p = src + (size_t)y * pl.vw + x0;
-            if (fast) {
-                v = __ldcs(reinterpret_cast<const uint2 *>(p));   // vw % 8 == 0 and base 8-byte aligned: all 8 bytes exist
-            } else {
-                uint32_t w[2] = {0u, 0u};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t b = (x0 + k < pl.vw) ? (uint32_t)p[k] : (pl.clear4 & 0xffu);
-                    w[k >> 2] |= b << (8 * (k & 3));
-                }
-                v = make_uint2(w[0], w[1]);
-            }
+            if (fast) v = __ldcs(reinterpret_cast<const uint2 *>(p));   // vw % 8 == 0 and base 8-byte aligned: all 8 bytes exist
+            else      v = load_src_row_ragged(p, x0, pl.vw, pl.clear4);
         }
         rows[r] = v;
     }
@@ -83,8 +86,13 @@ __device__ __forceinline__ uint32_t mb_entry_count_lanes(const SbRuns &r, uint32
     return n;
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(ENC_WARPS * 32, 4)
+// CTAS = resident CTAs per SM the kernel is compiled for (4: 128 registers, 3: 168 - room to keep the next tile's 16
+// source words in flight across the whole transform).  The loop has ONE copy of the forward and ONE of the inverse
+// transform (ncu on the first version: 5 400 instructions, a third of all stall samples "no instruction" - the
+// instruction cache): the next tile is fetched at the top of an iteration that then works on the previous one, and
+// what a warp has left in its ring at the end is drained by the same transform site with the idle lanes masked off.
+template <bool COUNT, int CTAS>
+__global__ void __launch_bounds__(ENC_WARPS * 32, CTAS)
 encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__restrict__ jobs)
 {
     __shared__ EncStreamSmem sm;
@@ -98,6 +106,7 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * ENC_WARPS + warp) * P.tiles_per_warp;
     const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
+    if (tile_begin >= tile_end) return;
     const EncJob job = jobs[blockIdx.y];
     const uint32_t sb = lane & 3u;
     const uint8_t *src = p == 0 ? job.src[0] : (p == 1 ? job.src[1] : job.src[2]);
@@ -105,67 +114,69 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
     uint4 *ring = sm.coef[warp];
     uint32_t *ring_id = sm.id[warp];
 
-    auto fetch = [&](uint32_t tile, uint2 (&rows)[8]) {
-        const uint32_t lm = min(tile * 8u + (lane >> 2), nmb - 1u);
-        uint32_t col;
-        const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
-        load_src_sb(src, pl, col * 16u + (sb & 1u) * 8u, row * 16u + (sb >> 1) * 8u, fast, rows);
-    };
-
     uint2 nxt[8];
-    if (tile_begin < tile_end) fetch(tile_begin, nxt);
     uint32_t head = 0, tail = 0;
 #pragma unroll 1
-    for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+    for (uint32_t tile = tile_begin - 1u; tile != tile_end; ++tile) {       // iteration `tile` works on `tile` and fetches tile + 1
+        const bool work = tile != tile_begin - 1u;
         const uint32_t lm = tile * 8u + (lane >> 2);
-        const bool valid = lm < nmb;
+        const bool valid = work && lm < nmb;
         int x[64];
+        if (work) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < 8; ++r) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t wd = k < 4 ? nxt[r].x : nxt[r].y;
-                x[r * 8 + k] = (int)((wd >> (8 * (k & 3))) & 0xffu) * 256 - 32768;   // (p - 128) << 8, src/common.rs:291
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t wd = k < 4 ? nxt[r].x : nxt[r].y;
+                    x[r * 8 + k] = (int)((wd >> (8 * (k & 3))) & 0xffu) * 256 - 32768;   // (p - 128) << 8, src/common.rs:291
+                }
             }
         }
-        if (tile + 1 < tile_end) fetch(tile + 1, nxt);          // in flight during the transform
-
-        uint32_t w[32];
-        encode_sb_regs(x, encM, w);
-        uint32_t ac = w[0] & 0xffff0000u;
-#pragma unroll
-        for (int i = 1; i < 32; ++i) ac |= w[i];
-        if (valid) {
-            uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64u));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) __stcs(dstc + k, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
+        if (tile + 1u != tile_end) {                            // in flight during the transform
+            const uint32_t lmn = min((tile + 1u) * 8u + (lane >> 2), nmb - 1u);
+            uint32_t col;
+            const uint32_t row = div_small(lmn, pl.bw, pl.rcp_bw, col);
+            load_src_sb(src, pl, col * 16u + (sb & 1u) * 8u, row * 16u + (sb >> 1) * 8u, fast, nxt);
         }
-        if (COUNT) {                                            // sparse seam: how many RLE entries this macroblock makes
-            const uint32_t n = mb_entry_count_lanes(sb_runs(w), sb);
-            if (valid && sb == 0u) job.mb_cnt[pl.mb_base + lm] = n;
-        }
-
-        // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
-        const bool general = valid && ac != 0u;
-        const uint32_t vote = __ballot_sync(0xffffffffu, general);
-        if (general) {
-            const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+        uint32_t vote = 0;
+        if (work) {
+            uint32_t w[32];
+            encode_sb_regs(x, encM, w);
+            uint32_t ac = w[0] & 0xffff0000u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                ring[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-            ring_id[slot] = (lm << 2) | sb;
-        } else if (valid) {
-            store_dc_only(sb_dst(job.dst, pl, lm, (int)sb), pl.pw, (int)(int16_t)(w[0] & 0xffffu), deq[0]);
+            for (int i = 1; i < 32; ++i) ac |= w[i];
+            if (valid) {
+                uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64u));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) __stcs(dstc + k, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
+            }
+            if (COUNT) {                                        // sparse seam: how many RLE entries this macroblock makes
+                const uint32_t n = mb_entry_count_lanes(sb_runs(w), sb);
+                if (valid && sb == 0u) job.mb_cnt[pl.mb_base + lm] = n;
+            }
+            // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
+            const bool general = valid && ac != 0u;
+            vote = __ballot_sync(0xffffffffu, general);
+            if (general) {
+                const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    ring[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+                ring_id[slot] = (lm << 2) | sb;
+            } else if (valid) {
+                store_dc_only(sb_dst(job.dst, pl, lm, (int)sb), pl.pw, (int)(int16_t)(w[0] & 0xffffu), deq[0]);
+            }
         }
         tail += (uint32_t)__popc(vote);
         __syncwarp();
-        if (tail - head >= 32u) {
-            transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
-            head += 32u;
+        const bool last = tile + 1u == tile_end;
+#pragma unroll 1
+        while (tail - head >= 32u || (last && tail != head)) {      // (at most 63 queued: twice only when draining)
+            if (lane < tail - head) transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
+            head += min(32u, tail - head);
             __syncwarp();
         }
     }
-    flush_rings_i<ENC_WARPS>(sm.coef, sm.id, sm.left_head, sm.left_cnt, head, tail, warp, lane, job.dst, pl, deq);
 }
 
 cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s)
@@ -185,8 +196,14 @@ cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t
     }
     P.cta_total = cta;
     dim3 grid(P.cta_total, njobs, 1), block(ENC_WARPS * 32, 1, 1);
-    if (count) encode_i_stream_kernel<true><<<grid, block, 0, s>>>(P, d_jobs);
-    else       encode_i_stream_kernel<false><<<grid, block, 0, s>>>(P, d_jobs);
+    static const int ctas_env = getenv("PFV_ENCODE_I_CTAS") ? atoi(getenv("PFV_ENCODE_I_CTAS")) : 0;   // tuning aid
+    if (ctas_env == 3) {
+        if (count) encode_i_stream_kernel<true, 3><<<grid, block, 0, s>>>(P, d_jobs);
+        else       encode_i_stream_kernel<false, 3><<<grid, block, 0, s>>>(P, d_jobs);
+    } else {
+        if (count) encode_i_stream_kernel<true, 4><<<grid, block, 0, s>>>(P, d_jobs);
+        else       encode_i_stream_kernel<false, 4><<<grid, block, 0, s>>>(P, d_jobs);
+    }
     return cudaGetLastError();
 }
 

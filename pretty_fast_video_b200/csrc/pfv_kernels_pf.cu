@@ -51,9 +51,20 @@ struct __align__(16) PfGroup {
     uint4         id[8];                                     // {byte offset of the macroblock in a frame slot, job, plane, valid}
 };
 
+constexpr int PF_MAX_JOBS = 64;                              // frames per launch (longer batches go out as several launches)
+
+struct PfJob {                                               // what the kernel needs of a DecJob, kept in shared memory: every
+    const int16_t  *coeff;                                   // field is read once per window, and a dependent global load per
+    const uint32_t *hdr;                                     // window (pointer, then data) was what the copy half waited for
+    uint8_t        *dst;
+    const uint8_t  *ref;
+    int32_t         ref_slot, pad;
+};
+
 struct __align__(128) PfSmem {
     unsigned char win[PF_STAGES][PF_STAGE];
     PfGroup  grp[PF_NG];
+    PfJob    job[PF_MAX_JOBS];
     int32_t  deq[3][64];
     uint64_t win_full[PF_STAGES];
     uint64_t grp_full[PF_NG];                                // 8 arrivals (one per slot) + the slots' coefficient bytes
@@ -146,6 +157,10 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = threadIdx.x; i < 3 * 64; i += PF_THREADS) (&sm.deq[0][0])[i] = (&P.deq[0][0])[i];
+    for (uint32_t i = threadIdx.x; i < njobs; i += PF_THREADS) {
+        const DecJob &j = jobs[i];
+        sm.job[i] = PfJob{j.coeff, reinterpret_cast<const uint32_t *>(j.hdr), j.dst, j.ref, j.ref_slot, 0};
+    }
     __syncthreads();
 
     auto plane = [&](uint32_t p) -> const PlaneGeom & { return p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]); };
@@ -157,8 +172,9 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         for (uint32_t G = warp - PF_ROWS;; G += PF_XF_WARPS) {
             const uint32_t rgp = G % PF_NG, par = (G / PF_NG) & 1u;
             bool stop = false;
-            while (!bar_try(&sm.grp_full[rgp], par)) {
+            while (!bar_try(&sm.grp_full[rgp], par)) {          // (try_wait itself suspends the warp for a while)
                 if (sm.total_groups <= G) { stop = true; break; }
+                __nanosleep(200);
             }
             if (stop) break;
             const PfGroup &grp = sm.grp[rgp];
@@ -177,7 +193,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
             const bool valid = id.w != 0u;
             const uint32_t pw = plane(p).pw;
             uint8_t *dst = nullptr;
-            if (valid) dst = jobs[id.y].dst + id.x + (size_t)((sb >> 1) * 8u) * pw + (sb & 1u) * 8u;
+            if (valid) dst = sm.job[id.y].dst + id.x + (size_t)((sb >> 1) * 8u) * pw + (sb & 1u) * 8u;
             idct8x8_regs(m);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -216,7 +232,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
     auto issue = [&](const PfItem &it, uint32_t st) {          // thread 0 only
         bar_arrive_tx(&sm.win_full[st], (uint32_t)PF_WIN_BYTES);
         const CUtensorMap *tm = it.p == 0 ? &tm_luma : &tm_chroma;
-        const int cx = (int)it.tx * 128 - 16, cy = (int)it.gy * (PF_ROWS * 16) - 15, cz = it.p == 2 ? 1 : 0, cw = jobs[it.job].ref_slot;
+        const int cx = (int)it.tx * 128 - 16, cy = (int)it.gy * (PF_ROWS * 16) - 15, cz = it.p == 2 ? 1 : 0, cw = sm.job[it.job].ref_slot;
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -229,14 +245,16 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         const PlaneGeom &pl = plane(it.p);
         const uint32_t row = it.gy * PF_ROWS + warp, col = it.tx * 8u + mb;
         if (row >= pl.bh || col >= pl.bw) return 0x80000000u;
-        return __ldg(reinterpret_cast<const uint32_t *>(jobs[it.job].hdr) + pl.mb_base + row * pl.bw + col);
+        return __ldg(sm.job[it.job].hdr + pl.mb_base + row * pl.bw + col);
     };
 
+    // Software pipeline over windows k (being copied), k+1 and k+2 (TMA in flight, headers loaded) and k+3 (TMA issued at the
+    // end of iteration k): no load is consumed in the iteration that issues it.
     uint32_t it = blockIdx.x;
     PfPos pc, pn, pt;
     pc.wi = it / njobs;
     pc.job = it - pc.wi * njobs;
-    pn = pc; advance(pn);
+    pn = pc; advance(pn);                                       // window k+1, then k+2 (the header two windows ahead)
     pt = pc;
 #pragma unroll 1
     for (uint32_t s = 0; s < (uint32_t)PF_STAGES; ++s) {
@@ -244,16 +262,18 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         advance(pt);
     }
     uint32_t hw_cur = it < nitems ? load_hw(item_of(pc)) : 0x80000000u;
+    uint32_t hw_n1 = it + G0 < nitems ? load_hw(item_of(pn)) : 0x80000000u;
+    advance(pn);
     uint32_t k = 0;
 #pragma unroll 1
     for (; it < nitems; it += G0, ++k) {
         const uint32_t st = k % PF_STAGES;
         const PfItem cur = item_of(pc);
-        uint32_t hw_next = 0x80000000u;
-        if (it + G0 < nitems) hw_next = load_hw(item_of(pn));
+        uint32_t hw_n2 = 0x80000000u;
+        if (it + 2u * G0 < nitems) hw_n2 = load_hw(item_of(pn));
 
         const PlaneGeom &pl = plane(cur.p);
-        const DecJob &job = jobs[cur.job];
+        const PfJob &job = sm.job[cur.job];
         const bool exists = !(hw_cur & 0x80000000u);
         const bool coded = exists && ((hw_cur >> 16) & 0xffu) != 0u;
         const int bx = (int)(cur.tx * 8u + mb) * 16, by = (int)(cur.gy * PF_ROWS + warp) * 16;
@@ -319,8 +339,8 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         asm volatile("bar.sync 1, %0;" ::"n"(PF_ROWS * 32) : "memory");   // the copy half is done with this window stage
         if (threadIdx.x == 0 && it + PF_STAGES * G0 < nitems) issue(item_of(pt), st);
         advance(pt);
-        pc = pn; advance(pn);
-        hw_cur = hw_next;
+        advance(pc); advance(pn);
+        hw_cur = hw_n1; hw_n1 = hw_n2;
     }
 
     // the copy half is done: complete the last, partly filled group with empty slots and tell the transform half where to stop
@@ -349,10 +369,15 @@ cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint3
         if (e != cudaSuccess) return e;
     }
     const McWin W = make_mc_windows(P.g, PF_ROWS);
-    uint32_t ctas = njobs * W.total;
-    if (ctas > 148u * 2u) ctas = 148u * 2u;
-    decode_p_fused_kernel<<<ctas, PF_THREADS, smem, s>>>(P, W, d_jobs, njobs, d_err, tm_luma, tm_chroma);
-    return cudaGetLastError();
+    for (uint32_t j0 = 0; j0 < njobs; j0 += PF_MAX_JOBS) {
+        const uint32_t n = njobs - j0 < (uint32_t)PF_MAX_JOBS ? njobs - j0 : (uint32_t)PF_MAX_JOBS;
+        uint32_t ctas = n * W.total;
+        if (ctas > 148u * 2u) ctas = 148u * 2u;
+        decode_p_fused_kernel<<<ctas, PF_THREADS, smem, s>>>(P, W, d_jobs + j0, n, d_err, tm_luma, tm_chroma);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace pfv

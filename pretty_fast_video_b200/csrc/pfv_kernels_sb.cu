@@ -98,7 +98,10 @@ struct __align__(128) StreamSmem {
 // WARPS x CTAS = resident warps per SM the kernel is compiled for.  Each warp owns 16 KB of shared memory (two stages
 // + the ring), so at most 14 warps fit an SM; the transform is issue bound with 4-cycle dependent chains, so resident
 // warps count as long as the 64-value sub-block stays in registers.
-template <int WARPS, int CTAS>
+// POOL: what the warps have left at the end is pooled across the CTA and transformed by full warps (a second copy of
+// the transform behind a CTA barrier); otherwise each warp drains its own ring through the loop's one transform site
+// with the idle lanes masked off (half the code, no barrier, a partly filled last pass per warp).
+template <int WARPS, int CTAS, bool POOL>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
 decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs)
 {
@@ -174,13 +177,15 @@ decode_i_stream_kernel(const __grid_constant__ SbParams P, const DecJob *__restr
         __syncwarp();
 
         // ---- B: a full warp of queued sub-blocks ----
-        if (tail - head >= 32u) {
-            transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
-            head += 32u;
+        const bool drain = !POOL && i + 1u == ntl;
+#pragma unroll 1
+        while (tail - head >= 32u || (drain && tail != head)) {
+            if (lane < tail - head) transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
+            head += min(32u, tail - head);
             __syncwarp();
         }
     }
-    flush_rings_i<WARPS>(sm.coef, sm.id, sm.left_head, sm.left_cnt, head, tail, warp, lane, job.dst, pl, deq);
+    if (POOL) flush_rings_i<WARPS>(sm.coef, sm.id, sm.left_head, sm.left_cnt, head, tail, warp, lane, job.dst, pl, deq);
 }
 
 cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
@@ -211,27 +216,27 @@ void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t wav
 }
 
 // Job coefficient pointers must be 16-byte aligned (bulk copies); pfv_decode_submit checks.
-template <int WARPS, int CTAS>
+template <int WARPS, int CTAS, bool POOL>
 static cudaError_t launch_decode_i_stream_t(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
     static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const int smem = (int)sizeof(StreamSmem<WARPS>);
     if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel<WARPS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel<WARPS, CTAS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     sbw_split(P, njobs, WARPS, 6u * 148u * (uint32_t)(CTAS * WARPS), 16u);
     dim3 grid(P.cta_total, njobs, 1), block(WARPS * 32, 1, 1);
-    decode_i_stream_kernel<WARPS, CTAS><<<grid, block, smem, s>>>(P, d_jobs);
+    decode_i_stream_kernel<WARPS, CTAS, POOL><<<grid, block, smem, s>>>(P, d_jobs);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
-    static const int shape_env = getenv("PFV_DECODE_I_SHAPE") ? atoi(getenv("PFV_DECODE_I_SHAPE")) : 0;   // tuning aid: warps*10 + CTAs
-    if (shape_env == 72) return launch_decode_i_stream_t<7, 2>(P, d_jobs, njobs, s);
-    if (shape_env == 62) return launch_decode_i_stream_t<6, 2>(P, d_jobs, njobs, s);
-    return launch_decode_i_stream_t<4, 3>(P, d_jobs, njobs, s);
+    // (CTAs of 6 or 7 warps, 2 per SM, measured slower: 0.80 / 0.61 of the roofline against 0.81 on the config-2 stream)
+    static const int drain_env = getenv("PFV_DECODE_I_DRAIN") ? atoi(getenv("PFV_DECODE_I_DRAIN")) : 0;   // tuning aid
+    if (drain_env) return launch_decode_i_stream_t<4, 3, false>(P, d_jobs, njobs, s);
+    return launch_decode_i_stream_t<4, 3, true>(P, d_jobs, njobs, s);
 }
 
 }  // namespace pfv

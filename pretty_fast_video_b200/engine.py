@@ -87,6 +87,7 @@ class DecodeJob:
     hdr: Buf = None                # MbHdr[nb] as uint8[nb,4] / structured, P only
     out: Optional[Sequence[Buf]] = None   # (y, u, v) tight host planes
     device_ptrs: bool = False
+    dense_hint: bool = False       # PFV_JOB_DENSE: most sub-blocks carry AC terms (key frames; a hint, never changes results)
 
 
 @dataclass
@@ -170,7 +171,7 @@ class Engine:
         arr = (N.DecodeJob * len(jobs))()
         for a, j in zip(arr, jobs):
             a.kind, a.dst_slot, a.ref_slot = j.kind, j.dst_slot, j.ref_slot
-            a.flags = N.PFV_JOB_DEVICE_PTRS if j.device_ptrs else 0
+            a.flags = (N.PFV_JOB_DEVICE_PTRS if j.device_ptrs else 0) | (N.PFV_JOB_DENSE if j.dense_hint else 0)
             for p in range(3):
                 a.qidx[p] = int(j.qidx[p])
             a.hdr, a.coeff = _addr(j.hdr), _addr(j.coeff)
