@@ -217,6 +217,7 @@ struct pfv_ctx {
     int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "fused" (default: warp-specialised copy + residual in one kernel),
                                            // 1 "win" (window copy kernel + list-driven residual kernel), 2 "warp" (also used without TMA)
     int encode_i_variant = 0;              // PFV_ENCODE_I_VARIANT: 0 "stream" (default: thread per sub-block), 2 "warp"
+    int encode_p_variant = 0;              // PFV_ENCODE_P_VARIANT: 0 "strip" (default: warp per tile, column-strip search), 1 "v1" (warp per macroblock)
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
     CUtensorMap tm_luma{}, tm_chroma{};          // encode-P search window boxes
@@ -519,6 +520,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     if (const char *v = getenv("PFV_DECODE_I_VARIANT")) c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : 0);
     if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "win") == 0 ? 1 : 0);
     if (const char *v = getenv("PFV_ENCODE_I_VARIANT")) c->encode_i_variant = strcmp(v, "warp") == 0 ? 2 : 0;
+    if (const char *v = getenv("PFV_ENCODE_P_VARIANT")) c->encode_p_variant = strcmp(v, "v1") == 0 ? 1 : 0;
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
 
@@ -1302,7 +1304,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         c->launches++;
     }
     if (njobs - n_i) {
-        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->s_compute));
+        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->encode_p_variant, c->s_compute));
         c->launches++;
     }
     if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 2; }

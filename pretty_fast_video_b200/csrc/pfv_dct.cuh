@@ -56,13 +56,28 @@ PFV_HD void idct8(int (&v)[8])
     v[4] = a3 - a7; v[5] = a2 - a6; v[6] = a1 - a5; v[7] = a0 - a4;
 }
 
-PFV_HD void fdct8(int (&v)[8])
+// The forward transform only ever sees multiples of 256 ((p - 128) << 8, src/common.rs:291; (delta / 2) << 8, :304).  Every
+// term of the row pass is such a value divided by at most 16, so its divisions are EXACT and its outputs are multiples
+// of 16; the column pass divides those by at most 16 again: exact too.  An exact division needs no rounding toward
+// zero - a plain arithmetic shift is the quotient - which takes the sign extraction and the bias (18 of 66 instructions)
+// out of each of the 16 one-dimensional passes of a sub-block.  tests/test_hostmath.py compares with the oracle's
+// truncating divisions on extreme and random blocks.
+struct Xdiv {
+    int x;
+    PFV_HD explicit Xdiv(int v) : x(v) {}
+    PFV_HD int d2() const { return x >> 1; }
+    PFV_HD int d4() const { return x >> 2; }
+    PFV_HD int d16() const { return x >> 4; }
+};
+
+template <typename DIV>
+PFV_HD void fdct8_t(int (&v)[8])
 {
     const int a0 = v[0] + v[7], a1 = v[1] + v[6], a2 = v[2] + v[5], a3 = v[3] + v[4];
     const int a4 = v[0] - v[7], a5 = v[1] - v[6], a6 = v[2] - v[5], a7 = v[3] - v[4];
     const int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
     const int c0 = b0 + b1, c1 = b0 - b1;
-    const Tdiv t2(b2), t3(b3), t4(a4), t5(a5), t6(a6), t7(a7);
+    const DIV t2(b2), t3(b3), t4(a4), t5(a5), t6(a6), t7(a7);
     const int c2 = b2 + t2.d4() + t3.d2();
     const int c3 = t2.d2() - b3 - t3.d4();
     const int b4 = t7.d4() + a4 + t4.d4() - t4.d16();
@@ -73,6 +88,11 @@ PFV_HD void fdct8(int (&v)[8])
     v[0] = c0; v[1] = c4; v[2] = c2; v[3] = c5 - c7;
     v[4] = c1; v[5] = c5 + c7; v[6] = c3; v[7] = c6;
 }
+
+// src/dct.rs:176-239 for ANY input (truncating divisions)
+PFV_HD void fdct8(int (&v)[8]) { fdct8_t<Tdiv>(v); }
+// the same for inputs that are multiples of 256 (row pass) or of 16 (column pass): see Xdiv
+PFV_HD void fdct8_exact(int (&v)[8]) { fdct8_t<Xdiv>(v); }
 
 // src/dct.rs:44-47 ZIGZAG_TABLE: raster index of scan position s (used only with compile-time indices)
 #define PFV_ZIGZAG_INIT { \
@@ -117,7 +137,7 @@ PFV_UNROLL
     34, 39, 35, 28, 34, 28, 35, 39, \
     37, 43, 39, 31, 37, 31, 39, 43 }
 
-// rows then columns (src/common.rs:294-295 / :307-308)
+// rows then columns (src/common.rs:294-295 / :307-308); m = multiples of 256 (see Xdiv)
 PFV_HD void fdct8x8_regs(int (&m)[64])
 {
 PFV_UNROLL
@@ -125,7 +145,7 @@ PFV_UNROLL
         int v[8];
 PFV_UNROLL
         for (int c = 0; c < 8; ++c) v[c] = m[r * 8 + c];
-        fdct8(v);
+        fdct8_exact(v);
 PFV_UNROLL
         for (int c = 0; c < 8; ++c) m[r * 8 + c] = v[c];
     }
@@ -134,7 +154,7 @@ PFV_UNROLL
         int v[8];
 PFV_UNROLL
         for (int r = 0; r < 8; ++r) v[r] = m[r * 8 + c];
-        fdct8(v);
+        fdct8_exact(v);
 PFV_UNROLL
         for (int r = 0; r < 8; ++r) m[r * 8 + c] = v[r];
     }

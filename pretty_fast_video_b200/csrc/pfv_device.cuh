@@ -168,7 +168,7 @@ __device__ __forceinline__ uint4 encode_mb_core(WarpScratch &ws, int lane, const
                                                 int (&x)[8])
 {
     const int sb = lane >> 3, c = lane & 7;
-    fdct8(x);                                            // rows first, src/common.rs:294
+    fdct8_exact(x);                                           // rows first, src/common.rs:294
     int32_t *trow = &ws.t[sb * T_SB_STRIDE + c * T_ROW_STRIDE];
     *reinterpret_cast<int4 *>(trow)     = make_int4(x[0], x[1], x[2], x[3]);
     *reinterpret_cast<int4 *>(trow + 4) = make_int4(x[4], x[5], x[6], x[7]);
@@ -177,7 +177,7 @@ __device__ __forceinline__ uint4 encode_mb_core(WarpScratch &ws, int lane, const
     int v[8];
 #pragma unroll
     for (int row = 0; row < 8; ++row) v[row] = tcol[row * T_ROW_STRIDE];
-    fdct8(v);                                            // then columns, src/common.rs:295
+    fdct8_exact(v);                                           // then columns, src/common.rs:295
     char *cbase = reinterpret_cast<char *>(ws.coef);
 #pragma unroll
     for (int row = 0; row < 8; ++row) {

@@ -169,8 +169,9 @@ cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const u
 cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, bool count, cudaStream_t s);
+// variant 0: warp per tile, column-strip search (default); 1: first generation (CTA per tile, warp per macroblock)
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
-                            bool count, cudaStream_t s);
+                            bool count, int variant, cudaStream_t s);
 
 }  // namespace pfv

@@ -426,6 +426,310 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
 }
 
 // -------------------------------------------------------------------------------------------------
+// encode-P, second generation (the default): one WARP per tile of 8 macroblocks, column-strip search
+// -------------------------------------------------------------------------------------------------
+// ncu on encode_p_kernel: 749 warp instructions per macroblock, issue bound; ~400 of them the search (one warp per
+// macroblock, lane = (candidate, row quarter): every candidate row is loaded on its own, 16 loads + 32 SSD instructions
+// + a reduction per lane and level), ~55 the window re-pitch and the source-row shuffles, two CTA barriers per tile.
+//
+// Here a warp owns the whole tile and its own search window (ONE 176 x 46 TMA box per tile into a per-warp double
+// buffer: the next tile's window is in flight while this one is searched - no CTA barrier anywhere).  Lane = (macroblock
+// m = lane >> 2, column strip q = lane & 3): it keeps the 4-pixel-wide strip of its macroblock's 16 source rows in 16
+// registers and evaluates ALL 8 candidates of a level on that strip.  For a fixed horizontal offset the three vertical
+// candidates read the same window words 8 / 4 / 2 / 1 rows apart, so each loaded word feeds up to three candidates:
+// 96 / 72 / ~110 loads per lane and level for 8 candidates instead of 128, and per macroblock (4 lanes instead of 32) a
+// quarter of the instructions.  The 32 lanes of a load read 32 consecutive words of a window row (4 m + q): no bank
+// conflicts at the TMA box's own pitch, so the re-pitch pass is gone.  Strip sums meet by two xor-shuffles per
+// candidate; the winner is the minimum of (ssd << 3 | visiting index) as before (src/common.rs:154-204, strict `<`
+// of :189 = earliest candidate among equals).  Exact integer SSD (src/common.rs:125-139).
+//
+// Skipped macroblocks (src/common.rs:221-222) write their predictor strip straight to the reconstruction slot (full
+// 128-byte rows per warp store).  Coded ones (~15 %) go one at a time through the warp-wide transform of the first
+// generation (encode_mb_core / decode_mb_core: residual, FDCT + quantiser, closed-loop reconstruction).
+constexpr int EP2_WARPS = 12;                                 // one CTA per SM: 12 x (two 8 KB window stages + transform scratch) = 224 KB
+constexpr int EP2_MAX_JOBS = 64;
+constexpr int EP2_WIN_STAGE = (WIN_BYTES + 127) & ~127;
+
+struct __align__(128) Ep2Smem {
+    uint8_t     win[EP2_WARPS][2][EP2_WIN_STAGE];
+    WarpScratch scratch[EP2_WARPS];
+    uint64_t    bar[EP2_WARPS][2];
+    EncJob      job[EP2_MAX_JOBS];
+};
+static_assert(sizeof(Ep2Smem) + 1024 <= 227 * 1024, "the encode-P CTA must fit one SM");
+
+// 4 bytes at an arbitrary byte offset of a shared-memory window
+__device__ __forceinline__ uint32_t lds_u8x4_unaligned(const uint8_t *win, uint32_t off)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(win + (off & ~3u));
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t ssd4(uint32_t a, uint32_t b, uint32_t acc)
+{
+    const uint32_t d = __vabsdiffu4(a, b);
+    return __dp4a(d, d, acc);
+}
+
+// 4 source bytes (x .. x+3, y) of a tight vw x vh plane, padded with the clear colour (src/common.rs:352-356)
+__device__ __noinline__ uint32_t load_src4_ragged(const uint8_t *__restrict__ src, uint32_t vw, uint32_t vh, uint32_t clear4,
+                                                  uint32_t x, uint32_t y)
+{
+    if (y >= vh) return clear4;
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w |= ((x + k < vw) ? (uint32_t)src[(size_t)y * vw + x + k] : (clear4 & 0xffu)) << (8 * k);
+    return w;
+}
+
+// One search level (src/common.rs:165-196 for one step): S = this lane's source strip, `base` = byte offset in the
+// window of the strip's top-left pixel displaced by the current centre.  Returns the level's best key
+// (ssd << 3 | g), 0xffffffff if no candidate lies inside the plane.  ALIGNED: every candidate is word aligned.
+// The loop over the horizontal offset is NOT unrolled: straight-line code of this size runs at the speed of the
+// instruction fetch (ncu on the encode-I kernel: a quarter of all stall samples "no instruction"), a loop body of
+// ~150 instructions stays in the instruction cache.  For mx = 0 the middle candidate is the centre itself: it is
+// computed with the others (its key is discarded) so that the three passes share one body.
+template <int STEP, bool ALIGNED>
+__device__ __forceinline__ uint32_t search_level(const uint8_t *win, const uint32_t (&S)[16], uint32_t base, uint32_t valid_mask)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    uint32_t kmin = 0xffffffffu;
+    // candidates in the reference's visiting order: g = 0,1,2: my = -1 (mx = -1,0,1); 3,4: my = 0 (mx = -1, 1); 5,6,7: my = +1
+#pragma unroll 1
+    for (int mx = -1; mx <= 1; ++mx) {
+        uint32_t up = 0, mid = 0, dn = 0;
+        const uint32_t col = base + (uint32_t)(mx * STEP) - (uint32_t)(STEP * WIN_W);     // top row of the my = -1 candidate
+#pragma unroll
+        for (int rho = 0; rho < 16 + 2 * STEP; ++rho) {
+            const uint32_t off = col + (uint32_t)(rho * WIN_W);
+            const uint32_t w = ALIGNED ? *reinterpret_cast<const uint32_t *>(win + off) : lds_u8x4_unaligned(win, off);
+            if (rho < 16) up = ssd4(S[rho], w, up);
+            if (rho >= STEP && rho < 16 + STEP) mid = ssd4(S[rho - STEP], w, mid);
+            if (rho >= 2 * STEP) dn = ssd4(S[rho - 2 * STEP], w, dn);
+        }
+        up += __shfl_xor_sync(FULL, up, 1);
+        up += __shfl_xor_sync(FULL, up, 2);
+        mid += __shfl_xor_sync(FULL, mid, 1);
+        mid += __shfl_xor_sync(FULL, mid, 2);
+        dn += __shfl_xor_sync(FULL, dn, 1);
+        dn += __shfl_xor_sync(FULL, dn, 2);
+        const uint32_t g_up = (uint32_t)(mx + 1), g_mid = mx < 0 ? 3u : 4u, g_dn = (uint32_t)(mx + 6);
+        if ((valid_mask >> g_up) & 1u) kmin = min(kmin, (up << 3) | g_up);
+        if (mx != 0 && ((valid_mask >> g_mid) & 1u)) kmin = min(kmin, (mid << 3) | g_mid);
+        if ((valid_mask >> g_dn) & 1u) kmin = min(kmin, (dn << 3) | g_dn);
+    }
+    return kmin;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(EP2_WARPS * 32, 1)
+encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ jobs, uint32_t njobs,
+                 const QTables *__restrict__ qt, float rcp_tiles,
+                 const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
+{
+    extern __shared__ __align__(128) unsigned char ep2_raw[];
+    Ep2Smem &sm = *reinterpret_cast<Ep2Smem *>(ep2_raw);
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t i = threadIdx.x; i < njobs; i += EP2_WARPS * 32) sm.job[i] = jobs[i];
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp][0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp][1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t nitems = njobs * g.total_tiles;
+    const uint32_t stride = gridDim.x * EP2_WARPS;
+    const uint32_t m8 = lane >> 2, q = lane & 3u;
+    WarpScratch &ws = sm.scratch[warp];
+
+    struct Item { uint32_t job; int p; uint32_t trow; int tile_x0, by; };
+    auto item_of = [&](uint32_t it) {
+        Item r;
+        uint32_t tile;
+        r.job = div_small(it, g.total_tiles, rcp_tiles, tile);
+        r.p = (tile >= g.pl[1].tile_base ? 1 : 0) + (tile >= g.pl[2].tile_base ? 1 : 0);
+        const PlaneGeom &pl = plane_of(g, r.p);
+        const uint32_t lt = tile - pl.tile_base;
+        r.trow = lt / pl.tiles_per_row;
+        r.tile_x0 = (int)(lt - r.trow * pl.tiles_per_row) * 128;
+        r.by = (int)r.trow * 16;
+        return r;
+    };
+    auto issue = [&](const Item &it, uint32_t st) {              // lane 0: the tile's search window into stage st
+        const uint32_t bar_a = smem_u32(&sm.bar[warp][st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)WIN_BYTES) : "memory");
+        const CUtensorMap *tm = (it.p == 0) ? &tm_luma : &tm_chroma;
+        const int cx = it.tile_x0 - 16, cy = it.by - 15, cz = (it.p == 2) ? 1 : 0, cw = sm.job[it.job].ref_slot;
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(sm.win[warp][st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(bar_a)
+            : "memory");
+    };
+    // this lane's source strip of an item: bytes (bx + 4q .. +3, by + r), r = 0..15
+    auto load_strip = [&](const Item &it, uint32_t (&S)[16]) {
+        const PlaneGeom &pl = plane_of(g, it.p);
+        const EncJob &job = sm.job[it.job];
+        const uint8_t *src = it.p == 0 ? job.src[0] : (it.p == 1 ? job.src[1] : job.src[2]);
+        const uint32_t x = (uint32_t)it.tile_x0 + m8 * 16u + q * 4u;
+        const bool fast = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 3u) == 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const uint32_t y = (uint32_t)it.by + (uint32_t)r;
+            if (fast) S[r] = (y < pl.vh && x < pl.vw) ? __ldcs(reinterpret_cast<const uint32_t *>(src + (size_t)y * pl.vw + x)) : pl.clear4;
+            else      S[r] = load_src4_ragged(src, pl.vw, pl.vh, pl.clear4, x, y);
+        }
+    };
+
+    uint32_t it = blockIdx.x * EP2_WARPS + warp;
+    if (it >= nitems) return;
+    Item cur = item_of(it);
+    if (lane == 0) issue(cur, 0);
+    uint32_t S[16];
+    load_strip(cur, S);
+    uint32_t k = 0;
+#pragma unroll 1
+    for (; it < nitems; it += stride, ++k) {
+        const uint32_t st = k & 1u;
+        const bool has_next = it + stride < nitems;
+        Item nxt = cur;
+        if (has_next) {
+            nxt = item_of(it + stride);
+            if (lane == 0) issue(nxt, st ^ 1u);                   // that stage was released by the __syncwarp at the end of the previous tile
+        }
+        const PlaneGeom &pl = plane_of(g, cur.p);
+        const EncJob &job = sm.job[cur.job];
+        const uint8_t *win = sm.win[warp][st];
+        {
+            const uint32_t bar_a = smem_u32(&sm.bar[warp][st]);
+            const uint32_t parity = (k >> 1) & 1u;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
+            }
+        }
+        const int bx = cur.tile_x0 + (int)m8 * 16, by = cur.by;
+        const bool active = bx < (int)pl.pw;                      // ragged last tile of a row
+        const int max_x = (int)pl.pw - 16, max_y = (int)pl.ph - 16;
+        // window byte offset of this lane's strip at motion (0, 0)
+        const uint32_t o0 = (uint32_t)(15 * WIN_W + 16) + m8 * 16u + q * 4u;
+
+        // src/common.rs:154-204, iteratively; the centre's error at every level after the first is the previous winner's
+        int cx = 0, cy = 0;
+        uint32_t best;
+        {
+            uint32_t a = 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) a = ssd4(S[r], *reinterpret_cast<const uint32_t *>(win + o0 + r * WIN_W), a);
+            a += __shfl_xor_sync(FULL, a, 1);
+            a += __shfl_xor_sync(FULL, a, 2);
+            best = a;
+        }
+        auto valid_mask_of = [&](int step) {
+            uint32_t vm = 0;
+#pragma unroll
+            for (int gi = 0; gi < 8; ++gi) {
+                const int mx = (gi == 0 || gi == 3 || gi == 5) ? -1 : ((gi == 1 || gi == 6) ? 0 : 1);
+                const int my = gi < 3 ? -1 : (gi < 5 ? 0 : 1);
+                const int ox = bx + cx + mx * step, oy = by + cy + my * step;
+                vm |= (ox >= 0 && ox <= max_x && oy >= 0 && oy <= max_y) ? (1u << gi) : 0u;      // src/common.rs:171,182
+            }
+            return vm;
+        };
+        auto take = [&](uint32_t kmin, int step) {
+            if (kmin != 0xffffffffu && (kmin >> 3) < best) {        // strict, src/common.rs:189
+                best = kmin >> 3;
+                const uint32_t gi = kmin & 7u;
+                const int mx = (int)((0x9224u >> (2u * gi)) & 3u) - 1;   // mx + 1 = 0,1,2,0,2,0,1,2 for g = 0..7, two bits each
+                const int my = gi < 3u ? -1 : (gi < 5u ? 0 : 1);
+                cx += mx * step;
+                cy += my * step;
+            }
+        };
+        take(search_level<8, true>(win, S, o0, valid_mask_of(8)), 8);
+        take(search_level<4, true>(win, S, (uint32_t)((int)o0 + cy * WIN_W + cx), valid_mask_of(4)), 4);
+        take(search_level<2, false>(win, S, (uint32_t)((int)o0 + cy * WIN_W + cx), valid_mask_of(2)), 2);
+        take(search_level<1, false>(win, S, (uint32_t)((int)o0 + cy * WIN_W + cx), valid_mask_of(1)), 1);
+
+        const bool coded = active && !((float)best <= job.min_err);    // src/common.rs:221
+        const uint32_t m = pl.mb_base + cur.trow * pl.bw + (uint32_t)(bx >> 4);
+        if (active && q == 0) {
+            pfv_mbhdr h;
+            h.mx = (int8_t)cx;                                     // src/common.rs:222,235 `as i8`
+            h.my = (int8_t)cy;
+            h.has_coeff = coded ? 1 : 0;
+            h.reserved = 0;
+            job.hdr[m] = h;
+            if (COUNT && !coded) job.mb_cnt[m] = 0;                // subblocks: None (src/enc.rs:357-358)
+        }
+        // source strip of the next tile: in flight during the rest of this one
+        uint32_t Sn[16];
+        if (has_next) load_strip(nxt, Sn);
+
+        if (active && !coded) {                                    // the predictor is the reconstruction (src/common.rs:281-283)
+            const uint32_t po = (uint32_t)((int)o0 + cy * WIN_W + cx);
+            uint8_t *dst = job.dst + pl.off + (size_t)(uint32_t)by * pl.pw + (uint32_t)bx + q * 4u;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                *reinterpret_cast<uint32_t *>(dst + (size_t)r * pl.pw) = lds_u8x4_unaligned(win, po + (uint32_t)(r * WIN_W));
+        }
+        // coded macroblocks, one at a time, the whole warp on each (lane = (sub-block, row) as in pfv_device.cuh)
+        uint32_t todo = __ballot_sync(FULL, coded && q == 0);
+        if (todo) {
+            const int sbk = (int)(lane >> 3), r8 = (int)(lane & 7u);
+            const uint32_t py = (uint32_t)(sbk >> 1) * 8u + (uint32_t)r8, px = (uint32_t)(sbk & 1) * 8u;
+            uint32_t gaddr[8];
+            lane_gather_offsets((int)lane, gaddr);
+            const QTables *qq = qt + (cur.p == 0 ? 2 : 3);         // inter_l, inter_c (src/enc.rs:134-140)
+            uint32_t encM[8];
+            int32_t scale[8], deq[8];
+            lane_load8(reinterpret_cast<const int32_t *>(qq->encM), r8, reinterpret_cast<int32_t(&)[8]>(encM));
+            lane_load8(qq->deqT, r8, deq);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) scale[kk] = c_scaleT[r8 * 8 + kk];
+            const uint8_t *src = cur.p == 0 ? job.src[0] : (cur.p == 1 ? job.src[1] : job.src[2]);
+            const bool fast8 = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
+#pragma unroll 1
+            while (todo) {
+                const int l0 = __ffs((int)todo) - 1;
+                todo &= todo - 1u;
+                const int mcx = __shfl_sync(FULL, cx, l0), mcy = __shfl_sync(FULL, cy, l0);
+                const uint32_t mm = __shfl_sync(FULL, m, l0);
+                const int mbx = cur.tile_x0 + (l0 >> 2) * 16;
+                const uint2 s8 = load_src_row(src, pl, (uint32_t)mbx + px, (uint32_t)by + py, fast8);
+                const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((15 + (int)py + mcy) * WIN_W + 16 + (l0 >> 2) * 16 + (int)px + mcx));
+                int x[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int d = byte_of(s8, kk) - byte_of(prev, kk);   // src/common.rs:118-119 (|d| <= 255)
+                    x[kk] = (d / 2) * 256;                               // src/common.rs:304
+                }
+                const uint4 craw = encode_mb_core(ws, (int)lane, gaddr, encM, scale, x);
+                __stcs(reinterpret_cast<uint4 *>(job.coeff + (size_t)mm * 256) + lane, craw);
+                if (COUNT) {
+                    const uint32_t n = tok::warp_count(craw, lane);
+                    if (lane == 0) job.mb_cnt[mm] = n;
+                }
+                int y[8];
+                decode_mb_core(ws, (int)lane, gaddr, deq, y);
+                uint8_t *dst = job.dst + pl.off + (size_t)((uint32_t)by + py) * pl.pw + (uint32_t)mbx + px;
+                *reinterpret_cast<uint2 *>(dst) = apply_residual_row(y, prev);   // src/common.rs:277
+            }
+        }
+        __syncwarp();                                              // every lane is done with this window stage
+#pragma unroll
+        for (int r = 0; r < 16; ++r) S[r] = Sn[r];
+        cur = nxt;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------------
 constexpr int DEC_MPW = 2;
@@ -453,13 +757,35 @@ cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
 
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
-                            bool count, cudaStream_t s)
+                            bool count, int variant, cudaStream_t s)
 {
-    dim3 grid(g.total_tiles, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
-    // compiled for 4 resident CTAs per SM (64 registers): measured on 32 x 1080p 3: 77.5 k, 4: 84.8 k, 5: 81.5 k, 6: 83.2 k frames/s
-    if (count) encode_p_kernel<4, true><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
-    else       encode_p_kernel<4, false><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
-    return cudaGetLastError();
+    if (variant == 1) {
+        // first generation: one CTA per tile, one warp per macroblock; compiled for 4 resident CTAs per SM (64 registers):
+        // measured on 32 x 1080p 3: 77.5 k, 4: 84.8 k, 5: 81.5 k, 6: 83.2 k frames/s
+        dim3 grid(g.total_tiles, njobs, 1), block(WARPS_PER_CTA * 32, 1, 1);
+        if (count) encode_p_kernel<4, true><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
+        else       encode_p_kernel<4, false><<<grid, block, 0, s>>>(g, d_jobs, d_qt, tm_luma, tm_chroma);
+        return cudaGetLastError();
+    }
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
+    const int smem = (int)sizeof(Ep2Smem);
+    if (first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(encode_p2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_p2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    const float rcp_tiles = 1.0f / (float)g.total_tiles;
+    for (uint32_t j0 = 0; j0 < njobs; j0 += EP2_MAX_JOBS) {
+        const uint32_t n = njobs - j0 < (uint32_t)EP2_MAX_JOBS ? njobs - j0 : (uint32_t)EP2_MAX_JOBS;
+        const uint32_t items = n * g.total_tiles;
+        uint32_t ctas = (items + EP2_WARPS - 1) / EP2_WARPS;
+        if (ctas > 148u) ctas = 148u;
+        if (count) encode_p2_kernel<true><<<ctas, EP2_WARPS * 32, smem, s>>>(g, d_jobs + j0, n, d_qt, rcp_tiles, tm_luma, tm_chroma);
+        else       encode_p2_kernel<false><<<ctas, EP2_WARPS * 32, smem, s>>>(g, d_jobs + j0, n, d_qt, rcp_tiles, tm_luma, tm_chroma);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace pfv

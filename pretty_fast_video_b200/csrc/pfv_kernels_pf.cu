@@ -52,6 +52,16 @@ struct __align__(16) PfGroup {
 };
 
 constexpr int PF_MAX_JOBS = 64;                              // frames per launch (longer batches go out as several launches)
+constexpr int PF_MAX_ITEMS = 256;                            // windows one CTA walks per launch (its item table, below)
+
+// One window of a CTA's walk, decoded once at kernel start: the first version re-derived (frame, plane, window row, window
+// column) from the item index three times per window in every thread - ~150 of the copy half's ~370 instructions.
+struct __align__(16) PfItemRec {
+    uint32_t job_p;                                          // job | plane << 16 | macroblock rows in the window << 20 | columns << 24
+    uint32_t bx0_by0;                                        // pixel origin of the window's first macroblock: x | y << 16
+    uint32_t hdr0;                                           // index of that macroblock in the frame's header / coefficient arrays
+    uint32_t dst0;                                           // byte offset of its top-left pixel inside a frame slot
+};
 
 struct PfJob {                                               // what the kernel needs of a DecJob, kept in shared memory: every
     const int16_t  *coeff;                                   // field is read once per window, and a dependent global load per
@@ -64,6 +74,7 @@ struct PfJob {                                               // what the kernel 
 struct __align__(128) PfSmem {
     unsigned char win[PF_STAGES][PF_STAGE];
     PfGroup  grp[PF_NG];
+    PfItemRec item[PF_MAX_ITEMS];
     PfJob    job[PF_MAX_JOBS];
     int32_t  deq[3][64];
     uint64_t win_full[PF_STAGES];
@@ -73,6 +84,8 @@ struct __align__(128) PfSmem {
     volatile uint32_t total_groups;                          // 0xffffffff until the copy half is done
 };
 
+static_assert(2 * (sizeof(PfSmem) + 1024) <= 227 * 1024, "two CTAs of the fused decode-P kernel must fit one SM");
+
 __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
@@ -81,6 +94,18 @@ __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity)
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+
+// the same with a suspend-time hint (ns): an idle warp sleeps in the barrier unit instead of spinning through issue slots
+__device__ __forceinline__ bool bar_try_sleepy(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_addr(bar)), "r"(parity), "r"(ns) : "memory");
     return done != 0;
 }
 
@@ -133,9 +158,6 @@ __device__ __forceinline__ void unpack_dequant_smem(const uint4 (&raw)[8], const
     }
 }
 
-struct PfPos { uint32_t job, wi; };
-struct PfItem { uint32_t job, p, gy, tx; };
-
 __global__ void __launch_bounds__(PF_THREADS, 2)
 decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant__ McWin W, const DecJob *__restrict__ jobs,
                       uint32_t njobs, int *__restrict__ err,
@@ -161,6 +183,25 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         const DecJob &j = jobs[i];
         sm.job[i] = PfJob{j.coeff, reinterpret_cast<const uint32_t *>(j.hdr), j.dst, j.ref, j.ref_slot, 0};
     }
+    // this CTA's windows: items blockIdx.x, + gridDim.x, ... in frame-interleaved order (CTAs that run at the same time work
+    // on DIFFERENT frames): item -> (window index wi = item / njobs, job = item % njobs)
+    const uint32_t nmine = blockIdx.x < nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    for (uint32_t i = threadIdx.x; i < nmine; i += PF_THREADS) {
+        const uint32_t it = blockIdx.x + i * gridDim.x;
+        const uint32_t wi = it / njobs, job = it - wi * njobs;
+        const uint32_t p = (wi >= W.base[1] ? 1u : 0u) + (wi >= W.base[2] ? 1u : 0u);
+        const PlaneGeom &pl = p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]);
+        const uint32_t li = wi - (p == 0 ? W.base[0] : (p == 1 ? W.base[1] : W.base[2]));
+        const uint32_t txs = p == 0 ? W.tiles_x[0] : (p == 1 ? W.tiles_x[1] : W.tiles_x[2]);
+        const uint32_t gy = li / txs, tx = li - gy * txs;
+        const uint32_t rows = min((uint32_t)PF_ROWS, pl.bh - gy * PF_ROWS), cols = min(8u, pl.bw - tx * 8u);
+        PfItemRec r;
+        r.job_p = job | p << 16 | rows << 20 | cols << 24;
+        r.bx0_by0 = (tx * 128u) | (gy * (PF_ROWS * 16u)) << 16;
+        r.hdr0 = pl.mb_base + gy * PF_ROWS * pl.bw + tx * 8u;
+        r.dst0 = pl.off + gy * (PF_ROWS * 16u) * pl.pw + tx * 128u;
+        sm.item[i] = r;
+    }
     __syncthreads();
 
     auto plane = [&](uint32_t p) -> const PlaneGeom & { return p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]); };
@@ -172,9 +213,8 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         for (uint32_t G = warp - PF_ROWS;; G += PF_XF_WARPS) {
             const uint32_t rgp = G % PF_NG, par = (G / PF_NG) & 1u;
             bool stop = false;
-            while (!bar_try(&sm.grp_full[rgp], par)) {          // (try_wait itself suspends the warp for a while)
+            while (!bar_try_sleepy(&sm.grp_full[rgp], par, 2000u)) {
                 if (sm.total_groups <= G) { stop = true; break; }
-                __nanosleep(200);
             }
             if (stop) break;
             const PfGroup &grp = sm.grp[rgp];
@@ -212,71 +252,44 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
     }
 
     // ==================================== COPY half ====================================
-    const uint32_t G0 = gridDim.x;
-    const uint32_t dj = G0 % njobs, dw = G0 / njobs;
-    auto advance = [&](PfPos &q) {
-        q.job += dj; q.wi += dw;
-        if (q.job >= njobs) { q.job -= njobs; q.wi++; }
-    };
-    auto item_of = [&](const PfPos &q) {
-        // frame-interleaved order: CTAs that run at the same time work on DIFFERENT frames
-        PfItem r;
-        r.job = q.job;
-        r.p = (q.wi >= W.base[1] ? 1u : 0u) + (q.wi >= W.base[2] ? 1u : 0u);
-        const uint32_t li = q.wi - (r.p == 0 ? W.base[0] : (r.p == 1 ? W.base[1] : W.base[2]));
-        const uint32_t txs = r.p == 0 ? W.tiles_x[0] : (r.p == 1 ? W.tiles_x[1] : W.tiles_x[2]);
-        const float rcp = r.p == 0 ? W.rcp_tiles_x[0] : (r.p == 1 ? W.rcp_tiles_x[1] : W.rcp_tiles_x[2]);
-        r.gy = div_small(li, txs, rcp, r.tx);
-        return r;
-    };
-    auto issue = [&](const PfItem &it, uint32_t st) {          // thread 0 only
+    const uint32_t mb = lane >> 2, rg = lane & 3u;
+    auto issue = [&](const PfItemRec &it, uint32_t st) {       // thread 0 only
         bar_arrive_tx(&sm.win_full[st], (uint32_t)PF_WIN_BYTES);
-        const CUtensorMap *tm = it.p == 0 ? &tm_luma : &tm_chroma;
-        const int cx = (int)it.tx * 128 - 16, cy = (int)it.gy * (PF_ROWS * 16) - 15, cz = it.p == 2 ? 1 : 0, cw = sm.job[it.job].ref_slot;
+        const uint32_t p = (it.job_p >> 16) & 3u;
+        const CUtensorMap *tm = p == 0 ? &tm_luma : &tm_chroma;
+        const int cx = (int)(it.bx0_by0 & 0xffffu) - 16, cy = (int)(it.bx0_by0 >> 16) - 15, cz = p == 2 ? 1 : 0;
+        const int cw = sm.job[it.job_p & 0xffffu].ref_slot;
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3, %4, %5}], [%6];"
             ::"r"(smem_addr(sm.win[st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(smem_addr(&sm.win_full[st]))
             : "memory");
     };
-    const uint32_t mb = lane >> 2, rg = lane & 3u;
-    // header word of this lane's macroblock (row = gy*4 + warp, column = tx*8 + mb); bit 31 set = no such macroblock
-    auto load_hw = [&](const PfItem &it) -> uint32_t {
-        const PlaneGeom &pl = plane(it.p);
-        const uint32_t row = it.gy * PF_ROWS + warp, col = it.tx * 8u + mb;
-        if (row >= pl.bh || col >= pl.bw) return 0x80000000u;
-        return __ldg(sm.job[it.job].hdr + pl.mb_base + row * pl.bw + col);
+    // header word of this lane's macroblock (row `warp`, column `mb` of the window); bit 31 set = no such macroblock
+    auto load_hw = [&](const PfItemRec &it) -> uint32_t {
+        if (warp >= ((it.job_p >> 20) & 15u) || mb >= (it.job_p >> 24)) return 0x80000000u;
+        return __ldg(sm.job[it.job_p & 0xffffu].hdr + it.hdr0 + warp * plane((it.job_p >> 16) & 3u).bw + mb);
     };
 
     // Software pipeline over windows k (being copied), k+1 and k+2 (TMA in flight, headers loaded) and k+3 (TMA issued at the
     // end of iteration k): no load is consumed in the iteration that issues it.
-    uint32_t it = blockIdx.x;
-    PfPos pc, pn, pt;
-    pc.wi = it / njobs;
-    pc.job = it - pc.wi * njobs;
-    pn = pc; advance(pn);                                       // window k+1, then k+2 (the header two windows ahead)
-    pt = pc;
+    if (threadIdx.x == 0)
+        for (uint32_t s = 0; s < (uint32_t)PF_STAGES && s < nmine; ++s) issue(sm.item[s], s);
+    uint32_t hw_cur = nmine > 0 ? load_hw(sm.item[0]) : 0x80000000u;
+    uint32_t hw_n1 = nmine > 1 ? load_hw(sm.item[1]) : 0x80000000u;
 #pragma unroll 1
-    for (uint32_t s = 0; s < (uint32_t)PF_STAGES; ++s) {
-        if (threadIdx.x == 0 && it + s * G0 < nitems) issue(item_of(pt), s);
-        advance(pt);
-    }
-    uint32_t hw_cur = it < nitems ? load_hw(item_of(pc)) : 0x80000000u;
-    uint32_t hw_n1 = it + G0 < nitems ? load_hw(item_of(pn)) : 0x80000000u;
-    advance(pn);
-    uint32_t k = 0;
-#pragma unroll 1
-    for (; it < nitems; it += G0, ++k) {
+    for (uint32_t k = 0; k < nmine; ++k) {
         const uint32_t st = k % PF_STAGES;
-        const PfItem cur = item_of(pc);
+        const PfItemRec cur = sm.item[k];
         uint32_t hw_n2 = 0x80000000u;
-        if (it + 2u * G0 < nitems) hw_n2 = load_hw(item_of(pn));
+        if (k + 2u < nmine) hw_n2 = load_hw(sm.item[k + 2u]);
 
-        const PlaneGeom &pl = plane(cur.p);
-        const PfJob &job = sm.job[cur.job];
+        const uint32_t cjob = cur.job_p & 0xffffu, cp = (cur.job_p >> 16) & 3u;
+        const PlaneGeom &pl = plane(cp);
+        const PfJob &job = sm.job[cjob];
         const bool exists = !(hw_cur & 0x80000000u);
         const bool coded = exists && ((hw_cur >> 16) & 0xffu) != 0u;
-        const int bx = (int)(cur.tx * 8u + mb) * 16, by = (int)(cur.gy * PF_ROWS + warp) * 16;
+        const int bx = (int)((cur.bx0_by0 & 0xffffu) + mb * 16u), by = (int)((cur.bx0_by0 >> 16) + warp * 16u);
         int mvx = (int)(int8_t)(hw_cur & 0xffu), mvy = (int)(int8_t)((hw_cur >> 8) & 0xffu);   // src/common.rs:255-256
         if (exists) {
             const int sx = bx + mvx, sy = by + mvy;
@@ -299,12 +312,12 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         if (coded) bar_wait(&sm.grp_empty[rgp], ((e / PF_RING_MB) & 1u) ^ 1u);   // the slot's previous tenant has been taken out
 
         bar_wait(&sm.win_full[st], (k / PF_STAGES) & 1u);
+        const uint32_t mb_off = cur.dst0 + warp * 16u * pl.pw + mb * 16u;        // this macroblock's top-left pixel in a frame slot
         if (exists) {
-            uint8_t *dst = job.dst + pl.off + (size_t)((uint32_t)by + rg) * pl.pw + (uint32_t)bx;
+            uint8_t *dst = job.dst + mb_off + (size_t)rg * pl.pw;
             const bool in_window = mvx >= -16 && mvx <= 15 && mvy >= -15 && mvy <= 15;
             // Vectors beyond +-15 are legal for the reference decoder (7-bit vectors, src/dec.rs:367-368) but outside the
             // staged window - its own encoder never searches further (src/common.rs:154-204).  Rare: fetch from global.
-            const uint8_t *gsrc = job.ref + pl.off + (size_t)((uint32_t)(by + mvy) + rg) * pl.pw + (uint32_t)(bx + mvx);
             const uint32_t wx = (uint32_t)(16 + (int)mb * 16 + mvx), wy = (uint32_t)(15 + (int)warp * 16 + mvy) + rg;
             const unsigned char *wrow = sm.win[st] + wy * PF_WIN_W;
 #pragma unroll
@@ -313,8 +326,9 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
                 if (in_window) {
                     o = win_row16(wrow + i * 4 * PF_WIN_W, wx);
                 } else {
-                    const uint2 a = ldg_u8x8_unaligned(gsrc + (size_t)(4 * i) * pl.pw);
-                    const uint2 b = ldg_u8x8_unaligned(gsrc + (size_t)(4 * i) * pl.pw + 8);
+                    const uint8_t *gsrc = job.ref + pl.off + (size_t)((uint32_t)(by + mvy) + rg + 4u * (uint32_t)i) * pl.pw + (uint32_t)(bx + mvx);
+                    const uint2 a = ldg_u8x8_unaligned(gsrc);
+                    const uint2 b = ldg_u8x8_unaligned(gsrc + 8);
                     o = make_uint4(a.x, a.y, b.x, b.y);
                 }
                 if (coded) {
@@ -328,18 +342,14 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
                 }
             }
         }
-        if (coded && rg == 0)
-            grp.id[sj] = make_uint4(pl.off + (uint32_t)by * pl.pw + (uint32_t)bx, cur.job, cur.p, 1u);
+        if (coded && rg == 0) grp.id[sj] = make_uint4(mb_off, cjob, cp, 1u);
         __syncwarp();                                           // the four lanes of a macroblock have written its predictor
-        if (coded && rg == 0) bar_arrive_tx(&sm.grp_full[rgp], 512u);
         if (coded && rg == 0) {
-            const uint32_t lm = (cur.gy * PF_ROWS + warp) * pl.bw + cur.tx * 8u + mb;
-            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(pl.mb_base + lm) * 256, 512u, &sm.grp_full[rgp]);
+            bar_arrive_tx(&sm.grp_full[rgp], 512u);
+            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(cur.hdr0 + warp * pl.bw + mb) * 256, 512u, &sm.grp_full[rgp]);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(PF_ROWS * 32) : "memory");   // the copy half is done with this window stage
-        if (threadIdx.x == 0 && it + PF_STAGES * G0 < nitems) issue(item_of(pt), st);
-        advance(pt);
-        advance(pc); advance(pn);
+        if (threadIdx.x == 0 && k + PF_STAGES < nmine) issue(sm.item[k + PF_STAGES], st);
         hw_cur = hw_n1; hw_n1 = hw_n2;
     }
 
@@ -369,10 +379,14 @@ cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint3
         if (e != cudaSuccess) return e;
     }
     const McWin W = make_mc_windows(P.g, PF_ROWS);
-    for (uint32_t j0 = 0; j0 < njobs; j0 += PF_MAX_JOBS) {
-        const uint32_t n = njobs - j0 < (uint32_t)PF_MAX_JOBS ? njobs - j0 : (uint32_t)PF_MAX_JOBS;
+    // frames per launch: at most PF_MAX_JOBS, and no more than lets every CTA's item table hold its share of the windows
+    uint32_t per_launch = (uint32_t)(((uint64_t)PF_MAX_ITEMS * 148u * 2u) / W.total);
+    per_launch = per_launch < 1u ? 1u : (per_launch > (uint32_t)PF_MAX_JOBS ? (uint32_t)PF_MAX_JOBS : per_launch);
+    for (uint32_t j0 = 0; j0 < njobs; j0 += per_launch) {
+        const uint32_t n = njobs - j0 < per_launch ? njobs - j0 : per_launch;
         uint32_t ctas = n * W.total;
         if (ctas > 148u * 2u) ctas = 148u * 2u;
+        if ((n * W.total + ctas - 1) / ctas > (uint32_t)PF_MAX_ITEMS) return cudaErrorInvalidConfiguration;   // (a frame of > 150 000 windows)
         decode_p_fused_kernel<<<ctas, PF_THREADS, smem, s>>>(P, W, d_jobs + j0, n, d_err, tm_luma, tm_chroma);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -340,6 +340,19 @@ def test_encode_i_kernel_variants_agree(ivar, monkeypatch):
             assert np.array_equal(e.slot_read(i), prev)
 
 
+@pytest.mark.parametrize("pvar", ["strip", "v1"])
+def test_encode_p_kernel_variants_agree(pvar, monkeypatch):
+    """PFV_ENCODE_P_VARIANT: the warp-per-tile column-strip search (default) and the first-generation warp-per-macroblock
+    kernel give the oracle's motion vectors, skip decisions, coefficients and reconstruction - ragged sizes, every content
+    kind, and a batch of dependent submits."""
+    monkeypatch.setenv("PFV_ENCODE_P_VARIANT", pvar)
+    test_encode_pframe_matches_oracle((50, 38), 2, "moving")
+    test_encode_pframe_matches_oracle((512, 384), 5, "moving")
+    test_encode_pframe_matches_oracle((512, 384), 5, "random")
+    test_encode_pframe_matches_oracle((64, 48), 5, "static")
+    test_encode_pframe_matches_oracle((1918, 1080), 0, "moving")
+
+
 def test_encode_rejects_zero_divisors():
     """The reference's quantiser divides by the table entry (src/dct.rs:95: a zero would panic); Encoder::new clamps its
     tables to >= 1 (src/enc.rs:48-51).  A context with a zero divisor in tables 0..3 decodes, but refuses to encode."""
