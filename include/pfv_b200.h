@@ -315,6 +315,11 @@ typedef struct pfv_decoder pfv_decoder;
  * 0 picks a default.  The decoded pictures are identical for any value. */
 int  pfv_decoder_open(const uint8_t *data, size_t len, int device, uint32_t num_threads, uint32_t read_ahead,
                       pfv_decoder **out);
+/* The same for a caller that holds a reader (Decoder<R: Read + Seek>, src/dec.rs:15-28) instead of a byte range: `read`
+ * is called until it returns 0 (end of stream; < 0 = error -> PFV_ERR_IO) and the decoder keeps the bytes. */
+typedef long long (*pfv_read_fn)(void *user, uint8_t *buf, size_t cap);
+int  pfv_decoder_open_reader(pfv_read_fn read, void *user, int device, uint32_t num_threads, uint32_t read_ahead,
+                             pfv_decoder **out);
 void pfv_decoder_close(pfv_decoder *d);
 uint32_t pfv_decoder_width(const pfv_decoder *d);        /* src/dec.rs:136 */
 uint32_t pfv_decoder_height(const pfv_decoder *d);       /* src/dec.rs:140 */
@@ -340,6 +345,12 @@ typedef struct pfv_encoder pfv_encoder;
 int  pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framerate, int quality, uint32_t num_threads,
                       int device, pfv_encoder **out);
 void pfv_encoder_close(pfv_encoder *e);                  /* Drop: finishes the stream if finish() was not called */
+/* Encoder<W: Write> (src/enc.rs:12-26): hand the stream to a writer instead of keeping it in memory.  Call right after
+ * pfv_encoder_open: the header goes out at once, every packet as soon as it is finished, in stream order, from the thread
+ * that calls encode_* / finish / close.  The callback returns 0, or non-zero for an I/O error (-> PFV_ERR_IO).  With a
+ * writer set pfv_encoder_bytes returns an empty range. */
+typedef int (*pfv_write_fn)(void *user, const uint8_t *data, size_t len);
+int  pfv_encoder_set_writer(pfv_encoder *e, pfv_write_fn writer, void *user);
 /* src/enc.rs:75-123 / :125-173.  y,u,v: tight planes w*h, w/2*h/2, w/2*h/2 (VideoFrame); read before return. */
 int  pfv_encoder_encode_iframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v);
 int  pfv_encoder_encode_pframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v);

@@ -96,6 +96,8 @@ class Packet(C.Structure):
 
 
 ONVIDEO = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+READ_FN = C.CFUNCTYPE(C.c_longlong, C.c_void_p, C.c_void_p, C.c_size_t)      # pfv_read_fn
+WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)          # pfv_write_fn
 
 # every symbol include/pfv_b200.h declares: name -> (restype, argtypes)
 _QT = C.POINTER(C.c_int32 * 64)
@@ -142,6 +144,7 @@ SYMBOLS = {
                                       C.c_void_p, C.c_void_p]),
     "pfv_packet_token_bound": (C.c_uint32, [C.POINTER(Geometry), C.c_void_p, C.c_size_t]),
     "pfv_decoder_open": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "pfv_decoder_open_reader": (C.c_int, [READ_FN, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "pfv_decoder_close": (None, [C.c_void_p]),
     "pfv_decoder_width": (C.c_uint32, [C.c_void_p]),
     "pfv_decoder_height": (C.c_uint32, [C.c_void_p]),
@@ -154,6 +157,7 @@ SYMBOLS = {
     "pfv_decoder_framebuffer_slot": (C.c_uint32, [C.c_void_p]),
     "pfv_encoder_open": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
     "pfv_encoder_close": (None, [C.c_void_p]),
+    "pfv_encoder_set_writer": (C.c_int, [C.c_void_p, WRITE_FN, C.c_void_p]),
     "pfv_encoder_encode_iframe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfv_encoder_encode_pframe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfv_encoder_encode_dropframe": (C.c_int, [C.c_void_p]),

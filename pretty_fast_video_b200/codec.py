@@ -141,11 +141,27 @@ Frame = Tuple[np.ndarray, np.ndarray, np.ndarray]
 
 
 class Decoder:
-    def __init__(self, data: bytes, num_threads: int = 1, device: int = 0, read_ahead: int = 0):
-        self._buf = np.frombuffer(data, np.uint8)          # the reader; must outlive the native decoder
+    """pfv_rs::dec::Decoder<R> (src/dec.rs:15-224).  `data` is the reader R: bytes-like, or any object with a
+    read(n) method (a file, a socket wrapper, io.BytesIO ...), which is then drained through pfv_decoder_open_reader."""
+
+    def __init__(self, data, num_threads: int = 1, device: int = 0, read_ahead: int = 0):
         self._d = C.c_void_p()
-        _check_dec(N.lib().pfv_decoder_open(self._buf.ctypes.data, self._buf.size, device, num_threads, read_ahead,
-                                            C.byref(self._d)))
+        if hasattr(data, "read"):
+            def _read(user, buf, cap):
+                try:
+                    chunk = data.read(min(int(cap), 1 << 20))
+                except Exception:
+                    return -1
+                if not chunk:
+                    return 0
+                C.memmove(buf, chunk, len(chunk))
+                return len(chunk)
+            cb = N.READ_FN(_read)
+            _check_dec(N.lib().pfv_decoder_open_reader(cb, None, device, num_threads, read_ahead, C.byref(self._d)))
+        else:
+            self._buf = np.frombuffer(data, np.uint8)      # the reader; must outlive the native decoder
+            _check_dec(N.lib().pfv_decoder_open(self._buf.ctypes.data, self._buf.size, device, num_threads, read_ahead,
+                                                C.byref(self._d)))
         self._w, self._h = self.width(), self.height()
         self._cache = {}
         self._got, self._y, self._u, self._v = C.c_int(), C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -218,10 +234,24 @@ class Decoder:
 
 # ---- Encoder -------------------------------------------------------------------------------------------
 class Encoder:
-    def __init__(self, width: int, height: int, framerate: int, quality: int, num_threads: int = 1, device: int = 0):
+    """pfv_rs::enc::Encoder<W> (src/enc.rs:12-188).  `writer` is W: any object with a write(bytes) method; packets reach it in
+    stream order as soon as they are finished.  Without one the stream is kept in memory (bytes())."""
+
+    def __init__(self, width: int, height: int, framerate: int, quality: int, num_threads: int = 1, device: int = 0,
+                 writer=None):
         self._e = C.c_void_p()
         N.check(N.lib().pfv_encoder_open(width, height, framerate, quality, num_threads, device, C.byref(self._e)))
         self._w, self._h = width, height
+        self._wcb = None
+        if writer is not None:
+            def _write(user, data, n):
+                try:
+                    writer.write(C.string_at(data, n))
+                    return 0
+                except Exception:
+                    return 1
+            self._wcb = N.WRITE_FN(_write)                  # must outlive the native encoder
+            N.check(N.lib().pfv_encoder_set_writer(self._e, self._wcb, None))
 
     def _planes(self, frame):
         y, u, v = (np.ascontiguousarray(p, np.uint8) for p in frame)

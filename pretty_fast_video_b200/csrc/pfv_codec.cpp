@@ -642,6 +642,7 @@ struct DecWork {
 struct pfv_decoder {
     const uint8_t *data = nullptr;
     size_t len = 0;
+    std::vector<uint8_t> owned;                       // pfv_decoder_open_reader: the stream as it came out of the caller's reader
     pfv_stream_info info{};
     pfv_geometry geo{};
     std::vector<pfv_packet> packets;
@@ -808,6 +809,31 @@ static int decoder_submit_ready(pfv_decoder *d, DecWork *must)
         }
         if (!must) break;                                           // one batch per call unless the needed picture is still behind
     }
+    return PFV_OK;
+}
+
+// Decoder<R: Read + Seek> (src/dec.rs:15-28) for a caller that has a reader instead of a byte range: the reader is drained
+// once (the packet index and the read-ahead pipeline work on the whole stream) and the decoder owns the bytes.
+extern "C" int pfv_decoder_open_reader(pfv_read_fn read, void *user, int device, uint32_t num_threads, uint32_t read_ahead, pfv_decoder **out)
+{
+    if (!out) return set_error(PFV_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (!read) return set_error(PFV_ERR_BAD_ARG, "read is NULL");
+    std::vector<uint8_t> buf;
+    size_t have = 0;
+    for (;;) {
+        if (buf.size() < have + ((size_t)1 << 20)) buf.resize(std::max(buf.size() * 2, have + ((size_t)1 << 20)));
+        const long long n = read(user, buf.data() + have, buf.size() - have);
+        if (n < 0) return set_error(PFV_ERR_IO, "the reader callback failed (io::Error of R::read)");
+        if (n == 0) break;
+        have += (size_t)n;
+    }
+    buf.resize(have);
+    int rc = pfv_decoder_open(buf.data(), buf.size(), device, num_threads, read_ahead, out);
+    if (rc) return rc;
+    // std::vector's move keeps the heap block: the decoder's data pointer stays valid
+    (*out)->owned = std::move(buf);
+    (*out)->data = (*out)->owned.data();
     return PFV_OK;
 }
 
@@ -1045,7 +1071,9 @@ struct pfv_encoder {
     std::mutex m;
     std::condition_variable cv;
     std::deque<std::shared_ptr<OutPacket>> pending;   // packets in stream order, not yet appended to `stream`
-    std::vector<uint8_t> stream;                      // the writer W
+    std::vector<uint8_t> stream;                      // the writer W (when no callback is set)
+    pfv_write_fn writer = nullptr;                    // pfv_encoder_set_writer: packets leave through it as soon as they are finished
+    void *writer_user = nullptr;
     uint32_t prev_slot = 0;
     bool finished = false;
     bool dense = false;            // PFV_ENCODER_DENSE=1: the dense seam (pfv_encode_submit + host run-length pass)
@@ -1111,7 +1139,13 @@ static int encoder_flush(pfv_encoder *e, bool wait_all)
         if (p->status != PFV_OK && rc == PFV_OK) rc = set_error(p->status, "%s", p->err);
         add += p->work ? p->work->packet.size() : p->bytes.size();
     }
-    if (rc == PFV_OK) {
+    if (rc == PFV_OK && e->writer) {
+        for (auto &p : ready) {
+            const std::vector<uint8_t> &b = p->work ? p->work->packet : p->bytes;
+            if (!b.empty() && e->writer(e->writer_user, b.data(), b.size()) != 0 && rc == PFV_OK)
+                rc = set_error(PFV_ERR_IO, "the writer callback failed (io::Error of W::write_all)");
+        }
+    } else if (rc == PFV_OK) {
         if (e->stream.size() + add > e->stream.capacity())
             e->stream.reserve(std::max(e->stream.capacity() * 2, e->stream.size() + add + ((size_t)1 << 20)));
         for (auto &p : ready) {
@@ -1299,6 +1333,21 @@ extern "C" int pfv_encoder_finish(pfv_encoder *e)
     e->finished = true;
     encoder_literal_packet(e, 0);                                    // write_eof, src/enc.rs:221-227
     return encoder_flush(e, true);
+}
+
+// Encoder<W: Write> (src/enc.rs:12-26): what has been written so far (the header) goes out at once, every later packet as
+// soon as it is finished and in order.
+extern "C" int pfv_encoder_set_writer(pfv_encoder *e, pfv_write_fn writer, void *user)
+{
+    if (!e || !writer) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
+    int rc = encoder_flush(e, true);
+    if (rc) return rc;
+    if (!e->stream.empty() && writer(user, e->stream.data(), e->stream.size()) != 0)
+        return set_error(PFV_ERR_IO, "the writer callback failed (io::Error of W::write_all)");
+    e->stream.clear();
+    e->writer = writer;
+    e->writer_user = user;
+    return PFV_OK;
 }
 
 extern "C" int pfv_encoder_bytes(pfv_encoder *e, const uint8_t **data, size_t *len)

@@ -32,18 +32,21 @@
 
 namespace pfv {
 
-constexpr int PF_ROWS = 4;                                   // macroblock rows per window = copy warps
+constexpr int PF_ROWS = 4;                                   // macroblock rows per window = warps per copy pipeline
 constexpr int PF_WIN_W = 176;                                // 16 + 8*16 + 15, rounded up to 16
 constexpr int PF_WIN_H = PF_ROWS * 16 + 30;
 constexpr int PF_WIN_BYTES = PF_WIN_W * PF_WIN_H;            // 16 544
 constexpr int PF_STAGE = (PF_WIN_BYTES + 127) & ~127;
-constexpr int PF_STAGES = 3;
-constexpr int PF_NG = 8;                                     // ring groups
-constexpr int PF_RING_MB = PF_NG * 8;                        // ring slots (macroblocks)
+constexpr int PF_PIPES = 3;                                  // independent copy pipelines per CTA (each: 4 warps, its own windows)
+constexpr int PF_STAGES = 2;                                 // windows in flight per pipeline
+constexpr int PF_COPY_WARPS = PF_PIPES * PF_ROWS;
+constexpr int PF_NG = 16;                                    // ring groups; the ring must hold more macroblocks (128) than the
+constexpr int PF_RING_MB = PF_NG * 8;                        // pipelines can have unfinished at once (3 x 32): see the empty-wait
 constexpr int PF_COEF_PITCH = 528;                           // bytes per slot: 512 + 16 (8 slots -> 8 different bank groups)
 constexpr int PF_PRED_PITCH = 80;                            // bytes per sub-block: 64 + 16
 constexpr int PF_XF_WARPS = 4;
-constexpr int PF_THREADS = (PF_ROWS + PF_XF_WARPS) * 32;
+constexpr int PF_THREADS = (PF_COPY_WARPS + PF_XF_WARPS) * 32;
+constexpr int PF_CTAS_PER_SM = 1;
 
 struct __align__(16) PfGroup {
     unsigned char coef[8 * PF_COEF_PITCH];
@@ -52,7 +55,7 @@ struct __align__(16) PfGroup {
 };
 
 constexpr int PF_MAX_JOBS = 64;                              // frames per launch (longer batches go out as several launches)
-constexpr int PF_MAX_ITEMS = 256;                            // windows one CTA walks per launch (its item table, below)
+constexpr int PF_PIPE_ITEMS = 84;                            // windows one pipeline walks per launch (its slice of the item table)
 
 // One window of a CTA's walk, decoded once at kernel start: the first version re-derived (frame, plane, window row, window
 // column) from the item index three times per window in every thread - ~150 of the copy half's ~370 instructions.
@@ -72,19 +75,20 @@ struct PfJob {                                               // what the kernel 
 };
 
 struct __align__(128) PfSmem {
-    unsigned char win[PF_STAGES][PF_STAGE];
+    unsigned char win[PF_PIPES][PF_STAGES][PF_STAGE];
     PfGroup  grp[PF_NG];
-    PfItemRec item[PF_MAX_ITEMS];
+    PfItemRec item[PF_PIPES][PF_PIPE_ITEMS];
     PfJob    job[PF_MAX_JOBS];
     int32_t  deq[3][64];
-    uint64_t win_full[PF_STAGES];
+    uint64_t win_full[PF_PIPES][PF_STAGES];
     uint64_t grp_full[PF_NG];                                // 8 arrivals (one per slot) + the slots' coefficient bytes
     uint64_t grp_empty[PF_NG];                               // the transform warp has taken the group into registers
     uint32_t tail;                                           // ring slots handed out so far
     volatile uint32_t total_groups;                          // 0xffffffff until the copy half is done
 };
 
-static_assert(2 * (sizeof(PfSmem) + 1024) <= 227 * 1024, "two CTAs of the fused decode-P kernel must fit one SM");
+static_assert(PF_CTAS_PER_SM * (sizeof(PfSmem) + 1024) <= 227 * 1024, "the fused decode-P kernel's CTAs must fit one SM");
+static_assert(PF_RING_MB > PF_PIPES * 32, "the ring must be larger than what the copy pipelines can have unfinished at once");
 
 __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity)
 {
@@ -158,7 +162,7 @@ __device__ __forceinline__ void unpack_dequant_smem(const uint4 (&raw)[8], const
     }
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 2)
+__global__ void __launch_bounds__(PF_THREADS, PF_CTAS_PER_SM)
 decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant__ McWin W, const DecJob *__restrict__ jobs,
                       uint32_t njobs, int *__restrict__ err,
                       const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
@@ -171,7 +175,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < PF_STAGES; ++s) bar_init(&sm.win_full[s], 1);
+        for (int s = 0; s < PF_PIPES * PF_STAGES; ++s) bar_init(&sm.win_full[0][0] + s, 1);
 #pragma unroll
         for (int s = 0; s < PF_NG; ++s) { bar_init(&sm.grp_full[s], 8); bar_init(&sm.grp_empty[s], 1); }
         sm.tail = 0;
@@ -183,11 +187,14 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         const DecJob &j = jobs[i];
         sm.job[i] = PfJob{j.coeff, reinterpret_cast<const uint32_t *>(j.hdr), j.dst, j.ref, j.ref_slot, 0};
     }
-    // this CTA's windows: items blockIdx.x, + gridDim.x, ... in frame-interleaved order (CTAs that run at the same time work
-    // on DIFFERENT frames): item -> (window index wi = item / njobs, job = item % njobs)
-    const uint32_t nmine = blockIdx.x < nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-    for (uint32_t i = threadIdx.x; i < nmine; i += PF_THREADS) {
-        const uint32_t it = blockIdx.x + i * gridDim.x;
+    // The windows of the launch are dealt out to the copy pipelines (3 per CTA) in frame-interleaved order (pipelines that run at
+    // the same time work on DIFFERENT frames): pipeline gp takes items gp, gp + npipes, ...; item -> (window wi = item / njobs,
+    // job = item % njobs)
+    const uint32_t npipes = gridDim.x * PF_PIPES;
+    for (uint32_t t = threadIdx.x; t < (uint32_t)(PF_PIPES * PF_PIPE_ITEMS); t += PF_THREADS) {
+        const uint32_t pipe = t / PF_PIPE_ITEMS, i = t - pipe * PF_PIPE_ITEMS;
+        const uint32_t it = blockIdx.x * PF_PIPES + pipe + i * npipes;
+        if (it >= nitems) continue;
         const uint32_t wi = it / njobs, job = it - wi * njobs;
         const uint32_t p = (wi >= W.base[1] ? 1u : 0u) + (wi >= W.base[2] ? 1u : 0u);
         const PlaneGeom &pl = p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]);
@@ -200,17 +207,17 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         r.bx0_by0 = (tx * 128u) | (gy * (PF_ROWS * 16u)) << 16;
         r.hdr0 = pl.mb_base + gy * PF_ROWS * pl.bw + tx * 8u;
         r.dst0 = pl.off + gy * (PF_ROWS * 16u) * pl.pw + tx * 128u;
-        sm.item[i] = r;
+        sm.item[pipe][i] = r;
     }
     __syncthreads();
 
     auto plane = [&](uint32_t p) -> const PlaneGeom & { return p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]); };
 
-    if (warp >= PF_ROWS) {
+    if (warp >= PF_COPY_WARPS) {
         // ================================ TRANSFORM half ================================
         const uint32_t sb = lane >> 3, sj = lane & 7u;
 #pragma unroll 1
-        for (uint32_t G = warp - PF_ROWS;; G += PF_XF_WARPS) {
+        for (uint32_t G = warp - PF_COPY_WARPS;; G += PF_XF_WARPS) {
             const uint32_t rgp = G % PF_NG, par = (G / PF_NG) & 1u;
             bool stop = false;
             while (!bar_try_sleepy(&sm.grp_full[rgp], par, 2000u)) {
@@ -252,9 +259,14 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
     }
 
     // ==================================== COPY half ====================================
+    const uint32_t pipe = warp / PF_ROWS, wrow = warp % PF_ROWS;           // this warp's pipeline and its macroblock row of the window
     const uint32_t mb = lane >> 2, rg = lane & 3u;
-    auto issue = [&](const PfItemRec &it, uint32_t st) {       // thread 0 only
-        bar_arrive_tx(&sm.win_full[st], (uint32_t)PF_WIN_BYTES);
+    const uint32_t gp = blockIdx.x * PF_PIPES + pipe;
+    const uint32_t nmine = gp < nitems ? min((uint32_t)PF_PIPE_ITEMS, (nitems - gp + npipes - 1) / npipes) : 0u;
+    const PfItemRec *items = sm.item[pipe];
+    const bool leader = wrow == 0 && lane == 0;
+    auto issue = [&](const PfItemRec &it, uint32_t st) {       // the pipeline's leader only
+        bar_arrive_tx(&sm.win_full[pipe][st], (uint32_t)PF_WIN_BYTES);
         const uint32_t p = (it.job_p >> 16) & 3u;
         const CUtensorMap *tm = p == 0 ? &tm_luma : &tm_chroma;
         const int cx = (int)(it.bx0_by0 & 0xffffu) - 16, cy = (int)(it.bx0_by0 >> 16) - 15, cz = p == 2 ? 1 : 0;
@@ -262,34 +274,34 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_addr(sm.win[st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(smem_addr(&sm.win_full[st]))
+            ::"r"(smem_addr(sm.win[pipe][st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(smem_addr(&sm.win_full[pipe][st]))
             : "memory");
     };
     // header word of this lane's macroblock (row `warp`, column `mb` of the window); bit 31 set = no such macroblock
     auto load_hw = [&](const PfItemRec &it) -> uint32_t {
-        if (warp >= ((it.job_p >> 20) & 15u) || mb >= (it.job_p >> 24)) return 0x80000000u;
-        return __ldg(sm.job[it.job_p & 0xffffu].hdr + it.hdr0 + warp * plane((it.job_p >> 16) & 3u).bw + mb);
+        if (wrow >= ((it.job_p >> 20) & 15u) || mb >= (it.job_p >> 24)) return 0x80000000u;
+        return __ldg(sm.job[it.job_p & 0xffffu].hdr + it.hdr0 + wrow * plane((it.job_p >> 16) & 3u).bw + mb);
     };
 
-    // Software pipeline over windows k (being copied), k+1 and k+2 (TMA in flight, headers loaded) and k+3 (TMA issued at the
-    // end of iteration k): no load is consumed in the iteration that issues it.
-    if (threadIdx.x == 0)
-        for (uint32_t s = 0; s < (uint32_t)PF_STAGES && s < nmine; ++s) issue(sm.item[s], s);
-    uint32_t hw_cur = nmine > 0 ? load_hw(sm.item[0]) : 0x80000000u;
-    uint32_t hw_n1 = nmine > 1 ? load_hw(sm.item[1]) : 0x80000000u;
+    // Software pipeline over windows k (being copied), k+1 (TMA in flight) and k+2 (TMA issued at the end of iteration k), headers
+    // loaded two windows ahead: no load is consumed in the iteration that issues it.
+    if (leader)
+        for (uint32_t s = 0; s < (uint32_t)PF_STAGES && s < nmine; ++s) issue(items[s], s);
+    uint32_t hw_cur = nmine > 0 ? load_hw(items[0]) : 0x80000000u;
+    uint32_t hw_n1 = nmine > 1 ? load_hw(items[1]) : 0x80000000u;
 #pragma unroll 1
     for (uint32_t k = 0; k < nmine; ++k) {
         const uint32_t st = k % PF_STAGES;
-        const PfItemRec cur = sm.item[k];
+        const PfItemRec cur = items[k];
         uint32_t hw_n2 = 0x80000000u;
-        if (k + 2u < nmine) hw_n2 = load_hw(sm.item[k + 2u]);
+        if (k + 2u < nmine) hw_n2 = load_hw(items[k + 2u]);
 
         const uint32_t cjob = cur.job_p & 0xffffu, cp = (cur.job_p >> 16) & 3u;
         const PlaneGeom &pl = plane(cp);
         const PfJob &job = sm.job[cjob];
         const bool exists = !(hw_cur & 0x80000000u);
         const bool coded = exists && ((hw_cur >> 16) & 0xffu) != 0u;
-        const int bx = (int)((cur.bx0_by0 & 0xffffu) + mb * 16u), by = (int)((cur.bx0_by0 >> 16) + warp * 16u);
+        const int bx = (int)((cur.bx0_by0 & 0xffffu) + mb * 16u), by = (int)((cur.bx0_by0 >> 16) + wrow * 16u);
         int mvx = (int)(int8_t)(hw_cur & 0xffu), mvy = (int)(int8_t)((hw_cur >> 8) & 0xffu);   // src/common.rs:255-256
         if (exists) {
             const int sx = bx + mvx, sy = by + mvy;
@@ -311,20 +323,20 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         PfGroup &grp = sm.grp[rgp];
         if (coded) bar_wait(&sm.grp_empty[rgp], ((e / PF_RING_MB) & 1u) ^ 1u);   // the slot's previous tenant has been taken out
 
-        bar_wait(&sm.win_full[st], (k / PF_STAGES) & 1u);
-        const uint32_t mb_off = cur.dst0 + warp * 16u * pl.pw + mb * 16u;        // this macroblock's top-left pixel in a frame slot
+        bar_wait(&sm.win_full[pipe][st], (k / PF_STAGES) & 1u);
+        const uint32_t mb_off = cur.dst0 + wrow * 16u * pl.pw + mb * 16u;        // this macroblock's top-left pixel in a frame slot
         if (exists) {
             uint8_t *dst = job.dst + mb_off + (size_t)rg * pl.pw;
             const bool in_window = mvx >= -16 && mvx <= 15 && mvy >= -15 && mvy <= 15;
             // Vectors beyond +-15 are legal for the reference decoder (7-bit vectors, src/dec.rs:367-368) but outside the
             // staged window - its own encoder never searches further (src/common.rs:154-204).  Rare: fetch from global.
-            const uint32_t wx = (uint32_t)(16 + (int)mb * 16 + mvx), wy = (uint32_t)(15 + (int)warp * 16 + mvy) + rg;
-            const unsigned char *wrow = sm.win[st] + wy * PF_WIN_W;
+            const uint32_t wx = (uint32_t)(16 + (int)mb * 16 + mvx), wy = (uint32_t)(15 + (int)wrow * 16 + mvy) + rg;
+            const unsigned char *wline = sm.win[pipe][st] + wy * PF_WIN_W;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint4 o;
                 if (in_window) {
-                    o = win_row16(wrow + i * 4 * PF_WIN_W, wx);
+                    o = win_row16(wline + i * 4 * PF_WIN_W, wx);
                 } else {
                     const uint8_t *gsrc = job.ref + pl.off + (size_t)((uint32_t)(by + mvy) + rg + 4u * (uint32_t)i) * pl.pw + (uint32_t)(bx + mvx);
                     const uint2 a = ldg_u8x8_unaligned(gsrc);
@@ -346,15 +358,15 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         __syncwarp();                                           // the four lanes of a macroblock have written its predictor
         if (coded && rg == 0) {
             bar_arrive_tx(&sm.grp_full[rgp], 512u);
-            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(cur.hdr0 + warp * pl.bw + mb) * 256, 512u, &sm.grp_full[rgp]);
+            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(cur.hdr0 + wrow * pl.bw + mb) * 256, 512u, &sm.grp_full[rgp]);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(PF_ROWS * 32) : "memory");   // the copy half is done with this window stage
-        if (threadIdx.x == 0 && k + PF_STAGES < nmine) issue(sm.item[k + PF_STAGES], st);
+        asm volatile("bar.sync %0, %1;" ::"r"(1u + pipe), "n"(PF_ROWS * 32) : "memory");   // the pipeline is done with this window stage
+        if (leader && k + PF_STAGES < nmine) issue(items[k + PF_STAGES], st);
         hw_cur = hw_n1; hw_n1 = hw_n2;
     }
 
     // the copy half is done: complete the last, partly filled group with empty slots and tell the transform half where to stop
-    asm volatile("bar.sync 1, %0;" ::"n"(PF_ROWS * 32) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"n"(1 + PF_PIPES), "n"(PF_COPY_WARPS * 32) : "memory");
     if (threadIdx.x == 0) {
         const uint32_t tail = *reinterpret_cast<volatile uint32_t *>(&sm.tail);
         const uint32_t rem = (8u - (tail & 7u)) & 7u;
@@ -379,14 +391,15 @@ cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint3
         if (e != cudaSuccess) return e;
     }
     const McWin W = make_mc_windows(P.g, PF_ROWS);
-    // frames per launch: at most PF_MAX_JOBS, and no more than lets every CTA's item table hold its share of the windows
-    uint32_t per_launch = (uint32_t)(((uint64_t)PF_MAX_ITEMS * 148u * 2u) / W.total);
+    // frames per launch: at most PF_MAX_JOBS, and no more than lets every pipeline's item table hold its share of the windows
+    const uint32_t max_pipes = 148u * PF_CTAS_PER_SM * PF_PIPES;
+    uint32_t per_launch = (uint32_t)(((uint64_t)PF_PIPE_ITEMS * max_pipes) / W.total);
     per_launch = per_launch < 1u ? 1u : (per_launch > (uint32_t)PF_MAX_JOBS ? (uint32_t)PF_MAX_JOBS : per_launch);
     for (uint32_t j0 = 0; j0 < njobs; j0 += per_launch) {
         const uint32_t n = njobs - j0 < per_launch ? njobs - j0 : per_launch;
-        uint32_t ctas = n * W.total;
-        if (ctas > 148u * 2u) ctas = 148u * 2u;
-        if ((n * W.total + ctas - 1) / ctas > (uint32_t)PF_MAX_ITEMS) return cudaErrorInvalidConfiguration;   // (a frame of > 150 000 windows)
+        uint32_t ctas = (n * W.total + PF_PIPES - 1) / PF_PIPES;
+        if (ctas > 148u * PF_CTAS_PER_SM) ctas = 148u * PF_CTAS_PER_SM;
+        if ((n * W.total + ctas * PF_PIPES - 1) / (ctas * PF_PIPES) > (uint32_t)PF_PIPE_ITEMS) return cudaErrorInvalidConfiguration;   // (a frame of > 37 000 windows)
         decode_p_fused_kernel<<<ctas, PF_THREADS, smem, s>>>(P, W, d_jobs + j0, n, d_err, tm_luma, tm_chroma);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

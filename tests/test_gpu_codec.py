@@ -383,6 +383,58 @@ def test_encoder_stream_is_byte_identical_to_oracle_encoder(size, quality, kind,
     assert np.array_equal(prev, fb)                                  # closed loop: encoder recon == decoder picture
 
 
+def test_encoder_writer_and_decoder_reader_stream_through_callbacks():
+    """Encoder<W: Write> / Decoder<R: Read + Seek> (src/enc.rs:12-26, src/dec.rs:15-28): the stream leaves through a writer
+    as packets finish (header first, same bytes as the in-memory encoder) and comes back in through a reader that hands out
+    odd-sized chunks; a failing writer surfaces as an I/O error."""
+    import io
+    w, h, n, key = 176, 144, 9, 4
+    want, _ = oracle_stream(w, h, n, 4, key, 97)
+    sv = SynthVideo(w, h, 97)
+    sink = io.BytesIO()
+    sizes = []
+
+    class W:
+        def write(self, b):
+            sizes.append(len(b))
+            sink.write(b)
+
+    with codec.Encoder(w, h, 30, 4, num_threads=2, writer=W()) as enc:
+        assert sink.getvalue()[:8] == b"PFVIDEO\0"                   # the header goes out at once (write_header, src/enc.rs:190-219)
+        for t in range(n):
+            (enc.encode_iframe if t % key == 0 else enc.encode_pframe)(sv.frame(t))
+        enc.finish()
+        assert enc.bytes() == b""
+    assert sink.getvalue() == want
+    assert len(sizes) >= n + 2                                       # header, one write per packet, eof
+
+    class R:
+        def __init__(self, data):
+            self.b, self.i = io.BytesIO(data), 0
+
+        def read(self, nbytes):
+            self.i += 1
+            return self.b.read(min(nbytes, 1 + (self.i * 7919) % 5000))
+
+    planes_a, planes_b = [], []
+    with codec.Decoder(R(want), num_threads=2) as dec:
+        while dec.advance_frame(lambda fr: planes_a.append(tuple(p.copy() for p in fr))):
+            pass
+    with codec.Decoder(want, num_threads=2) as dec:
+        while dec.advance_frame(lambda fr: planes_b.append(tuple(p.copy() for p in fr))):
+            pass
+    assert len(planes_a) == len(planes_b) == n
+    for a, b in zip(planes_a, planes_b):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+    class Broken:
+        def write(self, b):
+            raise OSError("disk full")
+
+    with pytest.raises(PfvError):
+        codec.Encoder(w, h, 30, 4, writer=Broken())
+
+
 def test_encoder_argument_errors():
     with pytest.raises(PfvError):
         codec.Encoder(64, 48, 30, 11)                                # assert!(quality >= 0 && quality <= 10)
