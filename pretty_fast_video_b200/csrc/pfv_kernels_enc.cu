@@ -28,9 +28,16 @@ namespace pfv {
 
 constexpr int ENC_WARPS = 4;
 
+constexpr int ENC_OUT_PITCH = 144;                           // bytes per sub-block in the output stage: 128 + 16
+
 struct __align__(16) EncStreamSmem {
     uint4    coef[ENC_WARPS][SBW_RING * 8];
     uint32_t id[ENC_WARPS][SBW_RING];
+    // A lane's 128 B of coefficients are 128 B apart from its neighbour's in the dense layout: stored straight from registers,
+    // every store instruction of the warp touched 32 different lines (ncu: the stores' source registers were what the next
+    // instructions waited for).  The tile goes through this per-warp stage instead - written sub-block by sub-block (pitch
+    // 144 B: conflict free), read back 512 contiguous bytes at a time - and leaves as 8 fully coalesced 512-byte stores.
+    uint4    out[ENC_WARPS][32 * ENC_OUT_PITCH / 16];
 };
 
 // 8 bytes of a source row whose plane width is not a multiple of 8 (or whose base is unaligned): byte by byte, padded with the
@@ -95,7 +102,8 @@ template <bool COUNT, int CTAS>
 __global__ void __launch_bounds__(ENC_WARPS * 32, CTAS)
 encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__restrict__ jobs)
 {
-    __shared__ EncStreamSmem sm;
+    extern __shared__ __align__(16) unsigned char enc_raw[];
+    EncStreamSmem &sm = *reinterpret_cast<EncStreamSmem *>(enc_raw);
 
     const uint32_t cta = blockIdx.x;
     const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
@@ -145,10 +153,22 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
             uint32_t ac = w[0] & 0xffff0000u;
 #pragma unroll
             for (int i = 1; i < 32; ++i) ac |= w[i];
-            if (valid) {
-                uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + ((size_t)(pl.mb_base + lm) * 256 + sb * 64u));
+            {
+                unsigned char *stg = reinterpret_cast<unsigned char *>(sm.out[warp]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) __stcs(dstc + k, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
+                for (int k = 0; k < 8; ++k)
+                    *reinterpret_cast<uint4 *>(stg + lane * ENC_OUT_PITCH + 16 * k) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+                __syncwarp();
+                // 16-byte chunk c = j*32 + lane of the tile's 4 KB: sub-block c >> 3, chunk c & 7 of it
+                const uint32_t tile_mbs = min(8u, nmb - tile * 8u);
+                uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + (size_t)(pl.mb_base + tile * 8u) * 256);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t c = (uint32_t)j * 32u + lane;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stg + (c >> 3) * ENC_OUT_PITCH + (c & 7u) * 16u);
+                    if ((c >> 5) < tile_mbs) __stcs(dstc + c, v);
+                }
+                __syncwarp();                                   // the stage is rewritten by the next tile
             }
             if (COUNT) {                                        // sparse seam: how many RLE entries this macroblock makes
                 const uint32_t n = mb_entry_count_lanes(sb_runs(w), sb);
@@ -198,8 +218,15 @@ cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t
     dim3 grid(P.cta_total, njobs, 1), block(ENC_WARPS * 32, 1, 1);
     // compiled for 3 resident CTAs per SM (168 registers, no spills): 156 k frames/s on 64 x 1080p against 139 k for 4 (128
     // registers, ~250 bytes of spills per thread)
-    if (count) encode_i_stream_kernel<true, 3><<<grid, block, 0, s>>>(P, d_jobs);
-    else       encode_i_stream_kernel<false, 3><<<grid, block, 0, s>>>(P, d_jobs);
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
+    const int smem = (int)sizeof(EncStreamSmem);
+    if (first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(encode_i_stream_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    if (count) encode_i_stream_kernel<true, 3><<<grid, block, smem, s>>>(P, d_jobs);
+    else       encode_i_stream_kernel<false, 3><<<grid, block, smem, s>>>(P, d_jobs);
     return cudaGetLastError();
 }
 

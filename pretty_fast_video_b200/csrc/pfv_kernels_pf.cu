@@ -81,6 +81,7 @@ struct __align__(128) PfSmem {
     PfJob    job[PF_MAX_JOBS];
     int32_t  deq[3][64];
     uint64_t win_full[PF_PIPES][PF_STAGES];
+    uint64_t win_empty[PF_PIPES][PF_STAGES];                 // the pipeline's four warps have read the stage (4 arrivals)
     uint64_t grp_full[PF_NG];                                // 8 arrivals (one per slot) + the slots' coefficient bytes
     uint64_t grp_empty[PF_NG];                               // the transform warp has taken the group into registers
     uint32_t tail;                                           // ring slots handed out so far
@@ -175,7 +176,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < PF_PIPES * PF_STAGES; ++s) bar_init(&sm.win_full[0][0] + s, 1);
+        for (int s = 0; s < PF_PIPES * PF_STAGES; ++s) { bar_init(&sm.win_full[0][0] + s, 1); bar_init(&sm.win_empty[0][0] + s, PF_ROWS); }
 #pragma unroll
         for (int s = 0; s < PF_NG; ++s) { bar_init(&sm.grp_full[s], 8); bar_init(&sm.grp_empty[s], 1); }
         sm.tail = 0;
@@ -360,8 +361,13 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
             bar_arrive_tx(&sm.grp_full[rgp], 512u);
             bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(cur.hdr0 + wrow * pl.bw + mb) * 256, 512u, &sm.grp_full[rgp]);
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(1u + pipe), "n"(PF_ROWS * 32) : "memory");   // the pipeline is done with this window stage
-        if (leader && k + PF_STAGES < nmine) issue(items[k + PF_STAGES], st);
+        // this warp is done with the window stage; the stage is refilled once all four are (no CTA or pipeline barrier: a
+        // warp that finishes early goes on to the next window, only the leader's lane 0 waits for the slowest one)
+        if (lane == 0) bar_arrive(&sm.win_empty[pipe][st]);
+        if (leader && k + PF_STAGES < nmine) {
+            bar_wait(&sm.win_empty[pipe][st], (k / PF_STAGES) & 1u);
+            issue(items[k + PF_STAGES], st);
+        }
         hw_cur = hw_n1; hw_n1 = hw_n2;
     }
 
