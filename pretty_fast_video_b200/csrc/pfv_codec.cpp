@@ -1071,6 +1071,15 @@ struct pfv_encoder {
     std::mutex m;
     std::condition_variable cv;
     std::deque<std::shared_ptr<OutPacket>> pending;   // packets in stream order, not yet appended to `stream`
+    // The calling thread only copies the planes into a pinned work item (the reference borrows them for the call) and queues it.
+    // Two internal threads do the rest: the SUBMITTER hands queued frames to the GPU in order (~75 us of driver calls per frame)
+    // and posts their entropy coding to the pool; the WRITER appends finished packets in stream order (or feeds the writer
+    // callback) and releases their work items.  Errors that happen there are sticky and come back from the next call.
+    std::deque<std::pair<EncWork *, std::shared_ptr<OutPacket>>> submit_q;
+    std::thread submitter, writer_thread;
+    bool stop = false;
+    int  async_rc = PFV_OK;
+    char async_err[256] = "";
     std::vector<uint8_t> stream;                      // the writer W (when no callback is set)
     pfv_write_fn writer = nullptr;                    // pfv_encoder_set_writer: packets leave through it as soon as they are finished
     void *writer_user = nullptr;
@@ -1115,51 +1124,87 @@ static void encoder_copy_planes(pfv_encoder *e, uint8_t *dst, const uint8_t *y, 
     while (done.load(std::memory_order_acquire) != helpers) std::this_thread::yield();
 }
 
-// append finished packets, in order; wait_all = block until everything submitted so far is in `stream`
-static int encoder_flush(pfv_encoder *e, bool wait_all)
+// the sticky error of the internal threads, if any
+static int encoder_async_error(pfv_encoder *e)
 {
-    // finished packets leave the queue under the lock; their bytes are appended outside it (the entropy threads take the same
-    // lock when they finish a frame)
-    std::vector<std::shared_ptr<OutPacket>> ready;
+    std::lock_guard<std::mutex> l(e->m);
+    return e->async_rc == PFV_OK ? PFV_OK : set_error(e->async_rc, "%s", e->async_err);
+}
+
+// block until everything queued so far has been appended to `stream` (or handed to the writer callback)
+static int encoder_flush(pfv_encoder *e)
+{
     {
         std::unique_lock<std::mutex> l(e->m);
-        while (!e->pending.empty()) {
-            std::shared_ptr<OutPacket> p = e->pending.front();
-            if (!p->ready) {
-                if (!wait_all) break;
-                e->cv.wait(l, [&p] { return p->ready; });
+        e->cv.wait(l, [e] { return e->pending.empty() && e->submit_q.empty(); });
+    }
+    return encoder_async_error(e);
+}
+
+static void encoder_set_async_error(pfv_encoder *e, int rc, const char *msg)     // e->m held
+{
+    if (e->async_rc == PFV_OK) {
+        e->async_rc = rc;
+        snprintf(e->async_err, sizeof(e->async_err), "%s", msg);
+    }
+}
+
+// WRITER thread: packets leave in stream order as soon as they are finished
+static void encoder_writer_main(pfv_encoder *e)
+{
+    for (;;) {
+        std::shared_ptr<OutPacket> p;
+        {
+            std::unique_lock<std::mutex> l(e->m);
+            e->cv.wait(l, [e] { return e->stop || (!e->pending.empty() && e->pending.front()->ready); });
+            if (e->pending.empty() || !e->pending.front()->ready) return;          // stop
+            p = e->pending.front();                                                // stays at the front until it is written
+        }
+        int rc = p->status;
+        const char *msg = p->err;
+        if (rc == PFV_OK) {
+            const std::vector<uint8_t> &b = p->work ? p->work->packet : p->bytes;
+            if (e->writer) {
+                if (!b.empty() && e->writer(e->writer_user, b.data(), b.size()) != 0) {
+                    rc = PFV_ERR_IO;
+                    msg = "the writer callback failed (io::Error of W::write_all)";
+                }
+            } else {
+                if (e->stream.size() + b.size() > e->stream.capacity())
+                    e->stream.reserve(std::max(e->stream.capacity() * 2, e->stream.size() + b.size() + ((size_t)1 << 20)));
+                e->stream.insert(e->stream.end(), b.begin(), b.end());
             }
+        }
+        {
+            std::lock_guard<std::mutex> l(e->m);
+            if (rc != PFV_OK) encoder_set_async_error(e, rc, msg);
+            if (p->work) p->work->busy = false;
             e->pending.pop_front();
-            ready.push_back(std::move(p));
         }
+        e->cv.notify_all();
     }
-    size_t add = 0;
-    int rc = PFV_OK;
-    for (auto &p : ready) {
-        if (p->status != PFV_OK && rc == PFV_OK) rc = set_error(p->status, "%s", p->err);
-        add += p->work ? p->work->packet.size() : p->bytes.size();
-    }
-    if (rc == PFV_OK && e->writer) {
-        for (auto &p : ready) {
-            const std::vector<uint8_t> &b = p->work ? p->work->packet : p->bytes;
-            if (!b.empty() && e->writer(e->writer_user, b.data(), b.size()) != 0 && rc == PFV_OK)
-                rc = set_error(PFV_ERR_IO, "the writer callback failed (io::Error of W::write_all)");
+}
+
+static void encoder_submit_one(pfv_encoder *e, EncWork *w, const std::shared_ptr<OutPacket> &pkt);
+
+// SUBMITTER thread: the only thread that drives the engine context
+static void encoder_submitter_main(pfv_encoder *e)
+{
+    for (;;) {
+        std::pair<EncWork *, std::shared_ptr<OutPacket>> item;
+        {
+            std::unique_lock<std::mutex> l(e->m);
+            e->cv.wait(l, [e] { return e->stop || !e->submit_q.empty(); });
+            if (e->submit_q.empty()) return;                                       // stop
+            item = e->submit_q.front();
         }
-    } else if (rc == PFV_OK) {
-        if (e->stream.size() + add > e->stream.capacity())
-            e->stream.reserve(std::max(e->stream.capacity() * 2, e->stream.size() + add + ((size_t)1 << 20)));
-        for (auto &p : ready) {
-            const std::vector<uint8_t> &b = p->work ? p->work->packet : p->bytes;
-            e->stream.insert(e->stream.end(), b.begin(), b.end());
+        encoder_submit_one(e, item.first, item.second);
+        {
+            std::lock_guard<std::mutex> l(e->m);
+            e->submit_q.pop_front();
         }
+        e->cv.notify_all();
     }
-    bool released = false;
-    {
-        std::lock_guard<std::mutex> l(e->m);
-        for (auto &p : ready) if (p->work) { p->work->busy = false; released = true; }
-    }
-    if (released) e->cv.notify_all();
-    return rc;
 }
 
 extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framerate, int quality, uint32_t num_threads, int device,
@@ -1212,6 +1257,8 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
     wr16(s, 4);
     for (int t = 0; t < 4; t++)                                      // intra_l, intra_c, inter_l, inter_c
         for (int i = 0; i < 64; i++) wr16(s, (uint32_t)qt[t][i]);
+    e->submitter = std::thread(encoder_submitter_main, e.get());
+    e->writer_thread = std::thread(encoder_writer_main, e.get());
     *out = e.release();
     return PFV_OK;
 }
@@ -1221,28 +1268,46 @@ static int encoder_frame(pfv_encoder *e, uint32_t kind, const uint8_t *y, const 
     if (!e) return set_error(PFV_ERR_BAD_ARG, "NULL encoder");
     if (e->finished) return set_error(PFV_ERR_STATE, "encoder is finished (assert!(!self.finished), src/enc.rs:80,130)");
     if (!y || !u || !v) return set_error(PFV_ERR_BAD_ARG, "NULL plane");
+    int rc = encoder_async_error(e);
+    if (rc) return rc;
     const double t0 = e->trace ? now_s() : 0;
-    int rc = PFV_OK;
-    double t1 = 0;
     EncWork *w = nullptr;
-    for (;;) {
-        // a work item is free again once its packet has been appended, which only this thread does: append what is ready,
-        // and if every item is still in flight wait for the oldest packet
-        rc = encoder_flush(e, false);
-        if (rc) return rc;
-        if (e->trace && t1 == 0) t1 = now_s();
+    {
+        // a work item is free again once its packet has been written (the writer thread releases it)
         std::unique_lock<std::mutex> l(e->m);
-        for (auto &x : e->work) if (!x->busy) { w = x.get(); break; }
-        if (w) { w->busy = true; break; }
-        std::shared_ptr<OutPacket> head = e->pending.front();
-        e->cv.wait(l, [&head] { return head->ready; });
+        e->cv.wait(l, [&] {
+            for (auto &x : e->work) if (!x->busy) { w = x.get(); return true; }
+            return false;
+        });
+        w->busy = true;
     }
-    const double t2 = e->trace ? now_s() : 0;
+    const double t1 = e->trace ? now_s() : 0;
+    encoder_copy_planes(e, static_cast<uint8_t *>(w->src.p), y, u, v);
+    w->kind = kind;
+    std::shared_ptr<OutPacket> pkt(new OutPacket());
+    pkt->work = w;
+    {
+        std::lock_guard<std::mutex> l(e->m);
+        e->pending.push_back(pkt);                                   // its place in the stream is fixed here
+        e->submit_q.emplace_back(w, pkt);
+    }
+    e->cv.notify_all();
+    if (e->trace) {
+        e->t_wait += t1 - t0; e->t_copy += now_s() - t1;
+        e->n_frames++;
+    }
+    return PFV_OK;
+}
+
+// (submitter thread) one frame: submit to the engine, then post its entropy coding
+static void encoder_submit_one(pfv_encoder *e, EncWork *w, const std::shared_ptr<OutPacket> &pkt)
+{
+    const double t0 = e->trace ? now_s() : 0;
     uint8_t *src = static_cast<uint8_t *>(w->src.p);
-    encoder_copy_planes(e, src, y, u, v);
-    const double t3 = e->trace ? now_s() : 0;
+    const uint32_t kind = w->kind;
     const uint32_t dst_slot = e->prev_slot ^ 1u;
     uint32_t *tok = static_cast<uint32_t *>(w->coeff.p), *stats = tok + (size_t)e->geo.nb * 256;
+    int rc;
     if (e->dense) {
         pfv_encode_job j;
         memset(&j, 0, sizeof(j));
@@ -1268,17 +1333,19 @@ static int encoder_frame(pfv_encoder *e, uint32_t kind, const uint8_t *y, const 
         j.stats_out = stats;
         rc = pfv_encode_submit_sparse(e->ctx, &j, 1);
     }
-    if (rc) { std::lock_guard<std::mutex> l(e->m); w->busy = false; return rc; }
-    if (e->trace) {
-        e->t_flush += t1 - t0; e->t_wait += t2 - t1; e->t_copy += t3 - t2; e->t_submit += now_s() - t3;
-        e->n_frames++;
+    if (rc) {
+        std::lock_guard<std::mutex> l(e->m);
+        snprintf(pkt->err, sizeof(pkt->err), "%s", pfv_last_error());
+        pkt->status = rc;
+        pkt->ready = true;                                           // the writer turns it into the sticky error and frees the item
+        return;
     }
-    e->prev_slot = dst_slot;                                         // src/enc.rs:95-97, :145-147
-    w->kind = kind;
+    {
+        std::lock_guard<std::mutex> l(e->m);
+        e->prev_slot = dst_slot;                                     // src/enc.rs:95-97, :145-147
+    }
     w->submit_id = pfv_ctx_last_submit_id(e->ctx);
-    std::shared_ptr<OutPacket> pkt(new OutPacket());
-    pkt->work = w;
-    { std::lock_guard<std::mutex> l(e->m); e->pending.push_back(pkt); }
+    if (e->trace) e->t_submit += now_s() - t0;
     e->pool->post([e, w, pkt, tok, stats] {
         int rc2 = pfv_ctx_wait_submit(e->ctx, w->submit_id);
         if (rc2 == PFV_OK) {
@@ -1295,7 +1362,6 @@ static int encoder_frame(pfv_encoder *e, uint32_t kind, const uint8_t *y, const 
         }
         e->cv.notify_all();
     });
-    return PFV_OK;
 }
 
 extern "C" int pfv_encoder_encode_iframe(pfv_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v)
@@ -1314,8 +1380,11 @@ static int encoder_literal_packet(pfv_encoder *e, uint8_t type)
     pkt->bytes.assign(5, 0);
     pkt->bytes[0] = type;                                            // u32 length 0 follows
     pkt->ready = true;
-    std::lock_guard<std::mutex> l(e->m);
-    e->pending.push_back(pkt);
+    {
+        std::lock_guard<std::mutex> l(e->m);
+        e->pending.push_back(pkt);
+    }
+    e->cv.notify_all();
     return PFV_OK;
 }
 
@@ -1332,7 +1401,7 @@ extern "C" int pfv_encoder_finish(pfv_encoder *e)
     if (e->finished) return set_error(PFV_ERR_STATE, "finish() called twice (assert!(!self.finished), src/enc.rs:183)");
     e->finished = true;
     encoder_literal_packet(e, 0);                                    // write_eof, src/enc.rs:221-227
-    return encoder_flush(e, true);
+    return encoder_flush(e);
 }
 
 // Encoder<W: Write> (src/enc.rs:12-26): what has been written so far (the header) goes out at once, every later packet as
@@ -1340,10 +1409,11 @@ extern "C" int pfv_encoder_finish(pfv_encoder *e)
 extern "C" int pfv_encoder_set_writer(pfv_encoder *e, pfv_write_fn writer, void *user)
 {
     if (!e || !writer) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
-    int rc = encoder_flush(e, true);
+    int rc = encoder_flush(e);
     if (rc) return rc;
     if (!e->stream.empty() && writer(user, e->stream.data(), e->stream.size()) != 0)
         return set_error(PFV_ERR_IO, "the writer callback failed (io::Error of W::write_all)");
+    std::lock_guard<std::mutex> l(e->m);                             // (the writer thread is idle: nothing is pending)
     e->stream.clear();
     e->writer = writer;
     e->writer_user = user;
@@ -1353,7 +1423,7 @@ extern "C" int pfv_encoder_set_writer(pfv_encoder *e, pfv_write_fn writer, void 
 extern "C" int pfv_encoder_bytes(pfv_encoder *e, const uint8_t **data, size_t *len)
 {
     if (!e || !data || !len) return set_error(PFV_ERR_BAD_ARG, "NULL argument");
-    int rc = encoder_flush(e, true);
+    int rc = encoder_flush(e);
     if (rc) return rc;
     *data = e->stream.data();
     *len = e->stream.size();
@@ -1367,12 +1437,18 @@ extern "C" void pfv_encoder_close(pfv_encoder *e)
 {
     if (!e) return;
     if (!e->finished) pfv_encoder_finish(e);                         // Drop, src/enc.rs:28-34
-    else encoder_flush(e, true);
+    else encoder_flush(e);
+    {
+        std::lock_guard<std::mutex> l(e->m);
+        e->stop = true;
+    }
+    e->cv.notify_all();
+    if (e->submitter.joinable()) e->submitter.join();
+    if (e->writer_thread.joinable()) e->writer_thread.join();
     if (e->trace && e->n_frames)
-        fprintf(stderr, "[pfv encoder] %llu frames, per frame on the calling thread: append packets %.1f us, wait for a free work item "
-                        "%.1f us, copy planes %.1f us, submit %.1f us\n", (unsigned long long)e->n_frames,
-                1e6 * e->t_flush / e->n_frames, 1e6 * e->t_wait / e->n_frames, 1e6 * e->t_copy / e->n_frames,
-                1e6 * e->t_submit / e->n_frames);
+        fprintf(stderr, "[pfv encoder] %llu frames, per frame: calling thread waits for a free work item %.1f us, copies the planes "
+                        "%.1f us; submitter thread %.1f us\n", (unsigned long long)e->n_frames,
+                1e6 * e->t_wait / e->n_frames, 1e6 * e->t_copy / e->n_frames, 1e6 * e->t_submit / e->n_frames);
     e->pool.reset();
     e->copy_pool.reset();
     if (e->ctx) { pfv_sync(e->ctx); pfv_ctx_destroy(e->ctx); }

@@ -221,7 +221,8 @@ struct pfv_ctx {
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
     CUtensorMap tm_luma{}, tm_chroma{};          // encode-P search window boxes
-    CUtensorMap tm_win_luma{}, tm_win_chroma{};  // decode-P windows of 8 x 4 macroblocks (176 x 94)
+    CUtensorMap tm_win_luma{}, tm_win_chroma{};  // decode-P windows of 8 x 4 macroblocks (176 x 94; the copy + residual pair)
+    CUtensorMap tm_pf_luma{}, tm_pf_chroma{};    // decode-P windows of 8 x PF_ROWS macroblocks (the fused kernel)
     bool have_tma = false;
     char tma_err[160] = "";
 };
@@ -244,13 +245,15 @@ int build_tensor_maps(pfv_ctx *c)
     EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
     const pfv_geometry &g = c->geo;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int which = 0; which < 2; which++) {
+    for (int which = 0; which < 3; which++) {
     const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     // which == 0: the search window of an encode-P tile of 8 macroblocks (176 x 46)
-    // which == 1: the window of every possible predictor of 8 x 4 macroblocks (176 x 94; decode-P)
-    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : 176u, which == 0 ? (cuuint32_t)WIN_H : 94u, 1, 1};
-    CUtensorMap *out_l = which == 0 ? &c->tm_luma : &c->tm_win_luma;
-    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : &c->tm_win_chroma;
+    // which == 1: the window of every possible predictor of 8 x 4 macroblocks (176 x 94; decode-P copy kernel)
+    // which == 2: the same for 8 x PF_ROWS macroblocks (fused decode-P kernel)
+    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : 176u,
+                               which == 0 ? (cuuint32_t)WIN_H : (which == 1 ? 94u : (cuuint32_t)PF_WIN_H), 1, 1};
+    CUtensorMap *out_l = which == 0 ? &c->tm_luma : (which == 1 ? &c->tm_win_luma : &c->tm_pf_luma);
+    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : (which == 1 ? &c->tm_win_chroma : &c->tm_pf_chroma);
     {   // luma: (x, y, 1, slot)
         const cuuint64_t dims[4] = {g.pw, g.ph, 1, c->nslots};
         const cuuint64_t strides[3] = {g.pw, c->slot_stride, c->slot_stride};
@@ -1005,7 +1008,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
             uint32_t b = a + 1;
             while (b < njobs && qkey(order[b]) == qkey(order[a])) b++;
             if (c->decode_p_variant == 0) {
-                CU_TRY(launch_decode_p_fused(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->tm_win_luma, c->tm_win_chroma, c->s_compute));
+                CU_TRY(launch_decode_p_fused(sb_params(order[a]), d_tab + a, b - a, c->d_err, c->tm_pf_luma, c->tm_pf_chroma, c->s_compute));
                 c->launches++;
             } else {
                 const uint32_t k0 = a - n_i, n = b - a;

@@ -99,6 +99,11 @@ struct EncSbParams {
     uint32_t  tiles_per_warp;
 };
 
+// fused decode-P kernel (pfv_kernels_pf.cu): macroblock rows per window and the TMA box that holds every predictor of them
+constexpr int PF_ROWS = 3;
+constexpr int PF_WIN_W = 176;                                // 16 + 8*16 + 15, rounded up to 16
+constexpr int PF_WIN_H = PF_ROWS * 16 + 30;
+
 // decode-P window items of one frame: a window covers 8 x `rows` macroblocks of one plane
 struct McWin {
     uint32_t base[3];         // first item of each plane

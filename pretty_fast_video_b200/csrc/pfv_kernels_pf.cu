@@ -32,16 +32,14 @@
 
 namespace pfv {
 
-constexpr int PF_ROWS = 4;                                   // macroblock rows per window = warps per copy pipeline
-constexpr int PF_WIN_W = 176;                                // 16 + 8*16 + 15, rounded up to 16
-constexpr int PF_WIN_H = PF_ROWS * 16 + 30;
-constexpr int PF_WIN_BYTES = PF_WIN_W * PF_WIN_H;            // 16 544
+// PF_ROWS (pfv_internal.h) = macroblock rows per window = warps per copy pipeline
+constexpr int PF_WIN_BYTES = PF_WIN_W * PF_WIN_H;
 constexpr int PF_STAGE = (PF_WIN_BYTES + 127) & ~127;
-constexpr int PF_PIPES = 3;                                  // independent copy pipelines per CTA (each: 4 warps, its own windows)
+constexpr int PF_PIPES = 4;                                  // independent copy pipelines per CTA (each: PF_ROWS warps, its own windows)
 constexpr int PF_STAGES = 2;                                 // windows in flight per pipeline
 constexpr int PF_COPY_WARPS = PF_PIPES * PF_ROWS;
-constexpr int PF_NG = 16;                                    // ring groups; the ring must hold more macroblocks (128) than the
-constexpr int PF_RING_MB = PF_NG * 8;                        // pipelines can have unfinished at once (3 x 32): see the empty-wait
+constexpr int PF_NG = 13;                                    // ring groups; the ring must hold more macroblocks (104) than the
+constexpr int PF_RING_MB = PF_NG * 8;                        // pipelines can have unfinished at once (4 x 24): see the empty-wait
 constexpr int PF_COEF_PITCH = 528;                           // bytes per slot: 512 + 16 (8 slots -> 8 different bank groups)
 constexpr int PF_PRED_PITCH = 80;                            // bytes per sub-block: 64 + 16
 constexpr int PF_XF_WARPS = 4;
@@ -89,7 +87,7 @@ struct __align__(128) PfSmem {
 };
 
 static_assert(PF_CTAS_PER_SM * (sizeof(PfSmem) + 1024) <= 227 * 1024, "the fused decode-P kernel's CTAs must fit one SM");
-static_assert(PF_RING_MB > PF_PIPES * 32, "the ring must be larger than what the copy pipelines can have unfinished at once");
+static_assert(PF_RING_MB > PF_PIPES * PF_ROWS * 8, "the ring must be larger than what the copy pipelines can have unfinished at once");
 
 __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity)
 {
