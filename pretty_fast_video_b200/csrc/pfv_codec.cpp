@@ -997,17 +997,23 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
     }
     const double t2 = now_s();
     rc = pfv_ctx_wait_submit(d->ctx, w->submit_id);
-    if (rc) return rc;
+    if (rc) {
+        // same recovery as a failed submit: the frame is consumed, everything decoded ahead is dropped and the framebuffer
+        // stays what the last returned picture left there (the reference reports an error only for the frame that fails)
+        decoder_drain(d);
+        d->fb_slot = d->delivered_slot;
+        d->cursor++;
+        d->sched = d->cursor;
+        return rc;
+    }
     const double t3 = now_s();
     d->inflight.pop_front();
     d->delivered = w;
     d->delivered_slot = w->slot;
     d->cursor++;
-    // keep the pipeline full for the next call
-    rc = decoder_schedule(d);
-    if (rc) return rc;
-    rc = decoder_submit_ready(d, nullptr);
-    if (rc) return rc;
+    // keep the pipeline full for the next call.  A failure here belongs to a LATER frame: this call's picture is decoded
+    // and is handed out; the frame that failed reports its error when its turn comes (its submit is retried then)
+    if (decoder_schedule(d) == PFV_OK) (void)decoder_submit_ready(d, nullptr);
     const double t4 = now_s();
     d->t_prof[0] += t1 - t0; d->t_prof[1] += t2 - t1; d->t_prof[2] += t3 - t2; d->t_prof[3] += t4 - t3; d->n_prof++;
     if (got_frame) *got_frame = 1;
