@@ -219,13 +219,21 @@ cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t
     // compiled for 3 resident CTAs per SM (168 registers, no spills): 156 k frames/s on 64 x 1080p against 139 k for 4 (128
     // registers, ~250 bytes of spills per thread)
     static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
-    const int smem = (int)sizeof(EncStreamSmem);
+    // tuning aid: PFV_ENCODE_I_RESIDENT = 1 / 2 keeps that many CTAs per SM resident (the kernel compiled for it, shared memory
+    // padded so that no more fit): fewer warps at different places of a 50 KB loop means fewer instruction-cache misses
+    static const int res_env = getenv("PFV_ENCODE_I_RESIDENT") ? atoi(getenv("PFV_ENCODE_I_RESIDENT")) : 3;
+    const int resident = res_env == 1 || res_env == 2 ? res_env : 3;
+    const int smem = resident == 3 ? (int)sizeof(EncStreamSmem) : (resident == 2 ? 100 * 1024 : 200 * 1024);
     if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(encode_i_stream_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(encode_i_stream_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
     }
     if (count) encode_i_stream_kernel<true, 3><<<grid, block, smem, s>>>(P, d_jobs);
+    else if (resident == 1) encode_i_stream_kernel<false, 1><<<grid, block, smem, s>>>(P, d_jobs);
+    else if (resident == 2) encode_i_stream_kernel<false, 2><<<grid, block, smem, s>>>(P, d_jobs);
     else       encode_i_stream_kernel<false, 3><<<grid, block, smem, s>>>(P, d_jobs);
     return cudaGetLastError();
 }
