@@ -1069,9 +1069,9 @@ def main():
     fps = r["frames"] * dist.world / (r["max_ms"] * 1e-3)
     launches = r["launches_per_step"]
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
-    kernel_of = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_stream_kernel",
+    kernel_of = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_sb_kernel",   # PFV_JOB_DENSE -> the plain kernel
                  "decode_p_1080p": "decode_p_fused_kernel", "decode_p_4k": "decode_p_fused_kernel",
-                 "encode_p_1080p": "encode_p_kernel", "encode_i_1080p": "encode_i_stream_kernel"}
+                 "encode_p_1080p": "encode_p2_kernel", "encode_i_1080p": "encode_i_stream_kernel"}
     kernel_key = kernel_of[args.workload]
 
     def stats_of(xs):
@@ -1101,7 +1101,7 @@ def main():
         line["candidate_pixels_per_s"] = fps * st.nb * SEARCH_CANDIDATES_PER_MB * 256
 
     nthreads = os.cpu_count() or 1
-    if dist.world == 1:
+    if dist.world == 1 and args.cpu_budget > 0:
         cfps, sample, _ = cpu_port_leg(args.workload, args.cpu_budget, nthreads)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": sample}
         if nthreads > 1 and args.cpu_budget >= 1.0:
@@ -1132,7 +1132,7 @@ def main():
                 }
                 if wl.startswith("encode_p"):
                     extras[wl]["candidate_pixels_per_s"] = xfps * xs.nb * SEARCH_CANDIDATES_PER_MB * 256
-                if dist.world == 1:
+                if dist.world == 1 and args.cpu_budget > 0:
                     cf, cs, _ = cpu_port_leg(wl, min(args.cpu_budget, 3.0 if wl == "decode_p_4k" else 6.0), nthreads)
                     extras[wl]["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": cs}
                 verified_all &= bool(x["verified"]) and all(bool(y.get("verified", True)) for y in ((x["e2e"] or {}), (x["e2e"] or {}).get("dense", {})))

@@ -83,7 +83,7 @@ struct __align__(128) PfSmem {
     uint64_t grp_full[PF_NG];                                // 8 arrivals (one per slot) + the slots' coefficient bytes
     uint64_t grp_empty[PF_NG];                               // the transform warp has taken the group into registers
     uint32_t tail;                                           // ring slots handed out so far
-    volatile uint32_t total_groups;                          // 0xffffffff until the copy half is done
+    uint32_t total_groups;                                   // 0xffffffff until the copy half is done (written and polled with atomics)
 };
 
 static_assert(PF_CTAS_PER_SM * (sizeof(PfSmem) + 1024) <= 227 * 1024, "the fused decode-P kernel's CTAs must fit one SM");
@@ -220,7 +220,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
             const uint32_t rgp = G % PF_NG, par = (G / PF_NG) & 1u;
             bool stop = false;
             while (!bar_try_sleepy(&sm.grp_full[rgp], par, 2000u)) {
-                if (sm.total_groups <= G) { stop = true; break; }
+                if (atomicOr(&sm.total_groups, 0u) <= G) { stop = true; break; }
             }
             if (stop) break;
             const PfGroup &grp = sm.grp[rgp];
@@ -381,7 +381,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
             bar_arrive(&sm.grp_full[rgp]);
         }
         __threadfence_block();
-        sm.total_groups = (tail + 7u) >> 3;
+        atomicExch(&sm.total_groups, (tail + 7u) >> 3);
     }
 }
 
