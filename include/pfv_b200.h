@@ -260,7 +260,9 @@ int  pfv_ctx_last_kernel_ms(pfv_ctx *ctx, float *ms_out);
  * pfv_rs::enc::Encoder (src/enc.rs:12-188): same constructor arguments, same packet semantics, same error
  * classes (PFV_ERR_BAD_STREAM = DecodeError::FormatError, PFV_ERR_BAD_VERSION = VersionError, PFV_ERR_IO =
  * io::Error / IOError).  The reader R / writer W of the Rust generics are an in-memory byte range / a growable
- * byte buffer here.
+ * byte buffer by default, or the caller's callbacks (pfv_decoder_open_reader, pfv_encoder_set_writer).
+ * encode_iframe / encode_pframe return once the planes have been copied; the GPU submit, the entropy coding and the
+ * packet append happen on internal threads, and an error there comes back from the next call on the encoder.
  */
 typedef struct pfv_stream_info {            /* file header, src/dec.rs:38-118 / src/enc.rs:190-219 */
     uint32_t version;                        /* 211 */
@@ -346,9 +348,9 @@ int  pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framerate, int q
                       int device, pfv_encoder **out);
 void pfv_encoder_close(pfv_encoder *e);                  /* Drop: finishes the stream if finish() was not called */
 /* Encoder<W: Write> (src/enc.rs:12-26): hand the stream to a writer instead of keeping it in memory.  Call right after
- * pfv_encoder_open: the header goes out at once, every packet as soon as it is finished, in stream order, from the thread
- * that calls encode_* / finish / close.  The callback returns 0, or non-zero for an I/O error (-> PFV_ERR_IO).  With a
- * writer set pfv_encoder_bytes returns an empty range. */
+ * pfv_encoder_open: the header goes out at once (from the calling thread), every packet as soon as it is finished, in
+ * stream order, one call at a time, from an internal writer thread.  The callback returns 0, or non-zero for an I/O error
+ * (-> PFV_ERR_IO from the next call on the encoder).  With a writer set pfv_encoder_bytes returns an empty range. */
 typedef int (*pfv_write_fn)(void *user, const uint8_t *data, size_t len);
 int  pfv_encoder_set_writer(pfv_encoder *e, pfv_write_fn writer, void *user);
 /* src/enc.rs:75-123 / :125-173.  y,u,v: tight planes w*h, w/2*h/2, w/2*h/2 (VideoFrame); read before return. */
