@@ -527,7 +527,8 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
             ph3[0] += 1
 
         h2d_s = int(4 * ntok_total + nframes * 4 * (st.nb + 1) + (G - 1) * L * st.nb * 4)
-        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * st.nb * 512, chunk * (ysz + 2 * csz))
+        # the box's ceiling for THIS leg's traffic mix: per submit, tokens + headers up and `chunk` pictures down
+        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, max(4096, h2d_s * chunk // nframes), chunk * (ysz + 2 * csz))
         outb[...] = 0
         s_max, s_my = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
         e2e = {"value": nframes * dist.world / (s_max * 1e-3), "unit": "frames/s", "ms_per_step": s_max,
@@ -560,11 +561,12 @@ def run_decode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
             ph2[0] += 1
 
         outb[...] = 0
+        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * st.nb * 512, chunk * (ysz + 2 * csz))
         e_max, e_my = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
         h2d = int(st.nb * 512 * nframes + (G - 1) * L * st.nb * 4)
         e2e["dense"] = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "pcie_gbs_each_way": [h2d / e_my / 1e6, d2h / e_my / 1e6],
+                        "pcie_gbs_each_way": [h2d / e_my / 1e6, d2h / e_my / 1e6], "pcie_ceiling_gbs": [ceil_h2d, ceil_d2h],
                         "frac_of_pcie_ceiling": max(h2d / e_my / 1e6 / ceil_h2d, d2h / e_my / 1e6 / ceil_d2h),
                         "seam": "dense: pfv_decode_submit - the reference's Vec<i16> of nb*256 coefficients over PCIe",
                         "verified": check_outputs()}
@@ -663,7 +665,8 @@ def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
                     eng3.encode_submit_sparse(jobs, prebuilt=arr)
             ph3[0] += 1
 
-        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * (ysz + 2 * csz), chunk * st.nb * 512)
+        # the box's ceiling for this leg's traffic mix: `chunk` source frames up, ~0.1 of the dense coefficient bytes down
+        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * (ysz + 2 * csz), chunk * st.nb * 48)
         s_max, s_my = time_steps(torch, dist, stream, step_sparse, eng3.sync, max(2, steps // 2), 2, wall=True)
         ntok = os_[:, :, N.PFV_TOKSTATS_NTOK].astype(np.int64)
         assert not (os_[:, :, N.PFV_TOKSTATS_FLAGS] != 0).any(), "token buffer overflow in the sparse encode leg"
@@ -716,11 +719,12 @@ def run_encode(torch, dist, stream, st: Streams, steps, warmup, do_e2e=True):
                     eng2.encode_submit(jobs, prebuilt=arr)
             ph2[0] += 1
 
+        ceil_h2d, ceil_d2h = pcie_ceiling(torch, dist, chunk * (ysz + 2 * csz), chunk * st.nb * 512)
         e_max, e_my = time_steps(torch, dist, stream, step_e2e, eng2.sync, max(2, steps // 2), 2, wall=True)
         d2h = int(nframes * st.nb * 512 + (G - 1) * L * st.nb * 4)
         e2e["dense"] = {"value": nframes * dist.world / (e_max * 1e-3), "unit": "frames/s", "ms_per_step": e_max,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "pcie_gbs_each_way": [h2d / e_my / 1e6, d2h / e_my / 1e6],
+                        "pcie_gbs_each_way": [h2d / e_my / 1e6, d2h / e_my / 1e6], "pcie_ceiling_gbs": [ceil_h2d, ceil_d2h],
                         "frac_of_pcie_ceiling": max(h2d / e_my / 1e6 / ceil_h2d, d2h / e_my / 1e6 / ceil_d2h),
                         "seam": "dense: pfv_encode_submit - nb*256 int16 coefficients per frame back over PCIe"}
         eng2.close()

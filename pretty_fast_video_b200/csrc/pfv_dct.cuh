@@ -8,6 +8,7 @@
 //   src/common.rs:287-325 sub-block drivers: encode = rows then columns, decode = columns then rows
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define PFV_HD __host__ __device__ __forceinline__
@@ -160,6 +161,78 @@ PFV_UNROLL
     }
 }
 
+// The same transform in fp32.  With exact divisions (above) the butterfly is LINEAR with dyadic coefficients
+// (x + x/4 - x/16 = 19/16 x, x - x/4 - x/16 = 11/16 x, ...): computed on the UNSCALED inputs y = p - 128 (or delta / 2), |y| <= 128,
+// every intermediate is a multiple of 2^-8 below 2^14 - 22 significant bits, exactly representable, and an FMA whose exact
+// result is representable returns it.  30 FMA-pipe instructions per pass instead of 48 ALU/FMA ones, and the quantiser's
+// input 256 * V comes out of ONE FFMA that also does the float -> int conversion (the 1.5 * 2^23 trick: |256 V| < 2^22).
+PFV_HD void fdct8_f32(float (&v)[8])
+{
+    const float a0 = v[0] + v[7], a1 = v[1] + v[6], a2 = v[2] + v[5], a3 = v[3] + v[4];
+    const float a4 = v[0] - v[7], a5 = v[1] - v[6], a6 = v[2] - v[5], a7 = v[3] - v[4];
+    const float b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
+    const float c0 = b0 + b1, c1 = b0 - b1;
+    const float c2 = fmaf(b2, 1.25f, b3 * 0.5f);              // b2 + b2/4 + b3/2
+    const float c3 = fmaf(b3, -1.25f, b2 * 0.5f);             // b2/2 - b3 - b3/4
+    const float b4 = fmaf(a4, 1.1875f, a7 * 0.25f);           // a7/4 + a4 + a4/4 - a4/16
+    const float b7 = fmaf(a7, -1.1875f, a4 * 0.25f);          // a4/4 - a7 - a7/4 + a7/16
+    const float b5 = fmaf(a6, 0.6875f, a5);                   // a5 + a6 - a6/4 - a6/16
+    const float b6 = fmaf(a5, -0.6875f, a6);                  // a6 - a5 + a5/4 + a5/16
+    const float c4 = b4 + b5, c5 = b4 - b5, c6 = b6 + b7, c7 = b6 - b7;
+    v[0] = c0; v[1] = c4; v[2] = c2; v[3] = c5 - c7;
+    v[4] = c1; v[5] = c5 + c7; v[6] = c3; v[7] = c6;
+}
+
+PFV_HD void fdct8x8_f32(float (&m)[64])
+{
+PFV_UNROLL
+    for (int r = 0; r < 8; ++r) {
+        float v[8];
+PFV_UNROLL
+        for (int c = 0; c < 8; ++c) v[c] = m[r * 8 + c];
+        fdct8_f32(v);
+PFV_UNROLL
+        for (int c = 0; c < 8; ++c) m[r * 8 + c] = v[c];
+    }
+PFV_UNROLL
+    for (int c = 0; c < 8; ++c) {
+        float v[8];
+PFV_UNROLL
+        for (int r = 0; r < 8; ++r) v[r] = m[r * 8 + c];
+        fdct8_f32(v);
+PFV_UNROLL
+        for (int r = 0; r < 8; ++r) m[r * 8 + c] = v[r];
+    }
+}
+
+PFV_HD float bits_as_float(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; __builtin_memcpy(&f, &u, 4); return f;
+#endif
+}
+PFV_HD uint32_t float_as_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; __builtin_memcpy(&u, &f, 4); return u;
+#endif
+}
+
+// byte k of a word as (p - 128) in fp32 without a conversion instruction: 0x4B000000 | p is the float 2^23 + p
+PFV_HD float byte_minus_128_f32(uint32_t w, int k)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t bits = __byte_perm(w, 0x4B000000u, 0x7440 | k);       // bytes: [w.k, 00, 00, 4B]
+#else
+    const uint32_t bits = 0x4B000000u | ((w >> (8 * k)) & 0xffu);
+#endif
+    return bits_as_float(bits) - 8388736.0f;                              // 2^23 + 128
+}
+
 PFV_HD int mulhi_s32(int a, int b)
 {
 #if defined(__CUDA_ARCH__)
@@ -186,6 +259,16 @@ PFV_HD int quant_one(int v, int scale, uint32_t M)
     return mulhi_s32(t, (int)M) + (int)((uint32_t)a >> 31);
 }
 
+// the quantiser on the fp32 transform's output V (unscaled: the reference's value is 256 V): the magic-number FFMA leaves
+// 256 V + 1.5 * 2^23 as a float whose bit pattern is 0x4B400000 + 256 V; the subtraction folds into the multiply-add
+PFV_HD int quant_one_f32(float V, int scale, uint32_t M)
+{
+    const int vi = (int)float_as_bits(fmaf(V, 256.0f, 12582912.0f));
+    const int a = vi * scale - 0x4B400000 * scale;                  // (256 V) * scale, wrapping like the integer path
+    const int t = (a >> 14) & ~3;
+    return mulhi_s32(t, (int)M) + (int)((uint32_t)a >> 31);
+}
+
 // two quantised coefficients -> one word of the dense layout (low half first)
 PFV_HD uint32_t pack_i16x2(int lo, int hi)
 {
@@ -199,6 +282,19 @@ PFV_HD uint32_t pack_i16x2(int lo, int hi)
 // src/common.rs:287-298 / :300-311 after the level shift: x = the 64 inputs in raster order ((p - 128) << 8 or
 // (delta / 2) << 8).  Leaves the quantised coefficients in SCAN order, two per word, exactly as the dense layout
 // stores them (src/dct.rs:88-99).  encM = quant_magic of the q-table by RASTER position.
+// the same on fp32 inputs y = p - 128 (or delta / 2), unscaled (see fdct8_f32)
+PFV_HD void encode_sb_regs_f32(float (&y)[64], const uint32_t *encM, uint32_t (&w)[32])
+{
+    constexpr int zz[64] = PFV_ZIGZAG_INIT;
+    constexpr int sc[64] = PFV_SCALE_INIT;
+    fdct8x8_f32(y);
+PFV_UNROLL
+    for (int i = 0; i < 32; ++i) {
+        const int z0 = zz[2 * i], z1 = zz[2 * i + 1];
+        w[i] = pack_i16x2(quant_one_f32(y[z0], sc[z0], encM[z0]), quant_one_f32(y[z1], sc[z1], encM[z1]));
+    }
+}
+
 PFV_HD void encode_sb_regs(int (&x)[64], const uint32_t *encM, uint32_t (&w)[32])
 {
     constexpr int zz[64] = PFV_ZIGZAG_INIT;

@@ -6,8 +6,8 @@
 //
 // The first-generation kernel (pfv_kernels.cu, one warp per macroblock, transposes and the zig-zag through shared
 // memory) ran at 0.18 of the HBM roofline.  Here, like the decode side: a thread keeps its sub-block's 64 values in
-// registers, both forward passes and the quantiser run without any exchange, the zig-zag is a compile-time register
-// renaming, the divisors are multipliers in the constant bank.  A warp walks tiles of 8 consecutive macroblocks
+// registers, both forward passes (in fp32, where they are exact: pfv_dct.cuh) and the quantiser run without any exchange, the
+// zig-zag is a compile-time register renaming, the divisors are multipliers in the constant bank.  A warp walks tiles of 8 consecutive macroblocks
 // (lane = macroblock*4 + sub-block): its 8-byte source loads cover full 128-byte lines of the tight source plane (the
 // rows of the next tile are fetched while this one is transformed) and a lane's 8 coefficient stores fill 128
 // contiguous bytes of the dense layout.
@@ -129,15 +129,13 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
         const bool work = tile != tile_begin - 1u;
         const uint32_t lm = tile * 8u + (lane >> 2);
         const bool valid = work && lm < nmb;
-        int x[64];
+        // (p - 128) << 8, src/common.rs:291 - kept unscaled in fp32: the forward transform is exact there (pfv_dct.cuh, fdct8_f32)
+        float x[64];
         if (work) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t wd = k < 4 ? nxt[r].x : nxt[r].y;
-                    x[r * 8 + k] = (int)((wd >> (8 * (k & 3))) & 0xffu) * 256 - 32768;   // (p - 128) << 8, src/common.rs:291
-                }
+                for (int k = 0; k < 8; ++k) x[r * 8 + k] = byte_minus_128_f32(k < 4 ? nxt[r].x : nxt[r].y, k & 3);
             }
         }
         if (tile + 1u != tile_end) {                            // in flight during the transform
@@ -149,7 +147,7 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
         uint32_t vote = 0;
         if (work) {
             uint32_t w[32];
-            encode_sb_regs(x, encM, w);
+            encode_sb_regs_f32(x, encM, w);
             uint32_t ac = w[0] & 0xffff0000u;
 #pragma unroll
             for (int i = 1; i < 32; ++i) ac |= w[i];

@@ -42,8 +42,6 @@ constexpr int PF_NG = 13;                                    // ring groups; the
 constexpr int PF_RING_MB = PF_NG * 8;                        // pipelines can have unfinished at once (4 x 24): see the empty-wait
 constexpr int PF_COEF_PITCH = 528;                           // bytes per slot: 512 + 16 (8 slots -> 8 different bank groups)
 constexpr int PF_PRED_PITCH = 80;                            // bytes per sub-block: 64 + 16
-constexpr int PF_XF_WARPS = 4;
-constexpr int PF_THREADS = (PF_COPY_WARPS + PF_XF_WARPS) * 32;
 constexpr int PF_CTAS_PER_SM = 1;
 
 struct __align__(16) PfGroup {
@@ -62,6 +60,9 @@ struct __align__(16) PfItemRec {
     uint32_t bx0_by0;                                        // pixel origin of the window's first macroblock: x | y << 16
     uint32_t hdr0;                                           // index of that macroblock in the frame's header / coefficient arrays
     uint32_t dst0;                                           // byte offset of its top-left pixel inside a frame slot
+    uint32_t pw, bw;                                         // the plane's padded width in pixels / in macroblocks
+    uint32_t max_xy;                                         // largest legal predictor origin: (pw - 16) | (ph - 16) << 16
+    uint32_t plane_off;                                      // byte offset of the plane inside a frame slot
 };
 
 struct PfJob {                                               // what the kernel needs of a DecJob, kept in shared memory: every
@@ -161,13 +162,15 @@ __device__ __forceinline__ void unpack_dequant_smem(const uint4 (&raw)[8], const
     }
 }
 
-__global__ void __launch_bounds__(PF_THREADS, PF_CTAS_PER_SM)
+template <int PF_XF_WARPS>
+__global__ void __launch_bounds__((PF_COPY_WARPS + PF_XF_WARPS) * 32, PF_CTAS_PER_SM)
 decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant__ McWin W, const DecJob *__restrict__ jobs,
                       uint32_t njobs, int *__restrict__ err,
                       const __grid_constant__ CUtensorMap tm_luma, const __grid_constant__ CUtensorMap tm_chroma)
 {
     extern __shared__ __align__(128) unsigned char pf_raw[];
     PfSmem &sm = *reinterpret_cast<PfSmem *>(pf_raw);
+    constexpr uint32_t PF_THREADS = (PF_COPY_WARPS + PF_XF_WARPS) * 32;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const FrameGeom &g = P.g;
     const uint32_t nitems = njobs * W.total;
@@ -206,6 +209,9 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         r.bx0_by0 = (tx * 128u) | (gy * (PF_ROWS * 16u)) << 16;
         r.hdr0 = pl.mb_base + gy * PF_ROWS * pl.bw + tx * 8u;
         r.dst0 = pl.off + gy * (PF_ROWS * 16u) * pl.pw + tx * 128u;
+        r.pw = pl.pw; r.bw = pl.bw;
+        r.max_xy = (pl.pw - 16u) | (pl.ph - 16u) << 16;
+        r.plane_off = pl.off;
         sm.item[pipe][i] = r;
     }
     __syncthreads();
@@ -279,7 +285,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
     // header word of this lane's macroblock (row `warp`, column `mb` of the window); bit 31 set = no such macroblock
     auto load_hw = [&](const PfItemRec &it) -> uint32_t {
         if (wrow >= ((it.job_p >> 20) & 15u) || mb >= (it.job_p >> 24)) return 0x80000000u;
-        return __ldg(sm.job[it.job_p & 0xffffu].hdr + it.hdr0 + wrow * plane((it.job_p >> 16) & 3u).bw + mb);
+        return __ldg(sm.job[it.job_p & 0xffffu].hdr + it.hdr0 + wrow * it.bw + mb);
     };
 
     // Software pipeline over windows k (being copied), k+1 (TMA in flight) and k+2 (TMA issued at the end of iteration k), headers
@@ -296,7 +302,6 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         if (k + 2u < nmine) hw_n2 = load_hw(items[k + 2u]);
 
         const uint32_t cjob = cur.job_p & 0xffffu, cp = (cur.job_p >> 16) & 3u;
-        const PlaneGeom &pl = plane(cp);
         const PfJob &job = sm.job[cjob];
         const bool exists = !(hw_cur & 0x80000000u);
         const bool coded = exists && ((hw_cur >> 16) & 0xffu) != 0u;
@@ -304,7 +309,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         int mvx = (int)(int8_t)(hw_cur & 0xffu), mvy = (int)(int8_t)((hw_cur >> 8) & 0xffu);   // src/common.rs:255-256
         if (exists) {
             const int sx = bx + mvx, sy = by + mvy;
-            if (sx < 0 || sy < 0 || sx > (int)pl.pw - 16 || sy > (int)pl.ph - 16) {
+            if (sx < 0 || sy < 0 || sx > (int)(cur.max_xy & 0xffffu) || sy > (int)(cur.max_xy >> 16)) {
                 // reference: debug_assert / slice panic (src/common.rs:258-259).  Never follow it: the stream is
                 // flagged bad and the co-located block is used.
                 if (rg == 0) atomicOr(err, ERRBIT_BAD_MV);
@@ -323,9 +328,10 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         if (coded) bar_wait(&sm.grp_empty[rgp], ((e / PF_RING_MB) & 1u) ^ 1u);   // the slot's previous tenant has been taken out
 
         bar_wait(&sm.win_full[pipe][st], (k / PF_STAGES) & 1u);
-        const uint32_t mb_off = cur.dst0 + wrow * 16u * pl.pw + mb * 16u;        // this macroblock's top-left pixel in a frame slot
+        const uint32_t pw = cur.pw;
+        const uint32_t mb_off = cur.dst0 + wrow * 16u * pw + mb * 16u;           // this macroblock's top-left pixel in a frame slot
         if (exists) {
-            uint8_t *dst = job.dst + mb_off + (size_t)rg * pl.pw;
+            uint8_t *dst = job.dst + mb_off + (size_t)rg * pw;
             const bool in_window = mvx >= -16 && mvx <= 15 && mvy >= -15 && mvy <= 15;
             // Vectors beyond +-15 are legal for the reference decoder (7-bit vectors, src/dec.rs:367-368) but outside the
             // staged window - its own encoder never searches further (src/common.rs:154-204).  Rare: fetch from global.
@@ -337,7 +343,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
                 if (in_window) {
                     o = win_row16(wline + i * 4 * PF_WIN_W, wx);
                 } else {
-                    const uint8_t *gsrc = job.ref + pl.off + (size_t)((uint32_t)(by + mvy) + rg + 4u * (uint32_t)i) * pl.pw + (uint32_t)(bx + mvx);
+                    const uint8_t *gsrc = job.ref + cur.plane_off + (size_t)((uint32_t)(by + mvy) + rg + 4u * (uint32_t)i) * pw + (uint32_t)(bx + mvx);
                     const uint2 a = ldg_u8x8_unaligned(gsrc);
                     const uint2 b = ldg_u8x8_unaligned(gsrc + 8);
                     o = make_uint4(a.x, a.y, b.x, b.y);
@@ -349,7 +355,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
                     *reinterpret_cast<uint2 *>(pp) = make_uint2(o.x, o.y);
                     *reinterpret_cast<uint2 *>(pp + 8 * PF_PRED_PITCH) = make_uint2(o.z, o.w);
                 } else {
-                    __stcg(reinterpret_cast<uint4 *>(dst + (size_t)(4 * i) * pl.pw), o);   // blit_block, src/common.rs:341-349
+                    __stcg(reinterpret_cast<uint4 *>(dst + (size_t)(4 * i) * pw), o);     // blit_block, src/common.rs:341-349
                 }
             }
         }
@@ -357,7 +363,7 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         __syncwarp();                                           // the four lanes of a macroblock have written its predictor
         if (coded && rg == 0) {
             bar_arrive_tx(&sm.grp_full[rgp], 512u);
-            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(cur.hdr0 + wrow * pl.bw + mb) * 256, 512u, &sm.grp_full[rgp]);
+            bulk_copy_g2s(grp.coef + sj * PF_COEF_PITCH, job.coeff + (size_t)(cur.hdr0 + wrow * cur.bw + mb) * 256, 512u, &sm.grp_full[rgp]);
         }
         // this warp is done with the window stage; the stage is refilled once all four are (no CTA or pipeline barrier: a
         // warp that finishes early goes on to the next window, only the leader's lane 0 waits for the slowest one)
@@ -385,13 +391,14 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
     }
 }
 
-cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, int *d_err,
-                                  const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s)
+template <int XF>
+static cudaError_t launch_decode_p_fused_t(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, int *d_err,
+                                           const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s)
 {
     static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const int smem = (int)sizeof(PfSmem);
     if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(decode_p_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(decode_p_fused_kernel<XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     const McWin W = make_mc_windows(P.g, PF_ROWS);
@@ -404,11 +411,20 @@ cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint3
         uint32_t ctas = (n * W.total + PF_PIPES - 1) / PF_PIPES;
         if (ctas > 148u * PF_CTAS_PER_SM) ctas = 148u * PF_CTAS_PER_SM;
         if ((n * W.total + ctas * PF_PIPES - 1) / (ctas * PF_PIPES) > (uint32_t)PF_PIPE_ITEMS) return cudaErrorInvalidConfiguration;   // (a frame of > 37 000 windows)
-        decode_p_fused_kernel<<<ctas, PF_THREADS, smem, s>>>(P, W, d_jobs + j0, n, d_err, tm_luma, tm_chroma);
+        decode_p_fused_kernel<XF><<<ctas, (PF_COPY_WARPS + XF) * 32, smem, s>>>(P, W, d_jobs + j0, n, d_err, tm_luma, tm_chroma);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, int *d_err,
+                                  const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s)
+{
+    static const int xf_env = getenv("PFV_PF_XF") ? atoi(getenv("PFV_PF_XF")) : 0;   // tuning aid: transform warps per CTA
+    if (xf_env == 4) return launch_decode_p_fused_t<4>(P, d_jobs, njobs, d_err, tm_luma, tm_chroma, s);
+    if (xf_env == 8) return launch_decode_p_fused_t<8>(P, d_jobs, njobs, d_err, tm_luma, tm_chroma, s);
+    return launch_decode_p_fused_t<6>(P, d_jobs, njobs, d_err, tm_luma, tm_chroma, s);
 }
 
 }  // namespace pfv

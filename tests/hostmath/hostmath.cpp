@@ -32,6 +32,21 @@ void pfv_hm_encode_sb(const void *in, int delta, const int32_t q[64], int16_t ou
     memcpy(out, w, 128);
 }
 
+// the fp32 formulation of the same (fdct8_f32 + quant_one_f32): must give the same bits
+void pfv_hm_encode_sb_f32(const void *in, int delta, const int32_t q[64], int16_t out[64])
+{
+    float y[64];
+    for (int i = 0; i < 64; i++) {
+        if (delta) y[i] = (float)(((const int16_t *)in)[i] / 2);
+        else       y[i] = byte_minus_128_f32((uint32_t)((const uint8_t *)in)[i], 0);
+    }
+    uint32_t M[64];
+    for (int i = 0; i < 64; i++) M[i] = quant_magic(q[i]);
+    uint32_t w[32];
+    encode_sb_regs_f32(y, M, w);
+    memcpy(out, w, 128);
+}
+
 // src/common.rs:313-325 through idct8x8_regs (the +128 folded into the row pass): out = clamp(m, 0, 255)
 void pfv_hm_decode_sb(const int16_t c[64], const int32_t q[64], uint8_t out[64])
 {

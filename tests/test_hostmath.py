@@ -59,6 +59,9 @@ def test_encode_subblock_matches_oracle(hm, quality):
         out = np.zeros(64, np.int16)
         hm.pfv_hm_encode_sb(_p(px), 0, _p(np.ascontiguousarray(q)), _p(out))
         assert np.array_equal(out, pfvo.encode_subblock(px, q)), (quality, trial)
+        outf = np.zeros(64, np.int16)
+        hm.pfv_hm_encode_sb_f32(_p(px), 0, _p(np.ascontiguousarray(q)), _p(outf))      # the fp32 formulation: same bits
+        assert np.array_equal(outf, out), (quality, trial, "f32")
 
 
 @pytest.mark.parametrize("quality", [0, 3, 5, 10])
@@ -74,6 +77,9 @@ def test_encode_subblock_delta_matches_oracle(hm, quality):
         out = np.zeros(64, np.int16)
         hm.pfv_hm_encode_sb(_p(d), 1, _p(np.ascontiguousarray(q)), _p(out))
         assert np.array_equal(out, pfvo.encode_subblock_delta(d, q)), (quality, trial)
+        outf = np.zeros(64, np.int16)
+        hm.pfv_hm_encode_sb_f32(_p(d), 1, _p(np.ascontiguousarray(q)), _p(outf))
+        assert np.array_equal(outf, out), (quality, trial, "f32")
 
 
 def test_encode_with_arbitrary_divisors(hm):
@@ -85,6 +91,9 @@ def test_encode_with_arbitrary_divisors(hm):
         out = np.zeros(64, np.int16)
         hm.pfv_hm_encode_sb(_p(px), 0, _p(q), _p(out))
         assert np.array_equal(out, pfvo.encode_subblock(px, q))
+        outf = np.zeros(64, np.int16)
+        hm.pfv_hm_encode_sb_f32(_p(px), 0, _p(q), _p(outf))
+        assert np.array_equal(outf, out)
 
 
 def test_decode_subblock_matches_oracle(hm):
