@@ -174,6 +174,8 @@ int  pfv_slot_device_ptr(pfv_ctx *ctx, uint32_t slot, void **out);
  * owns ("decode straight into a game-ready texture", README.md:20), ordered on the compute stream. */
 int  pfv_slot_read_rgb(pfv_ctx *ctx, uint32_t slot, uint8_t *rgb_host);
 int  pfv_slot_convert_rgb(pfv_ctx *ctx, uint32_t slot, void *rgb_device);
+/* the same for n slots in one launch per 64 pictures: picture i goes to rgb_device + i * stride (stride >= w*h*3) */
+int  pfv_slots_convert_rgb(pfv_ctx *ctx, const uint32_t *slots, uint32_t n, void *rgb_device, size_t stride);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Jobs of one call must be independent (no job's ref_slot is another job's dst_slot); calls are

@@ -121,6 +121,7 @@ SYMBOLS = {
     "pfv_slot_device_ptr": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "pfv_slot_read_rgb": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "pfv_slot_convert_rgb": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "pfv_slots_convert_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "pfv_decode_submit": (C.c_int, [C.c_void_p, C.POINTER(DecodeJob), C.c_uint32]),
     "pfv_encode_submit": (C.c_int, [C.c_void_p, C.POINTER(EncodeJob), C.c_uint32]),
     "pfv_decode_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(DecodeJobSparse), C.c_uint32]),

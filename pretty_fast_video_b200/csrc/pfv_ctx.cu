@@ -746,6 +746,23 @@ extern "C" int pfv_slot_convert_rgb(pfv_ctx *c, uint32_t slot, void *rgb_device)
     return convert_rgb(c, slot, static_cast<uint8_t *>(rgb_device), c->s_compute);
 }
 
+extern "C" int pfv_slots_convert_rgb(pfv_ctx *c, const uint32_t *slots, uint32_t n, void *rgb_device, size_t stride)
+{
+    if (!c || !slots || !rgb_device) return fail(PFV_ERR_BAD_ARG, "bad argument");
+    const size_t bytes = (size_t)c->geo.width * c->geo.height * 3;
+    if (stride < bytes) return fail(PFV_ERR_BAD_ARG, "stride %zu < %zu bytes of one RGB picture", stride, bytes);
+    for (uint32_t i = 0; i < n; i++)
+        if (slots[i] >= c->nslots) return fail(PFV_ERR_BAD_ARG, "slot %u out of range", slots[i]);
+    if (n == 0) return PFV_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    const pfv_geometry &g = c->geo;
+    const size_t ny = (size_t)g.pw * g.ph, nc = (size_t)g.cpw * g.cph;
+    CU_TRY(launch_yuv420_to_rgb_batch(c->d_pool, c->slot_stride, (uint32_t)ny, (uint32_t)(ny + nc), slots, n, g.width, g.height, g.pw,
+                                      g.cpw, static_cast<uint8_t *>(rgb_device), stride, c->s_compute));
+    c->launches += (n + 63) / 64;
+    return PFV_OK;
+}
+
 extern "C" int pfv_slot_read_rgb(pfv_ctx *c, uint32_t slot, uint8_t *rgb_host)
 {
     if (!c || slot >= c->nslots || !rgb_host) return fail(PFV_ERR_BAD_ARG, "bad argument");

@@ -283,6 +283,11 @@ class Engine:
     def slot_convert_rgb(self, slot: int, device_ptr: int):
         N.check(N.lib().pfv_slot_convert_rgb(self._ctx, slot, device_ptr))
 
+    def slots_convert_rgb(self, slots, device_ptr: int, stride: int):
+        """Batched pfv_slot_convert_rgb: picture i of `slots` goes to device_ptr + i * stride, one launch per 64 pictures."""
+        a = np.ascontiguousarray(slots, np.uint32)
+        N.check(N.lib().pfv_slots_convert_rgb(self._ctx, a.ctypes.data, a.size, device_ptr, stride))
+
     def slot_device_ptr(self, slot: int) -> int:
         p = C.c_void_p()
         N.check(N.lib().pfv_slot_device_ptr(self._ctx, slot, C.byref(p)))

@@ -92,3 +92,14 @@ def test_gpu_rgb_paths_match_oracle(size):
         e.slot_write(2, fr)
         y, u, v = pfvo.crop_frame(og, fr)
         assert np.array_equal(e.slot_read_rgb(2), pfvo.yuv420_to_rgb(y, u, v))
+        # (4) the batched entry point (pfv_slots_convert_rgb, one launch for several slots) against the oracle, slot by slot
+        nbytes = w * h * 3
+        stride = (nbytes + 255) & ~255
+        torch = pytest.importorskip("torch")                         # (only to own a piece of device memory)
+        buf = torch.empty(3 * stride, dtype=torch.uint8, device="cuda")
+        e.slots_convert_rgb([2, 0, 1], buf.data_ptr(), stride)
+        e.sync()
+        got = buf.cpu().numpy()
+        for i, (slot, rec) in enumerate(((2, fr), (0, rec0), (1, rec1))):
+            y, u, v = pfvo.crop_frame(og, rec)
+            assert np.array_equal(got[i * stride:i * stride + nbytes].reshape(h, w, 3), pfvo.yuv420_to_rgb(y, u, v)), f"batched picture {i}"
