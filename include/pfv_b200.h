@@ -251,7 +251,9 @@ int      pfv_ctx_wait_submit(pfv_ctx *ctx, uint64_t submit_id);
 /* number of kernel launches this context has issued (bench.py's gpu_launches) */
 uint64_t pfv_ctx_launch_count(const pfv_ctx *ctx);
 /* device time in ms of the compute-stream work between the first and last kernel of the most recent
- * *_submit call (CUDA events recorded on the compute stream around the launches); valid after pfv_sync. */
+ * *_submit call (CUDA events recorded on the compute stream around the launches); valid after pfv_sync.  Timing costs
+ * two driver calls per submit, so it is off until this function is called once: that first call switches it on and
+ * returns PFV_ERR_STATE. */
 int  pfv_ctx_last_kernel_ms(pfv_ctx *ctx, float *ms_out);
 
 

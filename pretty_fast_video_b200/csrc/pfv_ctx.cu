@@ -147,6 +147,19 @@ extern "C" void pfv_host_free(void *p)
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
+// cudaSetDevice costs a driver call; the calling thread is almost always on the context's device already.  A thread that
+// has never set a device reports device 0 WITHOUT having the primary context bound (cudaPointerGetAttributes then returns
+// no device pointer for pinned host memory): the first call on every thread always binds.
+inline cudaError_t ensure_device(int device)
+{
+    static thread_local bool bound = false;
+    int cur = -1;
+    if (bound && cudaGetDevice(&cur) == cudaSuccess && cur == device) return cudaSuccess;
+    const cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) bound = true;
+    return e;
+}
+
 constexpr int STAGES = 4;        // staging ring depth: H2D of submit n+1 overlaps the kernels of submit n
 constexpr int D2H_RING = 64;     // D2H completion events kept for slot-reuse ordering and pfv_ctx_wait_submit
 
@@ -169,6 +182,7 @@ struct Stage {
     cudaEvent_t ev_h2d = nullptr;    // job table + inputs are on the device
     cudaEvent_t ev_kernel = nullptr; // kernels that read/write the stage's device buffers are done
     cudaEvent_t ev_d2h = nullptr;    // copies out of the stage's device buffers are done (encode)
+    bool        d2h_used = false;    // an encode submit has recorded ev_d2h on this stage since a decode submit last waited for it
 };
 
 }  // namespace
@@ -207,8 +221,10 @@ struct pfv_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
     bool have_kernel_time = false;
+    bool want_kernel_time = false;         // pfv_ctx_last_kernel_ms has been called once: submits bracket their kernels with events
+                                           // from then on (two driver calls per submit that a caller who never asks does not pay)
     std::vector<int32_t> h_deq_scan;       // nq * 64: SCALE[s]*q[s] by scan position (src/dct.rs:78-83)
-    std::vector<uint32_t> h_enc_magic;     // nq * 64: quant_magic(q[raster]) by raster position (src/dct.rs:93-95)
+    std::vector<float> h_enc_recip;        // nq * 64: quant_recip_f32(q[raster]) by raster position (src/dct.rs:93-95)
     bool enc_tables_ok = false;            // tables 0..3 exist and every divisor is in 1..65535 (what an encoder needs)
     uint32_t cta_base[3] = {0, 0, 0}, cta_total = 0;   // sub-block kernels: CTAs of 32 macroblocks per plane
     // One default kernel per path plus independently written second implementations, selectable for the parity tests:
@@ -504,13 +520,13 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     for (uint32_t t = 0; t < c->nq; t++)
         for (int i = 0; i < 64; i++)
             c->h_deq_scan[t * 64 + i] = (int32_t)((uint32_t)kScale[i] * (uint32_t)qtables[t][i]);
-    c->h_enc_magic.resize((size_t)c->nq * 64);
+    c->h_enc_recip.resize((size_t)c->nq * 64);
     c->enc_tables_ok = c->nq >= 4;
     for (uint32_t t = 0; t < c->nq; t++)
         for (int i = 0; i < 64; i++) {
             const int32_t q = qtables[t][i];
             if (t < 4 && (q < 1 || q > QUANT_MAX_DIVISOR)) c->enc_tables_ok = false;
-            c->h_enc_magic[t * 64 + i] = quant_magic(q);
+            c->h_enc_recip[t * 64 + i] = quant_recip_f32(q);
         }
     {
         uint32_t cta = 0;
@@ -618,7 +634,7 @@ extern "C" uint64_t pfv_ctx_launch_count(const pfv_ctx *c) { return c ? c->launc
 extern "C" int pfv_sync(pfv_ctx *c)
 {
     if (!c) return fail(PFV_ERR_BAD_ARG, "NULL context");
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     CU_TRY(cudaStreamSynchronize(c->s_h2d));
     CU_TRY(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute));
     CU_TRY(cudaStreamSynchronize(c->s_compute));
@@ -628,9 +644,6 @@ extern "C" int pfv_sync(pfv_ctx *c)
         *c->h_err = 0;
         CU_TRY(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->s_compute));
         CU_TRY(cudaStreamSynchronize(c->s_compute));
-        if (bits & ERRBIT_TIMEOUT)
-            return fail(PFV_ERR_CUDA, "decode-P live mode: the residual kernel waited ~0.2 s for a frame the copy kernel never finished "
-                                      "(the two kernels were not co-resident?); pictures of that batch are incomplete");
         if (bits & ERRBIT_BAD_MV)
             return fail(PFV_ERR_BAD_MV, "a motion vector pointed outside the padded plane (src/common.rs:258-259); "
                                         "the co-located block was used instead");
@@ -642,8 +655,12 @@ extern "C" int pfv_sync(pfv_ctx *c)
 extern "C" int pfv_ctx_last_kernel_ms(pfv_ctx *c, float *ms_out)
 {
     if (!c || !ms_out) return fail(PFV_ERR_BAD_ARG, "NULL argument");
-    if (!c->have_kernel_time) return fail(PFV_ERR_STATE, "no kernel has been launched yet");
-    CU_TRY(cudaSetDevice(c->device));
+    if (!c->want_kernel_time) {
+        c->want_kernel_time = true;
+        return fail(PFV_ERR_STATE, "kernel timing was off: it is on from now on, ask again after the next submit");
+    }
+    if (!c->have_kernel_time) return fail(PFV_ERR_STATE, "no kernel has been launched since timing was switched on");
+    CU_TRY(ensure_device(c->device));
     CU_TRY(cudaEventSynchronize(c->ev_k1));
     CU_TRY(cudaEventElapsedTime(ms_out, c->ev_k0, c->ev_k1));
     return PFV_OK;
@@ -652,7 +669,7 @@ extern "C" int pfv_ctx_last_kernel_ms(pfv_ctx *c, float *ms_out)
 extern "C" int pfv_slot_reset(pfv_ctx *c, uint32_t slot)
 {
     if (!c || slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "bad slot");
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     int rc = wait_slot_readers(c, &slot, 1);
     if (rc) return rc;
     return init_slot(c, slot, c->s_compute);
@@ -714,7 +731,7 @@ static int copy_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint8_t *u, uint8
 extern "C" int pfv_slot_read_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint8_t *u, uint8_t *v)
 {
     if (!c || slot >= c->nslots) return fail(PFV_ERR_BAD_ARG, "bad slot");
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     // order after everything submitted so far on the compute stream; takes a submit id of its own so the
     // slot-reuse bookkeeping sees this read
     const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
@@ -742,7 +759,7 @@ static int convert_rgb(pfv_ctx *c, uint32_t slot, uint8_t *d_out, cudaStream_t s
 extern "C" int pfv_slot_convert_rgb(pfv_ctx *c, uint32_t slot, void *rgb_device)
 {
     if (!c || slot >= c->nslots || !rgb_device) return fail(PFV_ERR_BAD_ARG, "bad argument");
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     return convert_rgb(c, slot, static_cast<uint8_t *>(rgb_device), c->s_compute);
 }
 
@@ -754,7 +771,7 @@ extern "C" int pfv_slots_convert_rgb(pfv_ctx *c, const uint32_t *slots, uint32_t
     for (uint32_t i = 0; i < n; i++)
         if (slots[i] >= c->nslots) return fail(PFV_ERR_BAD_ARG, "slot %u out of range", slots[i]);
     if (n == 0) return PFV_OK;
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     const pfv_geometry &g = c->geo;
     const size_t ny = (size_t)g.pw * g.ph, nc = (size_t)g.cpw * g.cph;
     CU_TRY(launch_yuv420_to_rgb_batch(c->d_pool, c->slot_stride, (uint32_t)ny, (uint32_t)(ny + nc), slots, n, g.width, g.height, g.pw,
@@ -766,7 +783,7 @@ extern "C" int pfv_slots_convert_rgb(pfv_ctx *c, const uint32_t *slots, uint32_t
 extern "C" int pfv_slot_read_rgb(pfv_ctx *c, uint32_t slot, uint8_t *rgb_host)
 {
     if (!c || slot >= c->nslots || !rgb_host) return fail(PFV_ERR_BAD_ARG, "bad argument");
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     const size_t bytes = (size_t)c->geo.width * c->geo.height * 3;
     if (!c->d_rgb) {
         CU_TRY(cudaMalloc(&c->d_rgb, bytes));
@@ -844,7 +861,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                 if (jobs[k].dst_slot == jobs[i].ref_slot)
                     return fail(PFV_ERR_BAD_ARG, "jobs %u and %u of one submit are dependent (ref_slot == dst_slot)", i, k);
 
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     bool any_dense_host = false;
     if (c->host_compact)
         for (uint32_t i = 0; i < njobs; i++) any_dense_host |= !jobs[i].sparse && !(jobs[i].flags & PFV_JOB_DEVICE_PTRS);
@@ -856,11 +873,31 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         int rc = ensure_compact_staging(c);
         if (rc) return rc;
     }
+    // Small submits (a 512x384 frame: ~0.1 MB up, 0.3 MB down) are bound by the ~20 driver calls of the three-stream
+    // pipeline, not by bytes: they go out on the compute stream alone - copies, kernels and the copy back in stream order,
+    // no cross-stream events (8 fewer calls per submit).  Large submits keep the H2D / compute / D2H overlap.
+    size_t moved = 0;
+    for (uint32_t i = 0; i < njobs; i++) {
+        const DecIn &j = jobs[i];
+        if (j.sparse) moved += ((size_t)j.ntok + 2 * (size_t)g.nb + 1) * 4;
+        else if (!(j.flags & PFV_JOB_DEVICE_PTRS)) moved += (size_t)g.nb * 516;
+        if (j.out_y) moved += (size_t)g.width * g.height * 3 / 2;
+    }
+    // (a batch of device-resident frames moves nothing but is not small: its job table must travel on the copy stream while
+    // the previous submit's kernels still run, or every launch waits for a PCIe round trip)
+    static const int lean_env = getenv("PFV_LEAN_SUBMIT") ? atoi(getenv("PFV_LEAN_SUBMIT")) : 1;
+    const bool lean = lean_env && !any_dense_host && moved <= ((size_t)3 << 19) && (uint64_t)njobs * g.nb <= 4096u;   // 1.5 MB, 4 096 macroblocks
+    cudaStream_t s_up = lean ? c->s_compute : c->s_h2d, s_down = lean ? c->s_compute : c->s_d2h;
+
     const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
-    CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_kernel, 0));     // device buffers of this stage are free again
-    CU_TRY(cudaStreamWaitEvent(c->s_h2d, st.ev_d2h, 0));        // ... also for an encode submit that used the stage before
+    if (!lean) CU_TRY(cudaStreamWaitEvent(s_up, st.ev_kernel, 0));   // device buffers of this stage are free again (ev_kernel is
+                                                                     // always recorded on the compute stream: in order when lean)
+    if (st.d2h_used) {                                          // ... also for an encode submit that used the stage before
+        CU_TRY(cudaStreamWaitEvent(s_up, st.ev_d2h, 0));
+        st.d2h_used = false;
+    }
 
     // dense HOST coefficients: compact them to tokens on the host pool (the stage's pinned token buffers are free: the
     // H2D copies that read them were waited for above) and carry on as sparse jobs
@@ -912,7 +949,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     // pinned arena gets one big copy instead of njobs small ones)
     const int16_t *run_src = nullptr; int16_t *run_dst = nullptr; size_t run_elems = 0;
     auto flush_run = [&]() -> int {
-        if (run_elems) CU_TRY(cudaMemcpyAsync(run_dst, run_src, run_elems * sizeof(int16_t), cudaMemcpyHostToDevice, c->s_h2d));
+        if (run_elems) CU_TRY(cudaMemcpyAsync(run_dst, run_src, run_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s_up));
         run_elems = 0;
         return PFV_OK;
     };
@@ -935,12 +972,12 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
                 if (h_hdr32 && h_hdr32 == j.mb_off + (g.nb + 1) && (j.ntok == 0 || j.tok == h_hdr32 + g.nb)) {
                     // mb_off | headers | tokens adjacent in host memory: one copy
                     CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, ((size_t)(g.nb + 1) + g.nb + j.ntok) * sizeof(uint32_t),
-                                           cudaMemcpyHostToDevice, c->s_h2d));
+                                           cudaMemcpyHostToDevice, s_up));
                 } else {
-                    if (j.ntok) CU_TRY(cudaMemcpyAsync(d_tok, j.tok, (size_t)j.ntok * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
-                    CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, (size_t)(g.nb + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_h2d));
+                    if (j.ntok) CU_TRY(cudaMemcpyAsync(d_tok, j.tok, (size_t)j.ntok * sizeof(uint32_t), cudaMemcpyHostToDevice, s_up));
+                    CU_TRY(cudaMemcpyAsync(d_mboff, j.mb_off, (size_t)(g.nb + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s_up));
                     if (j.kind == PFV_FRAME_P)
-                        CU_TRY(cudaMemcpyAsync(d_shdr, j.hdr, (size_t)g.nb * sizeof(pfv_mbhdr), cudaMemcpyHostToDevice, c->s_h2d));
+                        CU_TRY(cudaMemcpyAsync(d_shdr, j.hdr, (size_t)g.nb * sizeof(pfv_mbhdr), cudaMemcpyHostToDevice, s_up));
                 }
                 SparseJob &sj = st.h_sjobs[nsparse++];
                 sj.mb_off = d_mboff;
@@ -960,7 +997,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
             d.coeff = d_coeff;
             d.hdr = nullptr;
             if (j.kind == PFV_FRAME_P) {
-                CU_TRY(cudaMemcpyAsync(d_hdr, j.hdr, (size_t)g.nb * sizeof(pfv_mbhdr), cudaMemcpyHostToDevice, c->s_h2d));
+                CU_TRY(cudaMemcpyAsync(d_hdr, j.hdr, (size_t)g.nb * sizeof(pfv_mbhdr), cudaMemcpyHostToDevice, s_up));
                 d.hdr = d_hdr;
             }
         }
@@ -974,19 +1011,19 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         int rc = flush_run();
         if (rc) return rc;
     }
-    if (nsparse) CU_TRY(cudaMemcpyAsync(st.d_sjobs, st.h_sjobs, sizeof(SparseJob) * nsparse, cudaMemcpyHostToDevice, c->s_h2d));
-    CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(DecJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
-    CU_TRY(cudaEventRecord(st.ev_h2d, c->s_h2d));
+    if (nsparse) CU_TRY(cudaMemcpyAsync(st.d_sjobs, st.h_sjobs, sizeof(SparseJob) * nsparse, cudaMemcpyHostToDevice, s_up));
+    CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(DecJob) * njobs, cudaMemcpyHostToDevice, s_up));
+    CU_TRY(cudaEventRecord(st.ev_h2d, s_up));
 
     // compute
-    CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
+    if (!lean) CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
     {
         std::vector<uint32_t> dsts(njobs);
         for (uint32_t i = 0; i < njobs; i++) dsts[i] = jobs[i].dst_slot;
         int rc = wait_slot_readers(c, dsts.data(), njobs);
         if (rc) return rc;
     }
-    CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
+    if (c->want_kernel_time) CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
     if (nsparse) {
         CU_TRY(launch_expand_tokens(g.nb, st.d_sjobs, nsparse, c->s_compute));
         c->launches++;
@@ -1011,7 +1048,8 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
             uint32_t b = a + 1;
             while (b < n_i && qkey(order[b]) == qkey(order[a])) b++;
             const SbParams P = sb_params(order[a]);
-            if (c->decode_i_variant == 1 || dense_hint(order[a])) CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
+            if (c->decode_i_variant == 1) CU_TRY(launch_decode_i_sb(P, d_tab + a, b - a, c->s_compute));
+            else if (dense_hint(order[a])) CU_TRY(launch_decode_i_direct(P, d_tab + a, b - a, c->s_compute));
             else CU_TRY(launch_decode_i_stream(P, d_tab + a, b - a, c->s_compute));
             c->launches++;
             a = b;
@@ -1043,24 +1081,23 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
             a = b;
         }
     }
-    CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
-    c->have_kernel_time = true;
+    if (c->want_kernel_time) { CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute)); c->have_kernel_time = true; }
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
 
     // copy out
     bool any_out = false;
     for (uint32_t i = 0; i < njobs; i++) any_out |= jobs[i].out_y != nullptr;
     if (any_out) {
-        CU_TRY(cudaStreamWaitEvent(c->s_d2h, st.ev_kernel, 0));
+        if (!lean) CU_TRY(cudaStreamWaitEvent(s_down, st.ev_kernel, 0));
         for (uint32_t i = 0; i < njobs; i++) {
             const DecIn &j = jobs[i];
             if (!j.out_y) continue;
-            int rc = copy_visible(c, j.dst_slot, j.out_y, j.out_u, j.out_v, c->s_d2h);
+            int rc = copy_visible(c, j.dst_slot, j.out_y, j.out_u, j.out_v, s_down);
             if (rc) return rc;
             c->slot_last_d2h[j.dst_slot] = id;
         }
     }
-    CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
+    CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], s_down));
     return PFV_OK;
 }
 
@@ -1127,7 +1164,7 @@ extern "C" int pfv_ctx_wait_submit(pfv_ctx *c, uint64_t id)
         return fail(PFV_ERR_BAD_ARG, "submit id %llu is older than the %d most recent submits", (unsigned long long)id, D2H_RING);
     if (__atomic_load_n(&c->failed_ring[id % D2H_RING], __ATOMIC_ACQUIRE) == id)
         return fail(PFV_ERR_CUDA, "submit %llu failed after it was issued (see the error it returned)", (unsigned long long)id);
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     CU_TRY(cudaEventSynchronize(c->ev_d2h_ring[id % D2H_RING]));
     return PFV_OK;
 }
@@ -1194,7 +1231,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         return fail(PFV_ERR_BAD_ARG, "encoding needs q-tables 0..3 (intra_l, intra_c, inter_l, inter_c) with every divisor in 1..%d",
                     (int)QUANT_MAX_DIVISOR);
 
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     const double t0 = c->trace ? host_now() : 0;
     {
         int rc = ensure_src_staging(c);
@@ -1301,7 +1338,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         int rc = wait_slot_readers(c, dsts.data(), njobs);
         if (rc) return rc;
     }
-    CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
+    if (c->want_kernel_time) CU_TRY(cudaEventRecord(c->ev_k0, c->s_compute));
     for (const RgbConv &rc : conv) {
         CU_TRY(launch_rgb_to_yuv420(rc.rgb, g.width, g.height, rc.planes + c->src_off[0], rc.planes + c->src_off[1],
                                     rc.planes + c->src_off[2], c->s_compute));
@@ -1316,7 +1353,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
             EncSbParams P;
             P.g = c->fg;
             for (int t = 0; t < 2; t++) {                              // intra_l, intra_c (src/enc.rs:84-90)
-                memcpy(P.encM[t], &c->h_enc_magic[(size_t)t * 64], 64 * sizeof(uint32_t));
+                memcpy(P.encR[t], &c->h_enc_recip[(size_t)t * 64], 64 * sizeof(float));
                 memcpy(P.deq[t], &c->h_deq_scan[(size_t)t * 64], 64 * sizeof(int32_t));
             }
             CU_TRY(launch_encode_i_stream(P, d_tab, n_i, count, c->s_compute));
@@ -1328,8 +1365,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         c->launches++;
     }
     if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 2; }
-    CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute));
-    c->have_kernel_time = true;
+    if (c->want_kernel_time) { CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute)); c->have_kernel_time = true; }
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
     const double t4 = c->trace ? host_now() : 0;
 
@@ -1352,6 +1388,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         }
     }
     CU_TRY(cudaEventRecord(st.ev_d2h, c->s_d2h));
+    st.d2h_used = true;
     CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], c->s_d2h));
     if (c->trace) {
         const double t5 = host_now();
@@ -1381,7 +1418,7 @@ extern "C" int pfv_encode_submit_sparse(pfv_ctx *c, const pfv_encode_job_sparse 
 {
     if (!c || !jobs) return fail(PFV_ERR_BAD_ARG, "NULL argument");
     if (njobs == 0) return PFV_OK;
-    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(ensure_device(c->device));
     std::vector<EncIn> in(njobs);
     for (uint32_t i = 0; i < njobs; i++) {
         const pfv_encode_job_sparse &j = jobs[i];

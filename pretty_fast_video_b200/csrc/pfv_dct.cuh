@@ -127,6 +127,41 @@ PFV_UNROLL
 }
 
 
+// The same with ONE copy of the eight 1-D transforms in the code: `t` holds the sub-block TRANSPOSED (t[c * 8 + r] = the
+// coefficient of row r, column c - a renaming where it is filled), both passes run the same loop body over contiguous
+// groups of eight and swap the roles of rows and columns on the way out, so the result comes back in raster order in `t`.
+// 64 register moves per pass buy half the instruction footprint (the straight-line form is ~15 KB of code; kernels that
+// carry a forward transform next to it outgrow the 32 KB instruction cache).  Same values as idct8x8_regs.
+PFV_HD void idct8x8_regs_rolled(int (&t)[64])
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int pass = 0; pass < 2; ++pass) {
+        int o[64];
+PFV_UNROLL
+        for (int g = 0; g < 8; ++g) {
+            int v[8];
+PFV_UNROLL
+            for (int k = 0; k < 8; ++k) v[k] = t[g * 8 + k];
+            idct8(v);
+PFV_UNROLL
+            for (int k = 0; k < 8; ++k) o[k * 8 + g] = v[k];
+        }
+        // after the column pass o[r * 8 + c] is raster order: the row pass wants +128 on each row's DC input (see
+        // idct8x8_regs); after the row pass the groups were rows, so o is the transposed result
+        const int bias = pass == 0 ? (128 << 8) : 0;
+PFV_UNROLL
+        for (int i = 0; i < 64; ++i) t[i] = o[i] + ((i & 7) == 0 ? bias : 0);
+    }
+    // t[c * 8 + r] now holds pixel (r, c) << 8: hand it back in raster order
+    int o[64];
+PFV_UNROLL
+    for (int i = 0; i < 64; ++i) o[(i & 7) * 8 + (i >> 3)] = t[i] >> 8;
+PFV_UNROLL
+    for (int i = 0; i < 64; ++i) t[i] = o[i];
+}
+
 // src/dct.rs:4-13 DCT_SCALE_FACTOR by raster position (used only with compile-time indices)
 #define PFV_SCALE_INIT { \
     32, 37, 34, 26, 32, 26, 34, 37, \
@@ -161,6 +196,23 @@ PFV_UNROLL
     }
 }
 
+PFV_HD float bits_as_float(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; __builtin_memcpy(&f, &u, 4); return f;
+#endif
+}
+PFV_HD uint32_t float_as_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; __builtin_memcpy(&u, &f, 4); return u;
+#endif
+}
+
 // The same transform in fp32.  With exact divisions (above) the butterfly is LINEAR with dyadic coefficients
 // (x + x/4 - x/16 = 19/16 x, x - x/4 - x/16 = 11/16 x, ...): computed on the UNSCALED inputs y = p - 128 (or delta / 2), |y| <= 128,
 // every intermediate is a multiple of 2^-8 below 2^14 - 22 significant bits, exactly representable, and an FMA whose exact
@@ -183,6 +235,61 @@ PFV_HD void fdct8_f32(float (&v)[8])
     v[4] = c1; v[5] = c5 + c7; v[6] = c3; v[7] = c6;
 }
 
+// the two halves of fdct8_f32: `a` = the first butterfly layer (sums a0..a3, differences a4..a7)
+PFV_HD void fdct8_f32_tail(const float (&a)[8], float (&v)[8])
+{
+    const float b0 = a[0] + a[3], b1 = a[1] + a[2], b2 = a[0] - a[3], b3 = a[1] - a[2];
+    const float c0 = b0 + b1, c1 = b0 - b1;
+    const float c2 = fmaf(b2, 1.25f, b3 * 0.5f);
+    const float c3 = fmaf(b3, -1.25f, b2 * 0.5f);
+    const float b4 = fmaf(a[4], 1.1875f, a[7] * 0.25f);
+    const float b7 = fmaf(a[7], -1.1875f, a[4] * 0.25f);
+    const float b5 = fmaf(a[6], 0.6875f, a[5]);
+    const float b6 = fmaf(a[5], -0.6875f, a[6]);
+    const float c4 = b4 + b5, c5 = b4 - b5, c6 = b6 + b7, c7 = b6 - b7;
+    v[0] = c0; v[1] = c4; v[2] = c2; v[3] = c5 - c7;
+    v[4] = c1; v[5] = c5 + c7; v[6] = c3; v[7] = c6;
+}
+
+// One row of eight PIXELS (two little-endian words) through the level shift (p - 128, src/common.rs:291) and fdct8_f32 without
+// converting the bytes one by one: 0x4B000000 | p is the float 2^23 + p, so a difference of two such floats is p_i - p_j
+// exactly, and a sum with its two level shifts is (f_i - (2^24 + 256)) + f_j - every intermediate an integer below 2^24.
+// 12 additions for the first layer instead of 8 conversions + 8.
+PFV_HD void fdct8_f32_row_of_bytes(uint32_t lo, uint32_t hi, float (&v)[8])
+{
+    float f[8];
+PFV_UNROLL
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t w = k < 4 ? lo : hi;
+#if defined(__CUDA_ARCH__)
+        f[k] = bits_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | (k & 3)));
+#else
+        f[k] = bits_as_float(0x4B000000u | ((w >> (8 * (k & 3))) & 0xffu));
+#endif
+    }
+    float a[8];
+PFV_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        a[k] = (f[k] - 16777472.0f) + f[7 - k];                  // p_k + p_(7-k) - 256
+        a[4 + k] = f[k] - f[7 - k];
+    }
+    fdct8_f32_tail(a, v);
+}
+
+// column pass of the fp32 forward transform over 64 values whose rows are already transformed
+PFV_HD void fdct8x8_f32_columns(float (&m)[64])
+{
+PFV_UNROLL
+    for (int c = 0; c < 8; ++c) {
+        float v[8];
+PFV_UNROLL
+        for (int r = 0; r < 8; ++r) v[r] = m[r * 8 + c];
+        fdct8_f32(v);
+PFV_UNROLL
+        for (int r = 0; r < 8; ++r) m[r * 8 + c] = v[r];
+    }
+}
+
 PFV_HD void fdct8x8_f32(float (&m)[64])
 {
 PFV_UNROLL
@@ -203,23 +310,6 @@ PFV_UNROLL
 PFV_UNROLL
         for (int r = 0; r < 8; ++r) m[r * 8 + c] = v[r];
     }
-}
-
-PFV_HD float bits_as_float(uint32_t u)
-{
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(u);
-#else
-    float f; __builtin_memcpy(&f, &u, 4); return f;
-#endif
-}
-PFV_HD uint32_t float_as_bits(float f)
-{
-#if defined(__CUDA_ARCH__)
-    return __float_as_uint(f);
-#else
-    uint32_t u; __builtin_memcpy(&u, &f, 4); return u;
-#endif
 }
 
 // byte k of a word as (p - 128) in fp32 without a conversion instruction: 0x4B000000 | p is the float 2^23 + p
@@ -259,14 +349,25 @@ PFV_HD int quant_one(int v, int scale, uint32_t M)
     return mulhi_s32(t, (int)M) + (int)((uint32_t)a >> 31);
 }
 
-// the quantiser on the fp32 transform's output V (unscaled: the reference's value is 256 V): the magic-number FFMA leaves
-// 256 V + 1.5 * 2^23 as a float whose bit pattern is 0x4B400000 + 256 V; the subtraction folds into the multiply-add
-PFV_HD int quant_one_f32(float V, int scale, uint32_t M)
+// The quantiser on the fp32 transform's output V (unscaled: the reference's value is 256 V), entirely on the FMA pipe:
+//   n = (256 V * scale) >> 16 = floor(V * scale / 256): ONE fused multiply-add that rounds toward minus infinity onto
+//       1.5 * 2^23 (ulp 1 there; the product is exact inside the FMA, so the rounding IS the floor), |n| < 2^12;
+//   n / q truncating = trunc(n * R), R = quant_recip_f32(q) a little ABOVE 1/q: n R >= n/q keeps exact multiples, and the
+//       excess |n| * 2^-15 / q stays below the 1/q that separates n/q from the next integer.
+// FFMA.RM, FADD, FMUL, F2I.TRUNC: 4 instructions per coefficient (the integer form above takes 6 to 8).
+// tests/test_hostmath.py checks trunc(n * R) == n / q for every |n| <= 4096 and every q in 1..65535.
+inline float quant_recip_f32(int32_t q) { return q > 0 ? (float)((1.0 / (double)q) * (1.0 + 1.0 / 32768.0)) : 0.0f; }
+
+PFV_HD int quant_trunc_f32(float nf, float R) { return (int)(nf * R); }         // cvt.rzi.s32.f32
+
+PFV_HD int quant_one_f32(float V, int scale, float R)
 {
-    const int vi = (int)float_as_bits(fmaf(V, 256.0f, 12582912.0f));
-    const int a = vi * scale - 0x4B400000 * scale;                  // (256 V) * scale, wrapping like the integer path
-    const int t = (a >> 14) & ~3;
-    return mulhi_s32(t, (int)M) + (int)((uint32_t)a >> 31);
+#if defined(__CUDA_ARCH__)
+    const float nf = __fmaf_rd(V, (float)scale * 0.00390625f, 12582912.0f) - 12582912.0f;
+#else
+    const float nf = (float)floor((double)V * (double)scale * 0.00390625);        // exact in double
+#endif
+    return quant_trunc_f32(nf, R);
 }
 
 // two quantised coefficients -> one word of the dense layout (low half first)
@@ -282,17 +383,38 @@ PFV_HD uint32_t pack_i16x2(int lo, int hi)
 // src/common.rs:287-298 / :300-311 after the level shift: x = the 64 inputs in raster order ((p - 128) << 8 or
 // (delta / 2) << 8).  Leaves the quantised coefficients in SCAN order, two per word, exactly as the dense layout
 // stores them (src/dct.rs:88-99).  encM = quant_magic of the q-table by RASTER position.
-// the same on fp32 inputs y = p - 128 (or delta / 2), unscaled (see fdct8_f32)
-PFV_HD void encode_sb_regs_f32(float (&y)[64], const uint32_t *encM, uint32_t (&w)[32])
+// the same on fp32 inputs y = p - 128 (or delta / 2), unscaled (see fdct8_f32); encR = quant_recip_f32 of the q-table by
+// RASTER position
+PFV_HD void quantise_sb_f32(const float (&y)[64], const float *encR, uint32_t (&w)[32])
 {
     constexpr int zz[64] = PFV_ZIGZAG_INIT;
     constexpr int sc[64] = PFV_SCALE_INIT;
-    fdct8x8_f32(y);
 PFV_UNROLL
     for (int i = 0; i < 32; ++i) {
         const int z0 = zz[2 * i], z1 = zz[2 * i + 1];
-        w[i] = pack_i16x2(quant_one_f32(y[z0], sc[z0], encM[z0]), quant_one_f32(y[z1], sc[z1], encM[z1]));
+        w[i] = pack_i16x2(quant_one_f32(y[z0], sc[z0], encR[z0]), quant_one_f32(y[z1], sc[z1], encR[z1]));
     }
+}
+
+PFV_HD void encode_sb_regs_f32(float (&y)[64], const float *encR, uint32_t (&w)[32])
+{
+    fdct8x8_f32(y);
+    quantise_sb_f32(y, encR, w);
+}
+
+// ... on the sub-block's eight rows of PIXELS as they were loaded (rows[r] = bytes 0..3, 4..7 of row r)
+PFV_HD void encode_sb_pixels_f32(const uint32_t (&lo)[8], const uint32_t (&hi)[8], const float *encR, uint32_t (&w)[32])
+{
+    float y[64];
+PFV_UNROLL
+    for (int r = 0; r < 8; ++r) {
+        float v[8];
+        fdct8_f32_row_of_bytes(lo[r], hi[r], v);
+PFV_UNROLL
+        for (int c = 0; c < 8; ++c) y[r * 8 + c] = v[c];
+    }
+    fdct8x8_f32_columns(y);
+    quantise_sb_f32(y, encR, w);
 }
 
 PFV_HD void encode_sb_regs(int (&x)[64], const uint32_t *encM, uint32_t (&w)[32])

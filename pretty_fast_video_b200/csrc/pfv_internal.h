@@ -92,7 +92,7 @@ struct SbParams {
 // as kernel parameters so that the quantiser's multiplies take them as constant-bank operands.
 struct EncSbParams {
     FrameGeom g;
-    uint32_t  encM[2][64];    // luma / chroma: quant_magic(q) by RASTER position (src/dct.rs:93-95)
+    float     encR[2][64];    // luma / chroma: quant_recip_f32(q) by RASTER position (src/dct.rs:93-95)
     int32_t   deq[2][64];     // luma / chroma: SCALE[s]*q[s] by SCAN position (the closed-loop reconstruction)
     uint32_t  cta_base[3];
     uint32_t  cta_total;
@@ -155,6 +155,8 @@ cudaError_t launch_decode(bool inter, const FrameGeom &g, const DecJob *d_jobs, 
                           int *d_err, cudaStream_t s);
 cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_decode_i_stream(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
+// frames flagged dense: cp.async-staged tiles, every sub-block through the full transform (pfv_kernels_sb.cu)
+cudaError_t launch_decode_i_direct(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s);
 // window copy + list-driven residual pass (pfv_kernels_p.cu); d_done != nullptr: the residual kernel clears d_counts itself
 cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, uint32_t *d_lists, uint32_t *d_counts,
                                       int *d_err, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s,

@@ -40,33 +40,52 @@ struct __align__(16) EncStreamSmem {
     uint4    out[ENC_WARPS][32 * ENC_OUT_PITCH / 16];
 };
 
-// 8 bytes of a source row whose plane width is not a multiple of 8 (or whose base is unaligned): byte by byte, padded with the
-// clear colour.  Rare and out of line: the streaming kernel's loop must stay small enough for the instruction cache.
-__device__ __noinline__ uint2 load_src_row_ragged(const uint8_t *__restrict__ p, uint32_t x0, uint32_t vw, uint32_t clear)
+// Rows y0 .. y0+7, bytes x0 .. x0+7 of a tight vw x vh source plane that are NOT all inside the plane (or whose rows are not
+// 8-byte aligned): byte by byte, padded with the clear colour (src/common.rs:352-356).  Rare (the bottom and right edges)
+// and out of line: the streaming kernel's loop must stay small enough for the instruction cache.
+__device__ __noinline__ void load_src_sb_edge(const uint8_t *__restrict__ src, uint32_t vw, uint32_t vh, uint32_t clear,
+                                              uint32_t x0, uint32_t y0, uint2 *rows)
 {
-    uint32_t w[2] = {0u, 0u};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t b = (x0 + k < vw) ? (uint32_t)p[k] : (clear & 0xffu);
-        w[k >> 2] |= b << (8 * (k & 3));
-    }
-    return make_uint2(w[0], w[1]);
-}
-
-// rows y0 .. y0+7, bytes x0 .. x0+7 of a tight vw x vh source plane, padded with the clear colour (src/common.rs:352-356)
-__device__ __forceinline__ void load_src_sb(const uint8_t *__restrict__ src, const PlaneGeom &pl, uint32_t x0, uint32_t y0,
-                                            bool fast, uint2 (&rows)[8])
-{
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
         const uint32_t y = y0 + (uint32_t)r;
-        uint2 v = make_uint2(pl.clear4, pl.clear4);
-        if (y < pl.vh && x0 < pl.vw) {
-            const uint8_t *p = src + (size_t)y * pl.vw + x0;
-            if (fast) v = __ldcs(reinterpret_cast<const uint2 *>(p));   // vw % 8 == 0 and base 8-byte aligned: all 8 bytes exist
-            else      v = load_src_row_ragged(p, x0, pl.vw, pl.clear4);
+        uint32_t w[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t x = x0 + (uint32_t)k;
+            const uint32_t b = (y < vh && x < vw) ? (uint32_t)src[(size_t)y * vw + x] : (clear & 0xffu);
+            w[k >> 2] |= b << (8 * (k & 3));
         }
-        rows[r] = v;
+        rows[r] = make_uint2(w[0], w[1]);
+    }
+}
+
+// the eight 8-byte rows of sub-block `sb` of macroblock `lm` of a tight source plane
+__device__ __forceinline__ void load_src_sb(const uint8_t *__restrict__ src, const PlaneGeom &pl, uint32_t lm, uint32_t sb,
+                                            bool aligned, uint2 (&rows)[8])
+{
+    uint32_t col;
+    const uint32_t row = div_small(lm, pl.bw, pl.rcp_bw, col);
+    const uint32_t x0 = col * 16u + (sb & 1u) * 8u, y0 = row * 16u + (sb >> 1) * 8u;
+    if (aligned && x0 + 8u <= pl.vw && y0 + 8u <= pl.vh) {        // vw % 8 == 0 and base 8-byte aligned: all 64 bytes exist
+        const uint8_t *q = src + (size_t)y0 * pl.vw + x0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) rows[r] = __ldcs(reinterpret_cast<const uint2 *>(q + (size_t)r * pl.vw));
+    } else {
+        uint2 tmp[8];                                             // (its address escapes: keep `rows` itself in registers)
+        load_src_sb_edge(src, pl.vw, pl.vh, pl.clear4, x0, y0, tmp);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) rows[r] = tmp[r];
+    }
+}
+
+// the last tile of a plane when it holds fewer than 8 macroblocks: the coalesced copy out of the stage, predicated
+__device__ __noinline__ void store_partial_tile(const unsigned char *stg, uint4 *dstc, uint32_t tile_mbs, uint32_t lane)
+{
+#pragma unroll 1
+    for (uint32_t j = 0; j < 8u; ++j) {
+        const uint32_t c = j * 32u + lane;
+        if ((c >> 5) < tile_mbs) __stcs(dstc + c, *reinterpret_cast<const uint4 *>(stg + (c >> 3) * 144u + (c & 7u) * 16u));
     }
 }
 
@@ -93,66 +112,61 @@ __device__ __forceinline__ uint32_t mb_entry_count_lanes(const SbRuns &r, uint32
     return n;
 }
 
-// CTAS = resident CTAs per SM the kernel is compiled for (3: 168 registers - room to keep the next tile's 16 source
-// words in flight across the whole transform).  The loop has ONE copy of the forward and ONE of the inverse
-// transform (ncu on the first version: 5 400 instructions, a third of all stall samples "no instruction" - the
-// instruction cache): the next tile is fetched at the top of an iteration that then works on the previous one, and
-// what a warp has left in its ring at the end is drained by the same transform site with the idle lanes masked off.
-template <bool COUNT, int CTAS>
-__global__ void __launch_bounds__(ENC_WARPS * 32, CTAS)
-encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__restrict__ jobs)
+// PC = plane class (0 luma, 1 chroma): the quantiser's reciprocals and the dequantiser's multipliers are then compile-time
+// offsets into the kernel parameters, i.e. constant-bank operands of the multiplies (selected at run time every one of the
+// 128 table reads of a sub-block was a uniform load instruction of its own).  The loop has ONE copy of the forward and ONE
+// of the inverse transform (ncu on the first version: 5 400 instructions, a third of all stall samples "no instruction" -
+// the instruction cache): what a warp has left in its ring at the end is drained by the same transform site with the idle
+// lanes masked off.
+template <bool COUNT, int PC, bool ROLLED>
+__device__ __forceinline__ void encode_i_tiles(const EncSbParams &P, const EncJob &job, EncStreamSmem &sm, const int p, const uint32_t cta_in_plane)
 {
-    extern __shared__ __align__(16) unsigned char enc_raw[];
-    EncStreamSmem &sm = *reinterpret_cast<EncStreamSmem *>(enc_raw);
-
-    const uint32_t cta = blockIdx.x;
-    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
-    const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
-    const uint32_t *encM = p == 0 ? P.encM[0] : P.encM[1];    // intra_l, intra_c (src/enc.rs:84-90)
-    const int32_t *deq = p == 0 ? P.deq[0] : P.deq[1];
+    static_assert(ENC_OUT_PITCH == 144, "store_partial_tile knows the pitch");
+    const PlaneGeom &pl = PC == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+    const float *encR = P.encR[PC];                            // intra_l, intra_c (src/enc.rs:84-90)
+    const int32_t *deq = P.deq[PC];
     const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * ENC_WARPS + warp) * P.tiles_per_warp;
+    const uint32_t tile_begin = (cta_in_plane * ENC_WARPS + warp) * P.tiles_per_warp;
     const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
     if (tile_begin >= tile_end) return;
-    const EncJob job = jobs[blockIdx.y];
     const uint32_t sb = lane & 3u;
-    const uint8_t *src = p == 0 ? job.src[0] : (p == 1 ? job.src[1] : job.src[2]);
-    const bool fast = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
+    const uint8_t *src = PC == 0 ? job.src[0] : (p == 1 ? job.src[1] : job.src[2]);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
     uint4 *ring = sm.coef[warp];
     uint32_t *ring_id = sm.id[warp];
+    unsigned char *stg = reinterpret_cast<unsigned char *>(sm.out[warp]);
+    const unsigned char *stg_rd = stg + (lane >> 3) * ENC_OUT_PITCH + (lane & 7u) * 16u;   // chunk c = j*32 + lane: + j*4*PITCH
 
     uint2 nxt[8];
-    uint32_t head = 0, tail = 0;
+    load_src_sb(src, pl, min(tile_begin * 8u + (lane >> 2), nmb - 1u), sb, aligned, nxt);
+    uint32_t head = 0, tail = 0, tile = tile_begin;
+    // One iteration = one tile (while there are tiles) and then AT MOST one pass of the inverse transform: the transform site
+    // is an `if`, not an inner loop (the compiler hoisted its 64 table reads in front of an inner loop, paid on every tile
+    // whether the loop ran or not); what is left at the end drains through extra iterations of the same loop.
 #pragma unroll 1
-    for (uint32_t tile = tile_begin - 1u; tile != tile_end; ++tile) {       // iteration `tile` works on `tile` and fetches tile + 1
-        const bool work = tile != tile_begin - 1u;
-        const uint32_t lm = tile * 8u + (lane >> 2);
-        const bool valid = work && lm < nmb;
-        // (p - 128) << 8, src/common.rs:291 - kept unscaled in fp32: the forward transform is exact there (pfv_dct.cuh, fdct8_f32)
-        float x[64];
-        if (work) {
+    for (;;) {
+        if (tile != tile_end) {
+            const uint32_t lm = tile * 8u + (lane >> 2);
+            const bool valid = lm < nmb;
+            // rows first (src/common.rs:294), straight from the packed pixels; then the next tile's rows go in flight for
+            // the rest of the iteration
+            float y[64];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
+                float v[8];
+                fdct8_f32_row_of_bytes(nxt[r].x, nxt[r].y, v);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) x[r * 8 + k] = byte_minus_128_f32(k < 4 ? nxt[r].x : nxt[r].y, k & 3);
+                for (int c = 0; c < 8; ++c) y[r * 8 + c] = v[c];
             }
-        }
-        if (tile + 1u != tile_end) {                            // in flight during the transform
-            const uint32_t lmn = min((tile + 1u) * 8u + (lane >> 2), nmb - 1u);
-            uint32_t col;
-            const uint32_t row = div_small(lmn, pl.bw, pl.rcp_bw, col);
-            load_src_sb(src, pl, col * 16u + (sb & 1u) * 8u, row * 16u + (sb >> 1) * 8u, fast, nxt);
-        }
-        uint32_t vote = 0;
-        if (work) {
+            if (tile + 1u != tile_end) load_src_sb(src, pl, min((tile + 1u) * 8u + (lane >> 2), nmb - 1u), sb, aligned, nxt);
             uint32_t w[32];
-            encode_sb_regs_f32(x, encM, w);
+            fdct8x8_f32_columns(y);
+            quantise_sb_f32(y, encR, w);
             uint32_t ac = w[0] & 0xffff0000u;
 #pragma unroll
             for (int i = 1; i < 32; ++i) ac |= w[i];
             {
-                unsigned char *stg = reinterpret_cast<unsigned char *>(sm.out[warp]);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     *reinterpret_cast<uint4 *>(stg + lane * ENC_OUT_PITCH + 16 * k) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
@@ -160,11 +174,12 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
                 // 16-byte chunk c = j*32 + lane of the tile's 4 KB: sub-block c >> 3, chunk c & 7 of it
                 const uint32_t tile_mbs = min(8u, nmb - tile * 8u);
                 uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + (size_t)(pl.mb_base + tile * 8u) * 256);
+                if (tile_mbs == 8u) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t c = (uint32_t)j * 32u + lane;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(stg + (c >> 3) * ENC_OUT_PITCH + (c & 7u) * 16u);
-                    if ((c >> 5) < tile_mbs) __stcs(dstc + c, v);
+                    for (int j = 0; j < 8; ++j)
+                        __stcs(dstc + j * 32 + lane, *reinterpret_cast<const uint4 *>(stg_rd + j * 4 * ENC_OUT_PITCH));
+                } else {
+                    store_partial_tile(stg, dstc, tile_mbs, lane);
                 }
                 __syncwarp();                                   // the stage is rewritten by the next tile
             }
@@ -174,7 +189,7 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
             }
             // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
             const bool general = valid && ac != 0u;
-            vote = __ballot_sync(0xffffffffu, general);
+            const uint32_t vote = __ballot_sync(0xffffffffu, general);
             if (general) {
                 const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
 #pragma unroll
@@ -184,17 +199,35 @@ encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__re
             } else if (valid) {
                 store_dc_only(sb_dst(job.dst, pl, lm, (int)sb), pl.pw, (int)(int16_t)(w[0] & 0xffffu), deq[0]);
             }
-        }
-        tail += (uint32_t)__popc(vote);
-        __syncwarp();
-        const bool last = tile + 1u == tile_end;
-#pragma unroll 1
-        while (tail - head >= 32u || (last && tail != head)) {      // (at most 63 queued: twice only when draining)
-            if (lane < tail - head) transform_entry_i(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
-            head += min(32u, tail - head);
+            tail += (uint32_t)__popc(vote);
+            ++tile;
             __syncwarp();
         }
+        const uint32_t queued = tail - head;                    // at most 63: 31 carried + 32 new
+        if (queued >= 32u || (tile == tile_end && queued != 0u)) {
+            if (lane < queued) transform_entry_i<ROLLED>(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
+            head += min(32u, queued);
+            __syncwarp();
+        } else if (tile == tile_end) {
+            break;
+        }
     }
+}
+
+// grid = (jobs, CTAs of a frame): consecutive CTAs work on the same part of DIFFERENT frames, so that all luma CTAs of the
+// launch come before all chroma CTAs and an SM runs one plane class's copy of the loop at a time (each is ~30 KB of code).
+// CTAS = resident CTAs per SM the kernel is compiled for.
+template <bool COUNT, bool ROLLED>
+__global__ void __launch_bounds__(ENC_WARPS * 32, 3)
+encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__restrict__ jobs)
+{
+    extern __shared__ __align__(16) unsigned char enc_raw[];
+    EncStreamSmem &sm = *reinterpret_cast<EncStreamSmem *>(enc_raw);
+    const uint32_t cta = blockIdx.y;
+    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
+    const EncJob job = jobs[blockIdx.x];
+    if (p == 0) encode_i_tiles<COUNT, 0, ROLLED>(P, job, sm, 0, cta);
+    else        encode_i_tiles<COUNT, 1, ROLLED>(P, job, sm, p, cta - (p == 1 ? P.cta_base[1] : P.cta_base[2]));
 }
 
 cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s)
@@ -213,26 +246,22 @@ cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t
         cta += (ntiles + ENC_WARPS * tpw - 1) / (ENC_WARPS * tpw);
     }
     P.cta_total = cta;
-    dim3 grid(P.cta_total, njobs, 1), block(ENC_WARPS * 32, 1, 1);
-    // compiled for 3 resident CTAs per SM (168 registers, no spills): 156 k frames/s on 64 x 1080p against 139 k for 4 (128
-    // registers, ~250 bytes of spills per thread)
+    if (cta > 65535u) return cudaErrorInvalidConfiguration;      // (a plane of more than 4 M macroblocks)
+    dim3 grid(njobs, P.cta_total, 1), block(ENC_WARPS * 32, 1, 1);
+    // 3 resident CTAs per SM (~160 registers, no spills): 4 need 128 registers and spill; 1 or 2 were slower (110 / 163 / 188 k
+    // frames/s for 1 / 2 / 3, round 2)
     static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
-    // tuning aid: PFV_ENCODE_I_RESIDENT = 1 / 2 keeps that many CTAs per SM resident (the kernel compiled for it, shared memory
-    // padded so that no more fit): fewer warps at different places of a 50 KB loop means fewer instruction-cache misses
-    static const int res_env = getenv("PFV_ENCODE_I_RESIDENT") ? atoi(getenv("PFV_ENCODE_I_RESIDENT")) : 3;
-    const int resident = res_env == 1 || res_env == 2 ? res_env : 3;
-    const int smem = resident == 3 ? (int)sizeof(EncStreamSmem) : (resident == 2 ? 100 * 1024 : 200 * 1024);
+    static const bool rolled = !(getenv("PFV_ENCODE_I_ROLLED") && atoi(getenv("PFV_ENCODE_I_ROLLED")) == 0);
+    const int smem = (int)sizeof(EncStreamSmem);
     if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(encode_i_stream_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(encode_i_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    if (count) encode_i_stream_kernel<true, 3><<<grid, block, smem, s>>>(P, d_jobs);
-    else if (resident == 1) encode_i_stream_kernel<false, 1><<<grid, block, smem, s>>>(P, d_jobs);
-    else if (resident == 2) encode_i_stream_kernel<false, 2><<<grid, block, smem, s>>>(P, d_jobs);
-    else       encode_i_stream_kernel<false, 3><<<grid, block, smem, s>>>(P, d_jobs);
+    if (count) { if (rolled) encode_i_stream_kernel<true, true><<<grid, block, smem, s>>>(P, d_jobs); else encode_i_stream_kernel<true, false><<<grid, block, smem, s>>>(P, d_jobs); }
+    else       { if (rolled) encode_i_stream_kernel<false, true><<<grid, block, smem, s>>>(P, d_jobs); else encode_i_stream_kernel<false, false><<<grid, block, smem, s>>>(P, d_jobs); }
     return cudaGetLastError();
 }
 

@@ -64,6 +64,82 @@ decode_i_sb_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict_
 }
 
 // -------------------------------------------------------------------------------------------------
+// decode-I for frames the caller flags as dense (PFV_JOB_DENSE): every sub-block takes the full transform, so there is
+// nothing to classify - but the plain kernel above stalls on its eight coefficient loads at the start of every CTA (ncu:
+// long-scoreboard 1.8 of 4.4 stall cycles per issue, 13 of 16 warps resident on average because CTAs are short-lived).
+// Here a warp walks tiles of 8 macroblocks; the NEXT tile's 4 KB are copied global -> shared by cp.async (16 bytes per lane
+// and instruction, no registers held) while this one is transformed.  Chunk k of sub-block L lands at
+// L*128 + ((k ^ (L & 7)) << 4): the copy instructions write and the transforming lanes read 16-byte columns that differ
+// inside every quarter-warp, i.e. both sides are bank-conflict free, and lane L finds chunk k in the SAME register
+// whatever L is (a lane-dependent rotation would need the ring of the streaming kernel to undo it).
+// -------------------------------------------------------------------------------------------------
+constexpr int DIR_WARPS = 4;
+void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t waves_x_warps, uint32_t max_tpw);
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(DIR_WARPS * 32, 4)
+decode_i_direct_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict__ jobs)
+{
+    __shared__ uint4 stage[DIR_WARPS][2][256];                  // per warp: two tiles of 8 macroblocks x 512 B
+    const uint32_t cta = blockIdx.x;
+    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
+    const PlaneGeom &pl = p == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
+    const int32_t *deq = p == 0 ? P.deq[0] : (p == 1 ? P.deq[1] : P.deq[2]);
+    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile_begin = ((cta - (p == 0 ? P.cta_base[0] : (p == 1 ? P.cta_base[1] : P.cta_base[2]))) * DIR_WARPS + warp) * P.tiles_per_warp;
+    const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
+    if (tile_begin >= tile_end) return;
+    const DecJob job = jobs[blockIdx.y];
+    const uint4 *plane_coeff = reinterpret_cast<const uint4 *>(job.coeff + (size_t)pl.mb_base * 256);
+    // copy side: chunk c = j*32 + lane of a tile is chunk (lane & 7) of sub-block j*4 + (lane >> 3)
+    const uint32_t wr = (lane >> 3) * 8u + ((lane & 7u) ^ (lane >> 3));       // + j*32: (j*4 + (lane >> 3)) & 7 == ((lane >> 3) + 4*(j & 1)) & 7
+    auto issue = [&](uint32_t tile) {
+        uint4 *stg = stage[warp][tile & 1u];
+        const uint4 *src = plane_coeff + (size_t)tile * 256u + lane;
+        const uint32_t mbs = min(8u, nmb - tile * 8u);
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j)
+            if (j < mbs) cp_async16(stg + j * 32u + (wr ^ ((j & 1u) << 2)), src + j * 32u);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(tile_begin);
+#pragma unroll 1
+    for (uint32_t tile = tile_begin; tile != tile_end; ++tile) {
+        if (tile + 1u != tile_end) {
+            issue(tile + 1u);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();                                           // every lane's copies of this tile have landed
+        const uint4 *stg = stage[warp][tile & 1u];
+        uint4 raw[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) raw[k] = stg[lane * 8u + (k ^ (lane & 7u))];
+        const uint32_t lm = tile * 8u + (lane >> 2);
+        if (lm < nmb) {
+            int m[64];
+            unpack_dequant(raw, deq, m);
+            idct8x8_regs(m);
+            uint8_t *dst = sb_dst(job.dst, pl, lm, (int)(lane & 3u));
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                uint2 o;
+                o.x = pack4_sat_u8(m[r * 8 + 0], m[r * 8 + 1], m[r * 8 + 2], m[r * 8 + 3]);
+                o.y = pack4_sat_u8(m[r * 8 + 4], m[r * 8 + 5], m[r * 8 + 6], m[r * 8 + 7]);
+                __stcg(reinterpret_cast<uint2 *>(dst + (size_t)r * pl.pw), o);
+            }
+        }
+        __syncwarp();                                           // the stage is refilled two iterations from now
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // decode-I, "classify, compact, transform" with TMA-staged tiles (the default for key frames)
 // -------------------------------------------------------------------------------------------------
 // The exact integer IDCT costs ~1300 instructions per sub-block, which at 48 960 sub-blocks per 1080p frame is
@@ -192,6 +268,14 @@ cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t
 {
     dim3 grid(P.cta_total, njobs, 1), block(SB_WARPS * 32, 1, 1);
     decode_i_sb_kernel<<<grid, block, 0, s>>>(P, d_jobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_i_direct(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
+{
+    sbw_split(P, njobs, DIR_WARPS, 6u * 148u * 16u, 16u);
+    dim3 grid(P.cta_total, njobs, 1), block(DIR_WARPS * 32, 1, 1);
+    decode_i_direct_kernel<<<grid, block, 0, s>>>(P, d_jobs);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,19 @@ __device__ __forceinline__ void unpack_dequant(const uint4 (&raw)[8], const int3
     }
 }
 
+// ... into the TRANSPOSED register layout idct8x8_regs_rolled takes (t[c * 8 + r])
+__device__ __forceinline__ void unpack_dequant_transposed(const uint4 (&raw)[8], const int32_t *deq, int (&t)[64])
+{
+    constexpr int zz[64] = PFV_ZIGZAG_INIT;
+#pragma unroll
+    for (int s = 0; s < 64; ++s) {
+        const uint4 &q = raw[s >> 3];
+        const uint32_t w = ((s >> 1) & 3) == 0 ? q.x : ((s >> 1) & 3) == 1 ? q.y : ((s >> 1) & 3) == 2 ? q.z : q.w;
+        const int c = (s & 1) ? __dp2a_hi((int)w, 0x01000000, 0) : __dp2a_lo((int)w, 0x00000001, 0);
+        t[(zz[s] & 7) * 8 + (zz[s] >> 3)] = c * deq[s];
+    }
+}
+
 // out = clamp(prev + delta) on four packed pixels; pos4/neg4 = max(delta,0) / min(max(-delta,0),255) in every byte
 // (src/common.rs:100-102; delta is in [-256, 254], and prev - 255 already clamps to 0 for every prev)
 __device__ __forceinline__ uint32_t add_delta_sat4(uint32_t prev, uint32_t pos4, uint32_t neg4)
@@ -84,7 +97,9 @@ __device__ __forceinline__ void ring_get(const uint4 *ring, uint32_t slot, uint4
     for (int k = 0; k < 8; ++k) r2[k] = ring[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
 }
 
-// full inverse transform of one queued intra sub-block (src/common.rs:313-325) and its 8 row stores
+// full inverse transform of one queued intra sub-block (src/common.rs:313-325) and its 8 row stores.  ROLLED: one copy of
+// the 1-D transforms in the code (idct8x8_regs_rolled) for kernels whose loop would otherwise outgrow the instruction cache.
+template <bool ROLLED = false>
 __device__ __forceinline__ void transform_entry_i(const uint4 *ring, const uint32_t *idv, uint32_t slot, uint8_t *slot_base,
                                                   const PlaneGeom &pl, const int32_t *deq)
 {
@@ -93,8 +108,13 @@ __device__ __forceinline__ void transform_entry_i(const uint4 *ring, const uint3
     const uint32_t id = idv[slot];
     uint8_t *dst = sb_dst(slot_base, pl, id >> 2, (int)(id & 3u));
     int m[64];
-    unpack_dequant(r2, deq, m);
-    idct8x8_regs(m);
+    if (ROLLED) {
+        unpack_dequant_transposed(r2, deq, m);
+        idct8x8_regs_rolled(m);
+    } else {
+        unpack_dequant(r2, deq, m);
+        idct8x8_regs(m);
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         uint2 o;

@@ -298,6 +298,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(N.lib().pfv_ctx_launch_count(self._ctx))
 
+    def enable_kernel_timing(self) -> None:
+        """pfv_ctx_last_kernel_ms is off until asked for once (it costs two driver calls per submit): switch it on."""
+        ms = C.c_float()
+        N.lib().pfv_ctx_last_kernel_ms(self._ctx, C.byref(ms))
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         N.check(N.lib().pfv_ctx_last_kernel_ms(self._ctx, C.byref(ms)))

@@ -31,6 +31,13 @@ def test_64_key_frames_1080p_in_one_submit():
         e.sync()
         for i in range(n):
             assert np.array_equal(e.slot_read(i), want[i]), f"job {i}"
+        # the same batch flagged dense (the kernel that walks several tiles per warp with cp.async staging)
+        for i in range(n):
+            e.slot_reset(i)
+        e.decode_submit([DecodeJob(PFV_FRAME_I, i, coeffs[i], (0, 1, 1), dense_hint=True) for i in range(n)])
+        e.sync()
+        for i in range(n):
+            assert np.array_equal(e.slot_read(i), want[i]), f"dense-flagged job {i}"
         # the same batch through the encoder: 64 jobs per launch, coefficients and reconstruction
         outs = [np.zeros(og.nb * 256, np.int16) for _ in range(n)]
         e.encode_submit([EncodeJob(PFV_FRAME_I, i, sv.frame(i), outs[i]) for i in range(n)])

@@ -77,7 +77,12 @@ def test_decode_iframe_matches_oracle(size, mode):
         e.decode_submit([DecodeJob(PFV_FRAME_I, 1, coeff, (0, 1, 1))])
         e.sync()
         got = e.slot_read(1)
+        # PFV_JOB_DENSE is a hint: it picks the kernel that transforms every sub-block, never the result
+        e.decode_submit([DecodeJob(PFV_FRAME_I, 0, coeff, (0, 1, 1), dense_hint=True)])
+        e.sync()
+        got_dense = e.slot_read(0)
     assert np.array_equal(got, want)
+    assert np.array_equal(got_dense, want)
 
 
 @pytest.mark.parametrize("size", SIZES)

@@ -22,6 +22,8 @@ def hm():
     subprocess.check_call(["make", "-s", "-C", d])
     lib = C.CDLL(os.path.join(d, "libpfv_hostmath.so"))
     lib.pfv_hm_quant_check.restype = C.c_long
+    lib.pfv_hm_quant_f32_check.restype = C.c_long
+    lib.pfv_hm_quant_f32_floor_check.restype = C.c_long
     lib.pfv_hm_escapes_check.restype = C.c_long
     lib.pfv_hm_mb_entry_count.restype = C.c_uint32
     return lib
@@ -38,6 +40,14 @@ def test_quantiser_reciprocal_is_exact(hm):
     assert hm.pfv_hm_quant_check(-(1 << 22), 1 << 22, 4099, 513, 65535) == 0
     assert hm.pfv_hm_quant_check(-70000, 70000, 1, 1, 64) == 0          # dense around zero, incl. n = -1, 0, exact multiples
     assert hm.pfv_hm_escapes_check() == 0
+
+
+def test_fp32_quantiser_is_exact(hm):
+    """quant_one_f32 (the encode-I kernel's quantiser: floor by a round-down FMA, division by a float reciprocal a little
+    above 1/q): every |n| <= 4096 (the transforms cannot produce more than ~1 700) against every divisor 1..65535, and the
+    floor step over every transform output 256 V in +-2^22."""
+    assert hm.pfv_hm_quant_f32_check(4096, 1, 65535) == 0
+    assert hm.pfv_hm_quant_f32_floor_check(-(1 << 22), 1 << 22, 1) == 0
 
 
 @pytest.mark.parametrize("quality", [0, 1, 2, 5, 8, 10])
@@ -62,6 +72,8 @@ def test_encode_subblock_matches_oracle(hm, quality):
         outf = np.zeros(64, np.int16)
         hm.pfv_hm_encode_sb_f32(_p(px), 0, _p(np.ascontiguousarray(q)), _p(outf))      # the fp32 formulation: same bits
         assert np.array_equal(outf, out), (quality, trial, "f32")
+        hm.pfv_hm_encode_sb_f32_generic(_p(px), _p(np.ascontiguousarray(q)), _p(outf))
+        assert np.array_equal(outf, out), (quality, trial, "f32 generic")
 
 
 @pytest.mark.parametrize("quality", [0, 3, 5, 10])
@@ -112,6 +124,9 @@ def test_decode_subblock_matches_oracle(hm):
         out = np.zeros(64, np.uint8)
         hm.pfv_hm_decode_sb(_p(c), _p(np.ascontiguousarray(q)), _p(out))
         assert np.array_equal(out, pfvo.decode_subblock(c, q)), trial
+        out2 = np.zeros(64, np.uint8)
+        hm.pfv_hm_decode_sb_rolled(_p(c), _p(np.ascontiguousarray(q)), _p(out2))
+        assert np.array_equal(out2, out), (trial, "rolled")
 
 
 def test_macroblock_entry_count_matches_rle_encode(hm):

@@ -25,6 +25,7 @@ d_tok = torch.zeros((L, nb * 256), dtype=torch.int32, device="cuda")
 d_st = torch.zeros((L, 64), dtype=torch.int32, device="cuda")
 with Engine(w, h, qt, nslots=2 * L + 2, max_jobs=L) as e:
     def planes(t): b = t.data_ptr(); return (b, b + ysz, b + ysz + csz)
+    e.enable_kernel_timing()
     e.encode_submit([EncodeJob(PFV_FRAME_I, 2 * i, planes(d0), d_c[i].data_ptr(), device_ptrs=True) for i in range(L)])
     e.sync()
     for kind, src, name in ((PFV_FRAME_P, d1, "P"), (PFV_FRAME_I, d2, "I")):
