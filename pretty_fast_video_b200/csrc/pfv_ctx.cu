@@ -873,27 +873,15 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         int rc = ensure_compact_staging(c);
         if (rc) return rc;
     }
-    // Small submits (a 512x384 frame: ~0.1 MB up, 0.3 MB down) are bound by the ~20 driver calls of the three-stream
-    // pipeline, not by bytes: they go out on the compute stream alone - copies, kernels and the copy back in stream order,
-    // no cross-stream events (8 fewer calls per submit).  Large submits keep the H2D / compute / D2H overlap.
-    size_t moved = 0;
-    for (uint32_t i = 0; i < njobs; i++) {
-        const DecIn &j = jobs[i];
-        if (j.sparse) moved += ((size_t)j.ntok + 2 * (size_t)g.nb + 1) * 4;
-        else if (!(j.flags & PFV_JOB_DEVICE_PTRS)) moved += (size_t)g.nb * 516;
-        if (j.out_y) moved += (size_t)g.width * g.height * 3 / 2;
-    }
-    // (a batch of device-resident frames moves nothing but is not small: its job table must travel on the copy stream while
-    // the previous submit's kernels still run, or every launch waits for a PCIe round trip)
-    static const int lean_env = getenv("PFV_LEAN_SUBMIT") ? atoi(getenv("PFV_LEAN_SUBMIT")) : 1;
-    const bool lean = lean_env && !any_dense_host && moved <= ((size_t)3 << 19) && (uint64_t)njobs * g.nb <= 4096u;   // 1.5 MB, 4 096 macroblocks
-    cudaStream_t s_up = lean ? c->s_compute : c->s_h2d, s_down = lean ? c->s_compute : c->s_d2h;
+    // (Measured and dropped, round 2: sending small submits - a 512x384 frame - down the compute stream alone, copies and
+    // kernels in stream order without the cross-stream events, saves 8 driver calls per submit but loses the overlap of one
+    // frame's copies with its neighbours' kernels: config 1 through the Decoder 14.5 k frames/s against 21-25 k.)
+    cudaStream_t s_up = c->s_h2d, s_down = c->s_d2h;
 
     const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     Stage &st = c->st[id % STAGES];
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
-    if (!lean) CU_TRY(cudaStreamWaitEvent(s_up, st.ev_kernel, 0));   // device buffers of this stage are free again (ev_kernel is
-                                                                     // always recorded on the compute stream: in order when lean)
+    CU_TRY(cudaStreamWaitEvent(s_up, st.ev_kernel, 0));         // device buffers of this stage are free again
     if (st.d2h_used) {                                          // ... also for an encode submit that used the stage before
         CU_TRY(cudaStreamWaitEvent(s_up, st.ev_d2h, 0));
         st.d2h_used = false;
@@ -1016,7 +1004,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     CU_TRY(cudaEventRecord(st.ev_h2d, s_up));
 
     // compute
-    if (!lean) CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
+    CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
     {
         std::vector<uint32_t> dsts(njobs);
         for (uint32_t i = 0; i < njobs; i++) dsts[i] = jobs[i].dst_slot;
@@ -1088,7 +1076,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     bool any_out = false;
     for (uint32_t i = 0; i < njobs; i++) any_out |= jobs[i].out_y != nullptr;
     if (any_out) {
-        if (!lean) CU_TRY(cudaStreamWaitEvent(s_down, st.ev_kernel, 0));
+        CU_TRY(cudaStreamWaitEvent(s_down, st.ev_kernel, 0));
         for (uint32_t i = 0; i < njobs; i++) {
             const DecIn &j = jobs[i];
             if (!j.out_y) continue;

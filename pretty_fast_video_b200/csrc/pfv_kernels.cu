@@ -531,7 +531,7 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
     Ep2Smem &sm = *reinterpret_cast<Ep2Smem *>(ep2_raw);
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    for (uint32_t i = threadIdx.x; i < njobs; i += EP2_WARPS * 32) sm.job[i] = jobs[i];
+    for (uint32_t i = threadIdx.x; i < njobs; i += blockDim.x) sm.job[i] = jobs[i];
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp][0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp][1])));
@@ -540,7 +540,8 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
     __syncthreads();
 
     const uint32_t nitems = njobs * g.total_tiles;
-    const uint32_t stride = gridDim.x * EP2_WARPS;
+    const uint32_t nwarps = blockDim.x >> 5;                      // EP2_WARPS (fewer only as a tuning experiment)
+    const uint32_t stride = gridDim.x * nwarps;
     const uint32_t m8 = lane >> 2, q = lane & 3u;
     WarpScratch &ws = sm.scratch[warp];
 
@@ -583,7 +584,7 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
         }
     };
 
-    uint32_t it = blockIdx.x * EP2_WARPS + warp;
+    uint32_t it = blockIdx.x * nwarps + warp;
     if (it >= nitems) return;
     Item cur = item_of(it);
     if (lane == 0) issue(cur, 0);
@@ -631,16 +632,17 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
             a += __shfl_xor_sync(FULL, a, 2);
             best = a;
         }
+        // which of the 8 candidates of a level lie inside the plane (src/common.rs:171,182): three column tests and three row
+        // tests combined (bit g = candidate g in visiting order: my = -1: g 0..2, my = 0: g 3 (mx = -1), 4 (mx = +1), my = +1: g 5..7)
         auto valid_mask_of = [&](int step) {
-            uint32_t vm = 0;
+            uint32_t vx = 0, vy = 0;
 #pragma unroll
-            for (int gi = 0; gi < 8; ++gi) {
-                const int mx = (gi == 0 || gi == 3 || gi == 5) ? -1 : ((gi == 1 || gi == 6) ? 0 : 1);
-                const int my = gi < 3 ? -1 : (gi < 5 ? 0 : 1);
-                const int ox = bx + cx + mx * step, oy = by + cy + my * step;
-                vm |= (ox >= 0 && ox <= max_x && oy >= 0 && oy <= max_y) ? (1u << gi) : 0u;      // src/common.rs:171,182
+            for (int d = -1; d <= 1; ++d) {
+                const int ox = bx + cx + d * step, oy = by + cy + d * step;
+                vx |= (ox >= 0 && ox <= max_x) ? (1u << (d + 1)) : 0u;
+                vy |= (oy >= 0 && oy <= max_y) ? (1u << (d + 1)) : 0u;
             }
-            return vm;
+            return ((vy & 1u) ? vx : 0u) | ((vy & 2u) ? ((vx & 1u) | ((vx >> 1) & 2u)) << 3 : 0u) | ((vy & 4u) ? vx << 5 : 0u);
         };
         auto take = [&](uint32_t kmin, int step) {
             if (kmin != 0xffffffffu && (kmin >> 3) < best) {        // strict, src/common.rs:189
@@ -675,9 +677,19 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
         if (active && !coded) {                                    // the predictor is the reconstruction (src/common.rs:281-283)
             const uint32_t po = (uint32_t)((int)o0 + cy * WIN_W + cx);
             uint8_t *dst = job.dst + pl.off + (size_t)(uint32_t)by * pl.pw + (uint32_t)bx + q * 4u;
+            // eight rows' loads first, then their shifts and stores (row by row every funnel shift waited for its own
+            // shared-memory round trip: ncu, ~50 stall samples on each of the 16)
+            const uint32_t *wbase = reinterpret_cast<const uint32_t *>(win + (po & ~3u));   // WIN_W % 4 == 0: one shift for all rows
+            const uint32_t sh = (po & 3u) * 8u;
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
-                *reinterpret_cast<uint32_t *>(dst + (size_t)r * pl.pw) = lds_u8x4_unaligned(win, po + (uint32_t)(r * WIN_W));
+            for (int r0 = 0; r0 < 16; r0 += 8) {
+                uint32_t a[8], b[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { a[r] = wbase[(r0 + r) * (WIN_W / 4)]; b[r] = wbase[(r0 + r) * (WIN_W / 4) + 1]; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    *reinterpret_cast<uint32_t *>(dst + (size_t)(r0 + r) * pl.pw) = __funnelshift_r(a[r], b[r], sh);
+            }
         }
         // coded macroblocks, one at a time, the whole warp on each (lane = (sub-block, row) as in pfv_device.cuh)
         uint32_t todo = __ballot_sync(FULL, coded && q == 0);
@@ -695,6 +707,10 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
             for (int kk = 0; kk < 8; ++kk) scale[kk] = c_scaleT[r8 * 8 + kk];
             const uint8_t *src = cur.p == 0 ? job.src[0] : (cur.p == 1 ? job.src[1] : job.src[2]);
             const bool fast8 = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
+            // this lane's 8 source pixels of the first coded macroblock; inside the loop the NEXT one's are fetched before
+            // the current one is transformed (the load's latency was fully exposed once per coded macroblock: ncu, 5 % of
+            // all stall samples on its first use)
+            uint2 s8n = load_src_row(src, pl, (uint32_t)(cur.tile_x0 + ((__ffs((int)todo) - 1) >> 2) * 16) + px, (uint32_t)by + py, fast8);
 #pragma unroll 1
             while (todo) {
                 const int l0 = __ffs((int)todo) - 1;
@@ -702,7 +718,8 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
                 const int mcx = __shfl_sync(FULL, cx, l0), mcy = __shfl_sync(FULL, cy, l0);
                 const uint32_t mm = __shfl_sync(FULL, m, l0);
                 const int mbx = cur.tile_x0 + (l0 >> 2) * 16;
-                const uint2 s8 = load_src_row(src, pl, (uint32_t)mbx + px, (uint32_t)by + py, fast8);
+                const uint2 s8 = s8n;
+                if (todo) s8n = load_src_row(src, pl, (uint32_t)(cur.tile_x0 + ((__ffs((int)todo) - 1) >> 2) * 16) + px, (uint32_t)by + py, fast8);
                 const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((15 + (int)py + mcy) * WIN_W + 16 + (l0 >> 2) * 16 + (int)px + mcx));
                 int x[8];
 #pragma unroll
@@ -778,10 +795,12 @@ cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
     for (uint32_t j0 = 0; j0 < njobs; j0 += EP2_MAX_JOBS) {
         const uint32_t n = njobs - j0 < (uint32_t)EP2_MAX_JOBS ? njobs - j0 : (uint32_t)EP2_MAX_JOBS;
         const uint32_t items = n * g.total_tiles;
-        uint32_t ctas = (items + EP2_WARPS - 1) / EP2_WARPS;
+        static const int warps_env = getenv("PFV_EP2_WARPS") ? atoi(getenv("PFV_EP2_WARPS")) : EP2_WARPS;   // tuning experiment
+        const uint32_t nw = warps_env >= 1 && warps_env <= EP2_WARPS ? (uint32_t)warps_env : (uint32_t)EP2_WARPS;
+        uint32_t ctas = (items + nw - 1) / nw;
         if (ctas > 148u) ctas = 148u;
-        if (count) encode_p2_kernel<true><<<ctas, EP2_WARPS * 32, smem, s>>>(g, d_jobs + j0, n, d_qt, rcp_tiles, tm_luma, tm_chroma);
-        else       encode_p2_kernel<false><<<ctas, EP2_WARPS * 32, smem, s>>>(g, d_jobs + j0, n, d_qt, rcp_tiles, tm_luma, tm_chroma);
+        if (count) encode_p2_kernel<true><<<ctas, nw * 32, smem, s>>>(g, d_jobs + j0, n, d_qt, rcp_tiles, tm_luma, tm_chroma);
+        else       encode_p2_kernel<false><<<ctas, nw * 32, smem, s>>>(g, d_jobs + j0, n, d_qt, rcp_tiles, tm_luma, tm_chroma);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

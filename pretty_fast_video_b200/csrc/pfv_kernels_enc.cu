@@ -159,7 +159,21 @@ __device__ __forceinline__ void encode_i_tiles(const EncSbParams &P, const EncJo
 #pragma unroll
                 for (int c = 0; c < 8; ++c) y[r * 8 + c] = v[c];
             }
-            if (tile + 1u != tile_end) load_src_sb(src, pl, min((tile + 1u) * 8u + (lane >> 2), nmb - 1u), sb, aligned, nxt);
+            // (unconditional - the last tile fetches itself again: a conditional fetch made the compiler keep a second copy of
+            // the 16 registers, 32 moves per tile, and wait for the fetch at the end of the iteration that issued it)
+            load_src_sb(src, pl, min(min(tile + 1u, tile_end - 1u) * 8u + (lane >> 2), nmb - 1u), sb, aligned, nxt);
+            // ... and the tile after next into L2: DRAM under this kernel's write load takes longer to answer than a warp
+            // spends on one tile (ncu: the first use of `nxt` was the top stall).  Lane r < 16 touches row r of the tile's
+            // first and of its last macroblock: the line(s) holding that row of all eight.
+            if (lane < 16u && tile + 2u < tile_end) {
+#pragma unroll
+                for (uint32_t e = 0; e < 8u; e += 7u) {
+                    uint32_t col;
+                    const uint32_t row = div_small(min((tile + 2u) * 8u + e, nmb - 1u), pl.bw, pl.rcp_bw, col);
+                    const uint32_t y = row * 16u + lane, x = col * 16u;
+                    if (y < pl.vh && x < pl.vw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)y * pl.vw + x));
+                }
+            }
             uint32_t w[32];
             fdct8x8_f32_columns(y);
             quantise_sb_f32(y, encR, w);

@@ -282,6 +282,9 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
             ::"r"(smem_addr(sm.win[pipe][st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(smem_addr(&sm.win_full[pipe][st]))
             : "memory");
     };
+    // (Measured and dropped, round 2: the same box as an L2 prefetch - cp.async.bulk.prefetch.tensor - two windows beyond the
+    // staged ones.  The wait for the window's TMA is the copy half's largest single stall, but with the prefetch the kernel
+    // took 57 us per 32 frames instead of 52: the prefetches compete with the demand loads for the same DRAM queues.)
     // header word of this lane's macroblock (row `warp`, column `mb` of the window); bit 31 set = no such macroblock
     auto load_hw = [&](const PfItemRec &it) -> uint32_t {
         if (wrow >= ((it.job_p >> 20) & 15u) || mb >= (it.job_p >> 24)) return 0x80000000u;
@@ -337,26 +340,34 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
             // staged window - its own encoder never searches further (src/common.rs:154-204).  Rare: fetch from global.
             const uint32_t wx = (uint32_t)(16 + (int)mb * 16 + mvx), wy = (uint32_t)(15 + (int)wrow * 16 + mvy) + rg;
             const unsigned char *wline = sm.win[pipe][st] + wy * PF_WIN_W;
+            // all four rows are fetched before anything is stored: the predictor stores below go to shared memory too, and
+            // the compiler must assume they alias the window (it kept every row's loads behind the previous row's stores and
+            // each row waited for its own shared-memory round trip)
+            uint4 o[4];
+            if (in_window) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint4 o;
-                if (in_window) {
-                    o = win_row16(wline + i * 4 * PF_WIN_W, wx);
-                } else {
+                for (int i = 0; i < 4; ++i) o[i] = win_row16(wline + i * 4 * PF_WIN_W, wx);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
                     const uint8_t *gsrc = job.ref + cur.plane_off + (size_t)((uint32_t)(by + mvy) + rg + 4u * (uint32_t)i) * pw + (uint32_t)(bx + mvx);
                     const uint2 a = ldg_u8x8_unaligned(gsrc);
                     const uint2 b = ldg_u8x8_unaligned(gsrc + 8);
-                    o = make_uint4(a.x, a.y, b.x, b.y);
+                    o[i] = make_uint4(a.x, a.y, b.x, b.y);
                 }
-                if (coded) {
+            }
+            if (coded) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
                     // row R = rg + 4i of the macroblock: left half -> sub-block (R >> 3) * 2, right half -> the next one
                     const uint32_t R = rg + 4u * (uint32_t)i, L = (R >> 3) * 16u + sj;
                     unsigned char *pp = grp.pred + L * PF_PRED_PITCH + (R & 7u) * 8u;
-                    *reinterpret_cast<uint2 *>(pp) = make_uint2(o.x, o.y);
-                    *reinterpret_cast<uint2 *>(pp + 8 * PF_PRED_PITCH) = make_uint2(o.z, o.w);
-                } else {
-                    __stcg(reinterpret_cast<uint4 *>(dst + (size_t)(4 * i) * pw), o);     // blit_block, src/common.rs:341-349
+                    *reinterpret_cast<uint2 *>(pp) = make_uint2(o[i].x, o[i].y);
+                    *reinterpret_cast<uint2 *>(pp + 8 * PF_PRED_PITCH) = make_uint2(o[i].z, o[i].w);
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) __stcg(reinterpret_cast<uint4 *>(dst + (size_t)(4 * i) * pw), o[i]);   // blit_block, src/common.rs:341-349
             }
         }
         if (coded && rg == 0) grp.id[sj] = make_uint4(mb_off, cjob, cp, 1u);
