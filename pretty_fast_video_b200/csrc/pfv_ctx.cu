@@ -199,6 +199,7 @@ struct pfv_ctx {
     uint8_t *d_pool = nullptr;
     QTables *d_qt = nullptr;
     int *d_err = nullptr;
+    uint32_t *d_work = nullptr;            // 16 zeroed words: work counters of the persistent kernels ([0..1] encode-P, [4..5] encode-I)
     int *h_err = nullptr;            // pinned
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaStream_t s_d2h2 = nullptr;         // second copy-out stream for batches of large pictures (decode_submit_impl)
@@ -235,7 +236,8 @@ struct pfv_ctx {
                                            // thread-per-sub-block), 2 "warp" (first generation, warp per macroblock)
     int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "fused" (default: warp-specialised copy + residual in one kernel),
                                            // 1 "win" (window copy kernel + list-driven residual kernel), 2 "warp" (also used without TMA)
-    int encode_i_variant = 0;              // PFV_ENCODE_I_VARIANT: 0 "stream" (default: thread per sub-block), 2 "warp"
+    int encode_i_variant = 0;              // PFV_ENCODE_I_VARIANT: 0 "persist" (default: thread per sub-block, persistent), 1 "stream" (the
+                                           // same loop as a grid of short-lived CTAs), 2 "warp" (first generation)
     int encode_p_variant = 0;              // PFV_ENCODE_P_VARIANT: 0 "strip" (default: warp per tile, column-strip search), 1 "v1" (warp per macroblock)
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
@@ -469,7 +471,7 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
     for (int i = 0; i < D2H_RING; i++) if (c->ev_d2h_ring[i]) cudaEventDestroy(c->ev_d2h_ring[i]);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
     if (c->ev_k1) cudaEventDestroy(c->ev_k1);
-    cudaFree(c->d_pool); cudaFree(c->d_qt); cudaFree(c->d_err); cudaFree(c->d_plist); cudaFree(c->d_pcount);
+    cudaFree(c->d_pool); cudaFree(c->d_qt); cudaFree(c->d_err); cudaFree(c->d_work); cudaFree(c->d_plist); cudaFree(c->d_pcount);
     if (c->h_err) cudaFreeHost(c->h_err);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -547,7 +549,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT")) c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : 0);
     if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "win") == 0 ? 1 : 0);
-    if (const char *v = getenv("PFV_ENCODE_I_VARIANT")) c->encode_i_variant = strcmp(v, "warp") == 0 ? 2 : 0;
+    if (const char *v = getenv("PFV_ENCODE_I_VARIANT")) c->encode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "stream") == 0 ? 1 : 0);
     if (const char *v = getenv("PFV_ENCODE_P_VARIANT")) c->encode_p_variant = strcmp(v, "v1") == 0 ? 1 : 0;
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
@@ -558,6 +560,8 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     CU_TRY(cudaMemset(c->d_pcount, 0, ((size_t)c->max_jobs * 6 + 4) * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&c->d_err, sizeof(int)));
     CU_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
+    CU_TRY(cudaMalloc(&c->d_work, 16 * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(c->d_work, 0, 16 * sizeof(uint32_t)));
     CU_TRY(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocDefault));
     *c->h_err = 0;
 
@@ -1365,12 +1369,13 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
                 memcpy(P.encR[t], &c->h_enc_recip[(size_t)t * 64], 64 * sizeof(float));
                 memcpy(P.deq[t], &c->h_deq_scan[(size_t)t * 64], 64 * sizeof(int32_t));
             }
-            CU_TRY(launch_encode_i_stream(P, d_tab, n_i, count, c->s_compute));
+            if (c->encode_i_variant == 1) CU_TRY(launch_encode_i_stream(P, d_tab, n_i, count, c->s_compute));
+            else CU_TRY(launch_encode_i_persist(P, d_tab, n_i, count, c->d_work + 4, c->s_compute));
         }
         c->launches++;
     }
     if (njobs - n_i) {
-        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->encode_p_variant, c->s_compute));
+        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->encode_p_variant, c->d_work, c->s_compute));
         c->launches++;
     }
     if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 2; }

@@ -177,11 +177,14 @@ cudaError_t launch_yuv420_to_rgb_batch(const uint8_t *d_pool, size_t slot_stride
                                        cudaStream_t s);
 // count: every job of the launch has EncJob::mb_cnt set (sparse encode seam)
 cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s);
+// the same loop as a persistent kernel with chunks of tiles handed out by a device counter; d_work: two zeroed device words
+cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, uint32_t *d_work, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, bool count, cudaStream_t s);
 // variant 0: warp per tile, column-strip search (default); 1: first generation (CTA per tile, warp per macroblock)
+// d_work: two zeroed device words (the default kernel's tile counter; it leaves them zeroed)
 cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma,
-                            bool count, int variant, cudaStream_t s);
+                            bool count, int variant, uint32_t *d_work, cudaStream_t s);
 
 }  // namespace pfv

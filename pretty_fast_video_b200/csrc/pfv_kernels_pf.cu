@@ -189,6 +189,10 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         const DecJob &j = jobs[i];
         sm.job[i] = PfJob{j.coeff, reinterpret_cast<const uint32_t *>(j.hdr), j.dst, j.ref, j.ref_slot, 0};
     }
+    // (Measured and dropped, round 2: handing the windows out dynamically - a device-wide counter, the pipeline's leader decoding
+    // the next record five windows ahead into a small ring.  It evens out the SMs (sm__cycles_active min / avg / max 93 k / 100 k /
+    // 102 k instead of 80 k / 86 k / 95 k) but the leader's extra work per window costs more than the balance returns: 56.8 us per
+    // 32 x 1080p against 52.1 us.)
     // The windows of the launch are dealt out to the copy pipelines (3 per CTA) in frame-interleaved order (pipelines that run at
     // the same time work on DIFFERENT frames): pipeline gp takes items gp, gp + npipes, ...; item -> (window wi = item / njobs,
     // job = item % njobs)
