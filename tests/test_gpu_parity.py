@@ -133,6 +133,26 @@ def test_decode_kernel_variants_agree(ivar, pvar, monkeypatch):
         assert np.array_equal(e.slot_read(1), want1)
 
 
+@pytest.mark.parametrize("ivar", ["stream", "sb"])
+@pytest.mark.parametrize("qidx", [(0, 1, 1), (0, 1, 3), (2, 2, 2)])
+def test_decode_iframe_batch_with_three_tables(ivar, qidx, monkeypatch):
+    """A batch of key frames in one submit with U and V on different q-tables, on the same one, and all three planes on one;
+    "mixed" coefficients keep the streaming kernel's ring busy."""
+    monkeypatch.setenv("PFV_DECODE_I_VARIANT", ivar)
+    w, h, n = 336, 208, 7
+    rng = np.random.default_rng(4242 + sum(qidx))
+    qt, _ = make_qtables(6)
+    og = pfvo.geometry_for(w, h)
+    coeffs = [rand_coeffs(rng, og.nb, "mixed" if i % 3 else "small") for i in range(n)]
+    with Engine(w, h, qt, nslots=n, max_jobs=n) as e:
+        e.decode_submit([DecodeJob(PFV_FRAME_I, i, coeffs[i], qidx) for i in range(n)])
+        e.sync()
+        for i in range(n):
+            want = pfvo.frame_init(og)
+            pfvo.decode_iframe_coeffs(og, qt, qidx, coeffs[i], want)
+            assert np.array_equal(e.slot_read(i), want), f"job {i}"
+
+
 @pytest.mark.parametrize("pvar", ["fused", "win", "warp"])
 def test_decode_pframe_long_motion_vectors(pvar, monkeypatch):
     """The stream format carries 7-bit vectors (src/dec.rs:367-368) and the reference decoder follows any vector that
