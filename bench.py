@@ -1129,7 +1129,7 @@ def main():
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
     kernel_of = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_direct_kernel",   # PFV_JOB_DENSE
                  "decode_p_1080p": "decode_p_fused_kernel", "decode_p_4k": "decode_p_fused_kernel",
-                 "encode_p_1080p": "encode_p2_kernel", "encode_i_1080p": "encode_i_stream_kernel"}
+                 "encode_p_1080p": "encode_p2_kernel", "encode_i_1080p": "encode_i_persist_kernel"}
     kernel_key = kernel_of[args.workload]
 
     def stats_of(xs):

@@ -236,8 +236,7 @@ struct pfv_ctx {
                                            // thread-per-sub-block), 2 "warp" (first generation, warp per macroblock)
     int decode_p_variant = 0;              // PFV_DECODE_P_VARIANT: 0 "fused" (default: warp-specialised copy + residual in one kernel),
                                            // 1 "win" (window copy kernel + list-driven residual kernel), 2 "warp" (also used without TMA)
-    int encode_i_variant = 0;              // PFV_ENCODE_I_VARIANT: 0 "persist" (default: thread per sub-block, persistent), 1 "stream" (the
-                                           // same loop as a grid of short-lived CTAs), 2 "warp" (first generation)
+    int encode_i_variant = 0;              // PFV_ENCODE_I_VARIANT: 0 "persist" (default: thread per sub-block, persistent), 2 "warp" (first generation)
     int encode_p_variant = 0;              // PFV_ENCODE_P_VARIANT: 0 "strip" (default: warp per tile, column-strip search), 1 "v1" (warp per macroblock)
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
@@ -549,7 +548,7 @@ static int ctx_create_impl(pfv_ctx *c, const int32_t (*qtables)[64], void *ext_s
     }
     if (const char *v = getenv("PFV_DECODE_I_VARIANT")) c->decode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "sb") == 0 ? 1 : 0);
     if (const char *v = getenv("PFV_DECODE_P_VARIANT")) c->decode_p_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "win") == 0 ? 1 : 0);
-    if (const char *v = getenv("PFV_ENCODE_I_VARIANT")) c->encode_i_variant = strcmp(v, "warp") == 0 ? 2 : (strcmp(v, "stream") == 0 ? 1 : 0);
+    if (const char *v = getenv("PFV_ENCODE_I_VARIANT")) c->encode_i_variant = strcmp(v, "warp") == 0 ? 2 : 0;
     if (const char *v = getenv("PFV_ENCODE_P_VARIANT")) c->encode_p_variant = strcmp(v, "v1") == 0 ? 1 : 0;
     CU_TRY(cudaMalloc(&c->d_qt, sizeof(QTables) * c->nq));
     CU_TRY(cudaMemcpy(c->d_qt, qt.data(), sizeof(QTables) * c->nq, cudaMemcpyHostToDevice));
@@ -1369,8 +1368,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
                 memcpy(P.encR[t], &c->h_enc_recip[(size_t)t * 64], 64 * sizeof(float));
                 memcpy(P.deq[t], &c->h_deq_scan[(size_t)t * 64], 64 * sizeof(int32_t));
             }
-            if (c->encode_i_variant == 1) CU_TRY(launch_encode_i_stream(P, d_tab, n_i, count, c->s_compute));
-            else CU_TRY(launch_encode_i_persist(P, d_tab, n_i, count, c->d_work + 4, c->s_compute));
+            CU_TRY(launch_encode_i_persist(P, d_tab, n_i, count, c->d_work + 4, c->s_compute));
         }
         c->launches++;
     }

@@ -176,8 +176,7 @@ cudaError_t launch_yuv420_to_rgb_batch(const uint8_t *d_pool, size_t slot_stride
                                        uint32_t n, uint32_t w, uint32_t h, uint32_t pw, uint32_t cpw, uint8_t *d_out, size_t out_stride,
                                        cudaStream_t s);
 // count: every job of the launch has EncJob::mb_cnt set (sparse encode seam)
-cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s);
-// the same loop as a persistent kernel with chunks of tiles handed out by a device counter; d_work: two zeroed device words
+// persistent, chunks of tiles handed out by a device counter; d_work: two zeroed device words (left zeroed)
 cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, uint32_t *d_work, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, bool count, cudaStream_t s);

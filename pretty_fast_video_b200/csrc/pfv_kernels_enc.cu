@@ -6,15 +6,27 @@
 //
 // The first-generation kernel (pfv_kernels.cu, one warp per macroblock, transposes and the zig-zag through shared
 // memory) ran at 0.18 of the HBM roofline.  Here, like the decode side: a thread keeps its sub-block's 64 values in
-// registers, both forward passes (in fp32, where they are exact: pfv_dct.cuh) and the quantiser run without any exchange, the
-// zig-zag is a compile-time register renaming, the divisors are multipliers in the constant bank.  A warp walks tiles of 8 consecutive macroblocks
-// (lane = macroblock*4 + sub-block): its 8-byte source loads cover full 128-byte lines of the tight source plane (the
-// rows of the next tile are fetched while this one is transformed) and a lane's 8 coefficient stores fill 128
-// contiguous bytes of the dense layout.
+// registers, both forward passes (in fp32, where they are exact: pfv_dct.cuh) and the quantiser (four FMA-pipe instructions
+// per coefficient) run without any exchange, the zig-zag is a compile-time register renaming, the divisors are reciprocals
+// in the constant bank.  A warp walks tiles of 8 consecutive macroblocks (lane = macroblock*4 + sub-block): its 8-byte source
+// loads cover full 128-byte lines of the tight source plane (the rows of the next tile are fetched while this one is
+// transformed) and the tile's coefficients leave through a shared-memory stage as 8 fully coalesced 512-byte stores.
 //
 // The reconstruction is the decode-I problem again: a sub-block whose AC terms all quantised to zero reconstructs to
 // one flat value (see pfv_sb.cuh) and is stored on the spot; the others are queued in the warp's shared-memory ring
 // and inverse-transformed 32 at a time by full warps (classify / compact / transform, as decode_i_stream_kernel).
+//
+// The kernel is PERSISTENT (3 CTAs per SM for the whole launch): chunks of ENC_CHUNK consecutive tiles are handed out in
+// order by a device-wide counter.  Its first form was a grid of short-lived CTAs, 16 tiles per warp (ncu, 64 x 1080p):
+//   * a warp's ring of queued sub-blocks now lives across chunks, frames and planes of a class: it is drained ONCE per plane
+//     class and warp (1 776 x 2 partly filled transform passes per launch instead of 10 240 - 9 % of all instructions);
+//   * nobody waits for the last wave of CTAs (sm__cycles_active min / avg / max was 389 k / 420 k / 452 k of 458 k elapsed).
+// 0.53 -> 0.59 of the HBM roofline.  The loop exists in two copies, specialised per plane class (luma / chroma): the
+// quantiser's reciprocals and the dequantiser's multipliers are then compile-time offsets into the kernel parameters, i.e.
+// constant-bank operands of the multiplies (selected at run time every one of the 128 table reads of a sub-block was a
+// uniform load instruction of its own), and with all luma chunks of a launch handed out before all chroma chunks an SM runs
+// one copy at a time (each is ~30 KB of code: the instruction cache).  The inverse transform is the rolled one
+// (idct8x8_regs_rolled): 64 register moves per pass buy 420 instructions of footprint.
 //
 // COUNT (sparse encode seam): each macroblock's number of RLE entries (rle_encode, src/rle.rs:9-39) is derived from
 // the non-zero masks of its four sub-blocks while they are still in registers (pfv_dct.cuh: sb_runs).
@@ -30,19 +42,19 @@ constexpr int ENC_WARPS = 4;
 
 constexpr int ENC_OUT_PITCH = 144;                           // bytes per sub-block in the output stage: 128 + 16
 
-struct __align__(16) EncStreamSmem {
+// A lane's 128 B of coefficients are 128 B apart from its neighbour's in the dense layout: stored straight from registers,
+// every store instruction of the warp touched 32 different lines (ncu: the stores' source registers were what the next
+// instructions waited for).  The tile goes through a per-warp stage instead - written sub-block by sub-block (pitch
+// 144 B: conflict free), read back 512 contiguous bytes at a time - and leaves as 8 fully coalesced 512-byte stores.
+struct __align__(16) EncPersistSmem {
     uint4    coef[ENC_WARPS][SBW_RING * 8];
-    uint32_t id[ENC_WARPS][SBW_RING];
-    // A lane's 128 B of coefficients are 128 B apart from its neighbour's in the dense layout: stored straight from registers,
-    // every store instruction of the warp touched 32 different lines (ncu: the stores' source registers were what the next
-    // instructions waited for).  The tile goes through this per-warp stage instead - written sub-block by sub-block (pitch
-    // 144 B: conflict free), read back 512 contiguous bytes at a time - and leaves as 8 fully coalesced 512-byte stores.
+    uint2    id[ENC_WARPS][SBW_RING];                          // {macroblock in plane << 2 | sub-block, job << 2 | plane}
     uint4    out[ENC_WARPS][32 * ENC_OUT_PITCH / 16];
 };
 
 // Rows y0 .. y0+7, bytes x0 .. x0+7 of a tight vw x vh source plane that are NOT all inside the plane (or whose rows are not
 // 8-byte aligned): byte by byte, padded with the clear colour (src/common.rs:352-356).  Rare (the bottom and right edges)
-// and out of line: the streaming kernel's loop must stay small enough for the instruction cache.
+// and out of line: the kernel's loop must stay small enough for the instruction cache.
 __device__ __noinline__ void load_src_sb_edge(const uint8_t *__restrict__ src, uint32_t vw, uint32_t vh, uint32_t clear,
                                               uint32_t x0, uint32_t y0, uint2 *rows)
 {
@@ -112,159 +124,14 @@ __device__ __forceinline__ uint32_t mb_entry_count_lanes(const SbRuns &r, uint32
     return n;
 }
 
-// PC = plane class (0 luma, 1 chroma): the quantiser's reciprocals and the dequantiser's multipliers are then compile-time
-// offsets into the kernel parameters, i.e. constant-bank operands of the multiplies (selected at run time every one of the
-// 128 table reads of a sub-block was a uniform load instruction of its own).  The loop has ONE copy of the forward and ONE
-// of the inverse transform (ncu on the first version: 5 400 instructions, a third of all stall samples "no instruction" -
-// the instruction cache): what a warp has left in its ring at the end is drained by the same transform site with the idle
-// lanes masked off.
-template <bool COUNT, int PC, bool ROLLED>
-__device__ __forceinline__ void encode_i_tiles(const EncSbParams &P, const EncJob &job, EncStreamSmem &sm, const int p, const uint32_t cta_in_plane)
-{
-    static_assert(ENC_OUT_PITCH == 144, "store_partial_tile knows the pitch");
-    const PlaneGeom &pl = PC == 0 ? P.g.pl[0] : (p == 1 ? P.g.pl[1] : P.g.pl[2]);
-    const float *encR = P.encR[PC];                            // intra_l, intra_c (src/enc.rs:84-90)
-    const int32_t *deq = P.deq[PC];
-    const uint32_t nmb = pl.bw * pl.bh, ntiles = (nmb + 7u) / 8u;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tile_begin = (cta_in_plane * ENC_WARPS + warp) * P.tiles_per_warp;
-    const uint32_t tile_end = min(tile_begin + P.tiles_per_warp, ntiles);
-    if (tile_begin >= tile_end) return;
-    const uint32_t sb = lane & 3u;
-    const uint8_t *src = PC == 0 ? job.src[0] : (p == 1 ? job.src[1] : job.src[2]);
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 7u) == 0;
-    uint4 *ring = sm.coef[warp];
-    uint32_t *ring_id = sm.id[warp];
-    unsigned char *stg = reinterpret_cast<unsigned char *>(sm.out[warp]);
-    const unsigned char *stg_rd = stg + (lane >> 3) * ENC_OUT_PITCH + (lane & 7u) * 16u;   // chunk c = j*32 + lane: + j*4*PITCH
-
-    uint2 nxt[8];
-    load_src_sb(src, pl, min(tile_begin * 8u + (lane >> 2), nmb - 1u), sb, aligned, nxt);
-    uint32_t head = 0, tail = 0, tile = tile_begin;
-    // One iteration = one tile (while there are tiles) and then AT MOST one pass of the inverse transform: the transform site
-    // is an `if`, not an inner loop (the compiler hoisted its 64 table reads in front of an inner loop, paid on every tile
-    // whether the loop ran or not); what is left at the end drains through extra iterations of the same loop.
-#pragma unroll 1
-    for (;;) {
-        if (tile != tile_end) {
-            const uint32_t lm = tile * 8u + (lane >> 2);
-            const bool valid = lm < nmb;
-            // rows first (src/common.rs:294), straight from the packed pixels; then the next tile's rows go in flight for
-            // the rest of the iteration
-            float y[64];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float v[8];
-                fdct8_f32_row_of_bytes(nxt[r].x, nxt[r].y, v);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) y[r * 8 + c] = v[c];
-            }
-            // (unconditional - the last tile fetches itself again: a conditional fetch made the compiler keep a second copy of
-            // the 16 registers, 32 moves per tile, and wait for the fetch at the end of the iteration that issued it)
-            load_src_sb(src, pl, min(min(tile + 1u, tile_end - 1u) * 8u + (lane >> 2), nmb - 1u), sb, aligned, nxt);
-            // ... and the tile after next into L2: DRAM under this kernel's write load takes longer to answer than a warp
-            // spends on one tile (ncu: the first use of `nxt` was the top stall).  Lane r < 16 touches row r of the tile's
-            // first and of its last macroblock: the line(s) holding that row of all eight.
-            if (lane < 16u && tile + 2u < tile_end) {
-#pragma unroll
-                for (uint32_t e = 0; e < 8u; e += 7u) {
-                    uint32_t col;
-                    const uint32_t row = div_small(min((tile + 2u) * 8u + e, nmb - 1u), pl.bw, pl.rcp_bw, col);
-                    const uint32_t y = row * 16u + lane, x = col * 16u;
-                    if (y < pl.vh && x < pl.vw) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)y * pl.vw + x));
-                }
-            }
-            uint32_t w[32];
-            fdct8x8_f32_columns(y);
-            quantise_sb_f32(y, encR, w);
-            uint32_t ac = w[0] & 0xffff0000u;
-#pragma unroll
-            for (int i = 1; i < 32; ++i) ac |= w[i];
-            {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    *reinterpret_cast<uint4 *>(stg + lane * ENC_OUT_PITCH + 16 * k) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-                __syncwarp();
-                // 16-byte chunk c = j*32 + lane of the tile's 4 KB: sub-block c >> 3, chunk c & 7 of it
-                const uint32_t tile_mbs = min(8u, nmb - tile * 8u);
-                uint4 *dstc = reinterpret_cast<uint4 *>(job.coeff + (size_t)(pl.mb_base + tile * 8u) * 256);
-                if (tile_mbs == 8u) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        __stcs(dstc + j * 32 + lane, *reinterpret_cast<const uint4 *>(stg_rd + j * 4 * ENC_OUT_PITCH));
-                } else {
-                    store_partial_tile(stg, dstc, tile_mbs, lane);
-                }
-                __syncwarp();                                   // the stage is rewritten by the next tile
-            }
-            if (COUNT) {                                        // sparse seam: how many RLE entries this macroblock makes
-                const uint32_t n = mb_entry_count_lanes(sb_runs(w), sb);
-                if (valid && sb == 0u) job.mb_cnt[pl.mb_base + lm] = n;
-            }
-            // closed-loop reconstruction (src/enc.rs:85,88,91: decode_plane of what was just encoded)
-            const bool general = valid && ac != 0u;
-            const uint32_t vote = __ballot_sync(0xffffffffu, general);
-            if (general) {
-                const uint32_t slot = (tail + (uint32_t)__popc(vote & ((1u << lane) - 1u))) & (SBW_RING - 1);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    ring[slot * 8u + ((uint32_t)k ^ (slot & 7u))] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-                ring_id[slot] = (lm << 2) | sb;
-            } else if (valid) {
-                store_dc_only(sb_dst(job.dst, pl, lm, (int)sb), pl.pw, (int)(int16_t)(w[0] & 0xffffu), deq[0]);
-            }
-            tail += (uint32_t)__popc(vote);
-            ++tile;
-            __syncwarp();
-        }
-        const uint32_t queued = tail - head;                    // at most 63: 31 carried + 32 new
-        if (queued >= 32u || (tile == tile_end && queued != 0u)) {
-            if (lane < queued) transform_entry_i<ROLLED>(ring, ring_id, (head + lane) & (SBW_RING - 1), job.dst, pl, deq);
-            head += min(32u, queued);
-            __syncwarp();
-        } else if (tile == tile_end) {
-            break;
-        }
-    }
-}
-
-// grid = (jobs, CTAs of a frame): consecutive CTAs work on the same part of DIFFERENT frames, so that all luma CTAs of the
-// launch come before all chroma CTAs and an SM runs one plane class's copy of the loop at a time (each is ~30 KB of code).
-// CTAS = resident CTAs per SM the kernel is compiled for.
-template <bool COUNT, bool ROLLED>
-__global__ void __launch_bounds__(ENC_WARPS * 32, 3)
-encode_i_stream_kernel(const __grid_constant__ EncSbParams P, const EncJob *__restrict__ jobs)
-{
-    extern __shared__ __align__(16) unsigned char enc_raw[];
-    EncStreamSmem &sm = *reinterpret_cast<EncStreamSmem *>(enc_raw);
-    const uint32_t cta = blockIdx.y;
-    const int p = (cta >= P.cta_base[1] ? 1 : 0) + (cta >= P.cta_base[2] ? 1 : 0);
-    const EncJob job = jobs[blockIdx.x];
-    if (p == 0) encode_i_tiles<COUNT, 0, ROLLED>(P, job, sm, 0, cta);
-    else        encode_i_tiles<COUNT, 1, ROLLED>(P, job, sm, p, cta - (p == 1 ? P.cta_base[1] : P.cta_base[2]));
-}
-
-// -------------------------------------------------------------------------------------------------
-// The same loop as a PERSISTENT kernel (the default): 3 CTAs per SM for the whole launch, chunks of ENC_CHUNK consecutive tiles
-// handed out in order by a device-wide counter.  What it buys over the grid of short-lived CTAs above (ncu, 64 x 1080p):
-//   * a warp's ring of queued sub-blocks lives across chunks, frames and planes of a class: it is drained ONCE per plane class
-//     and warp (1 776 x 2 partly filled transform passes per launch instead of 10 240 - they were 9 % of all instructions);
-//   * nobody waits for the last wave of CTAs (sm__cycles_active min / avg / max 389 k / 420 k / 452 k of 458 k elapsed).
-// Chunks are numbered luma first (all frames), then chroma: a warp runs the luma copy of the loop until the counter hands it a
-// chroma chunk, drains, and carries on in the chroma copy.  Ring entries carry their frame and plane (a second word).
-// -------------------------------------------------------------------------------------------------
 constexpr uint32_t ENC_CHUNK = 2;                              // tiles per chunk (what the slowest warp can finish after the others: ~5 us)
 
+// Chunks are numbered luma first (all frames), then chroma: a warp runs the luma copy of the loop until the counter hands it a
+// chroma chunk, drains, and carries on in the chroma copy.  Ring entries carry their frame and plane (a second word).
 struct EncChunks {
     uint32_t nl, nc;              // chunks per luma plane / per chroma plane
     float    rcp_nl, rcp_nc;
     uint32_t luma_total, total;   // njobs * nl, njobs * (nl + 2 nc)
-};
-
-struct __align__(16) EncPersistSmem {
-    uint4    coef[ENC_WARPS][SBW_RING * 8];
-    uint2    id[ENC_WARPS][SBW_RING];                          // {macroblock in plane << 2 | sub-block, job << 2 | plane}
-    uint4    out[ENC_WARPS][32 * ENC_OUT_PITCH / 16];
 };
 
 struct EncTilePos {               // one tile's place: which frame, which plane, which tile of it
@@ -387,7 +254,9 @@ __device__ __forceinline__ void encode_i_class(const EncSbParams &P, const EncCh
 #pragma unroll
                 for (int c = 0; c < 8; ++c) y[r * 8 + c] = v[c];
             }
-            fetch(nt, njr.src, nxt);                            // (the last tile of all fetches itself again: see the kernel above)
+            // (unconditional - the last tile of all fetches itself again: a conditional fetch made the compiler keep a second copy
+            // of the 16 registers, 32 moves per tile, and wait for the fetch at the end of the iteration that issued it)
+            fetch(nt, njr.src, nxt);
             uint32_t w[32];
             fdct8x8_f32_columns(y);
             quantise_sb_f32(y, encR, w);
@@ -498,41 +367,6 @@ cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_
     dim3 grid(ctas, 1, 1), block(ENC_WARPS * 32, 1, 1);
     if (count) { if (rolled) encode_i_persist_kernel<true, true><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); else encode_i_persist_kernel<true, false><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); }
     else       { if (rolled) encode_i_persist_kernel<false, true><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); else encode_i_persist_kernel<false, false><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_encode_i_stream(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, cudaStream_t s)
-{
-    // ~4 waves of the 148 SMs x 16 resident warps, at most 16 tiles per warp (what is left in a warp's ring at the end
-    // is one partly filled transform pass)
-    uint32_t tiles = 0;
-    for (int p = 0; p < 3; p++) tiles += (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
-    uint32_t tpw = (uint32_t)(((uint64_t)tiles * njobs) / (4u * 148u * 16u));
-    tpw = tpw < 1 ? 1 : (tpw > 16 ? 16 : tpw);
-    P.tiles_per_warp = tpw;
-    uint32_t cta = 0;
-    for (int p = 0; p < 3; p++) {
-        P.cta_base[p] = cta;
-        const uint32_t ntiles = (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
-        cta += (ntiles + ENC_WARPS * tpw - 1) / (ENC_WARPS * tpw);
-    }
-    P.cta_total = cta;
-    if (cta > 65535u) return cudaErrorInvalidConfiguration;      // (a plane of more than 4 M macroblocks)
-    dim3 grid(njobs, P.cta_total, 1), block(ENC_WARPS * 32, 1, 1);
-    // 3 resident CTAs per SM (~160 registers, no spills): 4 need 128 registers and spill; 1 or 2 were slower (110 / 163 / 188 k
-    // frames/s for 1 / 2 / 3, round 2)
-    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
-    static const bool rolled = !(getenv("PFV_ENCODE_I_ROLLED") && atoi(getenv("PFV_ENCODE_I_ROLLED")) == 0);
-    const int smem = (int)sizeof(EncStreamSmem);
-    if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(encode_i_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-    }
-    if (count) { if (rolled) encode_i_stream_kernel<true, true><<<grid, block, smem, s>>>(P, d_jobs); else encode_i_stream_kernel<true, false><<<grid, block, smem, s>>>(P, d_jobs); }
-    else       { if (rolled) encode_i_stream_kernel<false, true><<<grid, block, smem, s>>>(P, d_jobs); else encode_i_stream_kernel<false, false><<<grid, block, smem, s>>>(P, d_jobs); }
     return cudaGetLastError();
 }
 

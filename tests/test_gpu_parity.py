@@ -342,10 +342,10 @@ def test_encode_pframe_matches_oracle(size, quality, kind):
     assert np.array_equal(got_recon, prev)
 
 
-@pytest.mark.parametrize("ivar", ["persist", "stream", "warp"])
+@pytest.mark.parametrize("ivar", ["persist", "warp"])
 def test_encode_i_kernel_variants_agree(ivar, monkeypatch):
-    """PFV_ENCODE_I_VARIANT: the thread-per-sub-block loop as a persistent kernel (default) and as a grid of short-lived CTAs,
-    and the first-generation warp-per-macroblock kernel give the oracle's coefficients and reconstruction; a ragged size (padding with the clear colour, planes
+    """PFV_ENCODE_I_VARIANT: the persistent thread-per-sub-block kernel (default) and the first-generation warp-per-macroblock
+    kernel give the oracle's coefficients and reconstruction; a ragged size (padding with the clear colour, planes
     whose width is not a multiple of 8) and a batch of jobs in one launch."""
     monkeypatch.setenv("PFV_ENCODE_I_VARIANT", ivar)
     test_encode_iframe_matches_oracle((50, 38), 2)
