@@ -204,7 +204,11 @@ __device__ __forceinline__ void encode_i_class(const EncSbParams &P, const EncCh
 
     auto plane_of = [&](uint32_t p) -> const PlaneGeom & { return PC == 0 ? P.g.pl[0] : (p == 1u ? P.g.pl[1] : P.g.pl[2]); };
     // what the loop needs of a frame's job record, kept in registers and re-read (from global memory) only where a warp moves
-    // on to another chunk - one tile before the first use (read where they are used, ncu had every tile wait for them)
+    // on to another chunk - one tile before the first use (read where they are used, ncu had every tile wait for them).
+    // (Measured and dropped: taking the counter two chunks ahead and prefetching the next chunk's job record into L1 at the
+    // start of a chunk, and an L2 prefetch of the tile after next as the grid form had it - 210.6 us per 64 frames became
+    // 217.6 and 224.7: what ncu shows as long-scoreboard stalls at the bottom of a tile is the next tile's rows being moved
+    // into the loop-carried registers, and more address arithmetic in front of them only delays those loads.)
     struct JobRegs { const uint8_t *src; int16_t *coeff; uint8_t *dst; uint32_t *mb_cnt; };
     auto job_regs = [&](const EncTilePos &t) {
         const EncJob &j = jobs[t.job];

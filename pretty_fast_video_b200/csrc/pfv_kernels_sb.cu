@@ -309,7 +309,9 @@ static cudaError_t launch_decode_i_stream_t(SbParams P, const DecJob *d_jobs, ui
         cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel<WARPS, CTAS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    sbw_split(P, njobs, WARPS, 6u * 148u * (uint32_t)(CTAS * WARPS), 16u);
+    static const int waves_env = getenv("PFV_DECODE_I_WAVES") ? atoi(getenv("PFV_DECODE_I_WAVES")) : 6;   // tuning aid
+    const uint32_t waves = waves_env >= 1 && waves_env <= 64 ? (uint32_t)waves_env : 6u;
+    sbw_split(P, njobs, WARPS, waves * 148u * (uint32_t)(CTAS * WARPS), 16u);
     dim3 grid(P.cta_total, njobs, 1), block(WARPS * 32, 1, 1);
     decode_i_stream_kernel<WARPS, CTAS, POOL><<<grid, block, smem, s>>>(P, d_jobs);
     return cudaGetLastError();
