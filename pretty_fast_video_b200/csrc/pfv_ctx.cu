@@ -1280,7 +1280,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
 
     const size_t ysz = (size_t)g.width * g.height, csz = (size_t)g.cwidth * g.cheight;
     const size_t coeff_elems = (size_t)g.nb * 256;
-    uint32_t n_tok = 0;
+    uint32_t n_tok = 0, n_tok_key = 0;                             // (key frames come first in `order`)
     for (uint32_t k = 0; k < njobs; k++) {
         const EncIn &j = jobs[order[k]];
         EncJob &d = tab[k];
@@ -1335,6 +1335,10 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
             t.stats = pack + tp_off_words + (size_t)g.nb * 256;
             t.out_tok = j.tok_out; t.out_stats = j.stats_out; t.out_mb_off = j.mb_off_out;
             t.tok_cap = j.tok_cap;
+            // key frames: every macroblock carries coefficients - the tokenizer counts and emits them itself, one thread per
+            // sub-block (pfv_kernels_tok.cu), and the encode kernel does not count
+            t.padded = j.kind == PFV_FRAME_I ? 1u : 0u;
+            if (t.padded) { d.mb_cnt = nullptr; n_tok_key++; }
         }
     }
     CU_TRY(cudaMemcpyAsync(st.d_jobs, tab, sizeof(EncJob) * njobs, cudaMemcpyHostToDevice, c->s_h2d));
@@ -1357,10 +1361,11 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         c->launches++;
     }
     const EncJob *d_tab = static_cast<const EncJob *>(st.d_jobs);
-    const bool count = n_tok != 0;                                 // an entry point's jobs are all dense or all sparse
+    const bool count = n_tok != 0;                                 // an entry point's jobs are all dense or all sparse (P frames only:
+                                                                   // the key-frame tokenizer counts for itself)
     if (n_i) {
         if (c->encode_i_variant == 2) {
-            CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, count, c->s_compute));
+            CU_TRY(launch_encode_i(c->fg, d_tab, n_i, c->d_qt, false, c->s_compute));
         } else {
             EncSbParams P;
             P.g = c->fg;
@@ -1368,7 +1373,7 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
                 memcpy(P.encR[t], &c->h_enc_recip[(size_t)t * 64], 64 * sizeof(float));
                 memcpy(P.deq[t], &c->h_deq_scan[(size_t)t * 64], 64 * sizeof(int32_t));
             }
-            CU_TRY(launch_encode_i_persist(P, d_tab, n_i, count, c->d_work + 4, c->s_compute));
+            CU_TRY(launch_encode_i_persist(P, d_tab, n_i, c->d_work + 4, c->s_compute));
         }
         c->launches++;
     }
@@ -1376,7 +1381,10 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->encode_p_variant, c->d_work, c->s_compute));
         c->launches++;
     }
-    if (n_tok) { CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok, c->s_compute)); c->launches += 2; }
+    if (n_tok) {
+        CU_TRY(launch_tokenize(g.nb, st.d_tjobs, n_tok_key, n_tok, c->s_compute));
+        c->launches += (n_tok_key ? 3u : 0u) + (n_tok > n_tok_key ? 2u : 0u);
+    }
     if (c->want_kernel_time) { CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute)); c->have_kernel_time = true; }
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
     const double t4 = c->trace ? host_now() : 0;

@@ -438,6 +438,7 @@ PFV_UNROLL
 struct SbRuns {
     int      first, last;   // positions 0..63 of the first / last non-zero coefficient, -1 if none
     uint32_t inner;         // non-zero coefficients + the escapes of the gaps between them
+    uint64_t mask;          // bit i = coefficient i is non-zero
 };
 
 PFV_HD int clz64_(uint64_t v)
@@ -475,6 +476,7 @@ PFV_UNROLL
     }
     const uint64_t M = ((uint64_t)hi << 32) | lo;
     SbRuns r;
+    r.mask = M;
     r.first = ffs64_(M) - 1;
     r.last = 63 - clz64_(M);
     // z16 bit i: the 16 positions i-16 .. i-1 exist and are all zero

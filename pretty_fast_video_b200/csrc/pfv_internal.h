@@ -64,6 +64,7 @@ struct TokJob {
     uint32_t        *out_stats;
     uint32_t        *out_mb_off; // may be nullptr
     uint32_t         tok_cap;
+    uint32_t         padded;     // key frames: macroblock m's entries sit at tok[m * 256 ..] (tok_emit_sb_kernel), gathered by the store
 };
 
 struct EncJob {
@@ -167,7 +168,9 @@ cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint3
 // completes cta_base / cta_total / tiles_per_warp of the streaming kernels (pfv_kernels_sb.cu)
 void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t waves_x_warps, uint32_t max_tpw);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);
-cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
+// the first n_key jobs are key frames (thread-per-sub-block emit into padded slots, then the scan), the others P frames
+// (scan of the counts the encode kernel left, then the warp-per-macroblock emit)
+cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t n_key, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_token_store(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_rgb_to_yuv420(const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, cudaStream_t s);
 cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, uint32_t w, uint32_t h, uint32_t pw,
@@ -177,7 +180,7 @@ cudaError_t launch_yuv420_to_rgb_batch(const uint8_t *d_pool, size_t slot_stride
                                        cudaStream_t s);
 // count: every job of the launch has EncJob::mb_cnt set (sparse encode seam)
 // persistent, chunks of tiles handed out by a device counter; d_work: two zeroed device words (left zeroed)
-cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, uint32_t *d_work, cudaStream_t s);
+cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, uint32_t *d_work, cudaStream_t s);
 cudaError_t launch_encode_i(const FrameGeom &g, const EncJob *d_jobs, uint32_t njobs,
                             const QTables *d_qt, bool count, cudaStream_t s);
 // variant 0: warp per tile, column-strip search (default); 1: first generation (CTA per tile, warp per macroblock)

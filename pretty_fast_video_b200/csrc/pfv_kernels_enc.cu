@@ -28,8 +28,6 @@
 // one copy at a time (each is ~30 KB of code: the instruction cache).  The inverse transform is the rolled one
 // (idct8x8_regs_rolled): 64 register moves per pass buy 420 instructions of footprint.
 //
-// COUNT (sparse encode seam): each macroblock's number of RLE entries (rle_encode, src/rle.rs:9-39) is derived from
-// the non-zero masks of its four sub-blocks while they are still in registers (pfv_dct.cuh: sb_runs).
 #include <stdlib.h>
 
 #include "pfv_internal.h"
@@ -101,29 +99,6 @@ __device__ __noinline__ void store_partial_tile(const unsigned char *stg, uint4 
     }
 }
 
-// the macroblock's RLE entry count from the run bookkeeping of its four sub-blocks (lanes 4m .. 4m+3); every lane of
-// the group gets the result.  Same arithmetic as mb_entry_count (pfv_dct.cuh), the loop over sub-blocks as shuffles.
-__device__ __forceinline__ uint32_t mb_entry_count_lanes(const SbRuns &r, uint32_t sb)
-{
-    constexpr unsigned FULL = 0xffffffffu;
-    const int own_last = r.first >= 0 ? (int)(64u * sb) + r.last : -1;
-    int prev = -1;                                             // last non-zero position before this sub-block
-#pragma unroll
-    for (int d = 1; d <= 3; ++d) {
-        const int t = __shfl_up_sync(FULL, own_last, d, 4);
-        if ((int)sb >= d) prev = max(prev, t);
-    }
-    uint32_t n = r.inner;
-    if (r.first >= 0) n += rle_escapes((int)(64u * sb) + r.first - prev - 1);
-    if (sb == 3u) {
-        const int run = 255 - max(prev, own_last);
-        if (run > 0) n += 1u + rle_escapes(run);
-    }
-    n += __shfl_xor_sync(FULL, n, 1);
-    n += __shfl_xor_sync(FULL, n, 2);
-    return n;
-}
-
 constexpr uint32_t ENC_CHUNK = 2;                              // tiles per chunk (what the slowest warp can finish after the others: ~5 us)
 
 // Chunks are numbered luma first (all frames), then chroma: a warp runs the luma copy of the loop until the counter hands it a
@@ -158,7 +133,6 @@ __device__ __forceinline__ EncTilePos enc_chunk_pos(const EncChunks &C, uint32_t
     return t;
 }
 
-template <bool ROLLED>
 __device__ __forceinline__ void transform_entry_job(const uint4 *ring, const uint2 *idv, uint32_t slot, const EncJob *__restrict__ jobs,
                                                     const FrameGeom &g, const int32_t *deq)
 {
@@ -168,13 +142,8 @@ __device__ __forceinline__ void transform_entry_job(const uint4 *ring, const uin
     const PlaneGeom &pl = (id.y & 3u) == 0u ? g.pl[0] : ((id.y & 3u) == 1u ? g.pl[1] : g.pl[2]);
     uint8_t *dst = sb_dst(jobs[id.y >> 2].dst, pl, id.x >> 2, (int)(id.x & 3u));
     int m[64];
-    if (ROLLED) {
-        unpack_dequant_transposed(r2, deq, m);
-        idct8x8_regs_rolled(m);
-    } else {
-        unpack_dequant(r2, deq, m);
-        idct8x8_regs(m);
-    }
+    unpack_dequant_transposed(r2, deq, m);
+    idct8x8_regs_rolled(m);                                          // (one copy of the 1-D transforms: the instruction cache)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         uint2 o;
@@ -186,7 +155,7 @@ __device__ __forceinline__ void transform_entry_job(const uint4 *ring, const uin
 
 // All chunks of plane class PC this warp gets, starting with `chunk` (which is of this class); `next` is the chunk after it,
 // already taken from the counter.  Returns with `chunk` = the first chunk of another class (or >= C.total), `next` the one after.
-template <bool COUNT, int PC, bool ROLLED>
+template <int PC>
 __device__ __forceinline__ void encode_i_class(const EncSbParams &P, const EncChunks &C, const EncJob *__restrict__ jobs,
                                                EncPersistSmem &sm, uint32_t *work, const uint32_t first_dynamic,
                                                uint32_t &chunk, uint32_t &next)
@@ -209,12 +178,12 @@ __device__ __forceinline__ void encode_i_class(const EncSbParams &P, const EncCh
     // start of a chunk, and an L2 prefetch of the tile after next as the grid form had it - 210.6 us per 64 frames became
     // 217.6 and 224.7: what ncu shows as long-scoreboard stalls at the bottom of a tile is the next tile's rows being moved
     // into the loop-carried registers, and more address arithmetic in front of them only delays those loads.)
-    struct JobRegs { const uint8_t *src; int16_t *coeff; uint8_t *dst; uint32_t *mb_cnt; };
+    struct JobRegs { const uint8_t *src; int16_t *coeff; uint8_t *dst; };
     auto job_regs = [&](const EncTilePos &t) {
         const EncJob &j = jobs[t.job];
         JobRegs r;
         r.src = PC == 0 ? j.src[0] : (t.p == 1u ? j.src[1] : j.src[2]);
-        r.coeff = j.coeff; r.dst = j.dst; r.mb_cnt = COUNT ? j.mb_cnt : nullptr;
+        r.coeff = j.coeff; r.dst = j.dst;
         return r;
     };
     auto fetch = [&](const EncTilePos &t, const uint8_t *src, uint2 (&rows)[8]) {
@@ -283,10 +252,6 @@ __device__ __forceinline__ void encode_i_class(const EncSbParams &P, const EncCh
                 }
                 __syncwarp();
             }
-            if (COUNT) {
-                const uint32_t n = mb_entry_count_lanes(sb_runs(w), sb);
-                if (valid && sb == 0u) jr.mb_cnt[pl.mb_base + lm] = n;
-            }
             const bool general = valid && ac != 0u;
             const uint32_t vote = __ballot_sync(0xffffffffu, general);
             if (general) {
@@ -314,14 +279,13 @@ __device__ __forceinline__ void encode_i_class(const EncSbParams &P, const EncCh
         }
         const uint32_t queued = tail - head;                    // at most 63: 31 carried + 32 new
         if (queued >= 32u || (!more && queued != 0u)) {
-            if (lane < queued) transform_entry_job<ROLLED>(ring, ring_id, (head + lane) & (SBW_RING - 1), jobs, P.g, deq);
+            if (lane < queued) transform_entry_job(ring, ring_id, (head + lane) & (SBW_RING - 1), jobs, P.g, deq);
             head += min(32u, queued);
             __syncwarp();
         }
     }
 }
 
-template <bool COUNT, bool ROLLED>
 __global__ void __launch_bounds__(ENC_WARPS * 32, 3)
 encode_i_persist_kernel(const __grid_constant__ EncSbParams P, const __grid_constant__ EncChunks C, const EncJob *__restrict__ jobs,
                         uint32_t *__restrict__ work)
@@ -337,13 +301,16 @@ encode_i_persist_kernel(const __grid_constant__ EncSbParams P, const __grid_cons
         uint32_t g0 = 0;
         if (lane == 0) g0 = nwarps + atomicAdd(&work[0], 1u);
         next = __shfl_sync(0xffffffffu, g0, 0);
-        if (chunk < C.luma_total) encode_i_class<COUNT, 0, ROLLED>(P, C, jobs, sm, &work[0], nwarps, chunk, next);
-        if (chunk < C.total)      encode_i_class<COUNT, 1, ROLLED>(P, C, jobs, sm, &work[0], nwarps, chunk, next);
+        if (chunk < C.luma_total) encode_i_class<0>(P, C, jobs, sm, &work[0], nwarps, chunk, next);
+        if (chunk < C.total)      encode_i_class<1>(P, C, jobs, sm, &work[0], nwarps, chunk, next);
     }
     if (lane == 0 && atomicAdd(&work[1], 1u) == nwarps - 1u) { work[0] = 0u; work[1] = 0u; }
 }
 
-cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, bool count, uint32_t *d_work, cudaStream_t s)
+// (The sparse encode seam needs nothing from this kernel: the key-frame tokenizer counts a macroblock's run-length entries
+// itself, pfv_kernels_tok.cu.  A variant that counted them here while the coefficients were in registers cost 40 us per 32
+// frames on a 114 us kernel.)
+cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_t njobs, uint32_t *d_work, cudaStream_t s)
 {
     const uint32_t nty = (P.g.pl[0].bw * P.g.pl[0].bh + 7u) / 8u, ntc = (P.g.pl[1].bw * P.g.pl[1].bh + 7u) / 8u;
     EncChunks C;
@@ -356,21 +323,15 @@ cudaError_t launch_encode_i_persist(EncSbParams P, const EncJob *d_jobs, uint32_
     C.total = njobs * (C.nl + 2u * C.nc);
     P.tiles_per_warp = 0; P.cta_total = 0;
     for (int p = 0; p < 3; p++) P.cta_base[p] = 0;
-    static bool attr_done[64] = {};
-    static const bool rolled = !(getenv("PFV_ENCODE_I_ROLLED") && atoi(getenv("PFV_ENCODE_I_ROLLED")) == 0);
+    static bool attr_done[64] = {};           // cudaFuncSetAttribute is per DEVICE: one process may own contexts on several
     const int smem = (int)sizeof(EncPersistSmem);
     if (first_use_on_device(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(encode_i_persist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_persist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(encode_i_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(encode_i_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     uint32_t ctas = (C.total + ENC_WARPS - 1) / ENC_WARPS;
     if (ctas > 148u * 3u) ctas = 148u * 3u;
-    dim3 grid(ctas, 1, 1), block(ENC_WARPS * 32, 1, 1);
-    if (count) { if (rolled) encode_i_persist_kernel<true, true><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); else encode_i_persist_kernel<true, false><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); }
-    else       { if (rolled) encode_i_persist_kernel<false, true><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); else encode_i_persist_kernel<false, false><<<grid, block, smem, s>>>(P, C, d_jobs, d_work); }
+    encode_i_persist_kernel<<<ctas, ENC_WARPS * 32, smem, s>>>(P, C, d_jobs, d_work);
     return cudaGetLastError();
 }
 

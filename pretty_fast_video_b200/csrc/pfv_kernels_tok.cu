@@ -5,7 +5,8 @@
 // src/rle.rs:41-47) and only then writes bits.  A dense 1080p frame is 6.27 MB of i16 over PCIe and through a host
 // scan; >90 % of it is zeros.  Here the run-length pass runs on the device and only the RLE sequence crosses PCIe:
 //
-//   (encode kernels)   count the entries of each macroblock while its coefficients are still in registers (pfv_tok.cuh)
+// P frames (few macroblocks carry coefficients):
+//   (encode-P kernel)  counts the entries of each coded macroblock while its coefficients are still in registers (pfv_tok.cuh)
 //   tok_scan_kernel    one CTA per frame: exclusive prefix sum -> mb_off[nb+1]; clears the frame's statistics
 //   tok_emit_kernel    a warp takes 8 consecutive macroblocks, skips the ones without coefficients by one ballot over their
 //                      headers, compacts the non-zero coefficients of the others and writes their entries at their final
@@ -14,12 +15,23 @@
 //                      16-byte stores; the destination may be pinned HOST memory (zero-copy over PCIe), so the
 //                      transfer size follows the data without a host round trip
 //
+// Key frames (every macroblock carries coefficients, ~32 entries each at quality 5): the macroblock-at-a-time walk above costs
+// 390 warp instructions per macroblock (ncu: 170 us per 32 x 1080p, issue 83 %, ALU pipe 69 % - instruction bound) and the
+// counting inside the encode kernel another 40 us.  Instead:
+//   tok_emit_sb_kernel one THREAD per 8x8 sub-block, a warp = 8 macroblocks: 64-bit non-zero mask, entry counts and the
+//                      lane's offset inside its macroblock from the mask (sb_runs, pfv_dct.cuh), then every lane walks ITS
+//                      non-zeros and writes their entries into the macroblock's padded slot tok[m * 256 ..] (256 entries are
+//                      the most a macroblock can make); leaves the count in mb_off[m + 1] and adds to the statistics
+//   tok_scan_kernel    as above, without clearing the statistics
+//   tok_store_kernel   gathers the slots to their final offsets on the way out (and clears the staging statistics)
+//
 // Entry format (what pfv_packet_encode_tokens takes): run | size << 4 | uint16(value) << 16, exactly one word per
 // RLESequence {num_zeroes, coeff_size, coeff} (src/rle.rs:3-7).
 #include <cstdlib>
 
 #include "pfv_internal.h"
 #include "pfv_tok.cuh"
+#include "pfv_dct.cuh"
 
 namespace pfv {
 
@@ -31,6 +43,7 @@ constexpr uint32_t TOK_CHUNK = 8;       // macroblocks per warp
 
 // mb_off[m+1] holds the count of macroblock m on entry, the inclusive sum on exit; mb_off[0] = 0.
 constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 12;      // 12 288 counts per iteration: a 1080p frame (12 240) in one
+template <bool ZERO_STATS>
 __global__ void __launch_bounds__(SCAN_THREADS)
 tok_scan_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
 {
@@ -40,7 +53,7 @@ tok_scan_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     uint32_t *cnt = job.mb_off + 1;
     if (t == 0) { job.mb_off[0] = 0; carry_s = 0; }
-    if (t < PFV_TOKSTATS_WORDS) job.stats[t] = 0;
+    if (ZERO_STATS && t < PFV_TOKSTATS_WORDS) job.stats[t] = 0;
     __syncthreads();
     for (uint32_t base = 0; base < nb; base += SCAN_THREADS * SCAN_ITEMS) {
         const uint32_t i0 = base + t * SCAN_ITEMS;
@@ -248,6 +261,159 @@ tok_emit_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// key frames: one thread per sub-block (see the top of this file)
+// ---------------------------------------------------------------------------------------------------
+constexpr int TSB_WARPS = 4;
+constexpr int TSB_PITCH = 144;                                       // bytes per sub-block in the value stage: 128 + 16 (conflict free)
+constexpr uint32_t TSB_TILES = 3;                                    // tiles of 8 macroblocks per warp (3 x 64 entries per lane and
+                                                                     // symbol still fit the 8-bit fields of LaneHist)
+constexpr uint32_t TSB_SLOT = 64;                                    // entries of a macroblock staged in shared memory (the rest, rare,
+                                                                     // goes straight to global memory)
+
+struct __align__(16) TsbSmem {
+    uint4    val[TSB_WARPS][32 * TSB_PITCH / 16];                    // the tile's coefficients, looked up by position during the walk
+    uint32_t ent[TSB_WARPS][8][TSB_SLOT];                            // the tile's entries, macroblock by macroblock
+};
+
+__global__ void __launch_bounds__(TSB_WARPS * 32)
+tok_emit_sb_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
+{
+    __shared__ TsbSmem sm;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, sb = lane & 3u, mbi = lane >> 2;
+    const uint32_t tile0 = (blockIdx.x * TSB_WARPS + warp) * TSB_TILES;
+    if (tile0 * 8u >= nb) return;
+    const TokJob job = jobs[blockIdx.y];
+    unsigned char *mine = reinterpret_cast<unsigned char *>(sm.val[warp]) + lane * TSB_PITCH;
+    uint32_t *slot = sm.ent[warp][mbi];
+    LaneHist lh;
+    lh.acc[0] = lh.acc[1] = lh.acc[2] = lh.acc[3] = 0;
+    uint32_t esc_total = 0, range_bad = 0;
+
+    // the first tile's coefficients; inside the loop the NEXT tile's are fetched before this one is walked
+    auto fetch = [&](uint32_t tile, uint4 (&v)[8]) {
+        const uint32_t mm = tile * 8u + mbi;
+        const uint4 *src = reinterpret_cast<const uint4 *>(job.coeff + ((size_t)min(mm, nb - 1u) * 256 + sb * 64));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcs(src + k);
+    };
+    uint4 nxt[8];
+    fetch(tile0, nxt);
+#pragma unroll 1
+    for (uint32_t t = 0; t < TSB_TILES; ++t) {
+        const uint32_t m0 = (tile0 + t) * 8u;
+        if (m0 >= nb) break;
+        const uint32_t m = m0 + mbi;
+        const bool valid = m < nb;
+        // the sub-block's 64 coefficients: kept in shared memory for the walk (values are looked up by position there;
+        // registers cannot be indexed), their non-zero mask and run bookkeeping from registers
+        uint32_t w[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 v = nxt[k];
+            if (!valid) v = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(mine + 16 * k) = v;
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+        if (t + 1u < TSB_TILES && (tile0 + t + 1u) * 8u < nb) fetch(tile0 + t + 1u, nxt);
+        const SbRuns r = sb_runs(w);
+        // the macroblock's four lanes: last non-zero position before this sub-block, entries per lane, offsets (src/rle.rs:9-39)
+        const int own_last = r.first >= 0 ? (int)(64u * sb) + r.last : -1;
+        int prev = -1;
+#pragma unroll
+        for (int d = 1; d <= 3; ++d) {
+            const int u = __shfl_up_sync(FULL, own_last, d, 4);
+            if ((int)sb >= d) prev = max(prev, u);
+        }
+        const int tail_run = 255 - max(prev, own_last);              // lane 3 of the group: zeros after the last coefficient
+        const bool tail = sb == 3u && valid && tail_run > 0;
+        uint32_t n = r.inner;
+        if (r.first >= 0) n += rle_escapes((int)(64u * sb) + r.first - prev - 1);
+        if (tail) n += 1u + rle_escapes(tail_run);
+        uint32_t incl = n;
+        {
+            uint32_t u = __shfl_up_sync(FULL, incl, 1, 4);
+            if (sb >= 1u) incl += u;
+            u = __shfl_up_sync(FULL, incl, 2, 4);
+            if (sb >= 2u) incl += u;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 3, 4);
+        if (valid && sb == 0u) job.mb_off[m + 1u] = total;           // the scan turns the counts into offsets
+        __syncwarp();                                                // (the value stage; the entry slots of the previous tile are out)
+
+        // Entries go to the macroblock's slot in shared memory and leave as coalesced stores below: written straight to global
+        // memory every store instruction of the walk touched 32 different sectors (ncu on the first version: 148 us per 32
+        // frames at 39 % issue, the LSU the limit).  The walk itself is 32-bit arithmetic only: the 64-bit mask is taken half by
+        // half, the symbol counters are 8 bins x 4 bits per word.
+        uint32_t *gout = job.tok + (size_t)m * 256u;
+        uint32_t at = incl - n;                                      // entry index inside the macroblock
+        auto put = [&](uint32_t e) {
+            if (at < TSB_SLOT) slot[at] = e; else gout[at] = e;
+            ++at;
+        };
+        uint32_t rlo = 0, rhi = 0, slo = 0, shi = 0, pending = 0;
+        auto count = [&](uint32_t run, uint32_t size) {
+            const uint32_t rb = 1u << ((run & 7u) * 4u), sbit = 1u << ((size & 7u) * 4u);
+            rlo += run < 8u ? rb : 0u; rhi += run < 8u ? 0u : rb;
+            slo += size < 8u ? sbit : 0u; shi += size < 8u ? 0u : sbit;
+            if (++pending == 15u) {
+                hist_fold(lh, ((uint64_t)rhi << 32) | rlo, ((uint64_t)shi << 32) | slo);
+                rlo = rhi = slo = shi = 0; pending = 0;
+            }
+        };
+        uint32_t bits = (uint32_t)r.mask, more = (uint32_t)(r.mask >> 32);
+        int base = (int)(64u * sb), pp = prev;
+        const unsigned char *vals = mine;
+        while (bits | more) {
+            if (bits == 0u) { bits = more; more = 0u; base += 32; vals += 64; }
+            const int p = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            const int pos = base + p;
+            int run = pos - pp - 1;
+            pp = pos;
+            const int esc = (int)rle_escapes(run);                   // `while run > 15 { push(15,0,0); run -= 15 }` (src/rle.rs:18-21)
+            for (int q = 0; q < esc; ++q) put(15u);
+            run -= 15 * esc;
+            const uint32_t e16 = *reinterpret_cast<const uint16_t *>(vals + 2 * p);
+            const int v = (int)(int16_t)e16;
+            const uint32_t a = (uint32_t)(v < 0 ? -v : v) & 0xffffu; // val.abs() as u16 (src/rle.rs:23)
+            const uint32_t size = (32u - (uint32_t)__clz((int)a)) + 1u;   // (16 - leading_zeros) + 1 (src/rle.rs:24)
+            range_bad |= size > 15u ? PFV_TOKFLAG_RANGE : 0u;
+            put((uint32_t)run | (size << 4) | (e16 << 16));
+            esc_total += (uint32_t)esc;
+            count((uint32_t)run, size & 15u);
+        }
+        if (tail) {                                                  // the tail of the macroblock (src/rle.rs:31-38)
+            int run = tail_run;
+            const int esc = (int)rle_escapes(run);
+            for (int q = 0; q < esc; ++q) put(15u);
+            run -= 15 * esc;
+            esc_total += (uint32_t)esc;
+            put((uint32_t)run);                                      // {run, 0, 0}
+            count((uint32_t)run, 0u);
+        }
+        hist_fold(lh, ((uint64_t)rhi << 32) | rlo, ((uint64_t)shi << 32) | slo);
+        __syncwarp();
+        // the slots out: macroblock j's first min(total, TSB_SLOT) entries, 32 at a time
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j) {
+            const uint32_t nj = min(__shfl_sync(FULL, total, 4 * j), TSB_SLOT);
+            uint32_t *g = job.tok + (size_t)(m0 + j) * 256u;
+#pragma unroll
+            for (uint32_t i = 0; i < TSB_SLOT; i += 32u)
+                if (i + lane < nj) g[i + lane] = sm.ent[warp][j][i + lane];
+        }
+    }
+    __syncwarp();
+    hist_flush(lh, lane, job.stats);                                 // (a lane makes at most 3 x 64 entries of one symbol)
+    esc_total = __reduce_add_sync(FULL, esc_total);
+    if (lane == 0 && esc_total) {
+        atomicAdd(job.stats + 15, esc_total);
+        atomicAdd(job.stats + 16, esc_total);
+    }
+    if (__any_sync(FULL, range_bad != 0) && lane == 0) atomicOr(job.stats + PFV_TOKSTATS_FLAGS, PFV_TOKFLAG_RANGE);
+}
+
 constexpr int STORE_THREADS = 256;
 __global__ void __launch_bounds__(STORE_THREADS)
 tok_store_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
@@ -256,7 +422,15 @@ tok_store_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     const uint32_t ntok = job.stats[PFV_TOKSTATS_NTOK];
     const uint32_t n = min(ntok, job.tok_cap);
     const uint32_t tid = blockIdx.x * STORE_THREADS + threadIdx.x, nthr = gridDim.x * STORE_THREADS;
-    if ((reinterpret_cast<uintptr_t>(job.out_tok) & 15u) == 0) {
+    if (job.padded) {
+        // key frames: macroblock m's entries from its slot to [mb_off[m], mb_off[m + 1]) of the sequence, a warp per macroblock
+        const uint32_t lane = threadIdx.x & 31u, gw = tid >> 5, nw = nthr >> 5;
+        for (uint32_t mb = gw; mb < nb; mb += nw) {
+            const uint32_t o = job.mb_off[mb], e = min(job.mb_off[mb + 1u], n);
+            const uint32_t *src = job.tok + (size_t)mb * 256u;
+            for (uint32_t i = o + lane; i < e; i += 32u) job.out_tok[i] = src[i - o];
+        }
+    } else if ((reinterpret_cast<uintptr_t>(job.out_tok) & 15u) == 0) {
         const uint4 *s4 = reinterpret_cast<const uint4 *>(job.tok);
         uint4 *d4 = reinterpret_cast<uint4 *>(job.out_tok);
         const uint32_t n4 = n >> 2;
@@ -274,13 +448,29 @@ tok_store_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     }
 }
 
-// The per-macroblock entry counts are already in mb_off[1..] (written by the encode kernels, EncJob::mb_cnt).
-cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s)
+__global__ void tok_zero_kernel(const TokJob *__restrict__ jobs)
 {
-    tok_scan_kernel<<<njobs, SCAN_THREADS, 0, s>>>(nb, d_jobs);
-    const uint32_t chunks = (nb + TOK_CHUNK - 1u) / TOK_CHUNK;
-    dim3 grid((chunks + TOK_WARPS - 1) / TOK_WARPS, njobs, 1), block(TOK_WARPS * 32, 1, 1);
-    tok_emit_kernel<<<grid, block, 0, s>>>(nb, d_jobs);
+    if (threadIdx.x < PFV_TOKSTATS_WORDS) jobs[blockIdx.x].stats[threadIdx.x] = 0;
+}
+
+// Key frames (the first n_key jobs): statistics cleared, entries emitted into the padded slots with their counts, then the scan.
+// P frames: the per-macroblock entry counts are already in mb_off[1..] (written by the encode kernel, EncJob::mb_cnt).
+cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t n_key, uint32_t njobs, cudaStream_t s)
+{
+    if (n_key) {
+        tok_zero_kernel<<<n_key, 64, 0, s>>>(d_jobs);
+        const uint32_t tiles = (nb + 7u) / 8u;
+        dim3 grid((tiles + TSB_WARPS * TSB_TILES - 1) / (TSB_WARPS * TSB_TILES), n_key, 1);
+        tok_emit_sb_kernel<<<grid, TSB_WARPS * 32, 0, s>>>(nb, d_jobs);
+        tok_scan_kernel<false><<<n_key, SCAN_THREADS, 0, s>>>(nb, d_jobs);
+    }
+    if (njobs > n_key) {
+        const uint32_t np = njobs - n_key;
+        tok_scan_kernel<true><<<np, SCAN_THREADS, 0, s>>>(nb, d_jobs + n_key);
+        const uint32_t chunks = (nb + TOK_CHUNK - 1u) / TOK_CHUNK;
+        dim3 grid((chunks + TOK_WARPS - 1) / TOK_WARPS, np, 1), block(TOK_WARPS * 32, 1, 1);
+        tok_emit_kernel<<<grid, block, 0, s>>>(nb, d_jobs + n_key);
+    }
     return cudaGetLastError();
 }
 

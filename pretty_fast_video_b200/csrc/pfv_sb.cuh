@@ -97,9 +97,7 @@ __device__ __forceinline__ void ring_get(const uint4 *ring, uint32_t slot, uint4
     for (int k = 0; k < 8; ++k) r2[k] = ring[slot * 8u + ((uint32_t)k ^ (slot & 7u))];
 }
 
-// full inverse transform of one queued intra sub-block (src/common.rs:313-325) and its 8 row stores.  ROLLED: one copy of
-// the 1-D transforms in the code (idct8x8_regs_rolled) for kernels whose loop would otherwise outgrow the instruction cache.
-template <bool ROLLED = false>
+// full inverse transform of one queued intra sub-block (src/common.rs:313-325) and its 8 row stores
 __device__ __forceinline__ void transform_entry_i(const uint4 *ring, const uint32_t *idv, uint32_t slot, uint8_t *slot_base,
                                                   const PlaneGeom &pl, const int32_t *deq)
 {
@@ -108,13 +106,8 @@ __device__ __forceinline__ void transform_entry_i(const uint4 *ring, const uint3
     const uint32_t id = idv[slot];
     uint8_t *dst = sb_dst(slot_base, pl, id >> 2, (int)(id & 3u));
     int m[64];
-    if (ROLLED) {
-        unpack_dequant_transposed(r2, deq, m);
-        idct8x8_regs_rolled(m);
-    } else {
-        unpack_dequant(r2, deq, m);
-        idct8x8_regs(m);
-    }
+    unpack_dequant(r2, deq, m);
+    idct8x8_regs(m);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         uint2 o;
