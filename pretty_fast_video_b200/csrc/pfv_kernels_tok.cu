@@ -415,6 +415,8 @@ tok_emit_sb_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
 }
 
 constexpr int STORE_THREADS = 256;
+constexpr uint32_t STORE_MBS = 64;                                   // macroblocks a CTA packs at a time (key frames)
+constexpr uint32_t STORE_PACK = 4096;                                // ... if they make no more entries than this (else piece by piece)
 __global__ void __launch_bounds__(STORE_THREADS)
 tok_store_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
 {
@@ -423,12 +425,27 @@ tok_store_kernel(uint32_t nb, const TokJob *__restrict__ jobs)
     const uint32_t n = min(ntok, job.tok_cap);
     const uint32_t tid = blockIdx.x * STORE_THREADS + threadIdx.x, nthr = gridDim.x * STORE_THREADS;
     if (job.padded) {
-        // key frames: macroblock m's entries from its slot to [mb_off[m], mb_off[m + 1]) of the sequence, a warp per macroblock
-        const uint32_t lane = threadIdx.x & 31u, gw = tid >> 5, nw = nthr >> 5;
-        for (uint32_t mb = gw; mb < nb; mb += nw) {
-            const uint32_t o = job.mb_off[mb], e = min(job.mb_off[mb + 1u], n);
-            const uint32_t *src = job.tok + (size_t)mb * 256u;
-            for (uint32_t i = o + lane; i < e; i += 32u) job.out_tok[i] = src[i - o];
+        // Key frames: macroblock m's entries from its slot to [mb_off[m], mb_off[m + 1]) of the sequence.  A CTA takes
+        // STORE_MBS consecutive macroblocks at a time, packs their entries in shared memory (a warp per macroblock) and writes
+        // the packed run with consecutive threads on consecutive words - the destination is usually pinned host memory, and
+        // macroblock-sized pieces (~128 B at odd offsets) cost a tenth of the encode leg's end-to-end rate over PCIe.
+        __shared__ uint32_t pack_s[STORE_PACK];
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        for (uint32_t m0 = blockIdx.x * STORE_MBS; m0 < nb; m0 += gridDim.x * STORE_MBS) {
+            const uint32_t m1 = min(m0 + STORE_MBS, nb);
+            const uint32_t o0 = job.mb_off[m0], o1 = min(job.mb_off[m1], n);
+            const bool fits = o1 > o0 && o1 - o0 <= STORE_PACK;
+            for (uint32_t mb = m0 + warp; mb < m1; mb += STORE_THREADS / 32) {
+                const uint32_t o = job.mb_off[mb], e = min(job.mb_off[mb + 1u], n);
+                const uint32_t *src = job.tok + (size_t)mb * 256u;
+                for (uint32_t i = o + lane; i < e; i += 32u) {
+                    if (fits) pack_s[i - o0] = src[i - o]; else job.out_tok[i] = src[i - o];
+                }
+            }
+            __syncthreads();
+            if (fits)
+                for (uint32_t i = o0 + threadIdx.x; i < o1; i += STORE_THREADS) job.out_tok[i] = pack_s[i - o0];
+            __syncthreads();
         }
     } else if ((reinterpret_cast<uintptr_t>(job.out_tok) & 15u) == 0) {
         const uint4 *s4 = reinterpret_cast<const uint4 *>(job.tok);
