@@ -54,6 +54,8 @@ WORKLOADS = {
     # time the first launch of the timed region waits for its host submit (~50 us, once) does not weigh on a 2 ms measurement
     "decode_i_1080p": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465601),
     "decode_p_1080p": dict(w=1920, h=1080, frames=0, gops=32, gop=15, quality=5, seed=0x50465602),
+    # the same stream with 64 GOPs side by side (as many macroblocks per launch as decode_p_4k has): what a deeper batch is worth
+    "decode_p_1080p_64": dict(w=1920, h=1080, frames=0, gops=64, gop=15, quality=5, seed=0x50465602),
     "encode_p_1080p": dict(w=1920, h=1080, frames=0, gops=32, gop=15, quality=5, seed=0x50465602),
     "decode_p_4k": dict(w=3840, h=2160, frames=0, gops=16, gop=15, quality=5, seed=0x50465603),
     "encode_i_1080p": dict(w=1920, h=1080, frames=64, gops=0, gop=1, quality=5, seed=0x50465601),
@@ -1129,6 +1131,7 @@ def main():
     achieved = r["alg_bytes"] / (r["my_ms"] * 1e-3) / 1e9      # this rank's kernels
     kernel_of = {"decode_i_1080p": "decode_i_stream_kernel", "decode_i_1080p_dense": "decode_i_direct_kernel",   # PFV_JOB_DENSE
                  "decode_p_1080p": "decode_p_fused_kernel", "decode_p_4k": "decode_p_fused_kernel",
+                 "decode_p_1080p_64": "decode_p_fused_kernel",
                  "encode_p_1080p": "encode_p2_kernel", "encode_i_1080p": "encode_i_persist_kernel"}
     kernel_key = kernel_of[args.workload]
 
