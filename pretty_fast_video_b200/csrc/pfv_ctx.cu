@@ -240,7 +240,8 @@ struct pfv_ctx {
     int encode_p_variant = 0;              // PFV_ENCODE_P_VARIANT: 0 "strip" (default: warp per tile, column-strip search), 1 "v1" (warp per macroblock)
     uint32_t *d_plist = nullptr;           // max_jobs * nb: coded macroblocks per (job, plane), filled by mc_copy_kernel
     uint32_t *d_pcount = nullptr;          // max_jobs * 4
-    CUtensorMap tm_luma{}, tm_chroma{};          // encode-P search window boxes
+    CUtensorMap tm_luma{}, tm_chroma{};          // encode-P search window boxes (first-generation kernel: 176 x 46)
+    CUtensorMap tm_ep2_luma{}, tm_ep2_chroma{};  // ... of the warp-per-tile kernel (EP2_WIN_W x 46)
     CUtensorMap tm_win_luma{}, tm_win_chroma{};  // decode-P windows of 8 x 4 macroblocks (176 x 94; the copy + residual pair)
     CUtensorMap tm_pf_luma{}, tm_pf_chroma{};    // decode-P windows of 8 x PF_ROWS macroblocks (the fused kernel)
     bool have_tma = false;
@@ -265,15 +266,16 @@ int build_tensor_maps(pfv_ctx *c)
     EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
     const pfv_geometry &g = c->geo;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int which = 0; which < 3; which++) {
+    for (int which = 0; which < 4; which++) {
     const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     // which == 0: the search window of an encode-P tile of 8 macroblocks (176 x 46)
     // which == 1: the window of every possible predictor of 8 x 4 macroblocks (176 x 94; decode-P copy kernel)
     // which == 2: the same for 8 x PF_ROWS macroblocks (fused decode-P kernel)
-    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : 176u,
-                               which == 0 ? (cuuint32_t)WIN_H : (which == 1 ? 94u : (cuuint32_t)PF_WIN_H), 1, 1};
-    CUtensorMap *out_l = which == 0 ? &c->tm_luma : (which == 1 ? &c->tm_win_luma : &c->tm_pf_luma);
-    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : (which == 1 ? &c->tm_win_chroma : &c->tm_pf_chroma);
+    // which == 3: the search window again, at the warp-per-tile kernel's own pitch
+    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : (which == 3 ? (cuuint32_t)EP2_WIN_W : 176u),
+                               which == 0 || which == 3 ? (cuuint32_t)WIN_H : (which == 1 ? 94u : (cuuint32_t)PF_WIN_H), 1, 1};
+    CUtensorMap *out_l = which == 0 ? &c->tm_luma : (which == 1 ? &c->tm_win_luma : (which == 2 ? &c->tm_pf_luma : &c->tm_ep2_luma));
+    CUtensorMap *out_c = which == 0 ? &c->tm_chroma : (which == 1 ? &c->tm_win_chroma : (which == 2 ? &c->tm_pf_chroma : &c->tm_ep2_chroma));
     {   // luma: (x, y, 1, slot)
         const cuuint64_t dims[4] = {g.pw, g.ph, 1, c->nslots};
         const cuuint64_t strides[3] = {g.pw, c->slot_stride, c->slot_stride};
@@ -316,6 +318,7 @@ void fill_frame_geom(pfv_ctx *c)
         pl.mb_base = mb; pl.off = off;
         pl.rcp_bw = 1.0f / (float)pl.bw;
         pl.tiles_per_row = (pl.bw + 7) / 8;
+        pl.rcp_tiles_per_row = 1.0f / (float)pl.tiles_per_row;
         pl.tile_base = tile;
         pl.clear4 = p == 0 ? 0u : 0x80808080u;
         mb += pl.bw * pl.bh;
@@ -1378,7 +1381,11 @@ int encode_submit_impl(pfv_ctx *c, const EncIn *jobs, uint32_t njobs)
         c->launches++;
     }
     if (njobs - n_i) {
-        CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, c->tm_luma, c->tm_chroma, count, c->encode_p_variant, c->d_work, c->s_compute));
+        {
+            const bool gen1 = c->encode_p_variant == 1;
+            CU_TRY(launch_encode_p(c->fg, d_tab + n_i, njobs - n_i, c->d_qt, gen1 ? c->tm_luma : c->tm_ep2_luma, gen1 ? c->tm_chroma : c->tm_ep2_chroma,
+                                   count, c->encode_p_variant, c->d_work, c->s_compute));
+        }
         c->launches++;
     }
     if (n_tok) {

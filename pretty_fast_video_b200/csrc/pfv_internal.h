@@ -25,6 +25,7 @@ struct PlaneGeom {
     float    rcp_bw;          // 1.0f / bw
     uint32_t tiles_per_row;   // ceil(bw / 8): encode-P tiles of 8 horizontally adjacent macroblocks
     uint32_t tile_base;       // index of the plane's first tile
+    float    rcp_tiles_per_row;   // 1.0f / tiles_per_row
     uint32_t clear4;          // clear colour replicated in 4 bytes: 0 for Y, 0x80808080 for U,V (src/enc.rs:84-90)
 };
 
@@ -134,6 +135,15 @@ enum { ERRBIT_BAD_MV = 1, ERRBIT_TIMEOUT = 2 };
 constexpr int WIN_W = 176;
 constexpr int WIN_H = 46;
 constexpr int WIN_BYTES = WIN_W * WIN_H;
+// The same window for the warp-per-tile kernel (encode_p2_kernel): 16 + 128 + 15 = 159 -> 160 bytes per row and no more.
+// A row pitch of 40 words moves a macroblock's four banks by 8 per row: after the first search levels the eight macroblocks
+// of a warp read rows of their own (centres 4, 2, 1 rows apart), and with 44 words (12 banks per row) almost any two of them
+// met in a bank - ncu: 2.2 - 2.5 wavefronts per load at the fine levels.
+#ifndef PFV_EP2_WIN_W
+#define PFV_EP2_WIN_W 160
+#endif
+constexpr int EP2_WIN_W = PFV_EP2_WIN_W;
+constexpr int EP2_WIN_BYTES = EP2_WIN_W * WIN_H;
 constexpr int WINP_W = 188;                  // re-pitched window: 47 words per row (odd: rows spread over all banks)
 constexpr int WINP_BYTES = WINP_W * WIN_H;
 

@@ -432,8 +432,8 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
 // macroblock, lane = (candidate, row quarter): every candidate row is loaded on its own, 16 loads + 32 SSD instructions
 // + a reduction per lane and level), ~55 the window re-pitch and the source-row shuffles, two CTA barriers per tile.
 //
-// Here a warp owns the whole tile and its own search window (ONE 176 x 46 TMA box per tile into a per-warp double
-// buffer: the next tile's window is in flight while this one is searched - no CTA barrier anywhere).  Lane = (macroblock
+// Here a warp owns the whole tile and its own search window (ONE 160 x 46 TMA box per tile into the warp's buffer - no CTA
+// barrier anywhere; the other warps of the SM cover the window's arrival, see EP2_WARPS).  Lane = (macroblock
 // m = lane >> 2, column strip q = lane & 3): it keeps the 4-pixel-wide strip of its macroblock's 16 source rows in 16
 // registers and evaluates ALL 8 candidates of a level on that strip.  For a fixed horizontal offset the three vertical
 // candidates read the same window words 8 / 4 / 2 / 1 rows apart, so each loaded word feeds up to three candidates:
@@ -446,14 +446,23 @@ encode_p_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__ 
 // Skipped macroblocks (src/common.rs:221-222) write their predictor strip straight to the reconstruction slot (full
 // 128-byte rows per warp store).  Coded ones (~15 %) go one at a time through the warp-wide transform of the first
 // generation (encode_mb_core / decode_mb_core: residual, FDCT + quantiser, closed-loop reconstruction).
-constexpr int EP2_WARPS = 12;                                 // one CTA per SM: 12 x (two 8 KB window stages + transform scratch) = 224 KB
+// Warps per CTA (one CTA per SM).  Each warp has ONE window buffer: the next tile's window is requested when the last lane is
+// done with this one and the warp waits for it at the top of the next tile.  The first form kept two buffers per warp (the next
+// window in flight during the search) and, at 2 x 8 KB + scratch per warp, 12 warps per SM.  Measured on 32 x 1080p (round 2,
+// visits zd / ze): 12 warps x 2 buffers 132.2 k frames/s, 12 x 1 132.7 k - the window in flight buys nothing, the other warps
+// cover the ~1 us of a window's arrival - and with the room for more warps 16 x 1 142.3 k, 18 x 1 141.3 k, 20 x 1 144.1 k
+// (96 registers), 22 x 1 130.0 k (80 registers, spills).  16 = four per scheduler at 128 registers.
+#ifndef PFV_EP2_NWARPS
+#define PFV_EP2_NWARPS 16
+#endif
+constexpr int EP2_WARPS = PFV_EP2_NWARPS;
 constexpr int EP2_MAX_JOBS = 64;
-constexpr int EP2_WIN_STAGE = (WIN_BYTES + 127) & ~127;
+constexpr int EP2_WIN_STAGE = (EP2_WIN_BYTES + 127) & ~127;
 
 struct __align__(128) Ep2Smem {
-    uint8_t     win[EP2_WARPS][2][EP2_WIN_STAGE];
+    uint8_t     win[EP2_WARPS][EP2_WIN_STAGE];
     WarpScratch scratch[EP2_WARPS];
-    uint64_t    bar[EP2_WARPS][2];
+    uint64_t    bar[EP2_WARPS];
     EncJob      job[EP2_MAX_JOBS];
 };
 static_assert(sizeof(Ep2Smem) + 1024 <= 227 * 1024, "the encode-P CTA must fit one SM");
@@ -482,32 +491,108 @@ __device__ __noinline__ uint32_t load_src4_ragged(const uint8_t *__restrict__ sr
     return w;
 }
 
-// One search level (src/common.rs:165-196 for one step): S = this lane's source strip, `base` = byte offset in the
-// window of the strip's top-left pixel displaced by the current centre.  Returns the level's best key
+// One search level (src/common.rs:165-196 for one step): S = this lane's source strip, A = the sum of its squares, `base` =
+// byte offset in the window of the strip's top-left pixel displaced by the current centre.  Returns the level's best key
 // (ssd << 3 | g), 0xffffffff if no candidate lies inside the plane.  ALIGNED: every candidate is word aligned.
+//
+// The error of a candidate strip is taken apart, sum (a - b)^2 = sum a^2 + sum b^2 - 2 sum a b, all three exact integers
+// (< 2^24 for a whole macroblock; src/common.rs:125-139 adds the same squares in f32, exact below 2^24 as well): the three
+// vertical candidates of a column share every window word, so sum b^2 is ONE running dot product per loaded word (the
+// candidates' sums are differences of its prefix), and each candidate adds one dot product with the source word - 4 multiply-
+// add-pipe instructions per loaded word at most where |a - b| first (vabsdiff4 + dp4a per candidate) took 6, three of them on
+// the ALU pipe, which ncu had as this kernel's busiest (52 % against 22 % for the multiply-add pipe, math-pipe throttle 0.35).
+//
 // The loop over the horizontal offset is NOT unrolled: straight-line code of this size runs at the speed of the
 // instruction fetch (ncu on the encode-I kernel: a quarter of all stall samples "no instruction"), a loop body of
-// ~150 instructions stays in the instruction cache.  For mx = 0 the middle candidate is the centre itself: it is
+// ~120 instructions stays in the instruction cache.  For mx = 0 the middle candidate is the centre itself: it is
 // computed with the others (its key is discarded) so that the three passes share one body (a separate two-candidate
 // body for mx = 0 saves 4 % of the search's arithmetic and was measured 5 % SLOWER: 680 more instructions of code).
 template <int STEP, bool ALIGNED>
-__device__ __forceinline__ uint32_t search_level(const uint8_t *win, const uint32_t (&S)[16], uint32_t base, uint32_t valid_mask)
+__device__ __forceinline__ uint32_t search_level(const uint8_t *win, const uint32_t (&S)[16], uint32_t A, uint32_t base, uint32_t valid_mask)
 {
     constexpr unsigned FULL = 0xffffffffu;
     uint32_t kmin = 0xffffffffu;
     // candidates in the reference's visiting order: g = 0,1,2: my = -1 (mx = -1,0,1); 3,4: my = 0 (mx = -1, 1); 5,6,7: my = +1
 #pragma unroll 1
     for (int mx = -1; mx <= 1; ++mx) {
-        uint32_t up = 0, mid = 0, dn = 0;
-        const uint32_t col = base + (uint32_t)(mx * STEP) - (uint32_t)(STEP * WIN_W);     // top row of the my = -1 candidate
+        uint32_t cu = 0, cm = 0, cd = 0;                          // sum a b of the three candidates
+        uint32_t t = 0, t_s = 0, t_2s = 0, t_16 = 0, t_16s = 0;   // prefix of sum b^2 down the column, and where the candidates cut it
+        const uint32_t col = base + (uint32_t)(mx * STEP) - (uint32_t)(STEP * EP2_WIN_W);     // top row of the my = -1 candidate
 #pragma unroll
         for (int rho = 0; rho < 16 + 2 * STEP; ++rho) {
-            const uint32_t off = col + (uint32_t)(rho * WIN_W);
+            const uint32_t off = col + (uint32_t)(rho * EP2_WIN_W);
             const uint32_t w = ALIGNED ? *reinterpret_cast<const uint32_t *>(win + off) : lds_u8x4_unaligned(win, off);
-            if (rho < 16) up = ssd4(S[rho], w, up);
-            if (rho >= STEP && rho < 16 + STEP) mid = ssd4(S[rho - STEP], w, mid);
-            if (rho >= 2 * STEP) dn = ssd4(S[rho - 2 * STEP], w, dn);
+            if (rho == STEP) t_s = t;
+            if (rho == 2 * STEP) t_2s = t;
+            if (rho == 16) t_16 = t;
+            if (rho == 16 + STEP) t_16s = t;
+            t = __dp4a(w, w, t);
+            if (rho < 16) cu = __dp4a(S[rho], w, cu);
+            if (rho >= STEP && rho < 16 + STEP) cm = __dp4a(S[rho - STEP], w, cm);
+            if (rho >= 2 * STEP) cd = __dp4a(S[rho - 2 * STEP], w, cd);
         }
+        // this strip's share of the three errors (each a sum of squares itself: >= 0, < 2^22)
+        uint32_t up = A + t_16 - 2u * cu;
+        uint32_t mid = A + (t_16s - t_s) - 2u * cm;
+        uint32_t dn = A + (t - t_2s) - 2u * cd;
+        up += __shfl_xor_sync(FULL, up, 1);
+        up += __shfl_xor_sync(FULL, up, 2);
+        mid += __shfl_xor_sync(FULL, mid, 1);
+        mid += __shfl_xor_sync(FULL, mid, 2);
+        dn += __shfl_xor_sync(FULL, dn, 1);
+        dn += __shfl_xor_sync(FULL, dn, 2);
+        const uint32_t g_up = (uint32_t)(mx + 1), g_mid = mx < 0 ? 3u : 4u, g_dn = (uint32_t)(mx + 6);
+        if ((valid_mask >> g_up) & 1u) kmin = min(kmin, (up << 3) | g_up);
+        if (mx != 0 && ((valid_mask >> g_mid) & 1u)) kmin = min(kmin, (mid << 3) | g_mid);
+        if ((valid_mask >> g_dn) & 1u) kmin = min(kmin, (dn << 3) | g_dn);
+    }
+    return kmin;
+}
+
+// The two fine levels (steps 2 and 1), where no candidate is word aligned.  ncu, round 2: the kernel's busiest unit is the
+// shared-memory data pipe (52 M wavefronts per 32 x 1080p = 0.71 of its cycles) - every candidate word of these levels cost two
+// loads (the two words it straddles), and after the first level the eight macroblocks of a warp read rows and columns of
+// their own, so that a load is 2.2 - 2.5 wavefronts.  Here the 2 STEP + 4 bytes a row offers the three horizontal offsets are
+// loaded ONCE (three words) and brought to the left-most candidate's alignment in registers (X0, X1: two funnel shifts); the
+// candidate word of offset mx is then one more funnel shift by (mx + 1) STEP bytes (clamped: 4 bytes = the second register).
+// Loads per row 6 -> 3, instructions per row 9 -> 8.
+template <int STEP>
+__device__ __forceinline__ uint32_t search_level_fine(const uint8_t *win, const uint32_t (&S)[16], uint32_t A, uint32_t base, uint32_t valid_mask)
+{
+    static_assert(STEP == 1 || STEP == 2, "2 STEP + 4 bytes must fit two words");
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ROWS = 16 + 2 * STEP;
+    const uint32_t col0 = base - (uint32_t)STEP - (uint32_t)(STEP * EP2_WIN_W);    // first byte of the top row of candidate (-1, -1)
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(win + (col0 & ~3u));
+    const uint32_t sh = (col0 & 3u) * 8u;                                      // (EP2_WIN_W % 4 == 0: the same for every row)
+    uint32_t X0[ROWS], X1[ROWS];
+#pragma unroll
+    for (int rho = 0; rho < ROWS; ++rho) {
+        const uint32_t w0 = wp[rho * (EP2_WIN_W / 4)], w1 = wp[rho * (EP2_WIN_W / 4) + 1], w2 = wp[rho * (EP2_WIN_W / 4) + 2];
+        X0[rho] = __funnelshift_r(w0, w1, sh);
+        X1[rho] = __funnelshift_r(w1, w2, sh);
+    }
+    uint32_t kmin = 0xffffffffu;
+#pragma unroll 1
+    for (int mx = -1; mx <= 1; ++mx) {
+        const uint32_t shv = (uint32_t)((mx + 1) * STEP) * 8u;                 // 0, 8 STEP, 16 STEP <= 32
+        uint32_t cu = 0, cm = 0, cd = 0;
+        uint32_t t = 0, t_s = 0, t_2s = 0, t_16 = 0, t_16s = 0;
+#pragma unroll
+        for (int rho = 0; rho < ROWS; ++rho) {
+            const uint32_t w = __funnelshift_rc(X0[rho], X1[rho], shv);
+            if (rho == STEP) t_s = t;
+            if (rho == 2 * STEP) t_2s = t;
+            if (rho == 16) t_16 = t;
+            if (rho == 16 + STEP) t_16s = t;
+            t = __dp4a(w, w, t);
+            if (rho < 16) cu = __dp4a(S[rho], w, cu);
+            if (rho >= STEP && rho < 16 + STEP) cm = __dp4a(S[rho - STEP], w, cm);
+            if (rho >= 2 * STEP) cd = __dp4a(S[rho - 2 * STEP], w, cd);
+        }
+        uint32_t up = A + t_16 - 2u * cu;
+        uint32_t mid = A + (t_16s - t_s) - 2u * cm;
+        uint32_t dn = A + (t - t_2s) - 2u * cd;
         up += __shfl_xor_sync(FULL, up, 1);
         up += __shfl_xor_sync(FULL, up, 2);
         mid += __shfl_xor_sync(FULL, mid, 1);
@@ -534,8 +619,7 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (uint32_t i = threadIdx.x; i < njobs; i += blockDim.x) sm.job[i] = jobs[i];
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp][0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp][1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar[warp])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -554,20 +638,21 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
         r.p = (tile >= g.pl[1].tile_base ? 1 : 0) + (tile >= g.pl[2].tile_base ? 1 : 0);
         const PlaneGeom &pl = plane_of(g, r.p);
         const uint32_t lt = tile - pl.tile_base;
-        r.trow = lt / pl.tiles_per_row;
-        r.tile_x0 = (int)(lt - r.trow * pl.tiles_per_row) * 128;
+        uint32_t tcol;
+        r.trow = div_small(lt, pl.tiles_per_row, pl.rcp_tiles_per_row, tcol);
+        r.tile_x0 = (int)tcol * 128;
         r.by = (int)r.trow * 16;
         return r;
     };
-    auto issue = [&](const Item &it, uint32_t st) {              // lane 0: the tile's search window into stage st
-        const uint32_t bar_a = smem_u32(&sm.bar[warp][st]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)WIN_BYTES) : "memory");
+    auto issue = [&](const Item &it) {                           // lane 0: the tile's search window into the warp's buffer
+        const uint32_t bar_a = smem_u32(&sm.bar[warp]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)EP2_WIN_BYTES) : "memory");
         const CUtensorMap *tm = (it.p == 0) ? &tm_luma : &tm_chroma;
         const int cx = it.tile_x0 - 16, cy = it.by - 15, cz = (it.p == 2) ? 1 : 0, cw = sm.job[it.job].ref_slot;
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_u32(sm.win[warp][st])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(bar_a)
+            ::"r"(smem_u32(sm.win[warp])), "l"(tm), "r"(cx), "r"(cy), "r"(cz), "r"(cw), "r"(bar_a)
             : "memory");
     };
     // this lane's source strip of an item: bytes (bx + 4q .. +3, by + r), r = 0..15
@@ -577,6 +662,12 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
         const uint8_t *src = it.p == 0 ? job.src[0] : (it.p == 1 ? job.src[1] : job.src[2]);
         const uint32_t x = (uint32_t)it.tile_x0 + m8 * 16u + q * 4u;
         const bool fast = ((reinterpret_cast<uintptr_t>(src) | pl.vw) & 3u) == 0;
+        if (fast && (uint32_t)it.by + 16u <= pl.vh && (uint32_t)it.tile_x0 + 128u <= pl.vw) {      // the whole tile is picture (most are)
+            const uint8_t *s0 = src + (size_t)(uint32_t)it.by * pl.vw + x;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) S[r] = __ldcs(reinterpret_cast<const uint32_t *>(s0 + (size_t)r * pl.vw));
+            return;
+        }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const uint32_t y = (uint32_t)it.by + (uint32_t)r;
@@ -600,26 +691,22 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
     if (it >= nitems) { retire(); return; }
     uint32_t it_next = __shfl_sync(FULL, grab(), 0);
     Item cur = item_of(it);
-    if (lane == 0) issue(cur, 0);
+    if (lane == 0) issue(cur);
     uint32_t S[16];
     load_strip(cur, S);
     uint32_t k = 0;
 #pragma unroll 1
     for (; it < nitems; ++k) {
-        const uint32_t st = k & 1u;
         const bool has_next = it_next < nitems;
         Item nxt = cur;
-        if (has_next) {
-            nxt = item_of(it_next);
-            if (lane == 0) issue(nxt, st ^ 1u);                   // that stage was released by the __syncwarp at the end of the previous tile
-        }
+        if (has_next) nxt = item_of(it_next);
         const uint32_t grabbed = has_next ? grab() : 0xffffffffu;   // in flight until the bottom of the iteration
         const PlaneGeom &pl = plane_of(g, cur.p);
         const EncJob &job = sm.job[cur.job];
-        const uint8_t *win = sm.win[warp][st];
+        const uint8_t *win = sm.win[warp];
         {
-            const uint32_t bar_a = smem_u32(&sm.bar[warp][st]);
-            const uint32_t parity = (k >> 1) & 1u;
+            const uint32_t bar_a = smem_u32(&sm.bar[warp]);
+            const uint32_t parity = k & 1u;
             uint32_t done = 0;
             while (!done) {
                 asm volatile(
@@ -633,22 +720,27 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
         const bool active = bx < (int)pl.pw;                      // ragged last tile of a row
         const int max_x = (int)pl.pw - 16, max_y = (int)pl.ph - 16;
         // window byte offset of this lane's strip at motion (0, 0)
-        const uint32_t o0 = (uint32_t)(15 * WIN_W + 16) + m8 * 16u + q * 4u;
+        const uint32_t o0 = (uint32_t)(15 * EP2_WIN_W + 16) + m8 * 16u + q * 4u;
 
         // src/common.rs:154-204, iteratively; the centre's error at every level after the first is the previous winner's
         int cx = 0, cy = 0;
-        uint32_t best;
+        uint32_t best, A = 0;                                      // A: sum of squares of this lane's source strip
+#pragma unroll
+        for (int r = 0; r < 16; ++r) A = __dp4a(S[r], S[r], A);
         {
             uint32_t a = 0;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) a = ssd4(S[r], *reinterpret_cast<const uint32_t *>(win + o0 + r * WIN_W), a);
+            for (int r = 0; r < 16; ++r) a = ssd4(S[r], *reinterpret_cast<const uint32_t *>(win + o0 + r * EP2_WIN_W), a);
             a += __shfl_xor_sync(FULL, a, 1);
             a += __shfl_xor_sync(FULL, a, 2);
             best = a;
         }
         // which of the 8 candidates of a level lie inside the plane (src/common.rs:171,182): three column tests and three row
         // tests combined (bit g = candidate g in visiting order: my = -1: g 0..2, my = 0: g 3 (mx = -1), 4 (mx = +1), my = +1: g 5..7)
+        // (a macroblock at least 15 pixels from every edge has them all, at every level: most tiles skip the tests)
+        const bool all_inside = __all_sync(FULL, bx >= 15 && bx + 15 <= max_x && by >= 15 && by + 15 <= max_y);
         auto valid_mask_of = [&](int step) {
+            if (all_inside) return 0xffu;
             uint32_t vx = 0, vy = 0;
 #pragma unroll
             for (int d = -1; d <= 1; ++d) {
@@ -668,10 +760,10 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
                 cy += my * step;
             }
         };
-        take(search_level<8, true>(win, S, o0, valid_mask_of(8)), 8);
-        take(search_level<4, true>(win, S, (uint32_t)((int)o0 + cy * WIN_W + cx), valid_mask_of(4)), 4);
-        take(search_level<2, false>(win, S, (uint32_t)((int)o0 + cy * WIN_W + cx), valid_mask_of(2)), 2);
-        take(search_level<1, false>(win, S, (uint32_t)((int)o0 + cy * WIN_W + cx), valid_mask_of(1)), 1);
+        take(search_level<8, true>(win, S, A, o0, valid_mask_of(8)), 8);
+        take(search_level<4, true>(win, S, A, (uint32_t)((int)o0 + cy * EP2_WIN_W + cx), valid_mask_of(4)), 4);
+        take(search_level_fine<2>(win, S, A, (uint32_t)((int)o0 + cy * EP2_WIN_W + cx), valid_mask_of(2)), 2);
+        take(search_level_fine<1>(win, S, A, (uint32_t)((int)o0 + cy * EP2_WIN_W + cx), valid_mask_of(1)), 1);
 
         const bool coded = active && !((float)best <= job.min_err);    // src/common.rs:221
         const uint32_t m = pl.mb_base + cur.trow * pl.bw + (uint32_t)(bx >> 4);
@@ -689,17 +781,17 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
         if (has_next) load_strip(nxt, Sn);
 
         if (active && !coded) {                                    // the predictor is the reconstruction (src/common.rs:281-283)
-            const uint32_t po = (uint32_t)((int)o0 + cy * WIN_W + cx);
+            const uint32_t po = (uint32_t)((int)o0 + cy * EP2_WIN_W + cx);
             uint8_t *dst = job.dst + pl.off + (size_t)(uint32_t)by * pl.pw + (uint32_t)bx + q * 4u;
             // eight rows' loads first, then their shifts and stores (row by row every funnel shift waited for its own
             // shared-memory round trip: ncu, ~50 stall samples on each of the 16)
-            const uint32_t *wbase = reinterpret_cast<const uint32_t *>(win + (po & ~3u));   // WIN_W % 4 == 0: one shift for all rows
+            const uint32_t *wbase = reinterpret_cast<const uint32_t *>(win + (po & ~3u));   // EP2_WIN_W % 4 == 0: one shift for all rows
             const uint32_t sh = (po & 3u) * 8u;
 #pragma unroll
             for (int r0 = 0; r0 < 16; r0 += 8) {
                 uint32_t a[8], b[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) { a[r] = wbase[(r0 + r) * (WIN_W / 4)]; b[r] = wbase[(r0 + r) * (WIN_W / 4) + 1]; }
+                for (int r = 0; r < 8; ++r) { a[r] = wbase[(r0 + r) * (EP2_WIN_W / 4)]; b[r] = wbase[(r0 + r) * (EP2_WIN_W / 4) + 1]; }
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
                     *reinterpret_cast<uint32_t *>(dst + (size_t)(r0 + r) * pl.pw) = __funnelshift_r(a[r], b[r], sh);
@@ -734,7 +826,7 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
                 const int mbx = cur.tile_x0 + (l0 >> 2) * 16;
                 const uint2 s8 = s8n;
                 if (todo) s8n = load_src_row(src, pl, (uint32_t)(cur.tile_x0 + ((__ffs((int)todo) - 1) >> 2) * 16) + px, (uint32_t)by + py, fast8);
-                const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((15 + (int)py + mcy) * WIN_W + 16 + (l0 >> 2) * 16 + (int)px + mcx));
+                const uint2 prev = lds_u8x8_unaligned(win, (uint32_t)((15 + (int)py + mcy) * EP2_WIN_W + 16 + (l0 >> 2) * 16 + (int)px + mcx));
                 int x[8];
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
@@ -753,7 +845,8 @@ encode_p2_kernel(const __grid_constant__ FrameGeom g, const EncJob *__restrict__
                 *reinterpret_cast<uint2 *>(dst) = apply_residual_row(y, prev);   // src/common.rs:277
             }
         }
-        __syncwarp();                                              // every lane is done with this window stage
+        __syncwarp();                                              // every lane is done with the window
+        if (has_next && lane == 0) issue(nxt);
 #pragma unroll
         for (int r = 0; r < 16; ++r) S[r] = Sn[r];
         cur = nxt;

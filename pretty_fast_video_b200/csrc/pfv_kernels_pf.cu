@@ -201,6 +201,9 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
         const uint32_t pipe = t / PF_PIPE_ITEMS, i = t - pipe * PF_PIPE_ITEMS;
         const uint32_t it = blockIdx.x * PF_PIPES + pipe + i * npipes;
         if (it >= nitems) continue;
+        // (Measured and dropped, round 2: rotating the frame index by the window index - job = (item + item / njobs) % njobs - so that a
+        // pipeline, whose stride through the items is 592 = 16 mod 32, walks all frames of the launch instead of two.  The SMs finish
+        // as far apart as before (sm__cycles_active min / avg / max 80 k / 87 k / 99 k): it is not the frames' content.)
         const uint32_t wi = it / njobs, job = it - wi * njobs;
         const uint32_t p = (wi >= W.base[1] ? 1u : 0u) + (wi >= W.base[2] ? 1u : 0u);
         const PlaneGeom &pl = p == 0 ? g.pl[0] : (p == 1 ? g.pl[1] : g.pl[2]);
