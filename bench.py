@@ -1153,7 +1153,7 @@ def main():
         "e2e": {k: v for k, v in (r["e2e"] or {}).items()},
         "roofline": {"bound": "hbm", "kernel": kernel_key, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": r["alg_bytes"],
-                     "launches_per_step": launches, "traffic": ncu_traffic(kernel_key),
+                     "launches_per_step": launches, "traffic": ncu_traffic(kernel_key + ":" + args.workload) or ncu_traffic(kernel_key),
                      "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload, per launch)"},
         "clocks": clocks,
         "host_binding": binding,
@@ -1173,13 +1173,13 @@ def main():
         extras = {}
         # N > 1 (the scaling run): the P-stream configs ride along, resident legs only, so that BASELINE.json configs[2]
         # and configs[4] (GOPs sharded over the ranks) sit on the driver's record at every N
-        names = ("decode_i_1080p_dense", "decode_p_1080p", "encode_p_1080p", "encode_i_1080p", "decode_p_4k") if dist.world == 1 \
+        names = ("decode_i_1080p_dense", "decode_p_1080p", "decode_p_1080p_64", "encode_p_1080p", "encode_i_1080p", "decode_p_4k") if dist.world == 1 \
             else ("decode_p_1080p", "decode_p_4k")
         for wl in names:
             if wl == args.workload:
                 continue
             try:
-                x = run(wl, max(3, args.steps // 4), 3, do_e2e=(dist.world == 1 and wl != "decode_p_4k"))
+                x = run(wl, max(3, args.steps // 4), 3, do_e2e=(dist.world == 1 and wl not in ("decode_p_4k", "decode_p_1080p_64")))
                 xs = x["st"]
                 xfps = x["frames"] * dist.world / (x["max_ms"] * 1e-3)
                 extras[wl] = {
@@ -1193,7 +1193,7 @@ def main():
                 }
                 if wl.startswith("encode_p"):
                     extras[wl]["candidate_pixels_per_s"] = xfps * xs.nb * SEARCH_CANDIDATES_PER_MB * 256
-                if dist.world == 1 and args.cpu_budget > 0:
+                if dist.world == 1 and args.cpu_budget > 0 and wl != "decode_p_1080p_64":     # (the same stream as decode_p_1080p)
                     cf, cs, _ = cpu_port_leg(wl, min(args.cpu_budget, 3.0 if wl == "decode_p_4k" else 6.0), nthreads)
                     extras[wl]["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": nthreads, "kind": "port", "sample": cs}
                 verified_all &= bool(x["verified"]) and all(bool(y.get("verified", True)) for y in ((x["e2e"] or {}), (x["e2e"] or {}).get("dense", {})))
