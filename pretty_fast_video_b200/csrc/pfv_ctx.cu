@@ -272,7 +272,7 @@ int build_tensor_maps(pfv_ctx *c)
     // which == 1: the window of every possible predictor of 8 x 4 macroblocks (176 x 94; decode-P copy kernel)
     // which == 2: the same for 8 x PF_ROWS macroblocks (fused decode-P kernel)
     // which == 3: the search window again, at the warp-per-tile kernel's own pitch
-    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : (which == 3 ? (cuuint32_t)EP2_WIN_W : 176u),
+    const cuuint32_t box[4] = {which == 0 ? (cuuint32_t)WIN_W : (which == 3 ? (cuuint32_t)EP2_WIN_W : (which == 2 ? (cuuint32_t)PF_WIN_W : 176u)),
                                which == 0 || which == 3 ? (cuuint32_t)WIN_H : (which == 1 ? 94u : (cuuint32_t)PF_WIN_H), 1, 1};
     CUtensorMap *out_l = which == 0 ? &c->tm_luma : (which == 1 ? &c->tm_win_luma : (which == 2 ? &c->tm_pf_luma : &c->tm_ep2_luma));
     CUtensorMap *out_c = which == 0 ? &c->tm_chroma : (which == 1 ? &c->tm_win_chroma : (which == 2 ? &c->tm_pf_chroma : &c->tm_ep2_chroma));

@@ -103,7 +103,10 @@ struct EncSbParams {
 
 // fused decode-P kernel (pfv_kernels_pf.cu): macroblock rows per window and the TMA box that holds every predictor of them
 constexpr int PF_ROWS = 3;
-constexpr int PF_WIN_W = 176;                                // 16 + 8*16 + 15, rounded up to 16
+#ifndef PFV_PF_WIN_W
+#define PFV_PF_WIN_W 160
+#endif
+constexpr int PF_WIN_W = PFV_PF_WIN_W;                       // 16 + 8*16 + 15, rounded up to 16 (160) - or 176
 constexpr int PF_WIN_H = PF_ROWS * 16 + 30;
 
 // decode-P window items of one frame: a window covers 8 x `rows` macroblocks of one plane

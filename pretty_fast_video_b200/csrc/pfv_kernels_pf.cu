@@ -35,10 +35,19 @@ namespace pfv {
 // PF_ROWS (pfv_internal.h) = macroblock rows per window = warps per copy pipeline
 constexpr int PF_WIN_BYTES = PF_WIN_W * PF_WIN_H;
 constexpr int PF_STAGE = (PF_WIN_BYTES + 127) & ~127;
-constexpr int PF_PIPES = 4;                                  // independent copy pipelines per CTA (each: PF_ROWS warps, its own windows)
-constexpr int PF_STAGES = 2;                                 // windows in flight per pipeline
+#ifndef PFV_PF_PIPES
+#define PFV_PF_PIPES 4
+#endif
+#ifndef PFV_PF_STAGES
+#define PFV_PF_STAGES 2
+#endif
+#ifndef PFV_PF_NG
+#define PFV_PF_NG 13
+#endif
+constexpr int PF_PIPES = PFV_PF_PIPES;                       // independent copy pipelines per CTA (each: PF_ROWS warps, its own windows)
+constexpr int PF_STAGES = PFV_PF_STAGES;                     // windows in flight per pipeline
 constexpr int PF_COPY_WARPS = PF_PIPES * PF_ROWS;
-constexpr int PF_NG = 13;                                    // ring groups; the ring must hold more macroblocks (104) than the
+constexpr int PF_NG = PFV_PF_NG;                             // ring groups; the ring must hold more macroblocks (104) than the
 constexpr int PF_RING_MB = PF_NG * 8;                        // pipelines can have unfinished at once (4 x 24): see the empty-wait
 constexpr int PF_COEF_PITCH = 528;                           // bytes per slot: 512 + 16 (8 slots -> 8 different bank groups)
 constexpr int PF_PRED_PITCH = 80;                            // bytes per sub-block: 64 + 16
