@@ -179,7 +179,7 @@ cudaError_t launch_decode_p_two_pass4(const SbParams &P, const DecJob *d_jobs, u
 cudaError_t launch_decode_p_fused(const SbParams &P, const DecJob *d_jobs, uint32_t njobs, int *d_err,
                                   const CUtensorMap &tm_luma, const CUtensorMap &tm_chroma, cudaStream_t s);
 // completes cta_base / cta_total / tiles_per_warp of the streaming kernels (pfv_kernels_sb.cu)
-void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t waves_x_warps, uint32_t max_tpw);
+void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t resident_ctas, uint32_t max_tpw, uint32_t start_cost, uint32_t forced_tpw);
 cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t njobs, cudaStream_t s);
 // the first n_key jobs are key frames (thread-per-sub-block emit into padded slots, then the scan), the others P frames
 // (scan of the counts the encode kernel left, then the warp-per-macroblock emit)

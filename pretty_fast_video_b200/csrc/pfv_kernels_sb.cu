@@ -74,7 +74,7 @@ decode_i_sb_kernel(const __grid_constant__ SbParams P, const DecJob *__restrict_
 // whatever L is (a lane-dependent rotation would need the ring of the streaming kernel to undo it).
 // -------------------------------------------------------------------------------------------------
 constexpr int DIR_WARPS = 4;
-void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t waves_x_warps, uint32_t max_tpw);
+void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t resident_ctas, uint32_t max_tpw, uint32_t start_cost, uint32_t forced_tpw);
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
 {
@@ -273,28 +273,45 @@ cudaError_t launch_decode_i_sb(const SbParams &P, const DecJob *d_jobs, uint32_t
 
 cudaError_t launch_decode_i_direct(SbParams P, const DecJob *d_jobs, uint32_t njobs, cudaStream_t s)
 {
-    sbw_split(P, njobs, DIR_WARPS, 6u * 148u * 16u, 16u);
+    static const int tpw_env = getenv("PFV_DECODE_I_TPW") ? atoi(getenv("PFV_DECODE_I_TPW")) : 0;   // tuning aid: tiles per warp
+    sbw_split(P, njobs, DIR_WARPS, 148u * 4u, 16u, 0u, tpw_env > 0 ? (uint32_t)tpw_env : 0u);   // (__launch_bounds__: 4 CTAs per SM)
     dim3 grid(P.cta_total, njobs, 1), block(DIR_WARPS * 32, 1, 1);
     decode_i_direct_kernel<<<grid, block, 0, s>>>(P, d_jobs);
     return cudaGetLastError();
 }
 
-// `P` arrives with g and deq filled; the work split is completed here.  tiles_per_warp trades the per-warp
-// remainder (one partly filled transform pass per warp at the end) against having enough warps to fill the
-// chip: aim at ~6 waves of the 148 SMs x resident warps, at most 16 tiles per warp.
-void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t waves_x_warps, uint32_t max_tpw)
+// `P` arrives with g and deq filled; the work split is completed here.  A warp walks `tiles_per_warp` consecutive tiles, a CTA
+// never straddles a plane; `resident_ctas` of them run at a time.  Every CTA lives about as long as its warps have tiles, so the
+// launch takes ceil(CTAs / resident_ctas) x (tiles_per_warp + start_cost) tile times (start_cost: what a CTA's start is worth in tile
+// times - about one for the streaming kernel, whose bulk-copy pipeline has to fill, nothing measurable for the direct one): the
+// split takes the tiles_per_warp (<= max_tpw) with the smallest product, the larger one among equals (fewer CTA starts, fewer partly filled transform passes at the warps' ends).
+// The first form aimed at "about six waves" (tiles_per_warp = tiles / (6 x resident warps), rounded down) and for 64 x 1080p got
+// 9 tiles per warp = 2 880 CTAs = 6.49 waves of 444: the seventh wave was half empty and its planes' last CTAs nearly so (ncu:
+// sm__cycles_active avg 169 k of 191 k elapsed).  8 tiles per warp are 3 072 CTAs = 6.92 waves of full CTAs.  Measured (visit zj,
+// 64 x 1080p per launch, frames/s by tiles per warp): config-2 stream 4: 593 k, 8: 625 k, 9: 618 k, 10: 612 k, 12: 603 k, 15: 593 k;
+// all-dense frames through the direct kernel 3: 480 k, 5: 480 k, 9: 470 k, 11: 452 k, 16: 465 k.
+void sbw_split(SbParams &P, uint32_t njobs, uint32_t warps_per_cta, uint32_t resident_ctas, uint32_t max_tpw, uint32_t start_cost, uint32_t forced_tpw)
 {
-    uint32_t tiles = 0;
-    for (int p = 0; p < 3; p++) tiles += (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
-    const uint64_t total = (uint64_t)tiles * njobs;
-    uint32_t tpw = (uint32_t)(total / waves_x_warps);
-    tpw = tpw < 1 ? 1 : (tpw > max_tpw ? max_tpw : tpw);
-    P.tiles_per_warp = tpw;
+    uint32_t ntiles[3];
+    for (int p = 0; p < 3; p++) ntiles[p] = (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
+    auto ctas_per_frame = [&](uint32_t tpw) {
+        uint32_t n = 0;
+        for (int p = 0; p < 3; p++) n += (ntiles[p] + warps_per_cta * tpw - 1) / (warps_per_cta * tpw);
+        return n;
+    };
+    uint32_t best = 1;
+    uint64_t best_cost = ~0ull;
+    for (uint32_t tpw = max_tpw; tpw >= 1; --tpw) {
+        const uint64_t ctas = (uint64_t)ctas_per_frame(tpw) * njobs;
+        const uint64_t cost = ((ctas + resident_ctas - 1) / resident_ctas) * (tpw + start_cost);
+        if (cost < best_cost) { best_cost = cost; best = tpw; }
+    }
+    if (forced_tpw >= 1 && forced_tpw <= max_tpw) best = forced_tpw;
+    P.tiles_per_warp = best;
     uint32_t cta = 0;
     for (int p = 0; p < 3; p++) {
         P.cta_base[p] = cta;
-        const uint32_t ntiles = (P.g.pl[p].bw * P.g.pl[p].bh + 7u) / 8u;
-        cta += (ntiles + warps_per_cta * tpw - 1) / (warps_per_cta * tpw);
+        cta += (ntiles[p] + warps_per_cta * best - 1) / (warps_per_cta * best);
     }
     P.cta_total = cta;
 }
@@ -309,9 +326,8 @@ static cudaError_t launch_decode_i_stream_t(SbParams P, const DecJob *d_jobs, ui
         cudaError_t e = cudaFuncSetAttribute(decode_i_stream_kernel<WARPS, CTAS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
-    static const int waves_env = getenv("PFV_DECODE_I_WAVES") ? atoi(getenv("PFV_DECODE_I_WAVES")) : 6;   // tuning aid
-    const uint32_t waves = waves_env >= 1 && waves_env <= 64 ? (uint32_t)waves_env : 6u;
-    sbw_split(P, njobs, WARPS, waves * 148u * (uint32_t)(CTAS * WARPS), 16u);
+    static const int tpw_env = getenv("PFV_DECODE_I_TPW") ? atoi(getenv("PFV_DECODE_I_TPW")) : 0;   // tuning aid: tiles per warp
+    sbw_split(P, njobs, WARPS, 148u * (uint32_t)CTAS, 16u, 1u, tpw_env > 0 ? (uint32_t)tpw_env : 0u);
     dim3 grid(P.cta_total, njobs, 1), block(WARPS * 32, 1, 1);
     decode_i_stream_kernel<WARPS, CTAS, POOL><<<grid, block, smem, s>>>(P, d_jobs);
     return cudaGetLastError();
