@@ -54,7 +54,7 @@ def test_known_values():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("size", [(16, 16), (50, 38), (322, 242), (1920, 1080)])
+@pytest.mark.parametrize("size", [(16, 16), (24, 10), (72, 50), (50, 38), (322, 242), (1920, 1080)])   # (widths that are / are not multiples of 8; partly filled last warp)
 def test_gpu_rgb_paths_match_oracle(size):
     from pretty_fast_video_b200 import PFV_FRAME_I, PFV_FRAME_P, Engine, make_qtables
     from pretty_fast_video_b200.engine import EncodeJob
