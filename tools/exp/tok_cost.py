@@ -1,5 +1,6 @@
-"""Device time of the sparse encode seam next to the dense one: 32 x 1080p P frames per submit, everything resident.
-   python tools/exp/tok_cost.py"""
+"""Device time of the sparse encode seam next to the dense one: L x 1080p frames per submit (default 32; the Encoder object
+   submits ONE), everything resident.
+   python tools/exp/tok_cost.py [L]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
@@ -8,7 +9,7 @@ from pretty_fast_video_b200 import _native as N
 from pretty_fast_video_b200.engine import EncodeJob, SparseEncodeJob
 from pretty_fast_video_b200.synth import SynthVideo
 
-w, h, L = 1920, 1080, 32
+w, h, L = 1920, 1080, (int(sys.argv[1]) if len(sys.argv) > 1 else 32)
 qt, px_err = make_qtables(5)
 geo = geometry_for(w, h)
 nb = geo.nb
