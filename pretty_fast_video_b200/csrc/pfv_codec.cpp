@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1065,6 +1066,45 @@ struct OutPacket {
 
 }  // namespace
 
+// The Encoder's own output buffer (its `W` when no writer callback is set): bytes are only ever appended.  As a std::vector it cost the
+// writer thread - the one serial stage behind the entropy coders - 170-230 us per 1080p frame (PFV_TRACE, 150 KB packets): every
+// doubling moved the stream into fresh memory, so each byte of a 70 MB stream was page-faulted in twice, 4 KB at a time, and copied
+// once.  Here the buffer is an anonymous mapping that grows in place (mremap moves page tables, not bytes) and asks for huge pages.
+struct GrowBuf {
+    uint8_t *p = nullptr;
+    size_t   n = 0, cap = 0;
+    GrowBuf() = default;
+    GrowBuf(const GrowBuf &) = delete;
+    GrowBuf &operator=(const GrowBuf &) = delete;
+    ~GrowBuf() { if (p) munmap(p, cap); }
+    bool reserve(size_t want)
+    {
+        if (want <= cap) return true;
+        size_t nc = cap ? cap : ((size_t)8 << 20);
+        while (nc < want) nc *= 2;
+        void *q = p ? mremap(p, cap, nc, MREMAP_MAYMOVE) : mmap(nullptr, nc, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q == MAP_FAILED) return false;
+#ifdef MADV_HUGEPAGE
+        madvise(q, nc, MADV_HUGEPAGE);                               // (advice only: without huge pages the faults stay 4 KB ones)
+#endif
+        p = static_cast<uint8_t *>(q);
+        cap = nc;
+        return true;
+    }
+    bool append(const void *src, size_t k)
+    {
+        if (!k) return true;
+        if (!reserve(n + k)) return false;
+        memcpy(p + n, src, k);
+        n += k;
+        return true;
+    }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void clear() { n = 0; }
+};
+
 struct pfv_encoder {
     uint32_t width = 0, height = 0, framerate = 0;
     float px_err = 0.f;
@@ -1086,14 +1126,14 @@ struct pfv_encoder {
     bool stop = false;
     int  async_rc = PFV_OK;
     char async_err[256] = "";
-    std::vector<uint8_t> stream;                      // the writer W (when no callback is set)
+    GrowBuf stream;                                   // the writer W (when no callback is set)
     pfv_write_fn writer = nullptr;                    // pfv_encoder_set_writer: packets leave through it as soon as they are finished
     void *writer_user = nullptr;
     uint32_t prev_slot = 0;
     bool finished = false;
     bool dense = false;            // PFV_ENCODER_DENSE=1: the dense seam (pfv_encode_submit + host run-length pass)
     bool trace = false;            // PFV_TRACE=1: where the calling thread spends its time, printed at close
-    double t_flush = 0, t_wait = 0, t_copy = 0, t_submit = 0;
+    double t_flush = 0, t_wait = 0, t_copy = 0, t_submit = 0, t_gpuwait = 0, t_entropy = 0, t_write = 0;   // (the last three under e->m)
     uint64_t n_frames = 0;
     size_t ysz = 0, csz = 0;
 };
@@ -1168,6 +1208,7 @@ static void encoder_writer_main(pfv_encoder *e)
         }
         int rc = p->status;
         const char *msg = p->err;
+        const double tw0 = e->trace ? now_s() : 0;
         if (rc == PFV_OK) {
             const std::vector<uint8_t> &b = p->work ? p->work->packet : p->bytes;
             if (e->writer) {
@@ -1176,9 +1217,10 @@ static void encoder_writer_main(pfv_encoder *e)
                     msg = "the writer callback failed (io::Error of W::write_all)";
                 }
             } else {
-                if (e->stream.size() + b.size() > e->stream.capacity())
-                    e->stream.reserve(std::max(e->stream.capacity() * 2, e->stream.size() + b.size() + ((size_t)1 << 20)));
-                e->stream.insert(e->stream.end(), b.begin(), b.end());
+                if (!e->stream.append(b.data(), b.size())) {
+                    rc = PFV_ERR_NOMEM;
+                    msg = "out of host memory for the encoded stream";
+                }
             }
         }
         {
@@ -1186,6 +1228,7 @@ static void encoder_writer_main(pfv_encoder *e)
             if (rc != PFV_OK) encoder_set_async_error(e, rc, msg);
             if (p->work) p->work->busy = false;
             e->pending.pop_front();
+            if (e->trace) e->t_write += now_s() - tw0;
         }
         e->cv.notify_all();
     }
@@ -1252,10 +1295,14 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
         e->work.push_back(std::move(w));
     }
     e->pool.reset(new Pool(num_threads ? std::min<uint32_t>(num_threads, depth) : 1));
-    e->copy_helpers = num_threads >= 2 ? std::min<uint32_t>(num_threads - 1, 3) : 0;
+    e->copy_helpers = num_threads >= 2 ? std::min<uint32_t>(num_threads - 1, 5) : 0;   // (measured on a 16-thread host, frames/s: 2: 5.4-6.0 k, 3: 4.8-5.5 k, 5: 6.1-7.4 k, 7: 6.0-6.8 k)
+    if (const char *env = getenv("PFV_ENCODER_COPY_HELPERS")) {      // tuning aid
+        const int v = atoi(env);
+        if (v >= 0 && v <= 15) e->copy_helpers = (unsigned)v;
+    }
     if (e->copy_helpers) e->copy_pool.reset(new Pool(e->copy_helpers));
     // write_header, src/enc.rs:190-219
-    std::vector<uint8_t> &s = e->stream;
+    std::vector<uint8_t> s;
     s.insert(s.end(), kMagic, kMagic + 8);
     s.resize(12);
     wr32(&s[8], kVersion);
@@ -1263,6 +1310,10 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
     wr16(s, 4);
     for (int t = 0; t < 4; t++)                                      // intra_l, intra_c, inter_l, inter_c
         for (int i = 0; i < 64; i++) wr16(s, (uint32_t)qt[t][i]);
+    if (!e->stream.append(s.data(), s.size())) {
+        pfv_ctx_destroy(e->ctx);
+        return set_error(PFV_ERR_NOMEM, "out of host memory");
+    }
     e->submitter = std::thread(encoder_submitter_main, e.get());
     e->writer_thread = std::thread(encoder_writer_main, e.get());
     *out = e.release();
@@ -1353,7 +1404,9 @@ static void encoder_submit_one(pfv_encoder *e, EncWork *w, const std::shared_ptr
     w->submit_id = pfv_ctx_last_submit_id(e->ctx);
     if (e->trace) e->t_submit += now_s() - t0;
     e->pool->post([e, w, pkt, tok, stats] {
+        const double ta = e->trace ? now_s() : 0;
         int rc2 = pfv_ctx_wait_submit(e->ctx, w->submit_id);
+        const double tb = e->trace ? now_s() : 0;
         if (rc2 == PFV_OK) {
             static thread_local std::vector<uint32_t> scratch;
             const pfv_mbhdr *hdr = static_cast<const pfv_mbhdr *>(w->hdr.p);
@@ -1361,10 +1414,12 @@ static void encoder_submit_one(pfv_encoder *e, EncWork *w, const std::shared_ptr
                            : encode_packet_tokens(e->geo, w->kind, hdr, tok, stats, w->packet);
         }
         if (rc2) snprintf(pkt->err, sizeof(pkt->err), "%s", pfv_last_error());
+        const double tc = e->trace ? now_s() : 0;
         {
             std::lock_guard<std::mutex> l(e->m);
             pkt->status = rc2;
             pkt->ready = true;
+            e->t_gpuwait += tb - ta; e->t_entropy += tc - tb;
         }
         e->cv.notify_all();
     });
@@ -1453,8 +1508,10 @@ extern "C" void pfv_encoder_close(pfv_encoder *e)
     if (e->writer_thread.joinable()) e->writer_thread.join();
     if (e->trace && e->n_frames)
         fprintf(stderr, "[pfv encoder] %llu frames, per frame: calling thread waits for a free work item %.1f us, copies the planes "
-                        "%.1f us; submitter thread %.1f us\n", (unsigned long long)e->n_frames,
-                1e6 * e->t_wait / e->n_frames, 1e6 * e->t_copy / e->n_frames, 1e6 * e->t_submit / e->n_frames);
+                        "%.1f us; submitter thread %.1f us; a pool thread waits for the frame's GPU work %.1f us and codes it in %.1f us; "
+                        "writer thread %.1f us\n", (unsigned long long)e->n_frames,
+                1e6 * e->t_wait / e->n_frames, 1e6 * e->t_copy / e->n_frames, 1e6 * e->t_submit / e->n_frames,
+                1e6 * e->t_gpuwait / e->n_frames, 1e6 * e->t_entropy / e->n_frames, 1e6 * e->t_write / e->n_frames);
     e->pool.reset();
     e->copy_pool.reset();
     if (e->ctx) { pfv_sync(e->ctx); pfv_ctx_destroy(e->ctx); }

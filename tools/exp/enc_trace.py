@@ -18,6 +18,8 @@ for n in (gop, 32 * gop, 32 * gop, 32 * gop):
             (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(src[t % gop + ((t // gop) % 4) * 3])
         t1 = time.perf_counter()
         enc.finish()
-        enc.bytes()
         t2 = time.perf_counter()
-    print(f"{n} frames, {nthreads} threads: {n / (t2 - t0):.0f} frames/s (calls {1e3 * (t1 - t0):.1f} ms, finish {1e3 * (t2 - t1):.1f} ms)", flush=True)
+        nbytes = len(enc.bytes())
+        t3 = time.perf_counter()
+    print(f"{n} frames, {nthreads} threads: {n / (t2 - t0):.0f} frames/s (calls {1e3 * (t1 - t0):.1f} ms, finish {1e3 * (t2 - t1):.1f} ms; "
+          f"bytes() of {nbytes / 1e6:.1f} MB {1e3 * (t3 - t2):.1f} ms)", flush=True)
