@@ -764,9 +764,10 @@ extern "C" int pfv_slot_read_visible(pfv_ctx *c, uint32_t slot, uint8_t *y, uint
 static int convert_rgb(pfv_ctx *c, uint32_t slot, uint8_t *d_out, cudaStream_t s)
 {
     const pfv_geometry &g = c->geo;
-    const uint8_t *base = slot_ptr(c, slot);
     const size_t ny = (size_t)g.pw * g.ph, nc = (size_t)g.cpw * g.cph;
-    CU_TRY(launch_yuv420_to_rgb(base, base + ny, base + ny + nc, g.width, g.height, g.pw, g.cpw, d_out, s));
+    // (a batch of one: the batched kernels carry the fast 8-pixels-per-thread form for widths that are multiples of 8)
+    CU_TRY(launch_yuv420_to_rgb_batch(c->d_pool, c->slot_stride, (uint32_t)ny, (uint32_t)(ny + nc), &slot, 1, g.width, g.height, g.pw, g.cpw,
+                                      d_out, (size_t)g.width * g.height * 3, s));
     c->launches++;
     return PFV_OK;
 }

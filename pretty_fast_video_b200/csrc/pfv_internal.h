@@ -186,8 +186,6 @@ cudaError_t launch_expand_tokens(uint32_t nb, const SparseJob *d_jobs, uint32_t 
 cudaError_t launch_tokenize(uint32_t nb, const TokJob *d_jobs, uint32_t n_key, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_token_store(uint32_t nb, const TokJob *d_jobs, uint32_t njobs, cudaStream_t s);
 cudaError_t launch_rgb_to_yuv420(const uint8_t *d_rgb, uint32_t w, uint32_t h, uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, cudaStream_t s);
-cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, uint32_t w, uint32_t h, uint32_t pw,
-                                 uint32_t cpw, uint8_t *d_rgb, cudaStream_t s);
 cudaError_t launch_yuv420_to_rgb_batch(const uint8_t *d_pool, size_t slot_stride, uint32_t off_u, uint32_t off_v, const uint32_t *slots,
                                        uint32_t n, uint32_t w, uint32_t h, uint32_t pw, uint32_t cpw, uint8_t *d_out, size_t out_stride,
                                        cudaStream_t s);

@@ -4,12 +4,12 @@
 //                          YCbCr in f32, evaluated left to right, `as u8`) followed by VideoFrame::from_planes
 //                          (src/frame.rs:51-60), whose `reduce` (src/common.rs:523-536) keeps the chroma sample of the
 //                          top-left pixel of every 2x2 block.  One thread per 2x2 block.
-//   yuv420_to_rgb_kernel   a frame slot's visible crop (src/dec.rs:195-197) -> packed RGB8: save_frame
+//   yuv420_to_rgb_batch*   a frame slot's visible crop (src/dec.rs:195-197) -> packed RGB8: save_frame
 //                          (src/lib.rs:365-395) with its `double` (nearest-neighbour chroma, src/common.rs:538-556).
-//                          One thread per 4 horizontal pixels (three 32-bit stores).
+//                          One thread per 8 horizontal pixels (or per 4 when the width is not a multiple of 8).
 //
 // The reference does this arithmetic in f32 without fused multiply-adds; __fmul_rn / __fadd_rn / __fsub_rn keep nvcc
-// from contracting, so the bytes are identical to the CPU's.  Both kernels are pure streaming (HBM bound).
+// from contracting, so the bytes are identical to the CPU's.
 #include "pfv_internal.h"
 
 namespace pfv {
@@ -46,43 +46,8 @@ rgb_to_yuv420_kernel(const uint8_t *__restrict__ rgb, uint32_t w, uint32_t h, ui
     }
 }
 
-__global__ void __launch_bounds__(256)
-yuv420_to_rgb_kernel(const uint8_t *__restrict__ yplane, const uint8_t *__restrict__ uplane, const uint8_t *__restrict__ vplane,
-                     uint32_t w, uint32_t h, uint32_t pw, uint32_t cpw, uint8_t *__restrict__ rgb)
-{
-    const uint32_t qw = (w + 3) / 4;                                   // groups of 4 pixels per row
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= qw * h) return;
-    const uint32_t y = i / qw, x = (i - y * qw) * 4;
-    const uint32_t n = min(4u, w - x);                                 // 4, or 2 at the end of a row whose width is 2 mod 4
-    const uint8_t *yr = yplane + (size_t)y * pw + x;
-    const uint8_t *ur = uplane + (size_t)(y >> 1) * cpw + (x >> 1);
-    const uint8_t *vr = vplane + (size_t)(y >> 1) * cpw + (x >> 1);
-    uint8_t out[12];
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k) {
-        if (k >= n) break;
-        const float fy = (float)yr[k], fu = __fsub_rn((float)ur[k >> 1], 128.0f), fv = __fsub_rn((float)vr[k >> 1], 128.0f);
-        const float r = __fadd_rn(fy, __fmul_rn(1.402f, fv));
-        const float g = __fsub_rn(__fsub_rn(fy, __fmul_rn(0.344136f, fu)), __fmul_rn(0.714136f, fv));
-        const float b = __fadd_rn(fy, __fmul_rn(1.772f, fu));
-        out[k * 3] = (uint8_t)f32_as_u8(r);
-        out[k * 3 + 1] = (uint8_t)f32_as_u8(g);
-        out[k * 3 + 2] = (uint8_t)f32_as_u8(b);
-    }
-    uint8_t *dst = rgb + ((size_t)y * w + x) * 3;
-    if (n == 4 && ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0)) {
-        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            d32[k] = (uint32_t)out[4 * k] | ((uint32_t)out[4 * k + 1] << 8) | ((uint32_t)out[4 * k + 2] << 16) | ((uint32_t)out[4 * k + 3] << 24);
-    } else {
-        for (uint32_t k = 0; k < n * 3; ++k) dst[k] = out[k];
-    }
-}
-
-// The same for a batch of slots in ONE launch (grid.y = picture): one launch per picture left this step launch bound at
-// 1.1 TB/s.  4 pixels per thread: one 32-bit luma load, two 16-bit chroma loads (plane pitches are multiples of 16), three
+// A batch of slots in ONE launch (grid.y = picture; a single picture is a batch of one): one launch per picture left this step
+// launch bound at 1.1 TB/s.  4 pixels per thread: one 32-bit luma load, two 16-bit chroma loads (plane pitches are multiples of 16), three
 // 32-bit stores.  Picture i lands at out_base + i * out_stride.
 struct RgbBatch {
     uint32_t slot[64];
@@ -247,14 +212,6 @@ cudaError_t launch_rgb_to_yuv420(const uint8_t *d_rgb, uint32_t w, uint32_t h, u
 {
     const uint32_t n = (w / 2) * (h / 2);
     rgb_to_yuv420_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_rgb, w, h, d_y, d_u, d_v);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_yuv420_to_rgb(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, uint32_t w, uint32_t h, uint32_t pw,
-                                 uint32_t cpw, uint8_t *d_rgb, cudaStream_t s)
-{
-    const uint32_t n = ((w + 3) / 4) * h;
-    yuv420_to_rgb_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_y, d_u, d_v, w, h, pw, cpw, d_rgb);
     return cudaGetLastError();
 }
 

@@ -116,8 +116,11 @@ def test_cubin_is_sm_100a_and_the_staging_paths_are_tma():
         assert hits, kernel
         return all(any(mnemonic in x for x in body[k]) for k in hits)
     assert has("encode_p_kernel", "UTMALDG") and has("encode_p_kernel", "SYNCS")
+    assert has("encode_p2_kernel", "UTMALDG") and has("encode_p2_kernel", "SYNCS")          # the default encode-P kernel
+    assert has("decode_p_fused_kernel", "UTMALDG") and has("decode_p_fused_kernel", "UBLKCP")
     assert has("mc_copy4_kernel", "UTMALDG")
     assert has("decode_i_stream_kernel", "UBLKCP") and has("decode_i_stream_kernel", "SYNCS")
     for k in ("tok_scan_kernel", "tok_emit_kernel", "tok_store_kernel", "expand_tokens_kernel", "residual_sb2_kernel",
-              "encode_i_kernel", "rgb_to_yuv420_kernel", "yuv420_to_rgb_kernel"):
+              "encode_i_kernel", "rgb_to_yuv420_kernel", "yuv420_to_rgb_batch_kernel", "yuv420_to_rgb_batch8_kernel",
+              "encode_p2_kernel", "decode_p_fused_kernel", "encode_i_persist_kernel"):
         assert any(k in n for n in body), k
