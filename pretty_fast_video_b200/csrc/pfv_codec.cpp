@@ -890,6 +890,7 @@ extern "C" int pfv_decoder_open(const uint8_t *data, size_t len, int device, uin
                         // the reference's Decoder::new accepts such a header, so does this one
                         d->info.num_qtables > 256 ? 256u : d->info.num_qtables, d->nslots, d->lanes, nullptr, &d->ctx);
     if (rc) return rc;
+    if ((rc = pfv_ctx_reserve_staging(d->ctx, true, false)) != PFV_OK) { pfv_ctx_destroy(d->ctx); return rc; }   // (not inside the first advance_frame)
     // pinned buffers are sized once, from the largest frame packet of the stream (cudaHostAlloc costs milliseconds:
     // never on the per-frame path).  Token capacity: an emitted token costs at least 3 bits when the tree has two or
     // more symbols, and a one-symbol tree emits none.
@@ -1271,6 +1272,7 @@ extern "C" int pfv_encoder_open(uint32_t width, uint32_t height, uint32_t framer
     e->width = width; e->height = height; e->framerate = framerate; e->px_err = px_err;
     rc = pfv_ctx_create(device, width, height, qt, 4, 2, 1, nullptr, &e->ctx);
     if (rc) return rc;
+    if ((rc = pfv_ctx_reserve_staging(e->ctx, false, true)) != PFV_OK) { pfv_ctx_destroy(e->ctx); return rc; }
     pfv_ctx_geometry(e->ctx, &e->geo);
     e->ysz = (size_t)e->geo.width * e->geo.height;
     e->csz = (size_t)e->geo.cwidth * e->geo.cheight;

@@ -210,6 +210,8 @@ struct pfv_ctx {
     bool trace = false;                    // PFV_TRACE=1: host time of the encode submit path, printed at destroy
     double t_enc_alloc = 0, t_enc_wait = 0, t_enc_copy = 0, t_enc_launch = 0, t_enc_d2h = 0;
     uint64_t n_enc_submits = 0;
+    double t_dec_check = 0, t_dec_wait = 0, t_dec_copy = 0, t_dec_launch = 0, t_dec_d2h = 0;   // PFV_TRACE: the same split for decode submits
+    uint64_t n_dec_submits = 0, n_dec_jobs = 0;
     int host_compact = 0;                  // PFV_HOST_COMPACT=1: compact dense host coefficients to tokens on a host pool before the
                                            // copy.  Off by default: on the bench box (16 host threads) scanning 6.27 MB per 1080p
                                            // frame cost ~1 ms per frame per thread and halved e2e (7.9 k -> 3.9 k frames/s); hosts
@@ -444,6 +446,18 @@ int wait_slot_readers(pfv_ctx *c, const uint32_t *slots, uint32_t n)
 
 }  // namespace
 
+// (internal, pfv_internal.h) The staging buffers of the sparse decode seam / of encode submits are allocated on first use - a dozen
+// cudaMalloc / cudaHostAlloc calls, several milliseconds.  The Decoder and Encoder objects know at open what they will submit and
+// allocate there, like the reference's Decoder::new / Encoder::new allocate their planes (src/dec.rs:31-52, src/enc.rs:37-73).
+int pfv_ctx_reserve_staging(pfv_ctx *c, bool decode_sparse, bool encode)
+{
+    if (!c) return fail(PFV_ERR_BAD_ARG, "NULL context");
+    CU_TRY(ensure_device(c->device));
+    if (decode_sparse) { int rc = ensure_sparse_staging(c); if (rc) return rc; }
+    if (encode) { int rc = ensure_src_staging(c); if (rc) return rc; }
+    return PFV_OK;
+}
+
 extern "C" void pfv_ctx_destroy(pfv_ctx *c)
 {
     if (!c) return;
@@ -452,6 +466,11 @@ extern "C" void pfv_ctx_destroy(pfv_ctx *c)
                         "copies in %.1f us, launches %.1f us, copies out %.1f us\n", (unsigned long long)c->n_enc_submits,
                 1e6 * c->t_enc_alloc / c->n_enc_submits, 1e6 * c->t_enc_wait / c->n_enc_submits, 1e6 * c->t_enc_copy / c->n_enc_submits,
                 1e6 * c->t_enc_launch / c->n_enc_submits, 1e6 * c->t_enc_d2h / c->n_enc_submits);
+    if (c->trace && c->n_dec_submits)
+        fprintf(stderr, "[pfv ctx] %llu decode submits (%.2f jobs each), host time per submit: checks + staging %.1f us, wait for the stage %.1f us, "
+                        "copies in %.1f us, launches %.1f us, copies out %.1f us\n", (unsigned long long)c->n_dec_submits,
+                (double)c->n_dec_jobs / c->n_dec_submits, 1e6 * c->t_dec_check / c->n_dec_submits, 1e6 * c->t_dec_wait / c->n_dec_submits,
+                1e6 * c->t_dec_copy / c->n_dec_submits, 1e6 * c->t_dec_launch / c->n_dec_submits, 1e6 * c->t_dec_d2h / c->n_dec_submits);
     cudaSetDevice(c->device);
     if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
@@ -837,6 +856,7 @@ struct DecIn {
 
 static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
 {
+    const double tr0 = c->trace ? host_now() : 0;
     if (njobs > c->max_jobs) return fail(PFV_ERR_BAD_ARG, "%u jobs > max_jobs %u", njobs, c->max_jobs);
     const pfv_geometry &g = c->geo;
     bool any_sparse = false;
@@ -896,7 +916,9 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
 
     const uint64_t id = __atomic_add_fetch(&c->submit_id, 1, __ATOMIC_RELAXED);   // helper threads read it (pfv_ctx_wait_submit)
     Stage &st = c->st[id % STAGES];
+    const double tr1 = c->trace ? host_now() : 0;
     CU_TRY(cudaEventSynchronize(st.ev_h2d));                    // pinned job table of this stage is free again
+    const double tr2 = c->trace ? host_now() : 0;
     CU_TRY(cudaStreamWaitEvent(s_up, st.ev_kernel, 0));         // device buffers of this stage are free again
     if (st.d2h_used) {                                          // ... also for an encode submit that used the stage before
         CU_TRY(cudaStreamWaitEvent(s_up, st.ev_d2h, 0));
@@ -1020,6 +1042,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     CU_TRY(cudaEventRecord(st.ev_h2d, s_up));
 
     // compute
+    const double tr3 = c->trace ? host_now() : 0;
     CU_TRY(cudaStreamWaitEvent(c->s_compute, st.ev_h2d, 0));
     {
         std::vector<uint32_t> dsts(njobs);
@@ -1087,6 +1110,7 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
     }
     if (c->want_kernel_time) { CU_TRY(cudaEventRecord(c->ev_k1, c->s_compute)); c->have_kernel_time = true; }
     CU_TRY(cudaEventRecord(st.ev_kernel, c->s_compute));
+    const double tr4 = c->trace ? host_now() : 0;
 
     // copy out
     bool any_out = false;
@@ -1114,6 +1138,11 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         }
     }
     CU_TRY(cudaEventRecord(c->ev_d2h_ring[id % D2H_RING], s_down));
+    if (c->trace) {
+        const double tr5 = host_now();
+        c->t_dec_check += tr1 - tr0; c->t_dec_wait += tr2 - tr1; c->t_dec_copy += tr3 - tr2; c->t_dec_launch += tr4 - tr3; c->t_dec_d2h += tr5 - tr4;
+        c->n_dec_submits++; c->n_dec_jobs += njobs;
+    }
     return PFV_OK;
 }
 

@@ -201,3 +201,7 @@ cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
                             bool count, int variant, uint32_t *d_work, cudaStream_t s);
 
 }  // namespace pfv
+
+// pfv_ctx.cu, for the codec layer (pfv_codec.cpp): allocate the lazily allocated staging buffers now
+struct pfv_ctx;
+int pfv_ctx_reserve_staging(pfv_ctx *c, bool decode_sparse, bool encode);
