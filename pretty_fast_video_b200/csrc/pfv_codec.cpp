@@ -998,7 +998,7 @@ extern "C" int pfv_decoder_advance_frame(pfv_decoder *d, int *got_frame, const u
         d->delivered = nullptr;
     }
     const double t2 = now_s();
-    rc = pfv_ctx_wait_submit(d->ctx, w->submit_id);
+    rc = pfv_ctx_wait_submit_polling(d->ctx, w->submit_id, 300e-6);
     if (rc) {
         // same recovery as a failed submit: the frame is consumed, everything decoded ahead is dropped and the framebuffer
         // stays what the last returned picture left there (the reference reports an error only for the frame that fails)

@@ -1214,6 +1214,27 @@ extern "C" int pfv_ctx_wait_submit(pfv_ctx *c, uint64_t id)
     return PFV_OK;
 }
 
+// (internal, pfv_internal.h) The same for ONE thread that is about to hand the result to its caller (Decoder::advance_frame): the
+// events block (cudaEventBlockingSync - a pool of waiting threads must not spin, see pfv_ctx_create), and a blocked thread wakes up
+// tens of microseconds after its event; here the event is polled for up to `spin_s` seconds first.
+int pfv_ctx_wait_submit_polling(pfv_ctx *c, uint64_t id, double spin_s)
+{
+    if (!c) return fail(PFV_ERR_BAD_ARG, "NULL context");
+    const uint64_t last = __atomic_load_n(&c->submit_id, __ATOMIC_RELAXED);
+    if (id == 0 || id > last || id + D2H_RING <= last) return pfv_ctx_wait_submit(c, id);       // (its error messages)
+    if (__atomic_load_n(&c->failed_ring[id % D2H_RING], __ATOMIC_ACQUIRE) == id) return pfv_ctx_wait_submit(c, id);
+    CU_TRY(ensure_device(c->device));
+    const double t0 = host_now();
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(c->ev_d2h_ring[id % D2H_RING]);
+        if (e == cudaSuccess) return PFV_OK;
+        if (e != cudaErrorNotReady) CU_TRY(e);
+        if (host_now() - t0 > spin_s) break;
+    }
+    CU_TRY(cudaEventSynchronize(c->ev_d2h_ring[id % D2H_RING]));
+    return PFV_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------------------------------

@@ -205,3 +205,5 @@ cudaError_t launch_encode_p(const FrameGeom &g, const EncJob *d_jobs, uint32_t n
 // pfv_ctx.cu, for the codec layer (pfv_codec.cpp): allocate the lazily allocated staging buffers now
 struct pfv_ctx;
 int pfv_ctx_reserve_staging(pfv_ctx *c, bool decode_sparse, bool encode);
+// pfv_ctx_wait_submit that polls the event for up to spin_s seconds before it blocks (for the one thread that returns the frame)
+int pfv_ctx_wait_submit_polling(pfv_ctx *c, uint64_t id, double spin_s);

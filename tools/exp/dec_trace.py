@@ -14,8 +14,11 @@ with codec.Encoder(w, h, 30, 5, num_threads=16) as enc:
     enc.finish()
     data = enc.bytes()
     print("encoder: %.0f fps" % (gop * ngop / (time.perf_counter() - t0)))
-for threads, ahead in ((16, 0), (16, 48), (16, 24), (12, 48)):
-    for rep in range(2):
+cfgs = ((16, 0), (16, 48), (16, 24), (12, 48))
+if len(sys.argv) > 1:                                   # python tools/exp/dec_trace.py 10 12 14 16 : a sweep over pool sizes
+    cfgs = tuple((int(a), 0) for a in sys.argv[1:])
+for threads, ahead in cfgs:
+    for rep in range(3 if len(sys.argv) > 1 else 2):
         dec = codec.Decoder(data, num_threads=threads, read_ahead=ahead)
         t1 = time.perf_counter()
         n = 0
