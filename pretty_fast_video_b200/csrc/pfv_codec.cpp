@@ -798,7 +798,7 @@ static int decoder_submit_ready(pfv_decoder *d, DecWork *must)
             j.out_v = j.out_y + d->off_v;
         }
         const double ts = now_s();
-        int rc = pfv_decode_submit_sparse(d->ctx, jobs, (uint32_t)batch.size());
+        int rc = pfv_decode_submit_sparse_trusted(d->ctx, jobs, (uint32_t)batch.size());
         d->t_prof[6] += now_s() - ts;
         if (rc) return rc;
         const uint64_t id = pfv_ctx_last_submit_id(d->ctx);

@@ -207,3 +207,6 @@ struct pfv_ctx;
 int pfv_ctx_reserve_staging(pfv_ctx *c, bool decode_sparse, bool encode);
 // pfv_ctx_wait_submit that polls the event for up to spin_s seconds before it blocks (for the one thread that returns the frame)
 int pfv_ctx_wait_submit_polling(pfv_ctx *c, uint64_t id, double spin_s);
+// pfv_decode_submit_sparse without the walk over mb_off (the caller is this library's own entropy decoder)
+struct pfv_decode_job_sparse;
+int pfv_decode_submit_sparse_trusted(pfv_ctx *c, const pfv_decode_job_sparse *jobs, uint32_t njobs);
