@@ -1070,7 +1070,7 @@ struct OutPacket {
 // The Encoder's own output buffer (its `W` when no writer callback is set): bytes are only ever appended.  As a std::vector it cost the
 // writer thread - the one serial stage behind the entropy coders - 170-230 us per 1080p frame (PFV_TRACE, 150 KB packets): every
 // doubling moved the stream into fresh memory, so each byte of a 70 MB stream was page-faulted in twice, 4 KB at a time, and copied
-// once.  Here the buffer is an anonymous mapping that grows in place (mremap moves page tables, not bytes) and asks for huge pages.
+// once.  Here the buffer is an anonymous mapping that grows in place (mremap moves page tables, not bytes): every page is faulted in once.
 struct GrowBuf {
     uint8_t *p = nullptr;
     size_t   n = 0, cap = 0;
@@ -1086,7 +1086,10 @@ struct GrowBuf {
         void *q = p ? mremap(p, cap, nc, MREMAP_MAYMOVE) : mmap(nullptr, nc, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (q == MAP_FAILED) return false;
 #ifdef MADV_HUGEPAGE
-        madvise(q, nc, MADV_HUGEPAGE);                               // (advice only: without huge pages the faults stay 4 KB ones)
+        // Huge pages make the faults 512 times fewer, but where the host's transparent_hugepage/defrag is "madvise" (the default
+        // of most distributions) an advised region compacts memory ON the fault and can stall the writer for milliseconds: opt-in.
+        static const bool huge = getenv("PFV_STREAM_HUGEPAGES") && atoi(getenv("PFV_STREAM_HUGEPAGES")) != 0;
+        if (huge) madvise(q, nc, MADV_HUGEPAGE);
 #endif
         p = static_cast<uint8_t *>(q);
         cap = nc;

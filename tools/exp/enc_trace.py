@@ -11,7 +11,7 @@ nthreads = int(sys.argv[1]) if len(sys.argv) > 1 else (os.cpu_count() or 1)
 w, h, gop = 1920, 1080, 15
 sv = SynthVideo(w, h, 0x50465602)
 src = [sv.frame(t) for t in range(gop + 3 * 3)]
-for n in (gop, 32 * gop, 32 * gop, 32 * gop):
+for n in (gop, 32 * gop, 32 * gop, 32 * gop, 32 * gop, 32 * gop, 32 * gop):
     with codec.Encoder(w, h, 30, 5, num_threads=nthreads, device=0) as enc:
         t0 = time.perf_counter()
         for t in range(n):
