@@ -202,6 +202,10 @@ decode_p_fused_kernel(const __grid_constant__ SbParams P, const __grid_constant_
     // the next record five windows ahead into a small ring.  It evens out the SMs (sm__cycles_active min / avg / max 93 k / 100 k /
     // 102 k instead of 80 k / 86 k / 95 k) but the leader's extra work per window costs more than the balance returns: 56.8 us per
     // 32 x 1080p against 52.1 us.)
+    // (Measured and dropped as well, visit zx: the CTA's OWN windows handed to its four pipelines one at a time from a shared-memory
+    // counter - no global atomic, no record to decode, the leader publishes the index to its pipeline two windows ahead.  603 k ->
+    // 591 k frames/s at 32 frames per launch, 684 k -> 669 k at 64, 174 k -> 169 k at 3840x2160: the pipelines of an SM do not finish
+    // far enough apart to pay for the hand-shake; what is uneven is the SMs among each other.)
     // The windows of the launch are dealt out to the copy pipelines (3 per CTA) in frame-interleaved order (pipelines that run at
     // the same time work on DIFFERENT frames): pipeline gp takes items gp, gp + npipes, ...; item -> (window wi = item / njobs,
     // job = item % njobs)
