@@ -1124,6 +1124,9 @@ static int decode_submit_impl(pfv_ctx *c, const DecIn *jobs, uint32_t njobs)
         // (three more driver calls per submit would cost more than they hide).
         uint32_t n_out = 0;
         for (uint32_t i = 0; i < njobs; i++) n_out += jobs[i].out_y ? 1u : 0u;
+        // (Measured and dropped, visit zy: the whole batch as ONE strided copy - cudaMemcpy2DAsync with the pictures as rows - when
+        // slots and host buffers are equally spaced: 14.2 k frames/s against 14.9 k with one copy per picture on two streams, and
+        // two buffers that merely LOOK equally spaced may belong to different allocations, which the copy rejects.)
         const bool two = c->d2h_streams2 && n_out >= 2 && (size_t)g.width * g.height >= ((size_t)1 << 20);
         CU_TRY(cudaStreamWaitEvent(s_down, st.ev_kernel, 0));
         if (two) CU_TRY(cudaStreamWaitEvent(c->s_d2h2, st.ev_kernel, 0));
