@@ -383,6 +383,21 @@ def test_encoder_stream_is_byte_identical_to_oracle_encoder(size, quality, kind,
     assert np.array_equal(prev, fb)                                  # closed loop: encoder recon == decoder picture
 
 
+def test_encoder_stream_buffer_grows_in_place():
+    """The Encoder's own stream buffer starts as an 8 MB mapping and grows by mremap (pfv_codec.cpp, GrowBuf): a stream of noise
+    at quality 10 passes that size and must still equal the oracle encoder's, byte for byte."""
+    w, h, n, key, quality = 640, 480, 48, 4, 10
+    want, _ = oracle_stream(w, h, n, quality, key, 1357, kind="random")
+    assert len(want) > (8 << 20), len(want)                          # (10.7 MB)
+    sv = SynthVideo(w, h, 1357, kind="random")
+    with codec.Encoder(w, h, 30, quality, num_threads=4) as enc:
+        for t in range(n):
+            (enc.encode_iframe if t % key == 0 else enc.encode_pframe)(sv.frame(t))
+        enc.finish()
+        mine = enc.bytes()
+    assert mine == want
+
+
 def test_encoder_writer_and_decoder_reader_stream_through_callbacks():
     """Encoder<W: Write> / Decoder<R: Read + Seek> (src/enc.rs:12-26, src/dec.rs:15-28): the stream leaves through a writer
     as packets finish (header first, same bytes as the in-memory encoder) and comes back in through a reader that hands out
