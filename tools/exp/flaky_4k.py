@@ -9,12 +9,13 @@ from pretty_fast_video_b200 import codec
 from pretty_fast_video_b200.synth import SynthVideo
 from test_gpu_codec import gpu_decode_all, oracle_decode_all
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+nthreads = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 w, h, gop = 3840, 2160, 3
 sv = SynthVideo(w, h, 4711)
 frames = [sv.frame(t) for t in range(2 * gop)]
 ref_data = None
 for rep in range(reps):
-    with codec.Encoder(w, h, 30, 5, num_threads=4) as enc:
+    with codec.Encoder(w, h, 30, 5, num_threads=nthreads) as enc:
         for t in range(2 * gop):
             (enc.encode_iframe if t % gop == 0 else enc.encode_pframe)(frames[t])
         recon = enc.prev_frame()
@@ -24,7 +25,7 @@ for rep in range(reps):
         ref_data = data
         _, want_fb = oracle_decode_all(data)
     same_stream = data == ref_data
-    whole, fb = gpu_decode_all(data, num_threads=4)
+    whole, fb = gpu_decode_all(data, num_threads=nthreads)
     if same_stream:
         ofb = want_fb
     else:
@@ -38,5 +39,6 @@ for rep in range(reps):
     if bad_dec:
         idx = np.flatnonzero(fb != ofb)
         where += f" decoder first/last bad byte {idx[0]} {idx[-1]}"
-    print(f"rep {rep}: stream {'same' if same_stream else 'DIFFERENT'} ({len(data)} bytes); encoder recon vs oracle decode: {bad_recon} bytes off; "
-          f"GPU decoder vs oracle decode: {bad_dec} bytes off{where}", flush=True)
+    if bad_recon or bad_dec or not same_stream or rep == reps - 1:
+        print(f"threads {nthreads} rep {rep}: stream {'same' if same_stream else 'DIFFERENT'} ({len(data)} bytes); encoder recon vs oracle decode: {bad_recon} bytes off; "
+              f"GPU decoder vs oracle decode: {bad_dec} bytes off{where}", flush=True)
